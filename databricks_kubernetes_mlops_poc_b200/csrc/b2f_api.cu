@@ -1,0 +1,803 @@
+/*
+ * b2f_api.cu -- C ABI (include/b2f.h) of libb200forest.so: model lifetime, the pinned-ring /
+ * multi-stream staging around the kernels, timing helpers and the NCCL plumbing.
+ *
+ * The reference's counterpart of this file is Python glue: `lifespan` loading the model
+ * (reference app/main.py:20-31), `CustomModel.load_context` / `.predict`
+ * (databricks/src/02-register-model.ipynb:317-353).  Here the model is a flattened forest in HBM
+ * and "predict" is H2D copy -> one fused kernel -> D2H copy, pipelined over CUDA streams.
+ * There is no CPU fallback anywhere in this file: no device, no result.
+ */
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "../../include/b2f.h"
+#include "feature_moments.cuh"
+#include "forest_blob.h"
+#include "forest_predict.cuh"
+
+#define B2F_VERSION_STR "b200forest 0.1.0 (sm_100a)"
+#define B2F_STREAMS 4
+#define B2F_TICKETS 256
+#define B2F_CHUNK_ROWS 16384
+#define B2F_FLUSH_BYTES (256ull << 20) /* > 126 MB L2 */
+
+/* ------------------------------------------------------------------ errors */
+static thread_local char g_err[512] = "";
+
+static int set_err(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return set_err(B2F_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char *b2f_last_error(void) { return g_err; }
+extern "C" const char *b2f_version(void) { return B2F_VERSION_STR; }
+
+extern "C" int b2f_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) return set_err(B2F_ENODEV, "no CUDA device: %s", cudaGetErrorString(e));
+    return n;
+}
+
+/* ------------------------------------------------------------------ NCCL (lazy dlopen) */
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)(void) = nullptr;
+    ncclResult_t (*GroupEnd)(void) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load(void) {
+    if (g_nccl.handle) return B2F_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *nm : names) {
+        h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return set_err(B2F_ENCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define LOADSYM(field, sym)                                                        \
+    do {                                                                           \
+        *(void **)(&g_nccl.field) = dlsym(h, sym);                                 \
+        if (!g_nccl.field) return set_err(B2F_ENCCL, "NCCL symbol %s missing", sym); \
+    } while (0)
+    LOADSYM(GetUniqueId, "ncclGetUniqueId");
+    LOADSYM(CommInitRank, "ncclCommInitRank");
+    LOADSYM(CommInitAll, "ncclCommInitAll");
+    LOADSYM(CommDestroy, "ncclCommDestroy");
+    LOADSYM(AllGather, "ncclAllGather");
+    LOADSYM(GroupStart, "ncclGroupStart");
+    LOADSYM(GroupEnd, "ncclGroupEnd");
+    LOADSYM(GetErrorString, "ncclGetErrorString");
+#undef LOADSYM
+    g_nccl.handle = h;
+    return B2F_OK;
+}
+#define NCCL_TRY(expr)                                                                                      \
+    do {                                                                                                    \
+        ncclResult_t r_ = (expr);                                                                           \
+        if (r_ != ncclSuccess) return set_err(B2F_ENCCL, "%s failed: %s", #expr, g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+/* ------------------------------------------------------------------ model */
+struct Slot {
+    cudaStream_t stream = nullptr;
+    void *d_rows = nullptr;
+    void *d_proba = nullptr; /* sized for double */
+    int32_t *d_label = nullptr;
+    int64_t cap_rows = 0;
+};
+
+struct TicketRec {
+    uint64_t id = 0;
+    cudaEvent_t ev[B2F_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t used_mask = 0;
+};
+
+struct b2f_model {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    KParams kp;
+    b2f_blob_header hdr;
+    int walk_mode = B2F_WALK_GLOBAL;
+    int smem_bytes = 0;
+    int rows_per_warp_max = 2;
+    void *d_blob = nullptr;
+    int64_t forest_bytes = 0;
+    Slot slots[B2F_STREAMS];
+    cudaStream_t compute = nullptr; /* device-resident interface + moments */
+    TicketRec tickets[B2F_TICKETS];
+    uint64_t next_ticket = 1;
+    /* moments */
+    void *d_mom_rows = nullptr;
+    int64_t mom_cap_rows = 0;
+    double *d_mom_partials = nullptr;
+    int mom_blocks = 0;
+    unsigned int *d_mom_ticket = nullptr;
+    double *d_mom_out = nullptr;
+    double *d_gather = nullptr; /* nranks * 72 doubles */
+    int gather_cap = 0;
+    /* L2 flush scratch */
+    void *d_flush = nullptr;
+    /* nccl */
+    ncclComm_t comm = nullptr;
+    int nranks = 0;
+    int rank = 0;
+    int64_t launches = 0;
+};
+
+static int validate_blob(const uint8_t *blob, size_t nbytes, b2f_blob_header *hdr_out) {
+    if (!blob || nbytes < sizeof(b2f_blob_header)) return set_err(B2F_EINVAL, "forest blob too small (%zu bytes)", nbytes);
+    b2f_blob_header h;
+    memcpy(&h, blob, sizeof(h));
+    if (memcmp(h.magic, B2F_BLOB_MAGIC, 8) != 0) return set_err(B2F_EINVAL, "forest blob: bad magic");
+    if (h.version != B2F_BLOB_VERSION) return set_err(B2F_EINVAL, "forest blob: version %u, expected %u", h.version, B2F_BLOB_VERSION);
+    if (h.header_bytes != B2F_BLOB_HEADER_BYTES || h.row_words != B2F_ROW_WORDS)
+        return set_err(B2F_EINVAL, "forest blob: header_bytes=%u row_words=%u unsupported", h.header_bytes, h.row_words);
+    if (h.agg_mode != B2F_AGG_RF_MEAN && h.agg_mode != B2F_AGG_GBDT_LOGISTIC)
+        return set_err(B2F_EINVAL, "forest blob: unknown agg_mode %u", h.agg_mode);
+    if (h.n_trees == 0 || h.n_trees > B2F_MAX_TREES) return set_err(B2F_EINVAL, "forest blob: n_trees=%u out of range [1,%d]", h.n_trees, B2F_MAX_TREES);
+    if (h.n_groups != (h.n_trees + 31) / 32) return set_err(B2F_EINVAL, "forest blob: n_groups=%u inconsistent with n_trees=%u", h.n_groups, h.n_trees);
+    if (h.n_cat + h.n_num > B2F_SENTINEL_WORD) return set_err(B2F_EINVAL, "forest blob: n_cat+n_num=%u exceeds %u", h.n_cat + h.n_num, B2F_SENTINEL_WORD);
+    if (h.total_bytes != nbytes) return set_err(B2F_EINVAL, "forest blob: total_bytes=%llu but %zu given", (unsigned long long)h.total_bytes, nbytes);
+    if (h.groups_off < sizeof(h) || h.groups_off + (uint64_t)h.n_groups * sizeof(b2f_blob_group) > nbytes)
+        return set_err(B2F_EINVAL, "forest blob: group table out of bounds");
+    if (h.chunks_off % 256 || h.chunks_off + h.chunks_bytes > nbytes) return set_err(B2F_EINVAL, "forest blob: chunk area out of bounds");
+    if (!(h.denom > 0.0)) return set_err(B2F_EINVAL, "forest blob: denom must be positive");
+    const b2f_blob_group *gt = reinterpret_cast<const b2f_blob_group *>(blob + h.groups_off);
+    uint64_t expect_off = 0;
+    for (uint32_t g = 0; g < h.n_groups; ++g) {
+        b2f_blob_group gr;
+        memcpy(&gr, &gt[g], sizeof(gr));
+        if (gr.chunk_off != expect_off || gr.n_slots == 0 || gr.n_leaf_slots == 0 ||
+            gr.chunk_bytes != (gr.n_slots + gr.n_leaf_slots) * 256u || (uint64_t)gr.chunk_off + gr.chunk_bytes > h.chunks_bytes ||
+            gr.n_slots >= (1u << 26) || gr.n_leaf_slots >= B2F_LEAF_TAG || gr.n_trees == 0 || gr.n_trees > 32)
+            return set_err(B2F_EINVAL, "forest blob: group %u descriptor invalid", g);
+        expect_off += gr.chunk_bytes;
+        /* every reachable word must keep the walk in bounds: check all slots */
+        const uint32_t *T = reinterpret_cast<const uint32_t *>(blob + h.chunks_off + gr.chunk_off);
+        const uint32_t *M = T + (size_t)gr.n_slots * 32;
+        for (uint32_t s = 0; s < gr.n_slots; ++s)
+            for (uint32_t l = 0; l < 32; ++l) {
+                const uint32_t m = M[s * 32 + l], t = T[s * 32 + l];
+                const uint32_t feat = m & 31u, first = m >> 6;
+                const bool leaf = (first == s);
+                if (feat > B2F_SENTINEL_WORD) return set_err(B2F_EINVAL, "forest blob: group %u slot %u lane %u: row word %u", g, s, l, feat);
+                if (leaf) {
+                    if (!(m & B2F_META_CAT) || feat != B2F_SENTINEL_WORD || !(t & B2F_LEAF_TAG) || (t & (B2F_LEAF_TAG - 1)) >= gr.n_leaf_slots)
+                        return set_err(B2F_EINVAL, "forest blob: group %u slot %u lane %u: malformed leaf", g, s, l);
+                } else {
+                    if (first <= s || first + 1 >= gr.n_slots) return set_err(B2F_EINVAL, "forest blob: group %u slot %u lane %u: child %u out of range", g, s, l, first);
+                    if ((m & B2F_META_CAT) && feat >= h.n_cat && feat != B2F_SENTINEL_WORD)
+                        return set_err(B2F_EINVAL, "forest blob: group %u slot %u lane %u: categorical test on numeric word", g, s, l);
+                }
+            }
+    }
+    if (expect_off != h.chunks_bytes) return set_err(B2F_EINVAL, "forest blob: chunks_bytes mismatch");
+    *hdr_out = h;
+    return B2F_OK;
+}
+
+extern "C" int b2f_blob_validate(const void *forest_blob, size_t nbytes) {
+    b2f_blob_header h;
+    return validate_blob(static_cast<const uint8_t *>(forest_blob), nbytes, &h);
+}
+
+template <int R, bool SMEM, typename OutT>
+static cudaError_t set_smem_attr(int bytes) {
+    return cudaFuncSetAttribute(k_forest_predict<R, SMEM, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
+    CUDA_TRY(cudaSetDevice(m->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, m->device));
+    if (prop.major < 10)
+        return set_err(B2F_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", m->device, prop.major, prop.minor);
+    m->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaDeviceGetAttribute(&m->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
+
+    CUDA_TRY(cudaMalloc(&m->d_blob, nbytes));
+    CUDA_TRY(cudaMemcpy(m->d_blob, blob, nbytes, cudaMemcpyHostToDevice));
+    m->forest_bytes = (int64_t)m->hdr.chunks_bytes;
+
+    KParams &kp = m->kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.chunks = static_cast<const uint8_t *>(m->d_blob) + m->hdr.chunks_off;
+    kp.n_groups = (int)m->hdr.n_groups;
+    kp.agg_mode = (int)m->hdr.agg_mode;
+    kp.n_cat = (int)m->hdr.n_cat;
+    kp.n_num = (int)m->hdr.n_num;
+    kp.init_raw = m->hdr.init_raw;
+    kp.denom = m->hdr.denom;
+    memcpy(kp.impute, m->hdr.impute, sizeof(kp.impute));
+    const b2f_blob_group *gt = reinterpret_cast<const b2f_blob_group *>(blob + m->hdr.groups_off);
+    for (uint32_t g = 0; g < m->hdr.n_groups; ++g) {
+        kp.g[g].chunk_off = gt[g].chunk_off;
+        kp.g[g].chunk_bytes = gt[g].chunk_bytes;
+        kp.g[g].n_slots = gt[g].n_slots;
+        kp.g[g].n_leaf_slots = gt[g].n_leaf_slots;
+        kp.g[g].depth = gt[g].depth;
+    }
+
+    /* shared-memory residency: whole forest + static barriers must fit the opt-in limit */
+    const int64_t need = (int64_t)m->hdr.chunks_bytes;
+    const char *force = getenv("B2F_FORCE_WALK"); /* "smem" | "global": test hook */
+    bool fits = need + 1024 <= (int64_t)m->max_smem_optin;
+    if (force && !strcmp(force, "global")) fits = false;
+    if (force && !strcmp(force, "smem") && !fits) return set_err(B2F_EINVAL, "B2F_FORCE_WALK=smem but forest needs %lld bytes", (long long)need);
+    m->walk_mode = fits ? B2F_WALK_SMEM : B2F_WALK_GLOBAL;
+    m->smem_bytes = fits ? (int)need : 0;
+    if (fits) {
+        CUDA_TRY((set_smem_attr<1, true, float>(m->smem_bytes)));
+        CUDA_TRY((set_smem_attr<2, true, float>(m->smem_bytes)));
+        CUDA_TRY((set_smem_attr<4, true, float>(m->smem_bytes)));
+        CUDA_TRY((set_smem_attr<1, true, double>(m->smem_bytes)));
+        CUDA_TRY((set_smem_attr<2, true, double>(m->smem_bytes)));
+        CUDA_TRY((set_smem_attr<4, true, double>(m->smem_bytes)));
+    }
+    const char *rpw = getenv("B2F_ROWS_PER_WARP");
+    m->rows_per_warp_max = 2;
+    if (rpw) {
+        int v = atoi(rpw);
+        if (v == 1 || v == 2 || v == 4) m->rows_per_warp_max = v;
+    }
+
+    for (int s = 0; s < B2F_STREAMS; ++s) CUDA_TRY(cudaStreamCreateWithFlags(&m->slots[s].stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&m->compute, cudaStreamNonBlocking));
+
+    m->mom_blocks = m->sm_count * 4;
+    CUDA_TRY(cudaMalloc(&m->d_mom_partials, (size_t)m->mom_blocks * B2F_MOM_VALUES * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&m->d_mom_ticket, sizeof(unsigned int)));
+    CUDA_TRY(cudaMemset(m->d_mom_ticket, 0, sizeof(unsigned int)));
+    CUDA_TRY(cudaMalloc(&m->d_mom_out, B2F_MOM_VALUES * sizeof(double)));
+    return B2F_OK;
+}
+
+extern "C" b2f_model *b2f_model_create(const void *forest_blob, size_t nbytes, int device) {
+    int ndev = b2f_device_count();
+    if (ndev < 0) return nullptr;
+    if (device < 0 || device >= ndev) {
+        set_err(B2F_EINVAL, "device %d out of range (have %d)", device, ndev);
+        return nullptr;
+    }
+    b2f_model *m = new (std::nothrow) b2f_model();
+    if (!m) {
+        set_err(B2F_ENOMEM, "out of host memory");
+        return nullptr;
+    }
+    m->device = device;
+    if (validate_blob(static_cast<const uint8_t *>(forest_blob), nbytes, &m->hdr) != B2F_OK ||
+        model_init_cuda(m, static_cast<const uint8_t *>(forest_blob), nbytes) != B2F_OK) {
+        char keep[sizeof(g_err)];
+        memcpy(keep, g_err, sizeof(keep));
+        b2f_model_destroy(m);
+        memcpy(g_err, keep, sizeof(keep));
+        return nullptr;
+    }
+    return m;
+}
+
+extern "C" void b2f_model_destroy(b2f_model *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
+    for (int s = 0; s < B2F_STREAMS; ++s) {
+        Slot &sl = m->slots[s];
+        if (sl.d_rows) cudaFree(sl.d_rows);
+        if (sl.d_proba) cudaFree(sl.d_proba);
+        if (sl.d_label) cudaFree(sl.d_label);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
+    for (auto &t : m->tickets)
+        for (auto &e : t.ev)
+            if (e) cudaEventDestroy(e);
+    if (m->compute) cudaStreamDestroy(m->compute);
+    if (m->d_blob) cudaFree(m->d_blob);
+    if (m->d_mom_rows) cudaFree(m->d_mom_rows);
+    if (m->d_mom_partials) cudaFree(m->d_mom_partials);
+    if (m->d_mom_ticket) cudaFree(m->d_mom_ticket);
+    if (m->d_mom_out) cudaFree(m->d_mom_out);
+    if (m->d_gather) cudaFree(m->d_gather);
+    if (m->d_flush) cudaFree(m->d_flush);
+    delete m;
+}
+
+static int pick_rows_per_warp(const b2f_model *m, int64_t n) {
+    int r = m->rows_per_warp_max;
+    const int64_t warps = (int64_t)m->sm_count * B2F_PREDICT_WARPS;
+    while (r > 1 && n / r < warps) r >>= 1; /* small batches: spread rows over more warps */
+    return r;
+}
+
+extern "C" int b2f_model_info(const b2f_model *m, b2f_info *out) {
+    if (!m || !out) return set_err(B2F_EINVAL, "null argument");
+    memset(out, 0, sizeof(*out));
+    out->device = m->device;
+    out->sm_count = m->sm_count;
+    out->agg_mode = (int)m->hdr.agg_mode;
+    out->walk_mode = m->walk_mode;
+    out->n_trees = (int)m->hdr.n_trees;
+    out->n_groups = (int)m->hdr.n_groups;
+    out->max_depth = (int)m->hdr.max_depth;
+    out->n_cat = (int)m->hdr.n_cat;
+    out->n_num = (int)m->hdr.n_num;
+    out->smem_bytes = m->smem_bytes;
+    out->block_threads = B2F_PREDICT_THREADS;
+    out->rows_per_warp = m->rows_per_warp_max;
+    out->forest_bytes = m->forest_bytes;
+    out->launches = m->launches;
+    return B2F_OK;
+}
+
+/* ------------------------------------------------------------------ pinned memory */
+extern "C" void *b2f_pinned_alloc(size_t nbytes) {
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, nbytes ? nbytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        set_err(B2F_ENOMEM, "cudaHostAlloc(%zu) failed: %s", nbytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void b2f_pinned_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+/* ------------------------------------------------------------------ kernel launch */
+template <int R, bool SMEM, typename OutT>
+static cudaError_t launch_one(const b2f_model *m, cudaStream_t st, const void *rows, int64_t n, void *proba, int32_t *label) {
+    const int64_t n_batches = (n + R - 1) / R;
+    int64_t ctas = std::min<int64_t>(m->sm_count, n_batches);
+    if (ctas < 1) ctas = 1;
+    k_forest_predict<R, SMEM, OutT><<<(unsigned)ctas, B2F_PREDICT_THREADS, SMEM ? m->smem_bytes : 0, st>>>(
+        m->kp, static_cast<const uint32_t *>(rows), (long long)n, static_cast<OutT *>(proba), label);
+    return cudaGetLastError();
+}
+
+static int launch_predict(b2f_model *m, cudaStream_t st, const void *rows_dev, int64_t n, void *proba_dev, int f64, int32_t *label_dev) {
+    if (n <= 0) return B2F_OK;
+    const int r = pick_rows_per_warp(m, n);
+    const bool sm = m->walk_mode == B2F_WALK_SMEM;
+    cudaError_t e;
+#define DISPATCH(RR)                                                                                         \
+    (sm ? (f64 ? launch_one<RR, true, double>(m, st, rows_dev, n, proba_dev, label_dev)                      \
+               : launch_one<RR, true, float>(m, st, rows_dev, n, proba_dev, label_dev))                      \
+        : (f64 ? launch_one<RR, false, double>(m, st, rows_dev, n, proba_dev, label_dev)                     \
+               : launch_one<RR, false, float>(m, st, rows_dev, n, proba_dev, label_dev)))
+    if (r == 4)
+        e = DISPATCH(4);
+    else if (r == 2)
+        e = DISPATCH(2);
+    else
+        e = DISPATCH(1);
+#undef DISPATCH
+    if (e != cudaSuccess) return set_err(B2F_ECUDA, "k_forest_predict launch failed: %s", cudaGetErrorString(e));
+    m->launches++;
+    return B2F_OK;
+}
+
+/* ------------------------------------------------------------------ host-buffer pipeline */
+static int slot_reserve(b2f_model *m, Slot &sl, int64_t rows) {
+    if (rows <= sl.cap_rows) return B2F_OK;
+    CUDA_TRY(cudaStreamSynchronize(sl.stream));
+    if (sl.d_rows) cudaFree(sl.d_rows);
+    if (sl.d_proba) cudaFree(sl.d_proba);
+    if (sl.d_label) cudaFree(sl.d_label);
+    sl.d_rows = sl.d_proba = nullptr;
+    sl.d_label = nullptr;
+    sl.cap_rows = 0;
+    int64_t cap = std::max<int64_t>(rows, 1024);
+    CUDA_TRY(cudaMalloc(&sl.d_rows, (size_t)cap * B2F_ROW_BYTES));
+    CUDA_TRY(cudaMalloc(&sl.d_proba, (size_t)cap * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void **)&sl.d_label, (size_t)cap * sizeof(int32_t)));
+    sl.cap_rows = cap;
+    return B2F_OK;
+}
+
+/* enqueue the whole batch; on return used_mask tells which slot streams carry work */
+static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, void *proba, int f64, int32_t *label, uint32_t *used_mask) {
+    *used_mask = 0;
+    if (n < 0) return set_err(B2F_EINVAL, "negative row count");
+    if (n == 0) return B2F_OK;
+    if (!rows) return set_err(B2F_EINVAL, "rows is NULL");
+    CUDA_TRY(cudaSetDevice(m->device));
+    int64_t chunk = B2F_CHUNK_ROWS;
+    if (n <= chunk + chunk / 2) chunk = n; /* small batch: one H2D, one launch */
+    const size_t psz = f64 ? sizeof(double) : sizeof(float);
+    int c = 0;
+    for (int64_t off = 0; off < n; off += chunk, ++c) {
+        const int64_t cnt = std::min(chunk, n - off);
+        Slot &sl = m->slots[c % B2F_STREAMS];
+        int rc = slot_reserve(m, sl, cnt);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(sl.d_rows, static_cast<const uint8_t *>(rows) + (size_t)off * B2F_ROW_BYTES, (size_t)cnt * B2F_ROW_BYTES,
+                                 cudaMemcpyHostToDevice, sl.stream));
+        rc = launch_predict(m, sl.stream, sl.d_rows, cnt, proba ? sl.d_proba : nullptr, f64, label ? sl.d_label : nullptr);
+        if (rc) return rc;
+        if (proba)
+            CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(proba) + (size_t)off * psz, sl.d_proba, (size_t)cnt * psz, cudaMemcpyDeviceToHost, sl.stream));
+        if (label) CUDA_TRY(cudaMemcpyAsync(label + off, sl.d_label, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
+        *used_mask |= 1u << (c % B2F_STREAMS);
+    }
+    return B2F_OK;
+}
+
+static int sync_mask(b2f_model *m, uint32_t mask) {
+    for (int s = 0; s < B2F_STREAMS; ++s)
+        if (mask & (1u << s)) CUDA_TRY(cudaStreamSynchronize(m->slots[s].stream));
+    return B2F_OK;
+}
+
+static int predict_host(b2f_model *m, const void *rows, int64_t n, void *proba, int f64, int32_t *label) {
+    if (!m) return set_err(B2F_EINVAL, "model is NULL");
+    uint32_t mask = 0;
+    int rc = enqueue_host_batch(m, rows, n, proba, f64, label, &mask);
+    int rc2 = sync_mask(m, mask);
+    return rc ? rc : rc2;
+}
+
+extern "C" int b2f_predict(b2f_model *m, const void *rows, int64_t n, float *proba1, int32_t *label) {
+    return predict_host(m, rows, n, proba1, 0, label);
+}
+extern "C" int b2f_predict_f64(b2f_model *m, const void *rows, int64_t n, double *proba1, int32_t *label) {
+    return predict_host(m, rows, n, proba1, 1, label);
+}
+
+extern "C" int b2f_predict_async(b2f_model *m, const void *rows_pinned, int64_t n, void *proba1_pinned, int proba_is_f64,
+                                 int32_t *label_pinned, b2f_ticket *ticket) {
+    if (!m || !ticket) return set_err(B2F_EINVAL, "null argument");
+    const uint64_t id = m->next_ticket++;
+    TicketRec &t = m->tickets[id % B2F_TICKETS];
+    if (t.id != 0) { /* oldest ticket still outstanding in this ring position: retire it */
+        for (int s = 0; s < B2F_STREAMS; ++s)
+            if (t.used_mask & (1u << s)) CUDA_TRY(cudaEventSynchronize(t.ev[s]));
+    }
+    uint32_t mask = 0;
+    int rc = enqueue_host_batch(m, rows_pinned, n, proba1_pinned, proba_is_f64, label_pinned, &mask);
+    if (rc) {
+        sync_mask(m, mask);
+        return rc;
+    }
+    for (int s = 0; s < B2F_STREAMS; ++s)
+        if (mask & (1u << s)) {
+            if (!t.ev[s]) CUDA_TRY(cudaEventCreateWithFlags(&t.ev[s], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventRecord(t.ev[s], m->slots[s].stream));
+        }
+    t.id = id;
+    t.used_mask = mask;
+    *ticket = id;
+    return B2F_OK;
+}
+
+extern "C" int b2f_wait(b2f_model *m, b2f_ticket ticket) {
+    if (!m) return set_err(B2F_EINVAL, "model is NULL");
+    TicketRec &t = m->tickets[ticket % B2F_TICKETS];
+    if (t.id != ticket) return B2F_OK; /* already retired */
+    CUDA_TRY(cudaSetDevice(m->device));
+    for (int s = 0; s < B2F_STREAMS; ++s)
+        if (t.used_mask & (1u << s)) CUDA_TRY(cudaEventSynchronize(t.ev[s]));
+    t.id = 0;
+    t.used_mask = 0;
+    return B2F_OK;
+}
+
+extern "C" int b2f_predict_multi(b2f_model **models, int n_models, const void *rows, int64_t n, void *proba1, int proba_is_f64, int32_t *label) {
+    if (!models || n_models <= 0) return set_err(B2F_EINVAL, "no models");
+    if (n < 0) return set_err(B2F_EINVAL, "negative row count");
+    std::vector<uint32_t> masks(n_models, 0);
+    const size_t psz = proba_is_f64 ? sizeof(double) : sizeof(float);
+    int rc = B2F_OK;
+    for (int i = 0; i < n_models && rc == B2F_OK; ++i) {
+        const int64_t lo = n * i / n_models, hi = n * (i + 1) / n_models;
+        if (hi <= lo) continue;
+        rc = enqueue_host_batch(models[i], static_cast<const uint8_t *>(rows) + (size_t)lo * B2F_ROW_BYTES, hi - lo,
+                                proba1 ? static_cast<uint8_t *>(proba1) + (size_t)lo * psz : nullptr, proba_is_f64, label ? label + lo : nullptr,
+                                &masks[i]);
+    }
+    for (int i = 0; i < n_models; ++i) {
+        cudaSetDevice(models[i]->device);
+        int rc2 = sync_mask(models[i], masks[i]);
+        if (rc == B2F_OK) rc = rc2;
+    }
+    return rc;
+}
+
+/* ------------------------------------------------------------------ device-resident interface */
+extern "C" void *b2f_device_alloc(b2f_model *m, size_t nbytes) {
+    if (!m) return nullptr;
+    void *p = nullptr;
+    if (cudaSetDevice(m->device) != cudaSuccess || cudaMalloc(&p, nbytes ? nbytes : 1) != cudaSuccess) {
+        set_err(B2F_ENOMEM, "cudaMalloc(%zu) failed: %s", nbytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void b2f_device_free(b2f_model *m, void *dptr) {
+    if (!m || !dptr) return;
+    cudaSetDevice(m->device);
+    cudaFree(dptr);
+}
+extern "C" int b2f_copy_h2d(b2f_model *m, void *dst_dev, const void *src_host, size_t nbytes) {
+    if (!m) return set_err(B2F_EINVAL, "model is NULL");
+    CUDA_TRY(cudaSetDevice(m->device));
+    CUDA_TRY(cudaMemcpyAsync(dst_dev, src_host, nbytes, cudaMemcpyHostToDevice, m->compute));
+    CUDA_TRY(cudaStreamSynchronize(m->compute));
+    return B2F_OK;
+}
+extern "C" int b2f_copy_d2h(b2f_model *m, void *dst_host, const void *src_dev, size_t nbytes) {
+    if (!m) return set_err(B2F_EINVAL, "model is NULL");
+    CUDA_TRY(cudaSetDevice(m->device));
+    CUDA_TRY(cudaMemcpyAsync(dst_host, src_dev, nbytes, cudaMemcpyDeviceToHost, m->compute));
+    CUDA_TRY(cudaStreamSynchronize(m->compute));
+    return B2F_OK;
+}
+extern "C" int b2f_predict_device(b2f_model *m, const void *rows_dev, int64_t n, void *proba1_dev, int proba_is_f64, int32_t *label_dev) {
+    if (!m) return set_err(B2F_EINVAL, "model is NULL");
+    CUDA_TRY(cudaSetDevice(m->device));
+    return launch_predict(m, m->compute, rows_dev, n, proba1_dev, proba_is_f64, label_dev);
+}
+extern "C" int b2f_sync(b2f_model *m) {
+    if (!m) return set_err(B2F_EINVAL, "model is NULL");
+    CUDA_TRY(cudaSetDevice(m->device));
+    CUDA_TRY(cudaStreamSynchronize(m->compute));
+    return B2F_OK;
+}
+
+static int ensure_flush(b2f_model *m) {
+    if (!m->d_flush) CUDA_TRY(cudaMalloc(&m->d_flush, B2F_FLUSH_BYTES));
+    return B2F_OK;
+}
+
+extern "C" int b2f_predict_device_timed(b2f_model *m, const void *rows_dev, int64_t n, void *proba1_dev, int proba_is_f64, int32_t *label_dev,
+                                        int iters, int flush_l2, float *ms_each) {
+    if (!m || iters <= 0 || !ms_each) return set_err(B2F_EINVAL, "bad argument");
+    CUDA_TRY(cudaSetDevice(m->device));
+    if (flush_l2) {
+        int rc = ensure_flush(m);
+        if (rc) return rc;
+    }
+    std::vector<cudaEvent_t> ev(2 * (size_t)iters);
+    for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
+    int rc = B2F_OK;
+    for (int i = 0; i < iters && rc == B2F_OK; ++i) {
+        if (flush_l2) CUDA_TRY(cudaMemsetAsync(m->d_flush, i & 0xff, B2F_FLUSH_BYTES, m->compute));
+        CUDA_TRY(cudaEventRecord(ev[2 * i], m->compute));
+        rc = launch_predict(m, m->compute, rows_dev, n, proba1_dev, proba_is_f64, label_dev);
+        CUDA_TRY(cudaEventRecord(ev[2 * i + 1], m->compute));
+    }
+    CUDA_TRY(cudaStreamSynchronize(m->compute));
+    for (int i = 0; i < iters; ++i) CUDA_TRY(cudaEventElapsedTime(&ms_each[i], ev[2 * i], ev[2 * i + 1]));
+    for (auto &e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ moments */
+static int launch_moments(b2f_model *m, const void *rows_dev, int64_t n) {
+    int64_t blocks = std::min<int64_t>(m->mom_blocks, (n + B2F_MOM_ROWS_PER_BLOCK - 1) / B2F_MOM_ROWS_PER_BLOCK);
+    if (blocks < 1) blocks = 1;
+    k_feature_moments<<<(unsigned)blocks, B2F_MOM_THREADS, 0, m->compute>>>(static_cast<const uint4 *>(rows_dev), (long long)n, (int)m->hdr.n_cat,
+                                                                           m->d_mom_partials, m->d_mom_ticket, m->d_mom_out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_err(B2F_ECUDA, "k_feature_moments launch failed: %s", cudaGetErrorString(e));
+    m->launches++;
+    return B2F_OK;
+}
+
+extern "C" int b2f_moments_device(b2f_model *m, const void *rows_dev, int64_t n, double *out) {
+    if (!m || !out || n < 0) return set_err(B2F_EINVAL, "bad argument");
+    CUDA_TRY(cudaSetDevice(m->device));
+    int rc = launch_moments(m, rows_dev, n);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, m->d_mom_out, B2F_MOM_VALUES * sizeof(double), cudaMemcpyDeviceToHost, m->compute));
+    CUDA_TRY(cudaStreamSynchronize(m->compute));
+    return B2F_OK;
+}
+
+static int moments_stage(b2f_model *m, const void *rows, int64_t n) {
+    if (n > m->mom_cap_rows) {
+        CUDA_TRY(cudaStreamSynchronize(m->compute));
+        if (m->d_mom_rows) cudaFree(m->d_mom_rows);
+        m->d_mom_rows = nullptr;
+        m->mom_cap_rows = 0;
+        CUDA_TRY(cudaMalloc(&m->d_mom_rows, (size_t)std::max<int64_t>(n, 1024) * B2F_ROW_BYTES));
+        m->mom_cap_rows = std::max<int64_t>(n, 1024);
+    }
+    if (n > 0) CUDA_TRY(cudaMemcpyAsync(m->d_mom_rows, rows, (size_t)n * B2F_ROW_BYTES, cudaMemcpyHostToDevice, m->compute));
+    return B2F_OK;
+}
+
+extern "C" int b2f_moments(b2f_model *m, const void *rows, int64_t n, double *out) {
+    if (!m || !out || n < 0 || (n > 0 && !rows)) return set_err(B2F_EINVAL, "bad argument");
+    CUDA_TRY(cudaSetDevice(m->device));
+    int rc = moments_stage(m, rows, n);
+    if (rc) return rc;
+    return b2f_moments_device(m, m->d_mom_rows, n, out);
+}
+
+extern "C" int b2f_moments_device_timed(b2f_model *m, const void *rows_dev, int64_t n, int iters, int flush_l2, float *ms_each, double *out) {
+    if (!m || iters <= 0 || !ms_each) return set_err(B2F_EINVAL, "bad argument");
+    CUDA_TRY(cudaSetDevice(m->device));
+    if (flush_l2) {
+        int rc = ensure_flush(m);
+        if (rc) return rc;
+    }
+    std::vector<cudaEvent_t> ev(2 * (size_t)iters);
+    for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
+    int rc = B2F_OK;
+    for (int i = 0; i < iters && rc == B2F_OK; ++i) {
+        if (flush_l2) CUDA_TRY(cudaMemsetAsync(m->d_flush, i & 0xff, B2F_FLUSH_BYTES, m->compute));
+        CUDA_TRY(cudaEventRecord(ev[2 * i], m->compute));
+        rc = launch_moments(m, rows_dev, n);
+        CUDA_TRY(cudaEventRecord(ev[2 * i + 1], m->compute));
+    }
+    if (out) CUDA_TRY(cudaMemcpyAsync(out, m->d_mom_out, B2F_MOM_VALUES * sizeof(double), cudaMemcpyDeviceToHost, m->compute));
+    CUDA_TRY(cudaStreamSynchronize(m->compute));
+    for (int i = 0; i < iters; ++i) CUDA_TRY(cudaEventElapsedTime(&ms_each[i], ev[2 * i], ev[2 * i + 1]));
+    for (auto &e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
+/* Chan et al. pairwise merge of (count, mean, M2), in part order */
+extern "C" void b2f_moments_merge(const double *parts, int k, double *out) {
+    for (int w = 0; w < B2F_ROW_WORDS; ++w) {
+        double n = 0.0, mean = 0.0, m2 = 0.0;
+        for (int i = 0; i < k; ++i) {
+            const double nb = parts[(size_t)i * B2F_MOM_VALUES + w * 3 + 0];
+            const double mb = parts[(size_t)i * B2F_MOM_VALUES + w * 3 + 1];
+            const double sb = parts[(size_t)i * B2F_MOM_VALUES + w * 3 + 2];
+            if (nb <= 0.0) continue;
+            if (n == 0.0) {
+                n = nb, mean = mb, m2 = sb;
+                continue;
+            }
+            const double tot = n + nb, delta = mb - mean;
+            mean += delta * (nb / tot);
+            m2 += sb + delta * delta * (n * nb / tot);
+            n = tot;
+        }
+        out[w * 3 + 0] = n;
+        out[w * 3 + 1] = mean;
+        out[w * 3 + 2] = m2;
+    }
+}
+
+/* ------------------------------------------------------------------ NCCL plumbing */
+extern "C" int b2f_comm_unique_id(void *id_out128) {
+    if (!id_out128) return set_err(B2F_EINVAL, "null argument");
+    int rc = nccl_load();
+    if (rc) return rc;
+    ncclUniqueId id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id_out128, &id, 128);
+    return B2F_OK;
+}
+
+static int comm_buffers(b2f_model *m, int nranks) {
+    if (nranks > m->gather_cap) {
+        if (m->d_gather) cudaFree(m->d_gather);
+        m->d_gather = nullptr;
+        CUDA_TRY(cudaMalloc(&m->d_gather, (size_t)(nranks + 1) * B2F_MOM_VALUES * sizeof(double)));
+        m->gather_cap = nranks;
+    }
+    return B2F_OK;
+}
+
+extern "C" int b2f_comm_init_rank(b2f_model *m, int nranks, int rank, const void *id128) {
+    if (!m || !id128 || nranks <= 0 || rank < 0 || rank >= nranks) return set_err(B2F_EINVAL, "bad argument");
+    int rc = nccl_load();
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(m->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    NCCL_TRY(g_nccl.CommInitRank(&m->comm, nranks, id, rank));
+    m->nranks = nranks;
+    m->rank = rank;
+    return comm_buffers(m, nranks);
+}
+
+extern "C" int b2f_comm_init_all(b2f_model **models, int n_models) {
+    if (!models || n_models <= 0) return set_err(B2F_EINVAL, "no models");
+    int rc = nccl_load();
+    if (rc) return rc;
+    std::vector<ncclComm_t> comms(n_models);
+    std::vector<int> devs(n_models);
+    for (int i = 0; i < n_models; ++i) devs[i] = models[i]->device;
+    NCCL_TRY(g_nccl.CommInitAll(comms.data(), n_models, devs.data()));
+    for (int i = 0; i < n_models; ++i) {
+        models[i]->comm = comms[i];
+        models[i]->nranks = n_models;
+        models[i]->rank = i;
+        CUDA_TRY(cudaSetDevice(models[i]->device));
+        rc = comm_buffers(models[i], n_models);
+        if (rc) return rc;
+    }
+    return B2F_OK;
+}
+
+extern "C" int b2f_moments_allgather(b2f_model *m, const double *local, double *merged) {
+    if (!m || !local || !merged) return set_err(B2F_EINVAL, "null argument");
+    if (!m->comm) return set_err(B2F_ESTATE, "communicator not initialised (call b2f_comm_init_rank)");
+    CUDA_TRY(cudaSetDevice(m->device));
+    double *send = m->d_gather + (size_t)m->nranks * B2F_MOM_VALUES;
+    CUDA_TRY(cudaMemcpyAsync(send, local, B2F_MOM_VALUES * sizeof(double), cudaMemcpyHostToDevice, m->compute));
+    NCCL_TRY(g_nccl.AllGather(send, m->d_gather, B2F_MOM_VALUES, ncclDouble, m->comm, m->compute));
+    std::vector<double> parts((size_t)m->nranks * B2F_MOM_VALUES);
+    CUDA_TRY(cudaMemcpyAsync(parts.data(), m->d_gather, parts.size() * sizeof(double), cudaMemcpyDeviceToHost, m->compute));
+    CUDA_TRY(cudaStreamSynchronize(m->compute));
+    b2f_moments_merge(parts.data(), m->nranks, merged);
+    return B2F_OK;
+}
+
+extern "C" int b2f_moments_multi(b2f_model **models, int n_models, const void *rows, int64_t n, double *out) {
+    if (!models || n_models <= 0 || !out || n < 0) return set_err(B2F_EINVAL, "bad argument");
+    /* 1. every device reduces its contiguous slice */
+    int rc = B2F_OK;
+    for (int i = 0; i < n_models && rc == B2F_OK; ++i) {
+        b2f_model *m = models[i];
+        const int64_t lo = n * i / n_models, hi = n * (i + 1) / n_models;
+        CUDA_TRY(cudaSetDevice(m->device));
+        rc = moments_stage(m, static_cast<const uint8_t *>(rows) + (size_t)lo * B2F_ROW_BYTES, hi - lo);
+        if (rc == B2F_OK) rc = launch_moments(m, m->d_mom_rows, hi - lo);
+    }
+    if (rc) return rc;
+    const bool use_nccl = models[0]->comm != nullptr && models[0]->nranks == n_models;
+    std::vector<double> parts((size_t)n_models * B2F_MOM_VALUES);
+    if (use_nccl) {
+        /* 2a. all-gather the 576-byte triples over NVLink; every rank ends up with all partials */
+        NCCL_TRY(g_nccl.GroupStart());
+        for (int i = 0; i < n_models; ++i) {
+            b2f_model *m = models[i];
+            ncclResult_t r = g_nccl.AllGather(m->d_mom_out, m->d_gather, B2F_MOM_VALUES, ncclDouble, m->comm, m->compute);
+            if (r != ncclSuccess) {
+                g_nccl.GroupEnd();
+                return set_err(B2F_ENCCL, "ncclAllGather failed: %s", g_nccl.GetErrorString(r));
+            }
+        }
+        NCCL_TRY(g_nccl.GroupEnd());
+        CUDA_TRY(cudaSetDevice(models[0]->device));
+        CUDA_TRY(cudaMemcpyAsync(parts.data(), models[0]->d_gather, parts.size() * sizeof(double), cudaMemcpyDeviceToHost, models[0]->compute));
+        for (int i = 0; i < n_models; ++i) {
+            CUDA_TRY(cudaSetDevice(models[i]->device));
+            CUDA_TRY(cudaStreamSynchronize(models[i]->compute));
+        }
+    } else {
+        /* 2b. no communicator: gather through the host */
+        for (int i = 0; i < n_models; ++i) {
+            CUDA_TRY(cudaSetDevice(models[i]->device));
+            CUDA_TRY(cudaMemcpyAsync(parts.data() + (size_t)i * B2F_MOM_VALUES, models[i]->d_mom_out, B2F_MOM_VALUES * sizeof(double),
+                                     cudaMemcpyDeviceToHost, models[i]->compute));
+            CUDA_TRY(cudaStreamSynchronize(models[i]->compute));
+        }
+    }
+    b2f_moments_merge(parts.data(), n_models, out);
+    return B2F_OK;
+}

@@ -1,0 +1,77 @@
+/*
+ * forest_blob.h -- on-disk / in-HBM layout of a flattened forest ("forest blob", version 1).
+ *
+ * Written by databricks_kubernetes_mlops_poc_b200/flatten.py from a fitted sklearn Pipeline
+ * (the model artefact the reference serves: artifacts/classifier/model/model.pkl, reference
+ * databricks/src/02-register-model.ipynb:317-321), read by b2f_model_create().
+ *
+ * Trees are packed in GROUPS of 32: lane l of a warp walks tree 32*g + l.  Inside a group every
+ * per-node array is interleaved by tree, element (slot s, tree l) at index s*32 + l, so that the
+ * 32 lanes of a warp -- each at a different node of a different tree -- always touch 32 different
+ * shared-memory banks (and, from global memory, 32 consecutive words when the slots coincide).
+ *
+ * One group chunk, contiguous and 256-byte granular (so a chunk is one TMA bulk copy):
+ *     T  : uint32[n_slots][32]      threshold word: float32 threshold (numeric split),
+ *                                   int32 category code (one-hot split) or 0x40000000 | leaf_id (leaf)
+ *     M  : uint32[n_slots][32]      meta word: bits 0..4 row word index, bit 5 = categorical test,
+ *                                   bits 6..31 = slot of the FIRST child (second child = first + 1)
+ *     LV : float64[n_leaf_slots][32] leaf payload: RF class-1 fraction, or GBDT learning_rate*value
+ *
+ * Split semantics (x = row word M.feat of the encoded row, after in-kernel imputation):
+ *     numeric      : go to second child iff !(float(x) <= float(T))     (sklearn: x <= thr -> left)
+ *     categorical  : go to second child iff int(x) == int(T)            (one-hot column == 1 -> right)
+ * A leaf slot tests row word 23 (always 0 in the kernel's copy of the row) for equality with
+ * 0x40000000|leaf_id, which never holds, and names itself as first child: walking is a fixed
+ * `depth`-iteration loop with no leaf branch; leaves simply self-loop.
+ */
+#ifndef B2F_FOREST_BLOB_H
+#define B2F_FOREST_BLOB_H
+#include <stdint.h>
+
+#define B2F_BLOB_MAGIC "B2FOREST"
+#define B2F_BLOB_VERSION 1u
+#define B2F_BLOB_HEADER_BYTES 512u
+#define B2F_GROUP_TREES 32u
+#define B2F_MAX_GROUPS 32u
+#define B2F_SENTINEL_WORD 23u
+#define B2F_LEAF_TAG 0x40000000u
+#define B2F_META_CAT 0x20u
+
+typedef struct b2f_blob_header {
+    char magic[8];
+    uint32_t version;
+    uint32_t header_bytes;
+    uint32_t agg_mode;
+    uint32_t n_trees;
+    uint32_t n_groups;
+    uint32_t row_words;
+    uint32_t n_cat;
+    uint32_t n_num;
+    uint32_t max_depth;
+    uint32_t reserved0;
+    double init_raw; /* GBDT: raw prediction of the init estimator; RF: 0 */
+    double denom;    /* RF: n_trees (proba = sum / denom); GBDT: 1 */
+    uint64_t groups_off;
+    uint64_t chunks_off;
+    uint64_t chunks_bytes;
+    uint64_t total_bytes;
+    float impute[24];  /* per row word: replacement for NaN (numeric words), float32(median) */
+    int32_t vocab[24]; /* per row word: vocabulary size (categorical words), else 0 */
+    uint8_t pad[B2F_BLOB_HEADER_BYTES - 96 - 192];
+} b2f_blob_header;
+
+typedef struct b2f_blob_group {
+    uint32_t chunk_off;    /* bytes from chunks_off; multiple of 256 */
+    uint32_t chunk_bytes;  /* (n_slots + n_leaf_slots) * 256 */
+    uint32_t n_slots;      /* node slots per tree in this group (padded to the group's maximum) */
+    uint32_t n_leaf_slots; /* leaf slots per tree (padded) */
+    uint32_t depth;        /* walk iterations = deepest leaf in the group */
+    uint32_t n_trees;      /* real trees in this group (<= 32; the rest are zero-valued stubs) */
+    uint32_t reserved[2];
+} b2f_blob_group;
+
+#ifdef __cplusplus
+static_assert(sizeof(b2f_blob_header) == B2F_BLOB_HEADER_BYTES, "header size");
+static_assert(sizeof(b2f_blob_group) == 32, "group size");
+#endif
+#endif

@@ -1,0 +1,228 @@
+/*
+ * forest_predict.cuh -- K1: fused impute -> one-hot-as-equality -> tree walk -> aggregate kernel
+ * for sm_100a.  No tensor cores: the path is a branchy pointer walk, not a contraction.
+ *
+ * Replaces, on the GPU, what `classifier.predict_proba(df[all_features])[:, 1]` computes on the CPU
+ * (reference databricks/src/02-register-model.ipynb:335-337; pipeline definition
+ * 01-train-model.ipynb:195-231): SimpleImputer(median) + OneHotEncoder(ignore unknown) +
+ * RandomForestClassifier.predict_proba (float32 inputs, float64 mean of leaf class fractions), and
+ * for BASELINE configs 2-4 the binary GBDT form expit(init + sum lr*leaf).
+ *
+ * Geometry: ONE WARP PER ROW (R rows interleaved per warp for ILP); lane l walks tree 32*g + l of
+ * group g.  The encoded row lives in registers, one 32-bit word per lane (lanes 0..23), fetched with
+ * one coalesced 96-byte load per row; a split's feature value is a warp shuffle from the lane that
+ * holds it, so rows never touch shared memory.  The forest lives in shared memory as the
+ * tree-interleaved SoA described in forest_blob.h, brought in once per CTA by TMA bulk copies
+ * (cp.async.bulk, one mbarrier per tree group so walking group 0 overlaps the copy of groups 1..);
+ * CTAs are persistent (grid = #SMs) and stride over the batch.  Per-lane float64 partial sums are
+ * combined with a shuffle butterfly.  Forests that do not fit 227 KB of shared memory are walked
+ * from global memory / L2 with the same code (WALK_GLOBAL).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b2f.h"
+#include "forest_blob.h"
+
+#define B2F_PREDICT_THREADS 1024
+#define B2F_PREDICT_WARPS (B2F_PREDICT_THREADS / 32)
+#define B2F_BULK_PIECE (32u * 1024u) /* bytes per cp.async.bulk */
+
+struct KGroup {
+    uint32_t chunk_off;
+    uint32_t chunk_bytes;
+    uint32_t n_slots;
+    uint32_t n_leaf_slots;
+    uint32_t depth;
+};
+
+struct KParams {
+    const uint8_t *chunks; /* device pointer to the first chunk (256-byte aligned) */
+    int32_t n_groups;
+    int32_t agg_mode;
+    int32_t n_cat;
+    int32_t n_num;
+    double init_raw;
+    double denom;
+    float impute[24];
+    KGroup g[B2F_MAX_GROUPS];
+};
+
+/* ---------------------------------------------------------------- PTX helpers */
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <bool SMEM>
+__device__ __forceinline__ uint32_t ld_word(const uint32_t *p) {
+    if constexpr (SMEM) {
+        return *p;
+    } else {
+        return __ldg(p);
+    }
+}
+template <bool SMEM>
+__device__ __forceinline__ double ld_leaf(const double *p) {
+    if constexpr (SMEM) {
+        return *p;
+    } else {
+        return __ldg(p);
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+/* ---------------------------------------------------------------- the kernel */
+template <int R, bool SMEM, typename OutT>
+__global__ void __launch_bounds__(B2F_PREDICT_THREADS, 1)
+    k_forest_predict(const __grid_constant__ KParams p, const uint32_t *__restrict__ rows, long long n,
+                     OutT *__restrict__ proba, int32_t *__restrict__ label) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[B2F_MAX_GROUPS];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+
+    if constexpr (SMEM) {
+        /* one thread arms one mbarrier per tree group and issues the TMA bulk copies */
+        if (threadIdx.x == 0) {
+            for (int g = 0; g < p.n_groups; ++g) mbar_init(&bars[g], 1);
+            fence_mbar_init();
+            fence_proxy_async();
+            for (int g = 0; g < p.n_groups; ++g) {
+                const uint32_t bytes = p.g[g].chunk_bytes;
+                mbar_arrive_expect_tx(&bars[g], bytes);
+                for (uint32_t o = 0; o < bytes; o += B2F_BULK_PIECE) {
+                    const uint32_t piece = min(B2F_BULK_PIECE, bytes - o);
+                    tma_bulk_g2s(smem + p.g[g].chunk_off + o, p.chunks + p.g[g].chunk_off + o, piece, &bars[g]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    const uint8_t *base = SMEM ? smem : p.chunks;
+    uint32_t ready = 0; /* bit g: this warp has observed group g's chunk in shared memory */
+
+    const long long n_batches = (n + R - 1) / R;
+    /* CTA-minor numbering: consecutive row batches go to different SMs, so small batches spread
+     * over the whole chip instead of filling the first CTAs */
+    const long long warp_global = (long long)warp * gridDim.x + blockIdx.x;
+    const long long warp_stride = (long long)gridDim.x * B2F_PREDICT_WARPS;
+
+    /* numeric lanes impute NaN with the training median; lane 23 holds the sentinel 0 */
+    const bool lane_numeric = lane >= p.n_cat && lane < p.n_cat + p.n_num;
+    const uint32_t impute_bits = lane < 24 ? __float_as_uint(p.impute[lane]) : 0u;
+
+    for (long long b = warp_global; b < n_batches; b += warp_stride) {
+        uint32_t w[R];
+        double acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const long long row = b * R + r;
+            uint32_t v = 0;
+            if (row < n && lane < (int)B2F_SENTINEL_WORD) v = __ldg(rows + row * B2F_ROW_WORDS + lane);
+            if (lane_numeric && isnan(__uint_as_float(v))) v = impute_bits;
+            w[r] = v;
+            acc[r] = 0.0;
+        }
+
+        for (int g = 0; g < p.n_groups; ++g) {
+            if constexpr (SMEM) {
+                if (!((ready >> g) & 1u)) {
+                    mbar_wait(&bars[g], 0);
+                    ready |= 1u << g;
+                }
+            }
+            const uint32_t n_slots = p.g[g].n_slots;
+            const uint32_t *T = reinterpret_cast<const uint32_t *>(base + p.g[g].chunk_off) + lane;
+            const uint32_t *M = T + n_slots * 32u;
+            const double *LV = reinterpret_cast<const double *>(M - lane + n_slots * 32u) + lane;
+            const int depth = (int)p.g[g].depth;
+
+            uint32_t node[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) node[r] = 0;
+
+            for (int d = 0; d < depth; ++d) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t m = ld_word<SMEM>(M + node[r] * 32u);
+                    const uint32_t t = ld_word<SMEM>(T + node[r] * 32u);
+                    const uint32_t x = __shfl_sync(0xffffffffu, w[r], m & 31u);
+                    const bool second = (m & B2F_META_CAT) ? (x == t)
+                                                           : !(__uint_as_float(x) <= __uint_as_float(t));
+                    node[r] = (m >> 6) + (second ? 1u : 0u);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t leaf = ld_word<SMEM>(T + node[r] * 32u) & (B2F_LEAF_TAG - 1u);
+                acc[r] += ld_leaf<SMEM>(LV + leaf * 32u);
+            }
+        }
+
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double s = warp_sum(acc[r]);
+            const long long row = b * R + r;
+            if (lane == 0 && row < n) {
+                double p1;
+                int lab;
+                if (p.agg_mode == B2F_AGG_RF_MEAN) {
+                    p1 = s / p.denom;
+                    lab = s > (p.denom - s);
+                } else {
+                    const double raw = p.init_raw + s;
+                    p1 = 1.0 / (1.0 + exp(-raw));
+                    lab = raw >= 0.0;
+                }
+                if (proba) proba[row] = (OutT)p1;
+                if (label) label[row] = lab;
+            }
+        }
+    }
+
+    if constexpr (SMEM) {
+        /* never retire a CTA while a bulk copy into its shared memory is still in flight */
+        for (int g = 0; g < p.n_groups; ++g)
+            if (!((ready >> g) & 1u)) mbar_wait(&bars[g], 0);
+    }
+}

@@ -1,0 +1,88 @@
+"""Host-side row encoder: request columns -> 96-byte encoded rows (layout in ``include/b2f.h``).
+
+This is the host half of the "fused preprocess": everything sklearn's ColumnTransformer does
+that needs *strings* happens here, vectorised per column, straight into the (pinned) staging
+buffer; everything arithmetic (median imputation, one-hot comparison, float32 compare) happens
+in the kernel.
+
+Reference behaviour being matched (``databricks/src/01-train-model.ipynb:195-221``):
+
+* ``SimpleImputer(constant "missing")`` + ``OneHotEncoder(handle_unknown="ignore")``: a category
+  string is looked up in the sorted training vocabulary; unknown strings and missing values get
+  code -1 (== all-zero one-hot block) unless "missing" itself was a training category;
+* numeric columns are cast float64 -> float32 exactly as sklearn's tree predict does; NaN stays
+  NaN (the kernel imputes the median); +-inf or a value that overflows float32 raises the same
+  ``ValueError`` sklearn raises;
+* columns are selected by NAME (``df[self.all_features]``, ``02-register-model.ipynb:335``), so any
+  column order works (the reference's ``inference.csv`` puts ``credit_limit`` first).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+
+from .flatten import ROW_WORDS, FlatForest
+
+_F32_MAX = float(np.finfo(np.float32).max)
+
+
+class RowEncoder:
+    def __init__(self, flat: FlatForest):
+        self.cat_features = list(flat.cat_features)
+        self.num_features = list(flat.num_features)
+        self.n_cat = len(self.cat_features)
+        self.n_num = len(self.num_features)
+        self._dtypes = [pd.CategoricalDtype(categories=list(v), ordered=False) for v in flat.categories]
+        self._missing = list(flat.missing_codes) if flat.missing_codes else [-1] * self.n_cat
+
+    # ------------------------------------------------------------------ columns
+    def encode_categorical(self, j: int, values) -> np.ndarray:
+        """One categorical column (any array-like of str / None) -> int32 codes, -1 = unknown."""
+        arr = values if isinstance(values, (pd.Series, np.ndarray)) else np.asarray(values, dtype=object)
+        codes = pd.Categorical(arr, dtype=self._dtypes[j]).codes.astype(np.int32)
+        if self._missing[j] >= 0:
+            codes[np.asarray(pd.isna(arr))] = self._missing[j]
+        return codes
+
+    @staticmethod
+    def cast_numeric(block64: np.ndarray) -> np.ndarray:
+        """float64 (N, k) -> float32 with sklearn's finiteness rule (NaN allowed: missing)."""
+        bad = np.abs(block64) > _F32_MAX  # False for NaN
+        if bad.any():
+            raise ValueError("Input X contains infinity or a value too large for dtype('float32').")
+        return block64.astype(np.float32)
+
+    # ------------------------------------------------------------------ frames
+    def encode_frame(self, df: pd.DataFrame, out: np.ndarray | None = None) -> np.ndarray:
+        """DataFrame with (at least) the 23 named columns -> uint32 (N, 24) encoded rows."""
+        n = len(df)
+        if out is None:
+            out = np.empty((n, ROW_WORDS), dtype=np.uint32)
+        else:
+            assert out.shape == (n, ROW_WORDS) and out.dtype == np.uint32
+        missing = [c for c in self.cat_features + self.num_features if c not in df.columns]
+        if missing:
+            raise KeyError(f"{missing} not in index")  # what df[self.all_features] raises
+        as_i32 = out.view(np.int32)
+        for j, name in enumerate(self.cat_features):
+            as_i32[:, j] = self.encode_categorical(j, df[name])
+        if self.n_num:
+            block = np.empty((n, self.n_num), dtype=np.float64)
+            for k, name in enumerate(self.num_features):
+                block[:, k] = pd.to_numeric(df[name], errors="raise").to_numpy(dtype=np.float64, na_value=np.nan)
+            out.view(np.float32)[:, self.n_cat : self.n_cat + self.n_num] = self.cast_numeric(block)
+        out[:, self.n_cat + self.n_num :] = 0
+        return out
+
+    def encode_arrays(self, codes: np.ndarray, nums: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """Already-dictionary-encoded input (int codes (N, n_cat), float nums (N, n_num)) -> rows."""
+        n = codes.shape[0]
+        if out is None:
+            out = np.empty((n, ROW_WORDS), dtype=np.uint32)
+        out.view(np.int32)[:, : self.n_cat] = codes
+        out.view(np.float32)[:, self.n_cat : self.n_cat + self.n_num] = self.cast_numeric(
+            np.asarray(nums, dtype=np.float64)
+        )
+        out[:, self.n_cat + self.n_num :] = 0
+        return out

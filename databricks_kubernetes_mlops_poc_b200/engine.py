@@ -1,0 +1,228 @@
+"""ForestEngine: one flattened forest resident on one B200, driven through the C ABI.
+
+Python-side owner of a ``b2f_model*`` (``include/b2f.h``).  It replaces the object the
+reference keeps in ``self.classifier`` (``databricks/src/02-register-model.ipynb:318-322``) for the
+purposes of ``predict_proba(...)[:, 1]`` / ``predict`` (``:335-337``).  No CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import MOMENT_VALUES, ROW_WORDS, B2FError, Info, PinnedBuffer, check, ptr
+from .flatten import FlatForest
+
+
+def device_count() -> int:
+    n = _cabi.load_library().b2f_device_count()
+    if n < 0:
+        raise B2FError(f"no usable CUDA device: {_cabi.last_error()}")
+    return n
+
+
+def validate_blob(blob: bytes) -> None:
+    """Structural check of a forest blob (no GPU needed); raises B2FError when malformed."""
+    buf = np.frombuffer(blob, dtype=np.uint8)
+    check(_cabi.load_library().b2f_blob_validate(ptr(buf), buf.size), "b2f_blob_validate")
+
+
+class ForestEngine:
+    def __init__(self, flat: FlatForest, device: int = 0):
+        self._lib = _cabi.load_library()
+        self.flat = flat
+        self.device = int(device)
+        buf = np.frombuffer(flat.blob, dtype=np.uint8)
+        self._h = self._lib.b2f_model_create(ptr(buf), buf.size, self.device)
+        if not self._h:
+            raise B2FError(f"b2f_model_create(device={device}) failed: {_cabi.last_error()}")
+        self._pinned: dict[str, PinnedBuffer] = {}
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.b2f_model_destroy(self._h)
+            self._h = None
+        for b in self._pinned.values():
+            b.close()
+        self._pinned = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def info(self) -> dict:
+        inf = Info()
+        check(self._lib.b2f_model_info(self._h, C.byref(inf)), "b2f_model_info")
+        d = {name: getattr(inf, name) for name, _ in Info._fields_}
+        d["walk"] = _cabi.WALK_NAMES.get(d["walk_mode"], "?")
+        d["agg"] = _cabi.AGG_NAMES.get(d["agg_mode"], "?")
+        return d
+
+    # ------------------------------------------------------------------ pinned staging
+    def pinned(self, tag: str, nbytes: int) -> PinnedBuffer:
+        """A reusable page-locked buffer of at least nbytes (grown geometrically)."""
+        b = self._pinned.get(tag)
+        if b is None or b.nbytes < nbytes:
+            if b is not None:
+                b.close()
+            b = PinnedBuffer(max(int(nbytes * 1.5), 1 << 16))
+            self._pinned[tag] = b
+        return b
+
+    def staging(self, n: int):
+        """(rows uint32 (n,24), proba f64 (n,), label i32 (n,)) views over pinned memory."""
+        rows = self.pinned("rows", n * ROW_WORDS * 4).view(np.uint32, (n, ROW_WORDS))
+        proba = self.pinned("proba", n * 8).view(np.float64, (n,))
+        label = self.pinned("label", n * 4).view(np.int32, (n,))
+        return rows, proba, label
+
+    # ------------------------------------------------------------------ scoring (host buffers)
+    def predict_rows(self, rows: np.ndarray, proba_dtype=np.float64, want_label: bool = True, out_proba=None, out_label=None):
+        """Encoded rows (N, 24) uint32 in host memory -> (proba1, label)."""
+        rows = np.ascontiguousarray(rows)
+        if rows.dtype != np.uint32 or rows.ndim != 2 or rows.shape[1] != ROW_WORDS:
+            raise ValueError(f"rows must be uint32 (N, {ROW_WORDS})")
+        n = rows.shape[0]
+        f64 = np.dtype(proba_dtype) == np.float64
+        proba = out_proba if out_proba is not None else np.empty(n, dtype=np.float64 if f64 else np.float32)
+        label = out_label if out_label is not None else (np.empty(n, dtype=np.int32) if want_label else None)
+        fn = self._lib.b2f_predict_f64 if f64 else self._lib.b2f_predict
+        check(fn(self._h, ptr(rows), n, ptr(proba), ptr(label)), "b2f_predict")
+        return proba, label
+
+    def predict_rows_async(self, rows: np.ndarray, proba: np.ndarray, label: np.ndarray | None) -> int:
+        """Pinned buffers in, ticket out; pair with wait()."""
+        t = C.c_uint64(0)
+        check(
+            self._lib.b2f_predict_async(
+                self._h, ptr(rows), rows.shape[0], ptr(proba), int(proba.dtype == np.float64), ptr(label), C.byref(t)
+            ),
+            "b2f_predict_async",
+        )
+        return t.value
+
+    def wait(self, ticket: int) -> None:
+        check(self._lib.b2f_wait(self._h, ticket), "b2f_wait")
+
+    # ------------------------------------------------------------------ device-resident interface
+    def device_alloc(self, nbytes: int) -> int:
+        p = self._lib.b2f_device_alloc(self._h, nbytes)
+        if not p:
+            raise B2FError(f"b2f_device_alloc({nbytes}) failed: {_cabi.last_error()}")
+        return p
+
+    def device_free(self, dptr: int) -> None:
+        self._lib.b2f_device_free(self._h, dptr)
+
+    def h2d(self, dptr: int, a: np.ndarray) -> None:
+        a = np.ascontiguousarray(a)
+        check(self._lib.b2f_copy_h2d(self._h, dptr, ptr(a), a.nbytes), "b2f_copy_h2d")
+
+    def d2h(self, a: np.ndarray, dptr: int) -> None:
+        check(self._lib.b2f_copy_d2h(self._h, ptr(a), dptr, a.nbytes), "b2f_copy_d2h")
+
+    def predict_device(self, rows_dev: int, n: int, proba_dev: int, proba_is_f64: bool, label_dev: int) -> None:
+        check(self._lib.b2f_predict_device(self._h, rows_dev, n, proba_dev, int(proba_is_f64), label_dev), "b2f_predict_device")
+
+    def sync(self) -> None:
+        check(self._lib.b2f_sync(self._h), "b2f_sync")
+
+    def predict_device_timed(self, rows_dev, n, proba_dev, proba_is_f64, label_dev, iters: int, flush_l2: bool) -> np.ndarray:
+        ms = np.zeros(iters, dtype=np.float32)
+        check(
+            self._lib.b2f_predict_device_timed(
+                self._h, rows_dev, n, proba_dev, int(proba_is_f64), label_dev, iters, int(flush_l2), ptr(ms)
+            ),
+            "b2f_predict_device_timed",
+        )
+        return ms
+
+    # ------------------------------------------------------------------ moments
+    def moments(self, rows: np.ndarray) -> np.ndarray:
+        """Per-word (count, mean, M2) over host rows -> float64 (24, 3)."""
+        rows = np.ascontiguousarray(rows)
+        out = np.zeros(MOMENT_VALUES, dtype=np.float64)
+        check(self._lib.b2f_moments(self._h, ptr(rows), rows.shape[0], ptr(out)), "b2f_moments")
+        return out.reshape(ROW_WORDS, 3)
+
+    def moments_device(self, rows_dev: int, n: int) -> np.ndarray:
+        out = np.zeros(MOMENT_VALUES, dtype=np.float64)
+        check(self._lib.b2f_moments_device(self._h, rows_dev, n, ptr(out)), "b2f_moments_device")
+        return out.reshape(ROW_WORDS, 3)
+
+    def moments_device_timed(self, rows_dev: int, n: int, iters: int, flush_l2: bool):
+        ms = np.zeros(iters, dtype=np.float32)
+        out = np.zeros(MOMENT_VALUES, dtype=np.float64)
+        check(self._lib.b2f_moments_device_timed(self._h, rows_dev, n, iters, int(flush_l2), ptr(ms), ptr(out)), "b2f_moments_device_timed")
+        return ms, out.reshape(ROW_WORDS, 3)
+
+    # ------------------------------------------------------------------ NCCL (one process per GPU)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = np.zeros(128, dtype=np.uint8)
+        check(_cabi.load_library().b2f_comm_unique_id(ptr(buf)), "b2f_comm_unique_id")
+        return buf.tobytes()
+
+    def comm_init_rank(self, nranks: int, rank: int, unique_id: bytes) -> None:
+        buf = np.frombuffer(unique_id, dtype=np.uint8)
+        check(self._lib.b2f_comm_init_rank(self._h, nranks, rank, ptr(buf)), "b2f_comm_init_rank")
+
+    def moments_allgather(self, local: np.ndarray) -> np.ndarray:
+        local = np.ascontiguousarray(local, dtype=np.float64).reshape(-1)
+        out = np.zeros(MOMENT_VALUES, dtype=np.float64)
+        check(self._lib.b2f_moments_allgather(self._h, ptr(local), ptr(out)), "b2f_moments_allgather")
+        return out.reshape(ROW_WORDS, 3)
+
+
+def moments_merge(parts: np.ndarray) -> np.ndarray:
+    """Chan merge of k (24, 3) partials (host)."""
+    parts = np.ascontiguousarray(parts, dtype=np.float64).reshape(-1, MOMENT_VALUES)
+    out = np.zeros(MOMENT_VALUES, dtype=np.float64)
+    _cabi.load_library().b2f_moments_merge(ptr(parts), parts.shape[0], ptr(out))
+    return out.reshape(ROW_WORDS, 3)
+
+
+class EngineGroup:
+    """The same forest replicated on several GPUs of one box; batches are sliced across them
+    by one C call (``b2f_predict_multi``) -- rows are independent, so no collective on this path.
+    The reference's analogue is the k8s Service in front of pod replicas (``kubernetes/manifest.yml:23-36``)."""
+
+    def __init__(self, flat: FlatForest, devices=None, nccl: bool = False):
+        if devices is None:
+            devices = list(range(device_count()))
+        self.engines = [ForestEngine(flat, d) for d in devices]
+        self._lib = _cabi.load_library()
+        self._handles = (C.c_void_p * len(self.engines))(*[e.handle for e in self.engines])
+        if nccl and len(self.engines) > 1:
+            check(self._lib.b2f_comm_init_all(self._handles, len(self.engines)), "b2f_comm_init_all")
+
+    def close(self) -> None:
+        for e in self.engines:
+            e.close()
+
+    def predict_rows(self, rows: np.ndarray, proba_dtype=np.float64, out_proba=None, out_label=None):
+        rows = np.ascontiguousarray(rows)
+        n = rows.shape[0]
+        f64 = np.dtype(proba_dtype) == np.float64
+        proba = out_proba if out_proba is not None else np.empty(n, dtype=np.float64 if f64 else np.float32)
+        label = out_label if out_label is not None else np.empty(n, dtype=np.int32)
+        check(
+            self._lib.b2f_predict_multi(self._handles, len(self.engines), ptr(rows), n, ptr(proba), int(f64), ptr(label)),
+            "b2f_predict_multi",
+        )
+        return proba, label
+
+    def moments(self, rows: np.ndarray) -> np.ndarray:
+        rows = np.ascontiguousarray(rows)
+        out = np.zeros(MOMENT_VALUES, dtype=np.float64)
+        check(self._lib.b2f_moments_multi(self._handles, len(self.engines), ptr(rows), rows.shape[0], ptr(out)), "b2f_moments_multi")
+        return out.reshape(ROW_WORDS, 3)

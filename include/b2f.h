@@ -1,0 +1,163 @@
+/*
+ * b2f.h -- C ABI of libb200forest.so, the B200-native scoring engine behind the
+ * credit-default service's `model.predict()`.
+ *
+ * The reference has no native code and therefore no FFI of its own: its hot path is the
+ * Python call `ml_models["credit_default"].predict(input_df)` (reference app/main.py:72), which
+ * lands in `CustomModel.predict` (reference databricks/src/02-register-model.ipynb:330-353) and
+ * from there in scikit-learn.  This header is the boundary a maintainer of the reference binds
+ * with ctypes to replace that arithmetic (see INTEGRATION.md for the stub).  Each entry point
+ * names the reference call it replaces.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; all sizes explicit; little-endian host.
+ *   - functions returning int: 0 = success, negative = error (B2F_E*); the message for the
+ *     calling thread is available from b2f_last_error().
+ *   - the caller owns every host buffer; the library owns device memory and CUDA streams.
+ *   - one b2f_model per GPU; calls on one handle must be serialised by the caller
+ *     (different handles may be driven from different threads concurrently).
+ *   - there is NO CPU fallback: without a usable CUDA device every compute call fails.
+ *
+ * Row layout ("encoded row", what the host-side encoder produces from a LoanApplicant,
+ * reference app/model.py:8-34): B2F_ROW_WORDS = 24 little-endian 32-bit words = 96 bytes,
+ *   words 0 .. n_cat-1        int32   category code = index into the model's sorted vocabulary
+ *                                     of that feature, -1 = unknown or missing
+ *                                     (== OneHotEncoder(handle_unknown="ignore") all-zero block,
+ *                                     reference 01-train-model.ipynb:200-206)
+ *   words n_cat .. n_cat+n_num-1  float32 numeric feature (float64 -> float32 round-to-nearest,
+ *                                     as sklearn's predict does); NaN = missing, imputed on the
+ *                                     GPU with the training median (01-train-model.ipynb:212)
+ *   remaining words           ignored (padding to 96 B so a row is six 16-byte vectors)
+ * For the credit-default schema n_cat = 9, n_num = 14, in LoanApplicant field order.
+ */
+#ifndef B2F_H
+#define B2F_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2F_ROW_WORDS 24
+#define B2F_ROW_BYTES 96
+#define B2F_MAX_TREES 1024
+#define B2F_MOMENT_WORDS 3 /* per feature: count, mean, M2 */
+
+/* error codes */
+#define B2F_OK 0
+#define B2F_EINVAL (-1)  /* bad argument / malformed forest blob */
+#define B2F_ECUDA (-2)   /* CUDA runtime error (message has the cudaError string) */
+#define B2F_ENODEV (-3)  /* no usable CUDA device */
+#define B2F_ENOMEM (-4)  /* host or device allocation failed */
+#define B2F_ENCCL (-5)   /* NCCL error or NCCL library not loadable */
+#define B2F_ESTATE (-6)  /* call not valid in this state (e.g. communicator not initialised) */
+
+/* aggregation modes stored in the forest blob */
+#define B2F_AGG_RF_MEAN 0       /* RandomForestClassifier.predict_proba: mean of leaf class fractions */
+#define B2F_AGG_GBDT_LOGISTIC 1 /* binary GradientBoosting: expit(init + sum lr*leaf) */
+
+/* walk modes chosen at model creation */
+#define B2F_WALK_SMEM 0   /* whole forest resident in shared memory (TMA bulk copy per CTA) */
+#define B2F_WALK_GLOBAL 1 /* forest walked from global memory / L2 (too large for shared memory) */
+
+typedef struct b2f_model b2f_model;
+typedef uint64_t b2f_ticket;
+
+typedef struct b2f_info {
+    int32_t device;
+    int32_t sm_count;
+    int32_t agg_mode;
+    int32_t walk_mode;
+    int32_t n_trees;
+    int32_t n_groups;
+    int32_t max_depth;
+    int32_t n_cat;
+    int32_t n_num;
+    int32_t smem_bytes;     /* dynamic shared memory per CTA of the predict kernel */
+    int32_t block_threads;  /* threads per CTA of the predict kernel */
+    int32_t rows_per_warp;  /* rows walked concurrently by one warp */
+    int64_t forest_bytes;   /* bytes of the node + leaf arrays on the device */
+    int64_t launches;       /* kernels launched by this handle so far (predict + moments) */
+} b2f_info;
+
+/* ---- library / device ------------------------------------------------------------------ */
+const char *b2f_version(void);
+const char *b2f_last_error(void);
+int b2f_device_count(void); /* number of CUDA devices, or B2F_ENODEV */
+
+/* ---- model lifetime: replaces mlflow.pyfunc.load_model(...) in lifespan (app/main.py:20-31)
+ *      for the classifier part (CustomModel.load_context, 02-register-model.ipynb:317-328) ---- */
+/* structural check of a forest blob (header, group table, every node word keeps the walk in bounds);
+ * needs no GPU.  b2f_model_create() runs the same check. */
+int b2f_blob_validate(const void *forest_blob, size_t nbytes);
+b2f_model *b2f_model_create(const void *forest_blob, size_t nbytes, int device); /* NULL on error */
+void b2f_model_destroy(b2f_model *m);
+int b2f_model_info(const b2f_model *m, b2f_info *out);
+
+/* ---- pinned host memory for request batches (the batching ring lives in these) ------------- */
+void *b2f_pinned_alloc(size_t nbytes); /* NULL on error */
+void b2f_pinned_free(void *p);
+
+/* ---- scoring: replaces classifier.predict_proba(df[all_features])[:, 1]
+ *      (02-register-model.ipynb:335-337) and pipeline.predict (01-train-model.ipynb:290) --------
+ * rows:   n encoded rows in HOST memory (pinned memory makes the copies asynchronous).
+ * proba1: P(class 1) per row;  label: hard class label per row (sklearn tie rule: 1 iff p1 > p0,
+ *         GBDT: raw >= 0).  Either output pointer may be NULL.
+ * Copies host->device, runs the fused impute -> one-hot-as-equality -> tree-walk -> aggregate kernel
+ * and copies the results back, pipelined over internal streams; returns when outputs are written. */
+int b2f_predict(b2f_model *m, const void *rows, int64_t n, float *proba1, int32_t *label);
+int b2f_predict_f64(b2f_model *m, const void *rows, int64_t n, double *proba1, int32_t *label);
+
+/* asynchronous form for the request-batching ring: buffers must be pinned and stay valid until
+ * b2f_wait(ticket) returns.  proba_is_f64 selects double (1) or float (0) outputs. */
+int b2f_predict_async(b2f_model *m, const void *rows_pinned, int64_t n, void *proba1_pinned,
+                      int proba_is_f64, int32_t *label_pinned, b2f_ticket *ticket);
+int b2f_wait(b2f_model *m, b2f_ticket ticket);
+
+/* one call over several GPUs: contiguous slices of the batch go round-robin to the models
+ * (one per device); no inter-GPU traffic (rows are independent). */
+int b2f_predict_multi(b2f_model **models, int n_models, const void *rows, int64_t n, void *proba1,
+                      int proba_is_f64, int32_t *label);
+
+/* ---- device-resident interface (measurement and callers that already hold rows in HBM) ----- */
+void *b2f_device_alloc(b2f_model *m, size_t nbytes);
+void b2f_device_free(b2f_model *m, void *dptr);
+int b2f_copy_h2d(b2f_model *m, void *dst_dev, const void *src_host, size_t nbytes);
+int b2f_copy_d2h(b2f_model *m, void *dst_host, const void *src_dev, size_t nbytes);
+/* enqueue one predict launch on the model's compute stream (asynchronous) */
+int b2f_predict_device(b2f_model *m, const void *rows_dev, int64_t n, void *proba1_dev,
+                       int proba_is_f64, int32_t *label_dev);
+int b2f_sync(b2f_model *m);
+/* run `iters` launches back to back, each bracketed by CUDA events on the launching stream;
+ * ms_each[iters] receives each launch's device time.  flush_l2 != 0 writes a >L2-sized scratch
+ * buffer before every launch (outside the event bracket). */
+int b2f_predict_device_timed(b2f_model *m, const void *rows_dev, int64_t n, void *proba1_dev,
+                             int proba_is_f64, int32_t *label_dev, int iters, int flush_l2,
+                             float *ms_each);
+
+/* ---- drift-monitor moments (BASELINE config 5; nearest reference call is
+ *      self.drift.predict(...), 02-register-model.ipynb:338 -- no mean/var exists there) --------
+ * For each of the 24 row words f: out[3f+0] = count of non-NaN values, out[3f+1] = mean,
+ * out[3f+2] = M2 = sum (x-mean)^2, all float64.  Category words are read as integers. */
+int b2f_moments(b2f_model *m, const void *rows, int64_t n, double *out /* 24*3 */);
+int b2f_moments_device(b2f_model *m, const void *rows_dev, int64_t n, double *out /* host, 24*3 */);
+int b2f_moments_device_timed(b2f_model *m, const void *rows_dev, int64_t n, int iters, int flush_l2,
+                             float *ms_each, double *out);
+/* Chan merge of k partial (count, mean, M2) triples per word, on the host (used after an all-gather) */
+void b2f_moments_merge(const double *parts /* k*24*3 */, int k, double *out /* 24*3 */);
+
+/* ---- NCCL plumbing for the cross-GPU moments merge (552-byte all-gather per rank) ----------- */
+int b2f_comm_unique_id(void *id_out128);                                  /* rank 0 creates */
+int b2f_comm_init_rank(b2f_model *m, int nranks, int rank, const void *id128); /* one process per GPU */
+int b2f_comm_init_all(b2f_model **models, int n_models);                  /* one process, many GPUs */
+/* all-gather this rank's (count, mean, M2) triples over NVLink and Chan-merge them */
+int b2f_moments_allgather(b2f_model *m, const double *local /* 24*3 */, double *merged /* 24*3 */);
+/* single-process form: per-device moments of per-device row slices, merged across all models */
+int b2f_moments_multi(b2f_model **models, int n_models, const void *rows, int64_t n, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2F_H */

@@ -1,0 +1,52 @@
+"""numpy emulation of the predict kernel's semantics over a forest blob (TEST INFRASTRUCTURE).
+
+Mirrors ``csrc/forest_predict.cuh`` word for word -- impute, sentinel word, fixed-depth walk with
+self-looping leaves, per-lane float64 partial sums, butterfly order -- so that the flattener and the
+blob format can be checked against the oracle on a CPU-only box.  It is not a fallback: nothing in
+the product imports it.
+"""
+
+import numpy as np
+
+from databricks_kubernetes_mlops_poc_b200.flatten import LEAF_TAG, META_CAT, SENTINEL_WORD, parse_header
+
+
+def walk_blob(blob: bytes, rows: np.ndarray):
+    h = parse_header(blob)
+    n = rows.shape[0]
+    n_cat, n_num = h["n_cat"], h["n_num"]
+    w = rows.astype(np.uint32).copy()
+    f = w.view(np.float32)
+    nan = np.isnan(f[:, n_cat : n_cat + n_num])
+    imp = np.broadcast_to(h["impute"][n_cat : n_cat + n_num], nan.shape)
+    f[:, n_cat : n_cat + n_num][nan] = imp[nan]
+    w[:, SENTINEL_WORD] = 0
+    lane_acc = np.zeros((n, 32), dtype=np.float64)
+    buf = np.frombuffer(blob, dtype=np.uint8)
+    ridx = np.arange(n)
+    for g in h["groups"]:
+        base = h["chunks_off"] + g["chunk_off"]
+        ns, nl = g["n_slots"], g["n_leaf_slots"]
+        T = buf[base : base + ns * 128].view(np.uint32).reshape(ns, 32)
+        M = buf[base + ns * 128 : base + ns * 256].view(np.uint32).reshape(ns, 32)
+        LV = buf[base + ns * 256 : base + ns * 256 + nl * 256].view(np.float64).reshape(nl, 32)
+        for lane in range(32):
+            node = np.zeros(n, dtype=np.int64)
+            for _ in range(g["depth"]):
+                m = M[node, lane]
+                t = T[node, lane]
+                x = w[ridx, (m & 31).astype(np.int64)]
+                is_cat = (m & META_CAT) != 0
+                with np.errstate(invalid="ignore"):
+                    second = np.where(is_cat, x == t, ~(x.view(np.float32) <= t.view(np.float32)))
+                node = (m >> 6).astype(np.int64) + second.astype(np.int64)
+            leaf = (T[node, lane] & np.uint32(LEAF_TAG - 1)).astype(np.int64)
+            lane_acc[:, lane] += LV[leaf, lane]
+    v = lane_acc
+    for o in (16, 8, 4, 2, 1):  # xor butterfly, as warp_sum()
+        v = v + v[:, np.arange(32) ^ o]
+    s = v[:, 0]
+    if h["agg_mode"] == 0:
+        return s / h["denom"], (s > (h["denom"] - s)).astype(np.int32)
+    raw = h["init_raw"] + s
+    return 1.0 / (1.0 + np.exp(-raw)), (raw >= 0).astype(np.int32)

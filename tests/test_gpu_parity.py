@@ -1,0 +1,274 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the oracle (sklearn itself + the frozen
+golden outputs).  Bar: class labels bit-exact, |dP| <= 1e-6 (north_star); we assert 1e-12 for float64
+outputs and 2e-7 for float32 outputs, far inside it."""
+
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-12
+TOL32 = 2e-7
+
+
+def _engine(pipe, device=0):
+    from databricks_kubernetes_mlops_poc_b200 import flatten
+    from databricks_kubernetes_mlops_poc_b200.encode import RowEncoder
+    from databricks_kubernetes_mlops_poc_b200.engine import ForestEngine
+
+    flat = flatten.flatten_pipeline(pipe)
+    return ForestEngine(flat, device), RowEncoder(flat)
+
+
+def _check(pipe, frames, walk=None, rows_per_warp=None):
+    from oracle import reference_pipeline as rp
+
+    old = {k: os.environ.get(k) for k in ("B2F_FORCE_WALK", "B2F_ROWS_PER_WARP")}
+    try:
+        if walk:
+            os.environ["B2F_FORCE_WALK"] = walk
+        if rows_per_warp:
+            os.environ["B2F_ROWS_PER_WARP"] = str(rows_per_warp)
+        eng, enc = _engine(pipe)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    try:
+        if walk:
+            assert eng.info()["walk"] == walk
+        for df in frames:
+            want_p, want_l = rp.oracle_predict(pipe, df)
+            rows = enc.encode_frame(df)
+            p64, l64 = eng.predict_rows(rows, np.float64)
+            p32, l32 = eng.predict_rows(rows, np.float32)
+            assert np.abs(p64 - want_p).max() <= TOL64
+            assert np.abs(p32.astype(np.float64) - want_p).max() <= TOL32
+            assert (l64 == want_l).all() and (l32 == want_l).all()
+        return eng.info()
+    finally:
+        eng.close()
+
+
+def test_rf100d6_all_reference_rows(curated, inference, adversarial, rf100d6):
+    """All 30 000 curated.csv rows + the 80 inference.csv rows (other column order) + edge rows, and
+    the library outputs frozen in tests/golden (pins that this box's refit is the one we froze)."""
+    from oracle import datasets
+    from oracle import reference_pipeline as rp
+
+    exp = datasets.load_expected("rf100d6")
+    p, l = rp.oracle_predict(rf100d6, curated)
+    assert np.abs(p - exp["proba1"]).max() < 1e-13 and (l == exp["label"]).all()
+    info = _check(rf100d6, [curated, inference, adversarial])
+    assert info["walk"] == "smem", "100 x depth-6 forest must be shared-memory resident"
+
+    eng, enc = _engine(rf100d6)
+    try:
+        p64, l64 = eng.predict_rows(enc.encode_frame(curated), np.float64)
+        assert np.abs(p64 - exp["proba1"]).max() <= TOL64 and (l64 == exp["label"]).all()
+        pi, li = eng.predict_rows(enc.encode_frame(inference), np.float64)
+        assert np.abs(pi - exp["inf_proba1"]).max() <= TOL64 and (li == exp["inf_label"]).all()
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("rpw", [1, 2, 4])
+def test_rf100d6_rows_per_warp_variants(curated, adversarial, rf100d6, rpw):
+    _check(rf100d6, [curated.iloc[:20011], adversarial], rows_per_warp=rpw)
+
+
+def test_rf100d6_global_walk(curated, adversarial, rf100d6):
+    _check(rf100d6, [curated.iloc[:8000], adversarial], walk="global")
+
+
+def test_rf500d8_all_reference_rows(curated, inference, adversarial, rf500d8):
+    from oracle import datasets
+
+    exp = datasets.load_expected("rf500d8")
+    info = _check(rf500d8, [curated, inference, adversarial])
+    assert info["walk"] == "global"  # 160 480 nodes do not fit 227 KB
+    eng, enc = _engine(rf500d8)
+    try:
+        p64, l64 = eng.predict_rows(enc.encode_frame(curated), np.float64)
+        assert np.abs(p64 - exp["proba1"]).max() <= TOL64 and (l64 == exp["label"]).all()
+    finally:
+        eng.close()
+
+
+def test_deep_forest(curated, adversarial):
+    """max_depth 24 is the top of the reference's search space (01-train-model.ipynb:344)."""
+    from oracle import reference_pipeline as rp
+
+    pipe = rp.fit_reference_pipeline(curated.iloc[:6000], dict(n_estimators=37, max_depth=24, criterion="entropy", random_state=1))
+    info = _check(pipe, [curated.iloc[6000:9000], adversarial])
+    assert info["max_depth"] > 12
+
+
+def test_stumps_and_single_tree(curated, adversarial):
+    from oracle import reference_pipeline as rp
+
+    for params in (dict(n_estimators=1, max_depth=1, random_state=0), dict(n_estimators=33, max_depth=1, random_state=0),
+                   dict(n_estimators=32, max_depth=3, random_state=0)):
+        pipe = rp.fit_reference_pipeline(curated.iloc[:3000], params)
+        _check(pipe, [curated.iloc[3000:4000], adversarial])
+
+
+def test_gbdt(curated, adversarial, gbdt_small):
+    _check(gbdt_small, [curated.iloc[:5000], adversarial])
+    _check(gbdt_small, [curated.iloc[:2000]], walk="global")
+
+
+def test_batch_size_edges(curated, rf100d6):
+    from oracle import reference_pipeline as rp
+
+    eng, enc = _engine(rf100d6)
+    try:
+        want_p, want_l = rp.oracle_predict(rf100d6, curated)
+        rows = enc.encode_frame(curated)
+        for n in (0, 1, 2, 31, 32, 33, 147, 148 * 32 + 1, 16384, 24576, 24577, 30000):
+            p, l = eng.predict_rows(rows[:n], np.float64)
+            assert p.shape == (n,) and l.shape == (n,)
+            if n:
+                assert np.abs(p - want_p[:n]).max() <= TOL64 and (l == want_l[:n]).all()
+        # outputs are optional
+        p, l = eng.predict_rows(rows[:100], np.float64, want_label=False)
+        assert l is None and np.abs(p - want_p[:100]).max() <= TOL64
+    finally:
+        eng.close()
+
+
+def test_async_ring_and_multi(curated, rf100d6):
+    from databricks_kubernetes_mlops_poc_b200.engine import EngineGroup
+    from oracle import reference_pipeline as rp
+
+    eng, enc = _engine(rf100d6)
+    try:
+        want_p, want_l = rp.oracle_predict(rf100d6, curated)
+        n = 20000
+        rows, proba, label = eng.staging(n)
+        enc.encode_frame(curated.iloc[:n], out=rows)
+        proba[:] = -1
+        tickets = []
+        # several requests in flight on the pinned ring, disjoint slices
+        for lo in range(0, n, 5000):
+            tickets.append(eng.predict_rows_async(rows[lo : lo + 5000], proba[lo : lo + 5000], label[lo : lo + 5000]))
+        for t in tickets:
+            eng.wait(t)
+        assert np.abs(proba - want_p[:n]).max() <= TOL64 and (label == want_l[:n]).all()
+    finally:
+        eng.close()
+    grp = EngineGroup(enc_flat(rf100d6), devices=[0])
+    try:
+        p, l = grp.predict_rows(enc.encode_frame(curated.iloc[:7001]))
+        assert np.abs(p - want_p[:7001]).max() <= TOL64 and (l == want_l[:7001]).all()
+    finally:
+        grp.close()
+
+
+def enc_flat(pipe):
+    from databricks_kubernetes_mlops_poc_b200 import flatten
+
+    return flatten.flatten_pipeline(pipe)
+
+
+def test_full_size_properties(curated, rf100d6):
+    """BASELINE config 2 size (65 536 rows): size-independent properties instead of a row-by-row oracle:
+    run-to-run determinism, host-pipelined == device-resident single launch, permutation equivariance,
+    and agreement with the oracle on a random 4 096-row sample."""
+    from databricks_kubernetes_mlops_poc_b200 import training
+    from oracle import reference_pipeline as rp
+
+    eng, enc = _engine(rf100d6)
+    try:
+        n = 65536
+        vocabs, codes, nums = training.synth_arrays(curated, n, seed=20240)
+        rows = enc.encode_arrays(codes, nums)
+        p1, l1 = eng.predict_rows(rows, np.float64)
+        p2, l2 = eng.predict_rows(rows, np.float64)
+        assert (p1 == p2).all() and (l1 == l2).all()
+        # device-resident single launch
+        d_rows = eng.device_alloc(rows.nbytes)
+        d_p = eng.device_alloc(n * 8)
+        d_l = eng.device_alloc(n * 4)
+        eng.h2d(d_rows, rows)
+        eng.predict_device(d_rows, n, d_p, True, d_l)
+        eng.sync()
+        p3 = np.empty(n, dtype=np.float64)
+        l3 = np.empty(n, dtype=np.int32)
+        eng.d2h(p3, d_p)
+        eng.d2h(l3, d_l)
+        for d in (d_rows, d_p, d_l):
+            eng.device_free(d)
+        assert np.abs(p3 - p1).max() <= 1e-15 and (l3 == l1).all()
+        perm = np.random.default_rng(1).permutation(n)
+        p4, l4 = eng.predict_rows(rows[perm], np.float64)
+        assert np.abs(p4 - p1[perm]).max() <= 1e-15 and (l4 == l1[perm]).all()
+        idx = np.sort(np.random.default_rng(2).choice(n, 4096, replace=False))
+        df = training.arrays_to_frame(vocabs, codes[idx], nums[idx])
+        want_p, want_l = rp.oracle_predict(rf100d6, df)
+        assert np.abs(p1[idx] - want_p).max() <= TOL64 and (l1[idx] == want_l).all()
+        assert ((p1 >= 0) & (p1 <= 1)).all()
+    finally:
+        eng.close()
+
+
+def test_moments(curated, rf100d6):
+    from databricks_kubernetes_mlops_poc_b200 import training
+    from databricks_kubernetes_mlops_poc_b200.engine import moments_merge
+
+    eng, enc = _engine(rf100d6)
+    try:
+        n = 200_003
+        _, codes, nums = training.synth_arrays(curated, n, seed=20243)
+        rows = enc.encode_arrays(codes, nums)
+        got = eng.moments(rows)
+        f = rows.view(np.float32)[:, 9:23].astype(np.float64)
+        cnt = (~np.isnan(f)).sum(axis=0)
+        mean = np.nanmean(f, axis=0)
+        var = np.nanvar(f, axis=0)
+        assert (got[9:23, 0] == cnt).all()
+        assert np.allclose(got[9:23, 1], mean, rtol=1e-9, atol=0)
+        assert np.allclose(got[9:23, 2] / cnt, var, rtol=1e-9, atol=0)
+        c = codes.astype(np.float64)
+        assert (got[:9, 0] == n).all()
+        assert np.allclose(got[:9, 1], c.mean(axis=0), rtol=1e-10)
+        assert np.allclose(got[:9, 2] / n, c.var(axis=0), rtol=1e-9)
+        # split + Chan merge == whole
+        a, b = eng.moments(rows[:70001]), eng.moments(rows[70001:])
+        merged = moments_merge(np.stack([a, b]))
+        assert np.allclose(merged[:23], got[:23], rtol=1e-10, atol=1e-12)
+        # determinism
+        assert (eng.moments(rows) == got).all()
+        # tiny / empty
+        assert (eng.moments(rows[:0])[:, 0] == 0).all()
+        one = eng.moments(rows[:1])
+        assert (one[:9, 1] == c[0]).all() and (one[:23, 2] == 0).all()
+    finally:
+        eng.close()
+
+
+def test_model_predict_dict(curated, inference, rf100d6):
+    """End to end through the plugin boundary: DataFrame in, dict out (CustomModel.predict)."""
+    from databricks_kubernetes_mlops_poc_b200.model import B200Model
+    from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES, ModelOutput
+    from oracle import reference_pipeline as rp
+
+    model = B200Model.from_pipeline(rf100d6, reference_frame=curated, devices=[0])
+    try:
+        for df in (curated.iloc[:257], inference):
+            out = model.predict(df)
+            want_p, want_l = rp.oracle_predict(rf100d6, df)
+            assert set(out) == {"predictions", "outliers", "feature_drift_batch"}
+            assert np.abs(np.asarray(out["predictions"]) - want_p).max() <= TOL64
+            assert out["outliers"] == [0] * len(df)
+            assert list(out["feature_drift_batch"]) == ALL_FEATURES
+            ModelOutput.model_validate(out)
+            assert (model.predict_label(df) == want_l).all()
+        with pytest.raises(KeyError):
+            model.predict([])
+    finally:
+        model.close()
