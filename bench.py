@@ -1,0 +1,501 @@
+#!/usr/bin/env python
+"""bench.py -- rows/sec of the scoring hot path at batch = 65 536 x 23 features (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--model gbdt100d6|rf100d6]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one 65 536-row batch of synthetic credit-default rows
+(BASELINE configs[1]: 100-tree depth-6 GBDT in the reference's preprocessing; `--model rf100d6` times
+the reference's own RandomForest shape instead).  One rank per GPU; rows are independent, so ranks share
+nothing on the predict path (weak scaling, no collective); the only collective is the 576-byte NCCL
+all-gather of the drift-monitor moments (config 5), done through the engine's C ABI.
+
+Printed by rank 0: ONE JSON line.
+  value      whole-job rows/s with inputs resident in HBM: K launches cycling over a pool of 32 distinct
+             batches (201 MB > L2), CUDA events on the launching stream, max over ranks.
+  e2e        the same metric through the C-ABI call b2f_predict() with HOST (pinned) buffers: H2D of the
+             encoded rows and D2H of probabilities + labels inside the timed region, every step.
+  roofline   algorithmic bytes (100 B/row: 92 B features in, 4 B probability + 4 B label out) / the average
+             per-launch device time measured live in the timed region, against the measured HBM peak.
+  cpu_baseline  the reference-style sklearn pipeline's predict_proba on this box's host cores (rank 0, N=1).
+
+--impl reference times that CPU path alone (all host cores, process pool) and prints the same line shape.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 65536
+POOL = 32  # distinct device-resident batches: 32 * 6.29 MB = 201 MB > 126 MB L2
+ALG_BYTES_PER_ROW = 100  # 92 B in + 4 B proba + 4 B label
+MOM_BYTES_PER_ROW = 92
+METRIC = "rows/sec at batch=65536x23f"
+MODELS = {
+    "gbdt100d6": ("gbdt", dict(n_estimators=100, max_depth=6, random_state=0)),
+    "rf100d6": ("rf", dict(n_estimators=100, max_depth=6, criterion="gini", random_state=0)),
+    "gbdt500d8": ("gbdt", dict(n_estimators=500, max_depth=8, random_state=0)),
+    "rf500d8": ("rf", dict(n_estimators=500, max_depth=8, criterion="entropy", random_state=0)),
+}
+N_TRAIN = 20000
+TRAIN_SEED = 20239
+DATA_SEED = 20240
+
+
+# ----------------------------------------------------------------------------- distributed plumbing
+class Dist:
+    def __init__(self, want_gpus: int, use_cuda: bool, solo: bool = False):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = 1 if solo else int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.torch = None
+        self.use_cuda = use_cuda
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+
+            self.torch = torch
+            if use_cuda:
+                torch.cuda.set_device(self.local_rank)
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            else:
+                dist.init_process_group("gloo")
+            self.dist = dist
+        if want_gpus != self.world and self.rank == 0 and self.world > 1:
+            print(f"[bench] note: --gpus {want_gpus} but WORLD_SIZE={self.world}; using WORLD_SIZE", file=sys.stderr)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+            if self.use_cuda:
+                self.torch.cuda.synchronize()
+
+    def max(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda" if self.use_cuda else "cpu")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda" if self.use_cuda else "cpu")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def bcast_bytes(self, b: bytes | None) -> bytes:
+        if self.world == 1:
+            return b
+        obj = [b]
+        self.dist.broadcast_object_list(obj, src=0)
+        return obj[0]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- workload
+def get_pipeline(name: str, dist: Dist):
+    """Fitted sklearn pipeline for the named model (rank 0 fits, cached on local disk for the other
+    ranks and for the other arm run on the same box)."""
+    import joblib
+    import sklearn
+
+    from databricks_kubernetes_mlops_poc_b200 import training
+
+    kind, params = MODELS[name]
+    cache_dir = os.environ.get("B2F_BENCH_CACHE", "/tmp/b2f_bench_cache")
+    os.makedirs(cache_dir, exist_ok=True)
+    path = os.path.join(cache_dir, f"{name}_n{N_TRAIN}_s{TRAIN_SEED}_sk{sklearn.__version__}.joblib")
+    base = training.load_base_frame()
+    if dist.rank == 0 and not os.path.exists(path):
+        t0 = time.time()
+        pipe = training.fit_synthetic(kind, base, N_TRAIN, TRAIN_SEED, **params)
+        joblib.dump(pipe, path + ".tmp")
+        os.replace(path + ".tmp", path)
+        print(f"[bench] fitted {name} on {N_TRAIN} synthetic rows in {time.time() - t0:.1f}s", file=sys.stderr)
+    dist.barrier()
+    return joblib.load(path), base
+
+
+def make_batches(base, enc, n_batches: int, seed: int):
+    """-> (vocabs, codes, nums, rows uint32 (n_batches*BATCH, 24))"""
+    from databricks_kubernetes_mlops_poc_b200 import training
+
+    vocabs, codes, nums = training.synth_arrays(base, n_batches * BATCH, seed)
+    return vocabs, codes, nums, enc.encode_arrays(codes, nums)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.samples = []  # (t, sm, max, power, [reasons])
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+        def pump():
+            for line in self.proc.stdout:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    if int(f[0]) != self.idx:
+                        continue
+                    reasons = [n for n, v in zip(names, f[4:8]) if v == "Active"]
+                    self.samples.append((time.time(), float(f[1]), float(f[2]), float(f[3]), reasons))
+                except (ValueError, IndexError):
+                    continue
+
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self, t0: float, t1: float) -> dict:
+        win = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples
+        if not win:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        reasons = sorted({r for s in win for r in s[4]})
+        return {"sm_mhz": statistics.median(s[1] for s in win), "sm_max_mhz": max(s[2] for s in win),
+                "power_w_max": max(s[3] for s in win), "reasons": reasons, "samples": len(win)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(model_name: str):
+    """dram bytes per launch from the committed ncu capture, if one exists for this model."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(model_name, {}).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ----------------------------------------------------------------------------- CPU baseline
+_POOL_STATE = {}
+
+
+def _pool_predict(i):
+    pipe, frames = _POOL_STATE["pipe"], _POOL_STATE["frames"]
+    return pipe.predict_proba(frames[i])[:, 1]
+
+
+def cpu_reference_rate(pipe, df, repeats: int, procs: int):
+    """rows/s of pipeline.predict_proba over df split across `procs` forked worker processes
+    (sklearn's GBDT predict holds the GIL; its RandomForest threads itself with n_jobs=-1)."""
+    import multiprocessing as mp
+
+    n = len(df)
+    if procs <= 1:
+        times = []
+        for _ in range(repeats + 1):
+            t0 = time.perf_counter()
+            pipe.predict_proba(df)
+            times.append(time.perf_counter() - t0)
+        times = times[1:]
+        return n / min(times), n / statistics.median(times), times
+    idx = np.array_split(np.arange(n), procs)
+    _POOL_STATE["pipe"] = pipe
+    _POOL_STATE["frames"] = [df.iloc[i] for i in idx]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        pool.map(_pool_predict, range(procs))  # warm-up
+        times = []
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            pool.map(_pool_predict, range(procs))
+            times.append(time.perf_counter() - t0)
+    return n / min(times), n / statistics.median(times), times
+
+
+def cpu_port_rate(pipe, codes, nums, repeats: int):
+    """rows/s of the OpenMP C restatement (oracle/c/forest_walk.c) on all cores."""
+    from oracle import treewalk as tw
+
+    dump = tw.dump_pipeline(pipe)
+    tw.predict_c(dump, codes[:1024], nums[:1024])
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        tw.predict_c(dump, codes, nums)
+        times.append(time.perf_counter() - t0)
+    return len(codes) / min(times)
+
+
+# ----------------------------------------------------------------------------- arms
+def run_reference(args, dist: Dist):
+    """--impl reference: the reference-style CPU path (sklearn Pipeline.predict_proba, the library the
+    reference itself calls at 02-register-model.ipynb:335-337) on this box's host cores, rank 0 only.
+    Each step scores a bounded sample of the cfg2 batch, sized so K steps end within ~2 minutes."""
+    import sklearn
+
+    from databricks_kubernetes_mlops_poc_b200 import training
+    from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES
+
+    pipe, base = get_pipeline(args.model, dist)
+    kind = MODELS[args.model][0]
+    cores = os.cpu_count() or 1
+    vocabs, codes, nums = training.synth_arrays(base, BATCH, DATA_SEED)
+    df = training.arrays_to_frame(vocabs, codes, nums)[ALL_FEATURES]
+    procs = 1 if kind == "rf" else min(cores, 64)  # RF threads itself (n_jobs=-1, as the reference sets it)
+    K = max(args.steps, 1)
+    _, _, t_probe = cpu_reference_rate(pipe, df, 1, procs)
+    rows = BATCH
+    if K * t_probe[0] > 120.0:
+        rows = max(2048, int(BATCH * 120.0 / (K * t_probe[0])))
+    best, med, times = cpu_reference_rate(pipe, df.iloc[:rows], K, procs)
+    mean_t = statistics.mean(times)
+    value = rows / mean_t
+    how = "n_jobs=-1 threads" if procs == 1 else f"{procs} forked processes, rows split evenly"
+    sample = (f"{len(times)} steps x {rows} rows of the {BATCH}-row cfg2 batch through sklearn {sklearn.__version__} "
+              f"Pipeline.predict_proba ({how}); mean step time")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": len(times),
+        "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * mean_t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32cmp+f64acc", "data": "synthetic",
+        "config": {"workload": f"cfg2: {args.model} in the reference preprocessing, batch {BATCH} x 23 features", "batch": BATCH,
+                   "model": args.model, "rows_per_step": rows},
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores if procs == 1 else procs, "kind": "reference", "sample": sample,
+                         "host_cores": cores, "best": best},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args, dist: Dist):
+    from databricks_kubernetes_mlops_poc_b200 import flatten, training
+    from databricks_kubernetes_mlops_poc_b200.encode import RowEncoder
+    from databricks_kubernetes_mlops_poc_b200.engine import ForestEngine
+    from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES
+
+    K, W = args.steps, max(args.warmup, 3)
+    pipe, base = get_pipeline(args.model, dist)
+    flat = flatten.flatten_pipeline(pipe)
+    enc = RowEncoder(flat)
+    eng = ForestEngine(flat, dist.local_rank)
+    info0 = eng.info()
+
+    # ---- inputs: POOL distinct batches per rank (rank-seeded), resident in HBM and in pinned host memory
+    vocabs, codes, nums, rows = make_batches(base, enc, POOL, DATA_SEED + 1000 * dist.rank)
+    n_pool = POOL * BATCH
+    d_rows = eng.device_alloc(rows.nbytes)
+    d_proba = eng.device_alloc(n_pool * 4)
+    d_label = eng.device_alloc(n_pool * 4)
+    eng.h2d(d_rows, rows)
+    h_rows = eng.pinned("bench_rows", rows.nbytes).view(np.uint32, rows.shape)
+    h_rows[:] = rows
+    h_proba = eng.pinned("bench_proba", n_pool * 4).view(np.float32, (n_pool,))
+    h_label = eng.pinned("bench_label", n_pool * 4).view(np.int32, (n_pool,))
+
+    sampler = ClockSampler(dist.local_rank)
+    sampler.start()
+    t_load0 = time.time()
+
+    # ---- value: device-resident, K launches, CUDA events on the launching stream
+    eng.predict_stream_timed(d_rows, BATCH, POOL, d_proba, False, d_label, W)  # warm-up
+    dist.barrier()
+    l0 = eng.info()["launches"]
+    ms_each, ms_total = eng.predict_stream_timed(d_rows, BATCH, POOL, d_proba, False, d_label, K)
+    launches_value = eng.info()["launches"] - l0
+    dist.barrier()
+    ms_total_max = dist.max(ms_total)
+    value = dist.world * BATCH * K / (ms_total_max * 1e-3)
+
+    # ---- parity spot check inside the bench (GPU vs sklearn on 2 048 rows of batch 0), rank 0
+    parity = None
+    if dist.rank == 0:
+        got = np.empty(n_pool, dtype=np.float32)
+        eng.d2h(got, d_proba)
+        sel = np.arange(0, BATCH, BATCH // 2048)[:2048]
+        df = training.arrays_to_frame(vocabs, codes[sel], nums[sel])[ALL_FEATURES]
+        want = pipe.predict_proba(df)[:, 1]
+        parity = float(np.abs(got[sel].astype(np.float64) - want).max())
+
+    # ---- e2e: C-ABI call with host buffers, H2D + kernel + D2H every step, wall clock around synchronous calls
+    for i in range(W):
+        b = i % POOL
+        eng.predict_rows(h_rows[b * BATCH:(b + 1) * BATCH], np.float32, out_proba=h_proba[b * BATCH:(b + 1) * BATCH],
+                         out_label=h_label[b * BATCH:(b + 1) * BATCH])
+    dist.barrier()
+    lat = []
+    l0 = eng.info()["launches"]
+    t0 = time.perf_counter()
+    for i in range(K):
+        b = i % POOL
+        t1 = time.perf_counter()
+        eng.predict_rows(h_rows[b * BATCH:(b + 1) * BATCH], np.float32, out_proba=h_proba[b * BATCH:(b + 1) * BATCH],
+                         out_label=h_label[b * BATCH:(b + 1) * BATCH])
+        lat.append(time.perf_counter() - t1)
+    e2e_s = time.perf_counter() - t0
+    launches_e2e = eng.info()["launches"] - l0
+    dist.barrier()
+    e2e_s_max = dist.max(e2e_s)
+    e2e_value = dist.world * BATCH * K / e2e_s_max
+
+    # ---- sustained phase (>= 1.5 s of back-to-back launches) so the clock sampler sees the kernel under load
+    t_sus0 = time.time()
+    sus_steps, sus_ms = 0, 0.0
+    while time.time() - t_sus0 < args.sustain:
+        _, tot = eng.predict_stream_timed(d_rows, BATCH, POOL, d_proba, False, d_label, 2000)
+        sus_steps += 2000
+        sus_ms += tot
+    t_load1 = time.time()
+    sustained = BATCH * sus_steps / (sus_ms * 1e-3) if sus_steps else None
+
+    # ---- config 5: drift-monitor moments over 1M rows per job (K2), merged across ranks with NCCL
+    mom = None
+    if not args.no_moments:
+        n_mom = min(1_000_000 // dist.world, n_pool)
+        ms_m, local = eng.moments_device_timed(d_rows, n_mom, 20, False)
+        if dist.world > 1:
+            uid = dist.bcast_bytes(ForestEngine.comm_unique_id() if dist.rank == 0 else None)
+            eng.comm_init_rank(dist.world, dist.rank, uid)
+            eng.moments_allgather(local)  # warm-up (communicator setup)
+            dist.barrier()
+            t0 = time.perf_counter()
+            merged = eng.moments_allgather(local)
+            t_gather = time.perf_counter() - t0
+        else:
+            merged, t_gather = local, 0.0
+        # kernel-only roofline on the whole pool (>= 201 MB, larger than L2)
+        ms_big, _ = eng.moments_device_timed(d_rows, n_pool, 10, False)
+        peak, _ = measured_peak_gbs()
+        mom = {
+            "rows_total": n_mom * dist.world, "kernel_ms_per_rank": float(np.median(ms_m)),
+            "nccl_allgather_merge_ms": 1e3 * t_gather,
+            "kernel_gbs_201MB": MOM_BYTES_PER_ROW * n_pool / (float(np.median(ms_big)) * 1e-3) / 1e9,
+            "kernel_frac_of_hbm_peak_201MB": MOM_BYTES_PER_ROW * n_pool / (float(np.median(ms_big)) * 1e-3) / 1e9 / peak,
+            "count0": float(merged[9, 0]),
+        }
+
+    sampler.stop()
+    clocks = sampler.summary(t_load0, t_load1)
+    info1 = eng.info()
+
+    # ---- cpu baseline (rank 0, N=1 only): bounded sample = the same 65 536-row batch 0
+    cpu = None
+    if dist.rank == 0 and dist.world == 1 and not args.no_cpu:
+        import sklearn
+
+        kind = MODELS[args.model][0]
+        cores = os.cpu_count() or 1
+        df0 = training.arrays_to_frame(vocabs, codes[:BATCH], nums[:BATCH])[ALL_FEATURES]
+        procs = 1 if kind == "rf" else min(cores, 64)
+        best, med, times = cpu_reference_rate(pipe, df0, 5, procs)
+        one_best, _, _ = cpu_reference_rate(pipe, df0.iloc[:16384], 2, 1) if procs > 1 else (best, None, None)
+        port = cpu_port_rate(pipe, codes[:BATCH], nums[:BATCH], 5)
+        cpu = {
+            "value": med, "unit": "rows/s", "cores": cores if procs == 1 else procs, "kind": "reference",
+            "sample": (f"5 x batch 0 ({BATCH} rows) through sklearn {sklearn.__version__} Pipeline.predict_proba, "
+                       f"{'n_jobs=-1 threads' if procs == 1 else str(procs) + ' forked processes'}; median"),
+            "best": best, "single_process": one_best,
+            "port_openmp_rows_per_s": port, "host_cores": cores,
+        }
+
+    avg_launch_ms = float(np.mean(ms_each))
+    achieved = ALG_BYTES_PER_ROW * BATCH / (avg_launch_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak_gbs()
+    line = {
+        "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": dist.world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32cmp+f64acc", "data": "synthetic",
+        "config": {
+            "workload": f"cfg2: {args.model} ({info0['n_trees']} trees, depth {info0['max_depth']}, {flat.total_nodes} nodes) in the "
+                        f"reference preprocessing, batch {BATCH} x 23 features, per GPU",
+            "model": args.model, "batch": BATCH, "parallelism": f"dp{dist.world} (rows sharded, forest replicated, no collective)",
+            "l2": f"inputs rotate over {POOL} distinct batches ({POOL * BATCH * 96 / 1e6:.0f} MB > 126 MB L2)",
+            "walk": info0["walk"], "smem_bytes": info0["smem_bytes"], "rows_per_warp": info0["rows_per_warp"],
+        },
+        "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": BATCH * 96, "d2h_bytes_per_step": BATCH * 8,
+                "ms_per_step": 1e3 * e2e_s_max / K, "p50_ms": 1e3 * float(np.percentile(lat, 50)), "p99_ms": 1e3 * float(np.percentile(lat, 99)),
+                "api": "b2f_predict(host pinned rows) -> float32 proba + int32 label"},
+        "gpu_launches": int(launches_value),
+        "gpu_launches_e2e": int(launches_e2e),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic(args.model), "peak_source": peak_src, "kernel": "k_forest_predict",
+                     "alg_bytes_per_launch": ALG_BYTES_PER_ROW * BATCH, "avg_launch_ms": avg_launch_ms,
+                     "min_launch_ms": float(np.min(ms_each))},
+        "clocks": clocks,
+        "sustained_rows_per_s": sustained,
+        "parity_max_abs_dp_vs_sklearn_2048rows": parity,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    if mom is not None:
+        line["cfg5_moments"] = mom
+    for d in (d_rows, d_proba, d_label):
+        eng.device_free(d)
+    eng.close()
+    if dist.rank == 0:
+        print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="gbdt100d6", choices=sorted(MODELS))
+    ap.add_argument("--sustain", type=float, default=1.5, help="seconds of back-to-back launches for the clock record")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-moments", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        # under torchrun only rank 0 works; the other ranks exit 0 without joining anything
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_reference(args, Dist(args.gpus, use_cuda=False, solo=True))
+        return
+    dist = Dist(args.gpus, use_cuda=True)
+    try:
+        run_b200(args, dist)
+    finally:
+        dist.close()
+
+
+if __name__ == "__main__":
+    main()

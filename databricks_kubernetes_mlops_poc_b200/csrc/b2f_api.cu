@@ -599,6 +599,35 @@ extern "C" int b2f_predict_device_timed(b2f_model *m, const void *rows_dev, int6
     return rc;
 }
 
+/* Streaming measurement: `steps` launches over a pool of `pool` distinct device-resident batches
+ * (batch i%pool), so consecutive steps read different HBM lines (pool * n * 96 B should exceed L2).
+ * Per-launch events and one region event pair, all on the launching stream. */
+extern "C" int b2f_predict_stream_timed(b2f_model *m, const void *rows_dev, int64_t n, int pool, void *proba1_dev, int proba_is_f64,
+                                        int32_t *label_dev, int steps, float *ms_each, float *ms_total) {
+    if (!m || steps <= 0 || pool <= 0 || !ms_total) return set_err(B2F_EINVAL, "bad argument");
+    CUDA_TRY(cudaSetDevice(m->device));
+    std::vector<cudaEvent_t> ev(2 * (size_t)steps + 2);
+    for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
+    const size_t psz = proba_is_f64 ? sizeof(double) : sizeof(float);
+    int rc = B2F_OK;
+    CUDA_TRY(cudaEventRecord(ev[2 * steps], m->compute));
+    for (int i = 0; i < steps && rc == B2F_OK; ++i) {
+        const size_t b = (size_t)(i % pool);
+        CUDA_TRY(cudaEventRecord(ev[2 * i], m->compute));
+        rc = launch_predict(m, m->compute, static_cast<const uint8_t *>(rows_dev) + b * (size_t)n * B2F_ROW_BYTES, n,
+                            proba1_dev ? static_cast<uint8_t *>(proba1_dev) + b * (size_t)n * psz : nullptr, proba_is_f64,
+                            label_dev ? label_dev + b * (size_t)n : nullptr);
+        CUDA_TRY(cudaEventRecord(ev[2 * i + 1], m->compute));
+    }
+    CUDA_TRY(cudaEventRecord(ev[2 * steps + 1], m->compute));
+    CUDA_TRY(cudaStreamSynchronize(m->compute));
+    if (ms_each)
+        for (int i = 0; i < steps; ++i) CUDA_TRY(cudaEventElapsedTime(&ms_each[i], ev[2 * i], ev[2 * i + 1]));
+    CUDA_TRY(cudaEventElapsedTime(ms_total, ev[2 * steps], ev[2 * steps + 1]));
+    for (auto &e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
 /* ------------------------------------------------------------------ moments */
 static int launch_moments(b2f_model *m, const void *rows_dev, int64_t n) {
     int64_t blocks = std::min<int64_t>(m->mom_blocks, (n + B2F_MOM_ROWS_PER_BLOCK - 1) / B2F_MOM_ROWS_PER_BLOCK);

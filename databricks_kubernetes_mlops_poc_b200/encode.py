@@ -33,14 +33,14 @@ class RowEncoder:
         self.num_features = list(flat.num_features)
         self.n_cat = len(self.cat_features)
         self.n_num = len(self.num_features)
-        self._dtypes = [pd.CategoricalDtype(categories=list(v), ordered=False) for v in flat.categories]
+        self._index = [pd.Index(list(v), dtype=object) for v in flat.categories]
         self._missing = list(flat.missing_codes) if flat.missing_codes else [-1] * self.n_cat
 
     # ------------------------------------------------------------------ columns
     def encode_categorical(self, j: int, values) -> np.ndarray:
         """One categorical column (any array-like of str / None) -> int32 codes, -1 = unknown."""
         arr = values if isinstance(values, (pd.Series, np.ndarray)) else np.asarray(values, dtype=object)
-        codes = pd.Categorical(arr, dtype=self._dtypes[j]).codes.astype(np.int32)
+        codes = self._index[j].get_indexer(pd.Index(arr, dtype=object)).astype(np.int32)  # -1 = not in vocabulary
         if self._missing[j] >= 0:
             codes[np.asarray(pd.isna(arr))] = self._missing[j]
         return codes

@@ -146,6 +146,18 @@ class ForestEngine:
         )
         return ms
 
+    def predict_stream_timed(self, rows_dev, n, pool, proba_dev, proba_is_f64, label_dev, steps: int):
+        """``steps`` launches cycling over ``pool`` device-resident batches -> (ms_each, ms_total)."""
+        ms = np.zeros(steps, dtype=np.float32)
+        tot = C.c_float(0.0)
+        check(
+            self._lib.b2f_predict_stream_timed(
+                self._h, rows_dev, n, pool, proba_dev, int(proba_is_f64), label_dev, steps, ptr(ms), C.byref(tot)
+            ),
+            "b2f_predict_stream_timed",
+        )
+        return ms, float(tot.value)
+
     # ------------------------------------------------------------------ moments
     def moments(self, rows: np.ndarray) -> np.ndarray:
         """Per-word (count, mean, M2) over host rows -> float64 (24, 3)."""

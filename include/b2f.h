@@ -137,6 +137,13 @@ int b2f_predict_device_timed(b2f_model *m, const void *rows_dev, int64_t n, void
                              int proba_is_f64, int32_t *label_dev, int iters, int flush_l2,
                              float *ms_each);
 
+/* streaming form: `steps` launches cycling over `pool` distinct device-resident batches of n rows
+ * laid out back to back (rows, proba and label alike), so that successive launches read different
+ * HBM lines; ms_each[steps] (may be NULL) per launch, *ms_total for the whole region. */
+int b2f_predict_stream_timed(b2f_model *m, const void *rows_dev, int64_t n, int pool, void *proba1_dev,
+                             int proba_is_f64, int32_t *label_dev, int steps, float *ms_each,
+                             float *ms_total);
+
 /* ---- drift-monitor moments (BASELINE config 5; nearest reference call is
  *      self.drift.predict(...), 02-register-model.ipynb:338 -- no mean/var exists there) --------
  * For each of the 24 row words f: out[3f+0] = count of non-NaN values, out[3f+1] = mean,
