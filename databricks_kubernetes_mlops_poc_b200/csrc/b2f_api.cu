@@ -177,20 +177,20 @@ static int validate_blob(const uint8_t *blob, size_t nbytes, b2f_blob_header *hd
         memcpy(&gr, &gt[g], sizeof(gr));
         if (gr.chunk_off != expect_off || gr.n_slots == 0 || gr.n_leaf_slots == 0 ||
             gr.chunk_bytes != (gr.n_slots + gr.n_leaf_slots) * 256u || (uint64_t)gr.chunk_off + gr.chunk_bytes > h.chunks_bytes ||
-            gr.n_slots >= (1u << 26) || gr.n_leaf_slots >= B2F_LEAF_TAG || gr.n_trees == 0 || gr.n_trees > 32)
+            gr.n_slots >= (1u << 24) || gr.n_leaf_slots >= (1u << 24) || gr.n_trees == 0 || gr.n_trees > 32)
             return set_err(B2F_EINVAL, "forest blob: group %u descriptor invalid", g);
         expect_off += gr.chunk_bytes;
-        /* every reachable word must keep the walk in bounds: check all slots */
-        const uint32_t *T = reinterpret_cast<const uint32_t *>(blob + h.chunks_off + gr.chunk_off);
-        const uint32_t *M = T + (size_t)gr.n_slots * 32;
+        /* every node word must keep the walk in bounds: check all slots */
+        const uint32_t *N = reinterpret_cast<const uint32_t *>(blob + h.chunks_off + gr.chunk_off);
         for (uint32_t s = 0; s < gr.n_slots; ++s)
             for (uint32_t l = 0; l < 32; ++l) {
-                const uint32_t m = M[s * 32 + l], t = T[s * 32 + l];
-                const uint32_t feat = m & 31u, first = m >> 6;
+                const uint32_t t = N[(s * 32 + l) * 2], m = N[(s * 32 + l) * 2 + 1];
+                const uint32_t feat = m & 31u, first = (m & B2F_META_CHILD_MASK) / B2F_NODE_STRIDE;
                 const bool leaf = (first == s);
-                if (feat > B2F_SENTINEL_WORD) return set_err(B2F_EINVAL, "forest blob: group %u slot %u lane %u: row word %u", g, s, l, feat);
+                if ((m & 0xC0u) || feat > B2F_SENTINEL_WORD)
+                    return set_err(B2F_EINVAL, "forest blob: group %u slot %u lane %u: bad meta word 0x%08x", g, s, l, m);
                 if (leaf) {
-                    if (!(m & B2F_META_CAT) || feat != B2F_SENTINEL_WORD || !(t & B2F_LEAF_TAG) || (t & (B2F_LEAF_TAG - 1)) >= gr.n_leaf_slots)
+                    if (!(m & B2F_META_CAT) || feat != B2F_SENTINEL_WORD || (t % B2F_NODE_STRIDE) || t / B2F_NODE_STRIDE >= gr.n_leaf_slots)
                         return set_err(B2F_EINVAL, "forest blob: group %u slot %u lane %u: malformed leaf", g, s, l);
                 } else {
                     if (first <= s || first + 1 >= gr.n_slots) return set_err(B2F_EINVAL, "forest blob: group %u slot %u lane %u: child %u out of range", g, s, l, first);
@@ -272,7 +272,7 @@ static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
     for (int s = 0; s < B2F_STREAMS; ++s) CUDA_TRY(cudaStreamCreateWithFlags(&m->slots[s].stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&m->compute, cudaStreamNonBlocking));
 
-    m->mom_blocks = m->sm_count * 4;
+    m->mom_blocks = m->sm_count * 3; /* one full wave: 3 CTAs of 384 threads per SM (registers / 40 KB smem) */
     CUDA_TRY(cudaMalloc(&m->d_mom_partials, (size_t)m->mom_blocks * B2F_MOM_VALUES * sizeof(double)));
     CUDA_TRY(cudaMalloc(&m->d_mom_ticket, sizeof(unsigned int)));
     CUDA_TRY(cudaMemset(m->d_mom_ticket, 0, sizeof(unsigned int)));

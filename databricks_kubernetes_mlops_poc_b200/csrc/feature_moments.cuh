@@ -11,7 +11,7 @@
  * sum(x-K), sum((x-K)^2) and a count for its four words in float64 (K = the word's value in row 0,
  * read by every thread; the shift removes the catastrophic cancellation of the raw sum-of-squares
  * form).  Block partials are reduced through shared memory in a fixed order, written to global
- * memory, and the last block to finish (atomic ticket) reduces the partials in block order, so the
+ * memory, and the last block to finish (atomic ticket) reduces the partials in a fixed order, so the
  * result is deterministic.  NaN values are skipped (count is per word).
  */
 #pragma once
@@ -90,11 +90,24 @@ __global__ void __launch_bounds__(B2F_MOM_THREADS)
     if (!is_last) return;
     __threadfence();
 
-    /* last block: reduce block partials in block order, then (count, S, SS) -> (count, mean, M2) */
-    if (threadIdx.x < B2F_MOM_VALUES) {
-        double a = 0.0;
-        for (unsigned int b = 0; b < gridDim.x; ++b) a += __ldcg(partials + (size_t)b * B2F_MOM_VALUES + threadIdx.x);
-        tot[threadIdx.x] = a;
+    /* last block: reduce the block partials in a fixed order -- 5 interleaved segments per value so
+     * 360 threads work and every thread's loads are independent (the adds form 5 short chains) */
+    {
+        double *seg = &red[0][0]; /* reuse: [5][72] */
+        __syncthreads();
+        if (threadIdx.x < 5 * B2F_MOM_VALUES) {
+            const int v = threadIdx.x % B2F_MOM_VALUES, sgm = threadIdx.x / B2F_MOM_VALUES;
+            double a = 0.0;
+#pragma unroll 8
+            for (unsigned int b = sgm; b < gridDim.x; b += 5) a += __ldcg(partials + (size_t)b * B2F_MOM_VALUES + v);
+            seg[sgm * B2F_MOM_VALUES + v] = a;
+        }
+        __syncthreads();
+        if (threadIdx.x < B2F_MOM_VALUES) {
+            double a = 0.0;
+            for (int sgm = 0; sgm < 5; ++sgm) a += seg[sgm * B2F_MOM_VALUES + threadIdx.x];
+            tot[threadIdx.x] = a;
+        }
     }
     __syncthreads();
     if (threadIdx.x < B2F_ROW_WORDS) {

@@ -11,17 +11,24 @@
  * shared-memory banks (and, from global memory, 32 consecutive words when the slots coincide).
  *
  * One group chunk, contiguous and 256-byte granular (so a chunk is one TMA bulk copy):
- *     T  : uint32[n_slots][32]      threshold word: float32 threshold (numeric split),
- *                                   int32 category code (one-hot split) or 0x40000000 | leaf_id (leaf)
- *     M  : uint32[n_slots][32]      meta word: bits 0..4 row word index, bit 5 = categorical test,
- *                                   bits 6..31 = slot of the FIRST child (second child = first + 1)
- *     LV : float64[n_leaf_slots][32] leaf payload: RF class-1 fraction, or GBDT learning_rate*value
+ *     N  : {uint32 T, uint32 M}[n_slots][32]   one 8-byte node per (slot, tree): a single 64-bit
+ *                                              shared-memory load per visit, bank-conflict free
+ *     LV : float64[n_leaf_slots][32]           leaf payload: RF class-1 fraction, or GBDT
+ *                                              learning_rate*value
+ *   T  threshold word: float32 t' = nextup(floor32(threshold)) for a numeric split, int32 category
+ *      code for a one-hot split, leaf_id*256 (= byte offset of the leaf's LV row) for a leaf
+ *   M  meta word: bits 0..4 row word index (used directly as the shuffle source lane), bit 5 =
+ *      categorical test, bits 8..31 = byte offset (slot*256) of the FIRST child inside the chunk
+ *      (second child = first + 256)
  *
  * Split semantics (x = row word M.feat of the encoded row, after in-kernel imputation):
- *     numeric      : go to second child iff !(float(x) <= float(T))     (sklearn: x <= thr -> left)
- *     categorical  : go to second child iff int(x) == int(T)            (one-hot column == 1 -> right)
- * A leaf slot tests row word 23 (always 0 in the kernel's copy of the row) for equality with
- * 0x40000000|leaf_id, which never holds, and names itself as first child: walking is a fixed
+ *     numeric      : second child iff x >= t' or unordered     (sklearn: x <= thr -> left, and for
+ *                    float32 x:  x <= thr  <=>  x <= floor32(thr)  <=>  x < nextup(floor32(thr)))
+ *     categorical  : second child iff int(x) == int(T)         (one-hot column == 1 -> right)
+ *   evaluated branch-free as  second = (x ==bits T) or (geu(x, T) and not cat): for a numeric node
+ *   bit equality implies x >= t', so the extra term never changes the answer.
+ * A leaf slot is a categorical test of row word 23 (the kernel's copy of the row holds 0xFFFFFFFF
+ * there) against leaf_id*256, which never matches, with itself as first child: walking is a fixed
  * `depth`-iteration loop with no leaf branch; leaves simply self-loop.
  */
 #ifndef B2F_FOREST_BLOB_H
@@ -29,12 +36,14 @@
 #include <stdint.h>
 
 #define B2F_BLOB_MAGIC "B2FOREST"
-#define B2F_BLOB_VERSION 1u
+#define B2F_BLOB_VERSION 2u
 #define B2F_BLOB_HEADER_BYTES 512u
 #define B2F_GROUP_TREES 32u
 #define B2F_MAX_GROUPS 32u
 #define B2F_SENTINEL_WORD 23u
-#define B2F_LEAF_TAG 0x40000000u
+#define B2F_SENTINEL_BITS 0xFFFFFFFFu
+#define B2F_META_CHILD_MASK 0xFFFFFF00u
+#define B2F_NODE_STRIDE 256u /* bytes between consecutive slots of one tree (32 lanes x 8 B) */
 #define B2F_META_CAT 0x20u
 
 typedef struct b2f_blob_header {
@@ -63,7 +72,7 @@ typedef struct b2f_blob_header {
 typedef struct b2f_blob_group {
     uint32_t chunk_off;    /* bytes from chunks_off; multiple of 256 */
     uint32_t chunk_bytes;  /* (n_slots + n_leaf_slots) * 256 */
-    uint32_t n_slots;      /* node slots per tree in this group (padded to the group's maximum) */
+    uint32_t n_slots;      /* node slots per tree in this group (padded to the group's maximum; < 2^24) */
     uint32_t n_leaf_slots; /* leaf slots per tree (padded) */
     uint32_t depth;        /* walk iterations = deepest leaf in the group */
     uint32_t n_trees;      /* real trees in this group (<= 32; the rest are zero-valued stubs) */

@@ -87,20 +87,46 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 
 template <bool SMEM>
-__device__ __forceinline__ uint32_t ld_word(const uint32_t *p) {
+__device__ __forceinline__ uint2 ld_node(const uint8_t *p) {
     if constexpr (SMEM) {
-        return *p;
+        return *reinterpret_cast<const uint2 *>(p);
     } else {
-        return __ldg(p);
+        return __ldg(reinterpret_cast<const uint2 *>(p));
     }
 }
 template <bool SMEM>
-__device__ __forceinline__ double ld_leaf(const double *p) {
+__device__ __forceinline__ uint32_t ld_word(const uint8_t *p) {
     if constexpr (SMEM) {
-        return *p;
+        return *reinterpret_cast<const uint32_t *>(p);
     } else {
-        return __ldg(p);
+        return __ldg(reinterpret_cast<const uint32_t *>(p));
     }
+}
+template <bool SMEM>
+__device__ __forceinline__ double ld_leaf(const uint8_t *p) {
+    if constexpr (SMEM) {
+        return *reinterpret_cast<const double *>(p);
+    } else {
+        return __ldg(reinterpret_cast<const double *>(p));
+    }
+}
+
+/* Branch-free split decision (forest_blob.h): second = (x ==bits t) or (geu(x, t) and not cat);
+ * returns `if_second` or `if_first` -- three predicate instructions and one select. */
+__device__ __forceinline__ uint32_t pick_child(uint32_t x, uint32_t t, uint32_t m, uint32_t if_first, uint32_t if_second) {
+    uint32_t c;
+    asm("{\n\t"
+        ".reg .pred pc, p1, p2;\n\t"
+        ".reg .b32 cbit;\n\t"
+        "and.b32 cbit, %3, 32;\n\t"
+        "setp.ne.u32 pc, cbit, 0;\n\t"
+        "setp.geu.and.f32 p1, %1, %2, !pc;\n\t"
+        "setp.eq.or.u32 p2, %4, %5, p1;\n\t"
+        "selp.u32 %0, %7, %6, p2;\n\t"
+        "}"
+        : "=r"(c)
+        : "f"(__uint_as_float(x)), "f"(__uint_as_float(t)), "r"(m), "r"(x), "r"(t), "r"(if_first), "r"(if_second));
+    return c;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -147,21 +173,36 @@ __global__ void __launch_bounds__(B2F_PREDICT_THREADS, 1)
     const long long warp_global = (long long)warp * gridDim.x + blockIdx.x;
     const long long warp_stride = (long long)gridDim.x * B2F_PREDICT_WARPS;
 
-    /* numeric lanes impute NaN with the training median; lane 23 holds the sentinel 0 */
+    /* numeric lanes impute NaN with the training median; lanes >= 23 hold the sentinel 0xFFFFFFFF */
     const bool lane_numeric = lane >= p.n_cat && lane < p.n_cat + p.n_num;
     const uint32_t impute_bits = lane < 24 ? __float_as_uint(p.impute[lane]) : 0u;
+    const uint32_t lane8 = (uint32_t)lane * 8u;              /* this lane's node inside a 256-byte slot */
+    const uint32_t lane8_second = lane8 | B2F_NODE_STRIDE;  /* ... of the sibling slot */
+
+    auto load_row = [&](long long row) -> uint32_t {
+        uint32_t v = B2F_SENTINEL_BITS;
+        if (row < n && lane < (int)B2F_SENTINEL_WORD) v = __ldg(rows + row * B2F_ROW_WORDS + lane);
+        return v;
+    };
+
+    uint32_t wnext[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) wnext[r] = warp_global < n_batches ? load_row(warp_global * R + r) : B2F_SENTINEL_BITS;
 
     for (long long b = warp_global; b < n_batches; b += warp_stride) {
         uint32_t w[R];
         double acc[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const long long row = b * R + r;
-            uint32_t v = 0;
-            if (row < n && lane < (int)B2F_SENTINEL_WORD) v = __ldg(rows + row * B2F_ROW_WORDS + lane);
+            uint32_t v = wnext[r];
             if (lane_numeric && isnan(__uint_as_float(v))) v = impute_bits;
             w[r] = v;
             acc[r] = 0.0;
+        }
+        /* prefetch the next batch's rows; the loads complete behind this batch's walk */
+        if (b + warp_stride < n_batches) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) wnext[r] = load_row((b + warp_stride) * R + r);
         }
 
         for (int g = 0; g < p.n_groups; ++g) {
@@ -171,31 +212,27 @@ __global__ void __launch_bounds__(B2F_PREDICT_THREADS, 1)
                     ready |= 1u << g;
                 }
             }
-            const uint32_t n_slots = p.g[g].n_slots;
-            const uint32_t *T = reinterpret_cast<const uint32_t *>(base + p.g[g].chunk_off) + lane;
-            const uint32_t *M = T + n_slots * 32u;
-            const double *LV = reinterpret_cast<const double *>(M - lane + n_slots * 32u) + lane;
+            const uint8_t *nodes = base + p.g[g].chunk_off;                     /* warp-uniform */
+            const uint8_t *leaves = nodes + p.g[g].n_slots * B2F_NODE_STRIDE;  /* warp-uniform */
             const int depth = (int)p.g[g].depth;
 
-            uint32_t node[R];
+            uint32_t rel[R]; /* byte offset of this lane's current node inside the chunk */
 #pragma unroll
-            for (int r = 0; r < R; ++r) node[r] = 0;
+            for (int r = 0; r < R; ++r) rel[r] = lane8;
 
             for (int d = 0; d < depth; ++d) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const uint32_t m = ld_word<SMEM>(M + node[r] * 32u);
-                    const uint32_t t = ld_word<SMEM>(T + node[r] * 32u);
-                    const uint32_t x = __shfl_sync(0xffffffffu, w[r], m & 31u);
-                    const bool second = (m & B2F_META_CAT) ? (x == t)
-                                                           : !(__uint_as_float(x) <= __uint_as_float(t));
-                    node[r] = (m >> 6) + (second ? 1u : 0u);
+                    const uint2 tm = ld_node<SMEM>(nodes + rel[r]);
+                    const uint32_t x = __shfl_sync(0xffffffffu, w[r], (int)tm.y); /* lane = tm.y & 31 */
+                    const uint32_t c = pick_child(x, tm.x, tm.y, lane8, lane8_second);
+                    rel[r] = (tm.y & B2F_META_CHILD_MASK) | c;
                 }
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const uint32_t leaf = ld_word<SMEM>(T + node[r] * 32u) & (B2F_LEAF_TAG - 1u);
-                acc[r] += ld_leaf<SMEM>(LV + leaf * 32u);
+                const uint32_t leaf_off = ld_word<SMEM>(nodes + rel[r]); /* leaf_id * 256 */
+                acc[r] += ld_leaf<SMEM>(leaves + (leaf_off | lane8));
             }
         }
 

@@ -12,9 +12,10 @@ sklearn's attribute names.  It does arithmetic-free bookkeeping only:
   "second child iff code[f] == c"  (unknown / missing category = code -1 = all-zero
   one-hot block = always first child, which is ``handle_unknown="ignore"``,
   ``01-train-model.ipynb:203-206``);
-* float64 thresholds are floored to float32: for float32 ``x``,
-  ``x <= t64  <=>  x <= max{f32 <= t64}`` (sklearn compares float32 X with float64
-  thresholds, ``sklearn/tree/_tree.pyx`` ``_apply_dense``);
+* float64 thresholds become the float32 ``t' = nextup(floor32(t64))``: for float32 ``x``,
+  ``x <= t64  <=>  x <= max{f32 <= t64}  <=>  x < t'`` (sklearn compares float32 X with
+  float64 thresholds, ``sklearn/tree/_tree.pyx`` ``_apply_dense``), so the kernel's test is
+  "second child iff ``x >= t'``";
 * leaf payloads stay float64: RF class-1 fraction, or ``learning_rate * value`` for GBDT
   (the product sklearn's ``predict_stages`` forms before adding);
 * nodes are re-numbered breadth-first so siblings are adjacent, leaves become
@@ -31,14 +32,16 @@ import numpy as np
 
 ROW_WORDS = 24
 SENTINEL_WORD = 23
-LEAF_TAG = 0x40000000
+SENTINEL_BITS = 0xFFFFFFFF
 META_CAT = 0x20
+META_CHILD_MASK = 0xFFFFFF00
+NODE_STRIDE = 256
 GROUP_TREES = 32
 MAX_TREES = 1024
 HEADER_BYTES = 512
 AGG_RF_MEAN = 0
 AGG_GBDT_LOGISTIC = 1
-BLOB_VERSION = 1
+BLOB_VERSION = 2
 
 _HEADER_FMT = "<8s" + "I" * 10 + "dd" + "Q" * 4 + "24f" + "24i"  # 288 bytes, padded to 512
 _GROUP_FMT = "<8I"
@@ -118,11 +121,18 @@ def _bfs_slots(left: np.ndarray, right: np.ndarray):
     return slot, depth
 
 
+def strict_upper_f32(t64: np.ndarray) -> np.ndarray:
+    """t' = nextup(floor32(t64)): the float32 with  x <= t64  <=>  x < t'  for every finite float32 x."""
+    return np.nextafter(floor_to_f32(t64), np.float32(np.inf))
+
+
 def _flatten_tree(tree, col_word, col_cat_code, col_is_cat, leaf_value):
-    """One sklearn ``Tree`` -> (T uint32[n], M uint32[n], LV float64[n_leaves], depth)."""
+    """One sklearn ``Tree`` -> (T uint32[n], M uint32[n], LV float64[n_leaves], depth), slot-indexed."""
     left = tree.children_left.astype(np.int64)
     right = tree.children_right.astype(np.int64)
     n = left.shape[0]
+    if n >= (1 << 24):
+        raise NotImplementedError("tree too large for 24-bit slot offsets")
     slot, depth = _bfs_slots(left, right)
     T = np.zeros(n, dtype=np.uint32)
     M = np.zeros(n, dtype=np.uint32)
@@ -130,23 +140,23 @@ def _flatten_tree(tree, col_word, col_cat_code, col_is_cat, leaf_value):
     internal = np.nonzero(~is_leaf)[0]
     leaves = np.nonzero(is_leaf)[0]
 
-    # leaves: numbered in slot order
+    # leaves: numbered in slot order; T = byte offset of the leaf's payload row, M = self-loop
     leaf_order = leaves[np.argsort(slot[leaves])]
     leaf_id = np.arange(leaf_order.size, dtype=np.uint32)
     ls = slot[leaf_order]
-    T[ls] = np.uint32(LEAF_TAG) | leaf_id
-    M[ls] = (ls.astype(np.uint32) << np.uint32(6)) | np.uint32(META_CAT) | np.uint32(SENTINEL_WORD)
+    T[ls] = leaf_id * np.uint32(NODE_STRIDE)
+    M[ls] = (ls.astype(np.uint32) * np.uint32(NODE_STRIDE)) | np.uint32(META_CAT) | np.uint32(SENTINEL_WORD)
     LV = leaf_value[leaf_order].astype(np.float64)
 
     if internal.size:
         col = tree.feature[internal].astype(np.int64)
         thr = tree.threshold[internal].astype(np.float64)
         s = slot[internal]
-        first = slot[left[internal]].astype(np.uint32)
+        first = slot[left[internal]].astype(np.uint32) * np.uint32(NODE_STRIDE)
         word = col_word[col].astype(np.uint32)
         cat = col_is_cat[col]
-        t_words = floor_to_f32(thr).view(np.uint32).copy()
-        m_words = (first << np.uint32(6)) | word
+        t_words = strict_upper_f32(thr).view(np.uint32).copy()
+        m_words = first | word
         if cat.any():
             # one-hot column x in {0, 1}:  x <= thr ?  x=0 -> (0 <= thr), x=1 -> (1 <= thr)
             zero_left = 0.0 <= thr
@@ -158,9 +168,9 @@ def _flatten_tree(tree, col_word, col_cat_code, col_is_cat, leaf_value):
             m_words[normal] |= np.uint32(META_CAT)
             t_words[always_left] = np.uint32(0x7FFFFFFF)  # never equals a category code
             m_words[always_left] |= np.uint32(META_CAT)
-            # always second child: numeric test on the sentinel word (0.0): !(0.0 <= -1.0)
-            t_words[always_right] = np.float32(-1.0).view(np.uint32)
-            m_words[always_right] = (first[always_right] << np.uint32(6)) | np.uint32(SENTINEL_WORD)
+            # always second child: numeric test on the sentinel word (NaN bits): geu(NaN, t) is true
+            t_words[always_right] = np.uint32(0)
+            m_words[always_right] = first[always_right] | np.uint32(SENTINEL_WORD)
         T[s] = t_words
         M[s] = m_words
     return T, M, LV, depth
@@ -266,17 +276,16 @@ def flatten_pipeline(pipeline) -> FlatForest:
         n_slots = max(len(m[0]) for m in members)
         n_leaf = max(len(m[2]) for m in members)
         depth = max(m[3] for m in members)
-        T = np.empty((n_slots, GROUP_TREES), dtype=np.uint32)
-        M = np.empty((n_slots, GROUP_TREES), dtype=np.uint32)
+        N = np.empty((n_slots, GROUP_TREES, 2), dtype=np.uint32)  # [slot][tree] -> (T, M)
         LV = np.zeros((n_leaf, GROUP_TREES), dtype=np.float64)
-        # unused slots / stub trees: self-looping leaf with payload slot 0 (value 0.0 for stubs)
-        T[:, :] = np.uint32(LEAF_TAG)
-        M[:, :] = (np.arange(n_slots, dtype=np.uint32)[:, None] << np.uint32(6)) | np.uint32(META_CAT | SENTINEL_WORD)
+        # unused slots / stub trees: self-looping leaf with payload row 0 (value 0.0 for stubs)
+        N[:, :, 0] = 0
+        N[:, :, 1] = (np.arange(n_slots, dtype=np.uint32)[:, None] * np.uint32(NODE_STRIDE)) | np.uint32(META_CAT | SENTINEL_WORD)
         for lane, (t, m, lv, _) in enumerate(members):
-            T[: len(t), lane] = t
-            M[: len(m), lane] = m
+            N[: len(t), lane, 0] = t
+            N[: len(m), lane, 1] = m
             LV[: len(lv), lane] = lv
-        chunk = T.tobytes() + M.tobytes() + LV.tobytes()
+        chunk = N.tobytes() + LV.tobytes()
         assert len(chunk) == (n_slots + n_leaf) * 256
         groups.append((off, len(chunk), n_slots, n_leaf, depth, len(members), 0, 0))
         chunks.append(chunk)

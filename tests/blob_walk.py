@@ -8,7 +8,7 @@ the product imports it.
 
 import numpy as np
 
-from databricks_kubernetes_mlops_poc_b200.flatten import LEAF_TAG, META_CAT, SENTINEL_WORD, parse_header
+from databricks_kubernetes_mlops_poc_b200.flatten import META_CAT, META_CHILD_MASK, NODE_STRIDE, SENTINEL_BITS, SENTINEL_WORD, parse_header
 
 
 def walk_blob(blob: bytes, rows: np.ndarray):
@@ -20,15 +20,15 @@ def walk_blob(blob: bytes, rows: np.ndarray):
     nan = np.isnan(f[:, n_cat : n_cat + n_num])
     imp = np.broadcast_to(h["impute"][n_cat : n_cat + n_num], nan.shape)
     f[:, n_cat : n_cat + n_num][nan] = imp[nan]
-    w[:, SENTINEL_WORD] = 0
+    w[:, SENTINEL_WORD] = SENTINEL_BITS
     lane_acc = np.zeros((n, 32), dtype=np.float64)
     buf = np.frombuffer(blob, dtype=np.uint8)
     ridx = np.arange(n)
     for g in h["groups"]:
         base = h["chunks_off"] + g["chunk_off"]
         ns, nl = g["n_slots"], g["n_leaf_slots"]
-        T = buf[base : base + ns * 128].view(np.uint32).reshape(ns, 32)
-        M = buf[base + ns * 128 : base + ns * 256].view(np.uint32).reshape(ns, 32)
+        N = buf[base : base + ns * 256].view(np.uint32).reshape(ns, 32, 2)
+        T, M = N[:, :, 0], N[:, :, 1]
         LV = buf[base + ns * 256 : base + ns * 256 + nl * 256].view(np.float64).reshape(nl, 32)
         for lane in range(32):
             node = np.zeros(n, dtype=np.int64)
@@ -38,9 +38,10 @@ def walk_blob(blob: bytes, rows: np.ndarray):
                 x = w[ridx, (m & 31).astype(np.int64)]
                 is_cat = (m & META_CAT) != 0
                 with np.errstate(invalid="ignore"):
-                    second = np.where(is_cat, x == t, ~(x.view(np.float32) <= t.view(np.float32)))
-                node = (m >> 6).astype(np.int64) + second.astype(np.int64)
-            leaf = (T[node, lane] & np.uint32(LEAF_TAG - 1)).astype(np.int64)
+                    geu = ~(x.view(np.float32) < t.view(np.float32))  # x >= t or unordered
+                second = (x == t) | (geu & ~is_cat)
+                node = ((m & np.uint32(META_CHILD_MASK)) // NODE_STRIDE).astype(np.int64) + second.astype(np.int64)
+            leaf = (T[node, lane] // NODE_STRIDE).astype(np.int64)
             lane_acc[:, lane] += LV[leaf, lane]
     v = lane_acc
     for o in (16, 8, 4, 2, 1):  # xor butterfly, as warp_sum()
