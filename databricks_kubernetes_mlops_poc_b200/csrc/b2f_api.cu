@@ -185,12 +185,12 @@ static int validate_blob(const uint8_t *blob, size_t nbytes, b2f_blob_header *hd
         for (uint32_t s = 0; s < gr.n_slots; ++s)
             for (uint32_t l = 0; l < 32; ++l) {
                 const uint32_t t = N[(s * 32 + l) * 2], m = N[(s * 32 + l) * 2 + 1];
-                const uint32_t feat = m & 31u, first = (m & B2F_META_CHILD_MASK) / B2F_NODE_STRIDE;
+                const uint32_t feat = m >> B2F_META_FEAT_SHIFT, first = m & B2F_META_SLOT_MASK;
                 const bool leaf = (first == s);
-                if ((m & 0xC0u) || feat > B2F_SENTINEL_WORD)
+                if ((m & 0x03000000u) || feat > B2F_SENTINEL_WORD)
                     return set_err(B2F_EINVAL, "forest blob: group %u slot %u lane %u: bad meta word 0x%08x", g, s, l, m);
                 if (leaf) {
-                    if (!(m & B2F_META_CAT) || feat != B2F_SENTINEL_WORD || (t % B2F_NODE_STRIDE) || t / B2F_NODE_STRIDE >= gr.n_leaf_slots)
+                    if (!(m & B2F_META_CAT) || feat != B2F_SENTINEL_WORD || t >= gr.n_leaf_slots)
                         return set_err(B2F_EINVAL, "forest blob: group %u slot %u lane %u: malformed leaf", g, s, l);
                 } else {
                     if (first <= s || first + 1 >= gr.n_slots) return set_err(B2F_EINVAL, "forest blob: group %u slot %u lane %u: child %u out of range", g, s, l, first);

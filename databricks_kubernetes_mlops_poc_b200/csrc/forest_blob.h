@@ -16,10 +16,10 @@
  *     LV : float64[n_leaf_slots][32]           leaf payload: RF class-1 fraction, or GBDT
  *                                              learning_rate*value
  *   T  threshold word: float32 t' = nextup(floor32(threshold)) for a numeric split, int32 category
- *      code for a one-hot split, leaf_id*256 (= byte offset of the leaf's LV row) for a leaf
- *   M  meta word: bits 0..4 row word index (used directly as the shuffle source lane), bit 5 =
- *      categorical test, bits 8..31 = byte offset (slot*256) of the FIRST child inside the chunk
- *      (second child = first + 256)
+ *      code for a one-hot split, leaf_id (row of the leaf's payload in LV) for a leaf
+ *   M  meta word: bits 27..31 row word index, bit 26 = categorical test, bits 0..23 = slot of the
+ *      FIRST child (second child = first + 1).  The next node's address is one multiply-add:
+ *      (M << 8) + lane_base shifts the top byte out and scales the slot by the 256-byte stride.
  *
  * Split semantics (x = row word M.feat of the encoded row, after in-kernel imputation):
  *     numeric      : second child iff x >= t' or unordered     (sklearn: x <= thr -> left, and for
@@ -28,7 +28,7 @@
  *   evaluated branch-free as  second = (x ==bits T) or (geu(x, T) and not cat): for a numeric node
  *   bit equality implies x >= t', so the extra term never changes the answer.
  * A leaf slot is a categorical test of row word 23 (the kernel's copy of the row holds 0xFFFFFFFF
- * there) against leaf_id*256, which never matches, with itself as first child: walking is a fixed
+ * there) against leaf_id, which never matches, with itself as first child: walking is a fixed
  * `depth`-iteration loop with no leaf branch; leaves simply self-loop.
  */
 #ifndef B2F_FOREST_BLOB_H
@@ -42,9 +42,10 @@
 #define B2F_MAX_GROUPS 32u
 #define B2F_SENTINEL_WORD 23u
 #define B2F_SENTINEL_BITS 0xFFFFFFFFu
-#define B2F_META_CHILD_MASK 0xFFFFFF00u
+#define B2F_META_SLOT_MASK 0x00FFFFFFu
+#define B2F_META_FEAT_SHIFT 27u
 #define B2F_NODE_STRIDE 256u /* bytes between consecutive slots of one tree (32 lanes x 8 B) */
-#define B2F_META_CAT 0x20u
+#define B2F_META_CAT 0x04000000u
 
 typedef struct b2f_blob_header {
     char magic[8];

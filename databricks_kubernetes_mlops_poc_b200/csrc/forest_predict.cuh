@@ -86,47 +86,74 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 
+/* Node addresses are 32-bit shared-window addresses (SMEM) or 64-bit global addresses (GLOBAL). */
 template <bool SMEM>
-__device__ __forceinline__ uint2 ld_node(const uint8_t *p) {
+struct AddrOf {
+    using type = uint64_t;
+};
+template <>
+struct AddrOf<true> {
+    using type = uint32_t;
+};
+template <bool SMEM>
+__device__ __forceinline__ typename AddrOf<SMEM>::type node_addr(const uint8_t *p) {
     if constexpr (SMEM) {
-        return *reinterpret_cast<const uint2 *>(p);
+        return smem_addr(p);
     } else {
-        return __ldg(reinterpret_cast<const uint2 *>(p));
+        return reinterpret_cast<uint64_t>(p);
     }
 }
 template <bool SMEM>
-__device__ __forceinline__ uint32_t ld_word(const uint8_t *p) {
+__device__ __forceinline__ uint2 ld_node(typename AddrOf<SMEM>::type a) {
+    uint2 v;
     if constexpr (SMEM) {
-        return *reinterpret_cast<const uint32_t *>(p);
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
     } else {
-        return __ldg(reinterpret_cast<const uint32_t *>(p));
+        asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(a));
     }
+    return v;
 }
 template <bool SMEM>
-__device__ __forceinline__ double ld_leaf(const uint8_t *p) {
+__device__ __forceinline__ uint32_t ld_word(typename AddrOf<SMEM>::type a) {
+    uint32_t v;
     if constexpr (SMEM) {
-        return *reinterpret_cast<const double *>(p);
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     } else {
-        return __ldg(reinterpret_cast<const double *>(p));
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(a));
     }
+    return v;
+}
+template <bool SMEM>
+__device__ __forceinline__ double ld_leaf(typename AddrOf<SMEM>::type a) {
+    double v;
+    if constexpr (SMEM) {
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    } else {
+        asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(a));
+    }
+    return v;
 }
 
 /* Branch-free split decision (forest_blob.h): second = (x ==bits t) or (geu(x, t) and not cat);
  * returns `if_second` or `if_first` -- three predicate instructions and one select. */
-__device__ __forceinline__ uint32_t pick_child(uint32_t x, uint32_t t, uint32_t m, uint32_t if_first, uint32_t if_second) {
+__device__ __forceinline__ bool take_second(uint32_t x, uint32_t t, uint32_t m) {
     uint32_t c;
     asm("{\n\t"
         ".reg .pred pc, p1, p2;\n\t"
         ".reg .b32 cbit;\n\t"
-        "and.b32 cbit, %3, 32;\n\t"
+        "and.b32 cbit, %3, 0x04000000;\n\t"
         "setp.ne.u32 pc, cbit, 0;\n\t"
         "setp.geu.and.f32 p1, %1, %2, !pc;\n\t"
         "setp.eq.or.u32 p2, %4, %5, p1;\n\t"
-        "selp.u32 %0, %7, %6, p2;\n\t"
+        "selp.u32 %0, 1, 0, p2;\n\t"
         "}"
         : "=r"(c)
-        : "f"(__uint_as_float(x)), "f"(__uint_as_float(t)), "r"(m), "r"(x), "r"(t), "r"(if_first), "r"(if_second));
-    return c;
+        : "f"(__uint_as_float(x)), "f"(__uint_as_float(t)), "r"(m), "r"(x), "r"(t));
+    return c != 0;
+}
+template <typename A>
+__device__ __forceinline__ A pick_child(uint32_t x, uint32_t t, uint32_t m, A if_first, A if_second) {
+    return take_second(x, t, m) ? if_second : if_first;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -143,6 +170,7 @@ __global__ void __launch_bounds__(B2F_PREDICT_THREADS, 1)
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[B2F_MAX_GROUPS];
 
+    using addr_t = typename AddrOf<SMEM>::type;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
 
@@ -176,8 +204,7 @@ __global__ void __launch_bounds__(B2F_PREDICT_THREADS, 1)
     /* numeric lanes impute NaN with the training median; lanes >= 23 hold the sentinel 0xFFFFFFFF */
     const bool lane_numeric = lane >= p.n_cat && lane < p.n_cat + p.n_num;
     const uint32_t impute_bits = lane < 24 ? __float_as_uint(p.impute[lane]) : 0u;
-    const uint32_t lane8 = (uint32_t)lane * 8u;              /* this lane's node inside a 256-byte slot */
-    const uint32_t lane8_second = lane8 | B2F_NODE_STRIDE;  /* ... of the sibling slot */
+    const uint32_t lane8 = (uint32_t)lane * 8u; /* this lane's node inside a 256-byte slot */
 
     auto load_row = [&](long long row) -> uint32_t {
         uint32_t v = B2F_SENTINEL_BITS;
@@ -215,24 +242,28 @@ __global__ void __launch_bounds__(B2F_PREDICT_THREADS, 1)
             const uint8_t *nodes = base + p.g[g].chunk_off;                     /* warp-uniform */
             const uint8_t *leaves = nodes + p.g[g].n_slots * B2F_NODE_STRIDE;  /* warp-uniform */
             const int depth = (int)p.g[g].depth;
+            /* 32-bit (shared window) or 64-bit (global) address of this lane's node in slot 0 / slot 1 */
+            const addr_t a_first = node_addr<SMEM>(nodes) + lane8;
+            const addr_t a_second = a_first + B2F_NODE_STRIDE;
+            const addr_t a_leaf = node_addr<SMEM>(leaves) + lane8;
 
-            uint32_t rel[R]; /* byte offset of this lane's current node inside the chunk */
+            addr_t at[R]; /* address of this lane's current node */
 #pragma unroll
-            for (int r = 0; r < R; ++r) rel[r] = lane8;
+            for (int r = 0; r < R; ++r) at[r] = a_first;
 
             for (int d = 0; d < depth; ++d) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const uint2 tm = ld_node<SMEM>(nodes + rel[r]);
-                    const uint32_t x = __shfl_sync(0xffffffffu, w[r], (int)tm.y); /* lane = tm.y & 31 */
-                    const uint32_t c = pick_child(x, tm.x, tm.y, lane8, lane8_second);
-                    rel[r] = (tm.y & B2F_META_CHILD_MASK) | c;
+                    const uint2 tm = ld_node<SMEM>(at[r]);
+                    const uint32_t x = __shfl_sync(0xffffffffu, w[r], (int)(tm.y >> B2F_META_FEAT_SHIFT));
+                    /* (M << 8): top byte (word index, flags) falls out, slot index becomes a byte offset */
+                    at[r] = pick_child(x, tm.x, tm.y, a_first, a_second) + (addr_t)(tm.y << 8);
                 }
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const uint32_t leaf_off = ld_word<SMEM>(nodes + rel[r]); /* leaf_id * 256 */
-                acc[r] += ld_leaf<SMEM>(leaves + (leaf_off | lane8));
+                const uint32_t leaf_id = ld_word<SMEM>(at[r]);
+                acc[r] += ld_leaf<SMEM>(a_leaf + (addr_t)(leaf_id << 8));
             }
         }
 

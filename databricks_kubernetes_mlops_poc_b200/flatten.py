@@ -33,8 +33,9 @@ import numpy as np
 ROW_WORDS = 24
 SENTINEL_WORD = 23
 SENTINEL_BITS = 0xFFFFFFFF
-META_CAT = 0x20
-META_CHILD_MASK = 0xFFFFFF00
+META_CAT = 0x04000000
+META_SLOT_MASK = 0x00FFFFFF
+META_FEAT_SHIFT = 27
 NODE_STRIDE = 256
 GROUP_TREES = 32
 MAX_TREES = 1024
@@ -140,20 +141,20 @@ def _flatten_tree(tree, col_word, col_cat_code, col_is_cat, leaf_value):
     internal = np.nonzero(~is_leaf)[0]
     leaves = np.nonzero(is_leaf)[0]
 
-    # leaves: numbered in slot order; T = byte offset of the leaf's payload row, M = self-loop
+    # leaves: numbered in slot order; T = row of the leaf's payload in LV, M = self-loop
     leaf_order = leaves[np.argsort(slot[leaves])]
     leaf_id = np.arange(leaf_order.size, dtype=np.uint32)
     ls = slot[leaf_order]
-    T[ls] = leaf_id * np.uint32(NODE_STRIDE)
-    M[ls] = (ls.astype(np.uint32) * np.uint32(NODE_STRIDE)) | np.uint32(META_CAT) | np.uint32(SENTINEL_WORD)
+    T[ls] = leaf_id
+    M[ls] = ls.astype(np.uint32) | np.uint32(META_CAT) | np.uint32(SENTINEL_WORD << META_FEAT_SHIFT)
     LV = leaf_value[leaf_order].astype(np.float64)
 
     if internal.size:
         col = tree.feature[internal].astype(np.int64)
         thr = tree.threshold[internal].astype(np.float64)
         s = slot[internal]
-        first = slot[left[internal]].astype(np.uint32) * np.uint32(NODE_STRIDE)
-        word = col_word[col].astype(np.uint32)
+        first = slot[left[internal]].astype(np.uint32)
+        word = col_word[col].astype(np.uint32) << np.uint32(META_FEAT_SHIFT)
         cat = col_is_cat[col]
         t_words = strict_upper_f32(thr).view(np.uint32).copy()
         m_words = first | word
@@ -170,7 +171,7 @@ def _flatten_tree(tree, col_word, col_cat_code, col_is_cat, leaf_value):
             m_words[always_left] |= np.uint32(META_CAT)
             # always second child: numeric test on the sentinel word (NaN bits): geu(NaN, t) is true
             t_words[always_right] = np.uint32(0)
-            m_words[always_right] = first[always_right] | np.uint32(SENTINEL_WORD)
+            m_words[always_right] = first[always_right] | np.uint32(SENTINEL_WORD << META_FEAT_SHIFT)
         T[s] = t_words
         M[s] = m_words
     return T, M, LV, depth
@@ -280,7 +281,7 @@ def flatten_pipeline(pipeline) -> FlatForest:
         LV = np.zeros((n_leaf, GROUP_TREES), dtype=np.float64)
         # unused slots / stub trees: self-looping leaf with payload row 0 (value 0.0 for stubs)
         N[:, :, 0] = 0
-        N[:, :, 1] = (np.arange(n_slots, dtype=np.uint32)[:, None] * np.uint32(NODE_STRIDE)) | np.uint32(META_CAT | SENTINEL_WORD)
+        N[:, :, 1] = np.arange(n_slots, dtype=np.uint32)[:, None] | np.uint32(META_CAT | (SENTINEL_WORD << META_FEAT_SHIFT))
         for lane, (t, m, lv, _) in enumerate(members):
             N[: len(t), lane, 0] = t
             N[: len(m), lane, 1] = m

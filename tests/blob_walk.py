@@ -8,7 +8,7 @@ the product imports it.
 
 import numpy as np
 
-from databricks_kubernetes_mlops_poc_b200.flatten import META_CAT, META_CHILD_MASK, NODE_STRIDE, SENTINEL_BITS, SENTINEL_WORD, parse_header
+from databricks_kubernetes_mlops_poc_b200.flatten import META_CAT, META_FEAT_SHIFT, META_SLOT_MASK, SENTINEL_BITS, SENTINEL_WORD, parse_header
 
 
 def walk_blob(blob: bytes, rows: np.ndarray):
@@ -35,13 +35,13 @@ def walk_blob(blob: bytes, rows: np.ndarray):
             for _ in range(g["depth"]):
                 m = M[node, lane]
                 t = T[node, lane]
-                x = w[ridx, (m & 31).astype(np.int64)]
+                x = w[ridx, (m >> META_FEAT_SHIFT).astype(np.int64)]
                 is_cat = (m & META_CAT) != 0
                 with np.errstate(invalid="ignore"):
                     geu = ~(x.view(np.float32) < t.view(np.float32))  # x >= t or unordered
                 second = (x == t) | (geu & ~is_cat)
-                node = ((m & np.uint32(META_CHILD_MASK)) // NODE_STRIDE).astype(np.int64) + second.astype(np.int64)
-            leaf = (T[node, lane] // NODE_STRIDE).astype(np.int64)
+                node = (m & np.uint32(META_SLOT_MASK)).astype(np.int64) + second.astype(np.int64)
+            leaf = T[node, lane].astype(np.int64)
             lane_acc[:, lane] += LV[leaf, lane]
     v = lane_acc
     for o in (16, 8, 4, 2, 1):  # xor butterfly, as warp_sum()
