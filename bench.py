@@ -375,6 +375,14 @@ def run_b200(args, dist: Dist):
     e2e_s_max = dist.max(e2e_s)
     e2e_value = dist.world * BATCH * K / e2e_s_max
 
+    # ---- PCIe probe: one batch, pinned host -> device, synchronous copy (the e2e floor is set by this)
+    tt = []
+    for _ in range(10):
+        t1 = time.perf_counter()
+        eng.h2d(d_rows, h_rows[:BATCH])
+        tt.append(time.perf_counter() - t1)
+    h2d_gbs = BATCH * 96 / min(tt) / 1e9
+
     # ---- sustained phase (>= 1.5 s of back-to-back launches) so the clock sampler sees the kernel under load
     t_sus0 = time.time()
     sus_steps, sus_ms = 0, 0.0
@@ -451,7 +459,7 @@ def run_b200(args, dist: Dist):
         },
         "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": BATCH * 96, "d2h_bytes_per_step": BATCH * 8,
                 "ms_per_step": 1e3 * e2e_s_max / K, "p50_ms": 1e3 * float(np.percentile(lat, 50)), "p99_ms": 1e3 * float(np.percentile(lat, 99)),
-                "api": "b2f_predict(host pinned rows) -> float32 proba + int32 label"},
+                "api": "b2f_predict(host pinned rows) -> float32 proba + int32 label", "pcie_h2d_gbs_one_batch": h2d_gbs},
         "gpu_launches": int(launches_value),
         "gpu_launches_e2e": int(launches_e2e),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

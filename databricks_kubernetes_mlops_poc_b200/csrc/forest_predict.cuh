@@ -162,25 +162,87 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+/* aggregate -> (probability, label) for one row per lane; rows < 0 are empty slots */
+template <typename OutT>
+__device__ __forceinline__ void finalize_store(const KParams &p, double s, long long row, OutT *__restrict__ proba,
+                                               int32_t *__restrict__ label) {
+    if (row < 0) return;
+    double p1;
+    int lab;
+    if (p.agg_mode == B2F_AGG_RF_MEAN) {
+        p1 = s / p.denom;            /* sklearn: proba /= n_estimators */
+        lab = s > (p.denom - s);     /* argmax: class 1 iff p1 > p0 */
+    } else {
+        const double raw = p.init_raw + s;
+        p1 = 1.0 / (1.0 + exp(-raw)); /* expit */
+        lab = raw >= 0.0;
+    }
+    if (proba) proba[row] = (OutT)p1;
+    if (label) label[row] = lab;
+}
+
 /* ---------------------------------------------------------------- the kernel */
+/* One group for R rows: D dependent levels, R independent chains interleaved for ILP.
+ * D > 0: fully unrolled (the common shallow forests); D == 0: run-time depth. */
+template <int R, bool SMEM, int D>
+__device__ __forceinline__ void walk_group(typename AddrOf<SMEM>::type a_first, typename AddrOf<SMEM>::type a_leaf, int depth,
+                                           const uint32_t (&w)[R], double (&acc)[R]) {
+    using addr_t = typename AddrOf<SMEM>::type;
+    const addr_t a_second = a_first + B2F_NODE_STRIDE;
+    addr_t at[R]; /* address of this lane's current node */
+#pragma unroll
+    for (int r = 0; r < R; ++r) at[r] = a_first;
+
+    auto level = [&]() {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint2 tm = ld_node<SMEM>(at[r]);
+            const uint32_t x = __shfl_sync(0xffffffffu, w[r], (int)(tm.y >> B2F_META_FEAT_SHIFT));
+            /* (M << 8): top byte (word index, flags) falls out, slot index becomes a byte offset */
+            at[r] = pick_child(x, tm.x, tm.y, a_first, a_second) + (addr_t)(tm.y << 8);
+        }
+    };
+    if constexpr (D > 0) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) level();
+    } else {
+#pragma unroll 4
+        for (int d = 0; d < depth; ++d) level();
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t leaf_id = ld_word<SMEM>(at[r]);
+        acc[r] += ld_leaf<SMEM>(a_leaf + (addr_t)(leaf_id << 8));
+    }
+}
+
 template <int R, bool SMEM, typename OutT>
 __global__ void __launch_bounds__(B2F_PREDICT_THREADS, 1)
     k_forest_predict(const __grid_constant__ KParams p, const uint32_t *__restrict__ rows, long long n,
                      OutT *__restrict__ proba, int32_t *__restrict__ label) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[B2F_MAX_GROUPS];
+    /* per group: {node area, leaf area, depth}: shared-window addresses (SMEM) or byte offsets from
+     * p.chunks (GLOBAL); one broadcast 16-byte load per group instead of indexed constant loads */
+    __shared__ uint4 gtab[B2F_MAX_GROUPS];
 
     using addr_t = typename AddrOf<SMEM>::type;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    const int n_groups = p.n_groups;
 
+    if (threadIdx.x < n_groups) {
+        const KGroup gd = p.g[threadIdx.x];
+        const uint32_t origin = SMEM ? smem_addr(smem) : 0u;
+        gtab[threadIdx.x] = make_uint4(origin + gd.chunk_off, origin + gd.chunk_off + gd.n_slots * B2F_NODE_STRIDE, gd.depth, 0u);
+    }
     if constexpr (SMEM) {
         /* one thread arms one mbarrier per tree group and issues the TMA bulk copies */
         if (threadIdx.x == 0) {
-            for (int g = 0; g < p.n_groups; ++g) mbar_init(&bars[g], 1);
+            for (int g = 0; g < n_groups; ++g) mbar_init(&bars[g], 1);
             fence_mbar_init();
             fence_proxy_async();
-            for (int g = 0; g < p.n_groups; ++g) {
+            for (int g = 0; g < n_groups; ++g) {
                 const uint32_t bytes = p.g[g].chunk_bytes;
                 mbar_arrive_expect_tx(&bars[g], bytes);
                 for (uint32_t o = 0; o < bytes; o += B2F_BULK_PIECE) {
@@ -189,11 +251,11 @@ __global__ void __launch_bounds__(B2F_PREDICT_THREADS, 1)
                 }
             }
         }
-        __syncthreads();
     }
+    __syncthreads();
 
-    const uint8_t *base = SMEM ? smem : p.chunks;
-    uint32_t ready = 0; /* bit g: this warp has observed group g's chunk in shared memory */
+    const uint32_t all_ready = n_groups >= 32 ? 0xffffffffu : ((1u << n_groups) - 1u);
+    uint32_t ready = SMEM ? 0u : all_ready; /* bit g: this warp has seen group g's chunk land in shared memory */
 
     const long long n_batches = (n + R - 1) / R;
     /* CTA-minor numbering: consecutive row batches go to different SMs, so small batches spread
@@ -205,12 +267,17 @@ __global__ void __launch_bounds__(B2F_PREDICT_THREADS, 1)
     const bool lane_numeric = lane >= p.n_cat && lane < p.n_cat + p.n_num;
     const uint32_t impute_bits = lane < 24 ? __float_as_uint(p.impute[lane]) : 0u;
     const uint32_t lane8 = (uint32_t)lane * 8u; /* this lane's node inside a 256-byte slot */
+    const addr_t origin_lane = (SMEM ? (addr_t)0 : (addr_t)reinterpret_cast<uint64_t>(p.chunks)) + lane8;
 
     auto load_row = [&](long long row) -> uint32_t {
         uint32_t v = B2F_SENTINEL_BITS;
         if (row < n && lane < (int)B2F_SENTINEL_WORD) v = __ldg(rows + row * B2F_ROW_WORDS + lane);
         return v;
     };
+
+    double pend_sum = 0.0; /* lane j: tree sum of the j-th row this warp finished since the last flush */
+    long long pend_row = -1;
+    int pend_n = 0;
 
     uint32_t wnext[R];
 #pragma unroll
@@ -232,65 +299,54 @@ __global__ void __launch_bounds__(B2F_PREDICT_THREADS, 1)
             for (int r = 0; r < R; ++r) wnext[r] = load_row((b + warp_stride) * R + r);
         }
 
-        for (int g = 0; g < p.n_groups; ++g) {
+        for (int g = 0; g < n_groups; ++g) {
             if constexpr (SMEM) {
-                if (!((ready >> g) & 1u)) {
-                    mbar_wait(&bars[g], 0);
-                    ready |= 1u << g;
+                if (ready != all_ready) { /* only while the forest is still streaming in */
+                    if (!((ready >> g) & 1u)) {
+                        mbar_wait(&bars[g], 0);
+                        ready |= 1u << g;
+                    }
                 }
             }
-            const uint8_t *nodes = base + p.g[g].chunk_off;                     /* warp-uniform */
-            const uint8_t *leaves = nodes + p.g[g].n_slots * B2F_NODE_STRIDE;  /* warp-uniform */
-            const int depth = (int)p.g[g].depth;
-            /* 32-bit (shared window) or 64-bit (global) address of this lane's node in slot 0 / slot 1 */
-            const addr_t a_first = node_addr<SMEM>(nodes) + lane8;
-            const addr_t a_second = a_first + B2F_NODE_STRIDE;
-            const addr_t a_leaf = node_addr<SMEM>(leaves) + lane8;
-
-            addr_t at[R]; /* address of this lane's current node */
-#pragma unroll
-            for (int r = 0; r < R; ++r) at[r] = a_first;
-
-            for (int d = 0; d < depth; ++d) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const uint2 tm = ld_node<SMEM>(at[r]);
-                    const uint32_t x = __shfl_sync(0xffffffffu, w[r], (int)(tm.y >> B2F_META_FEAT_SHIFT));
-                    /* (M << 8): top byte (word index, flags) falls out, slot index becomes a byte offset */
-                    at[r] = pick_child(x, tm.x, tm.y, a_first, a_second) + (addr_t)(tm.y << 8);
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const uint32_t leaf_id = ld_word<SMEM>(at[r]);
-                acc[r] += ld_leaf<SMEM>(a_leaf + (addr_t)(leaf_id << 8));
+            const uint4 gd = gtab[g];
+            const addr_t a_first = origin_lane + gd.x;
+            const addr_t a_leaf = origin_lane + gd.y;
+            switch (gd.z) {
+                case 1: walk_group<R, SMEM, 1>(a_first, a_leaf, 1, w, acc); break;
+                case 2: walk_group<R, SMEM, 2>(a_first, a_leaf, 2, w, acc); break;
+                case 3: walk_group<R, SMEM, 3>(a_first, a_leaf, 3, w, acc); break;
+                case 4: walk_group<R, SMEM, 4>(a_first, a_leaf, 4, w, acc); break;
+                case 5: walk_group<R, SMEM, 5>(a_first, a_leaf, 5, w, acc); break;
+                case 6: walk_group<R, SMEM, 6>(a_first, a_leaf, 6, w, acc); break;
+                case 7: walk_group<R, SMEM, 7>(a_first, a_leaf, 7, w, acc); break;
+                case 8: walk_group<R, SMEM, 8>(a_first, a_leaf, 8, w, acc); break;
+                default: walk_group<R, SMEM, 0>(a_first, a_leaf, (int)gd.z, w, acc); break;
             }
         }
 
+        /* every lane now holds the row's tree sum; lane `pend_n` keeps it.  The float64 divide / exp
+         * of the aggregate and the stores then run once per 32 rows with all lanes busy, instead of
+         * once per row on a single lane. */
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const double s = warp_sum(acc[r]);
             const long long row = b * R + r;
-            if (lane == 0 && row < n) {
-                double p1;
-                int lab;
-                if (p.agg_mode == B2F_AGG_RF_MEAN) {
-                    p1 = s / p.denom;
-                    lab = s > (p.denom - s);
-                } else {
-                    const double raw = p.init_raw + s;
-                    p1 = 1.0 / (1.0 + exp(-raw));
-                    lab = raw >= 0.0;
-                }
-                if (proba) proba[row] = (OutT)p1;
-                if (label) label[row] = lab;
+            if (lane == pend_n) {
+                pend_sum = s;
+                pend_row = row < n ? row : -1;
+            }
+            if (++pend_n == 32) {
+                finalize_store(p, pend_sum, pend_row, proba, label);
+                pend_n = 0;
+                pend_row = -1;
             }
         }
     }
+    if (pend_n > 0) finalize_store(p, pend_sum, pend_row, proba, label);
 
     if constexpr (SMEM) {
         /* never retire a CTA while a bulk copy into its shared memory is still in flight */
-        for (int g = 0; g < p.n_groups; ++g)
+        for (int g = 0; g < n_groups; ++g)
             if (!((ready >> g) & 1u)) mbar_wait(&bars[g], 0);
     }
 }
