@@ -47,6 +47,10 @@ class B200Model:
         self.drift = drift
         self.proba_dtype = np.dtype(proba_dtype)
         self.classes = np.asarray(flat.classes)
+        # one scoring replica per GPU for the server's round-robin batcher (each has its own handle,
+        # pinned staging and worker thread; the forest is replicated, rows are independent)
+        engines = self.group.engines if self.group is not None else [self.engine]
+        self.replicas = [_Replica(self.encoder, e) for e in engines]
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -102,6 +106,20 @@ class B200Model:
             "outliers": [0] * n,
             "feature_drift_batch": dict(zip(self.all_features, drift_scores)),
         }
+
+
+class _Replica:
+    """One GPU's view of the model: encode into that engine's pinned staging and score there."""
+
+    def __init__(self, encoder: RowEncoder, engine: ForestEngine):
+        self.encoder, self.engine = encoder, engine
+
+    def predict_proba1(self, df: pd.DataFrame) -> np.ndarray:
+        n = len(df)
+        rows, proba, label = self.engine.staging(n)
+        self.encoder.encode_frame(df, out=rows)
+        self.engine.predict_rows(rows, proba_dtype=np.float64, want_label=False, out_proba=proba)
+        return np.array(proba, dtype=np.float64)
 
 
 # ---------------------------------------------------------------------- loading

@@ -1,0 +1,210 @@
+"""FastAPI serving layer: the reference's ``app/main.py`` with the new request-batching loop.
+
+Same HTTP surface as the reference (``app/main.py:35-43``): ``POST /predict`` takes a JSON list of
+``LoanApplicant`` rows and returns ``ModelOutput``; Swagger UI at ``/``; ``MODEL_DIRECTORY`` and
+``SERVICE_NAME`` environment variables; the model is loaded once in ``lifespan`` (``:20-31``) and cleared
+at shutdown; both log records (``type: InferenceData`` ``:60-69`` and ``type: ModelOutput`` ``:75-84``) keep
+their schema because the reference's KQL dashboards query it.  Error behaviour is the reference's too:
+type errors are FastAPI's 422, anything raised while scoring is a 500, an empty list is a 500.
+
+What is new sits between the reference's lines 54 and 72:
+
+* rows are turned into columns straight from the validated request (no ``pd.DataFrame(list_of_models)``);
+* a micro-batcher collects concurrent requests for up to ``B200_BATCH_WINDOW_US`` microseconds (or
+  ``B200_MAX_BATCH`` rows), dictionary-encodes them into one pinned staging slot, and scores the whole
+  slot with ONE engine call (H2D + fused kernel + D2H); batches are dealt round-robin to the GPUs listed
+  in ``B200_DEVICES`` -- the reference instead blocks its event loop per request (``async def`` calling
+  blocking code, ``app/main.py:43,72``), so requests are strictly serialised there;
+* the two JSON log lines are produced on a logging thread, off the request's critical path.
+"""
+
+from __future__ import annotations
+
+import asyncio
+import json
+import logging
+import os
+import queue
+import threading
+import time
+import uuid
+from concurrent.futures import ThreadPoolExecutor
+from contextlib import asynccontextmanager
+from typing import AsyncGenerator
+
+import numpy as np
+import pandas as pd
+from fastapi import FastAPI
+
+from .schema import ALL_FEATURES, CATEGORICAL_FEATURES, NUMERIC_FEATURES, LoanApplicant, ModelOutput
+
+ml_models: dict = {}
+
+
+def _service_name() -> str:
+    return os.environ.get("SERVICE_NAME", "credit-default-api")
+
+
+def rows_to_frame(data) -> pd.DataFrame:
+    """Validated request rows -> the 23 named columns, built column-wise."""
+    cols = {}
+    for name in CATEGORICAL_FEATURES:
+        cols[name] = np.array([getattr(r, name) for r in data], dtype=object)
+    for name in NUMERIC_FEATURES:
+        cols[name] = np.array([getattr(r, name) for r in data], dtype=np.float64)
+    return pd.DataFrame(cols, columns=ALL_FEATURES)
+
+
+class _Pending:
+    __slots__ = ("frame", "future", "loop", "n")
+
+    def __init__(self, frame, future, loop):
+        self.frame, self.future, self.loop, self.n = frame, future, loop, len(frame)
+
+
+class MicroBatcher:
+    """Cross-request batching in front of ``model.predict_proba1`` (one worker thread per model).
+
+    ``models`` is a list (one per GPU); consecutive batches go round-robin over it."""
+
+    def __init__(self, models, max_rows: int = 65536, window_us: int = 200):
+        self.models = list(models)
+        self.max_rows = int(max_rows)
+        self.window_s = window_us * 1e-6
+        self.q: queue.Queue = queue.Queue()
+        self.batches = 0
+        self.rows = 0
+        self._stop = False
+        self._threads = [threading.Thread(target=self._run, args=(i,), daemon=True, name=f"b200-batcher-{i}")
+                         for i in range(len(self.models))]
+        for t in self._threads:
+            t.start()
+
+    async def score(self, frame: pd.DataFrame) -> np.ndarray:
+        loop = asyncio.get_running_loop()
+        fut = loop.create_future()
+        self.q.put(_Pending(frame, fut, loop))
+        return await fut
+
+    def close(self) -> None:
+        self._stop = True
+        for _ in self._threads:
+            self.q.put(None)
+        for t in self._threads:
+            t.join(timeout=5)
+
+    def _collect(self):
+        first = self.q.get()
+        if first is None:
+            return None
+        items, rows = [first], first.n
+        deadline = time.perf_counter() + self.window_s
+        while rows < self.max_rows:
+            left = deadline - time.perf_counter()
+            try:
+                nxt = self.q.get(timeout=left) if left > 0 else self.q.get_nowait()
+            except queue.Empty:
+                break
+            if nxt is None:
+                self.q.put(None)
+                break
+            items.append(nxt)
+            rows += nxt.n
+        return items
+
+    def _run(self, idx: int) -> None:
+        model = self.models[idx]
+        while not self._stop:
+            items = self._collect()
+            if items is None:
+                return
+            try:
+                frame = items[0].frame if len(items) == 1 else pd.concat([it.frame for it in items], ignore_index=True)
+                proba = model.predict_proba1(frame)  # encode -> pinned slot -> H2D -> kernel -> D2H
+                self.batches += 1
+                self.rows += len(frame)
+                off = 0
+                for it in items:
+                    part = proba[off:off + it.n]
+                    off += it.n
+                    it.loop.call_soon_threadsafe(_resolve, it.future, part, None)
+            except BaseException as e:  # surfaces as HTTP 500, like any model exception in the reference
+                for it in items:
+                    it.loop.call_soon_threadsafe(_resolve, it.future, None, e)
+
+
+def _resolve(fut, value, err):
+    if fut.cancelled():
+        return
+    if err is not None:
+        fut.set_exception(err)
+    else:
+        fut.set_result(value)
+
+
+def _log_record(kind: str, request_id: str, payload) -> None:
+    logging.info(json.dumps({"service_name": _service_name(), "type": kind, "request_id": request_id, "data": payload}))
+
+
+def create_app(model=None, loader=None) -> FastAPI:
+    """Build the app.  ``model``: an already-built B200Model (tests); otherwise ``loader`` (default
+    ``databricks_kubernetes_mlops_poc_b200.load_model``) is called in ``lifespan`` on ``MODEL_DIRECTORY``."""
+    log_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="b200-log")
+
+    @asynccontextmanager
+    async def lifespan(app: FastAPI) -> AsyncGenerator[None, None]:
+        if model is not None:
+            ml_models["credit_default"] = model
+        else:
+            from . import load_model
+
+            ml_models["credit_default"] = (loader or load_model)(os.getenv("MODEL_DIRECTORY", "./app/model"))
+        m = ml_models["credit_default"]
+        ml_models["_batcher"] = MicroBatcher(
+            getattr(m, "replicas", None) or [m],
+            max_rows=int(os.environ.get("B200_MAX_BATCH", "65536")),
+            window_us=int(os.environ.get("B200_BATCH_WINDOW_US", "200")),
+        )
+        yield
+        ml_models["_batcher"].close()
+        closer = getattr(ml_models.get("credit_default"), "close", None)
+        ml_models.clear()
+        if closer and model is None:
+            closer()
+
+    app = FastAPI(title=_service_name(), docs_url="/", lifespan=lifespan)
+
+    @app.post("/predict", response_model=ModelOutput)
+    async def predict(data: list[LoanApplicant]):
+        """Score a list of loan applicants: default probability, outlier flag, per-feature batch drift."""
+        if len(data) == 0:
+            # the reference's empty DataFrame has no columns and dies in df[self.all_features] -> HTTP 500
+            raise KeyError(f"None of {ALL_FEATURES} are in the [columns]")
+        m = ml_models["credit_default"]
+        input_df = rows_to_frame(data)
+        request_id = uuid.uuid4().hex
+        log_pool.submit(lambda: _log_record("InferenceData", request_id, input_df.to_json(orient="records")))
+
+        proba = await ml_models["_batcher"].score(input_df)
+        drift = getattr(m, "drift", None)
+        if drift is not None:
+            drift_scores = await asyncio.get_running_loop().run_in_executor(None, drift.score, input_df)
+        else:
+            drift_scores = [0.0] * len(ALL_FEATURES)
+        model_output = {
+            "predictions": proba.tolist(),
+            "outliers": [0] * len(data),
+            "feature_drift_batch": dict(zip(ALL_FEATURES, drift_scores)),
+        }
+        log_pool.submit(_log_record, "ModelOutput", request_id, model_output)
+        return model_output
+
+    return app
+
+
+logging.basicConfig(level=logging.INFO)
+
+if __name__ == "__main__":
+    import uvicorn
+
+    uvicorn.run(create_app(), host="0.0.0.0", port=5000)

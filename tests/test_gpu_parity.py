@@ -272,3 +272,35 @@ def test_model_predict_dict(curated, inference, rf100d6):
             model.predict([])
     finally:
         model.close()
+
+
+def test_http_end_to_end_and_load_model(curated, rf100d6, tmp_path):
+    """POST /predict served by the CUDA engine, model loaded through the drop-in load_model(dir)
+    (cached forest blob + drift reference), answers == the reference CustomModel restatement."""
+    from fastapi.testclient import TestClient
+
+    from databricks_kubernetes_mlops_poc_b200 import flatten, load_model
+    from databricks_kubernetes_mlops_poc_b200.model import save_model_dir
+    from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES, sample_request
+    from databricks_kubernetes_mlops_poc_b200.server import create_app
+    from oracle.custom_model import ReferenceCustomModel
+
+    save_model_dir(str(tmp_path), flatten.flatten_pipeline(rf100d6), reference_frame=curated)
+    ref = ReferenceCustomModel(rf100d6, curated)
+    os.environ["MODEL_DIRECTORY"] = str(tmp_path)
+    try:
+        with TestClient(create_app(loader=load_model)) as c:
+            body = curated[ALL_FEATURES].iloc[:64].to_dict(orient="records")
+            r = c.post("/predict", json=body)
+            assert r.status_code == 200
+            got = r.json()
+            want = ref.predict(None, curated[ALL_FEATURES].iloc[:64])
+            assert np.abs(np.asarray(got["predictions"]) - np.asarray(want["predictions"])).max() <= TOL64
+            assert got["outliers"] == [float(v) for v in want["outliers"]]
+            for k in ALL_FEATURES:  # same scipy statistics on both sides, float32 p-values
+                assert abs(got["feature_drift_batch"][k] - want["feature_drift_batch"][k]) <= 1e-6
+            assert c.post("/predict", json=sample_request()).status_code == 200
+            assert c.post("/predict", json=[]).status_code == 500
+            assert c.post("/predict", json=[{"age": "old"}]).status_code == 422
+    finally:
+        os.environ.pop("MODEL_DIRECTORY", None)

@@ -1,0 +1,236 @@
+"""Host-side logic on a CPU-only box: flattener + blob format (through a numpy emulation of the kernel),
+row encoder, C-ABI surface.  No compute call touches the GPU here."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ----------------------------------------------------------------------------- C ABI surface
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "b2f.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2f_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from databricks_kubernetes_mlops_poc_b200 import _cabi
+
+    lib = _cabi.load_library()
+    names = _declared_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/b2f.h but not exported"
+        assert n in _cabi.SIGNATURES, f"{n} has no ctypes prototype"
+    assert set(_cabi.SIGNATURES) == set(names)
+    assert lib.b2f_version().startswith(b"b200forest")
+
+
+def test_no_device_means_no_result(rf100d6):
+    """No CPU fallback: on a box without a GPU model creation fails loudly (on a GPU box this is skipped)."""
+    from conftest import has_gpu
+    from databricks_kubernetes_mlops_poc_b200 import flatten
+    from databricks_kubernetes_mlops_poc_b200._cabi import B2FError
+    from databricks_kubernetes_mlops_poc_b200.engine import ForestEngine
+
+    if has_gpu():
+        pytest.skip("GPU present")
+    with pytest.raises(B2FError, match="no CUDA device|failed"):
+        ForestEngine(flatten.flatten_pipeline(rf100d6), 0)
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    from databricks_kubernetes_mlops_poc_b200 import _cabi
+
+    with pytest.raises(_cabi.B2FError, match="no CPU fallback"):
+        _cabi.load_library(str(tmp_path / "nope.so"))
+
+
+def test_moments_merge_is_chan(rf100d6):
+    from databricks_kubernetes_mlops_poc_b200.engine import moments_merge
+
+    rng = np.random.default_rng(0)
+    x = rng.normal(5e4, 7e3, size=(5000, 24))
+    cuts = [0, 700, 701, 3000, 5000]
+    parts = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        seg = x[a:b]
+        parts.append(np.stack([np.full(24, b - a, float), seg.mean(0), ((seg - seg.mean(0)) ** 2).sum(0)], axis=1))
+    parts.append(np.zeros((24, 3)))  # an empty shard
+    got = moments_merge(np.stack(parts))
+    assert np.allclose(got[:, 0], 5000)
+    assert np.allclose(got[:, 1], x.mean(0), rtol=1e-13)
+    assert np.allclose(got[:, 2] / 5000, x.var(0), rtol=1e-11)
+
+
+# ----------------------------------------------------------------------------- flattener / blob
+def _emulate(pipe, df):
+    from blob_walk import walk_blob
+    from databricks_kubernetes_mlops_poc_b200 import flatten
+    from databricks_kubernetes_mlops_poc_b200.encode import RowEncoder
+    from databricks_kubernetes_mlops_poc_b200.engine import validate_blob
+
+    flat = flatten.flatten_pipeline(pipe)
+    validate_blob(flat.blob)
+    return walk_blob(flat.blob, RowEncoder(flat).encode_frame(df)), flat
+
+
+def test_blob_semantics_match_oracle(curated, inference, adversarial, rf100d6, gbdt_small):
+    from oracle import reference_pipeline as rp
+
+    for pipe in (rf100d6, gbdt_small):
+        for df in (curated.iloc[:1500], inference, adversarial):
+            (p, l), _ = _emulate(pipe, df)
+            want_p, want_l = rp.oracle_predict(pipe, df)
+            assert np.abs(p - want_p).max() < 1e-14 and (l == want_l).all()
+
+
+def test_blob_layout_invariants(rf100d6):
+    from databricks_kubernetes_mlops_poc_b200 import flatten
+
+    flat = flatten.flatten_pipeline(rf100d6)
+    h = flatten.parse_header(flat.blob)
+    assert h["magic"] == b"B2FOREST" and h["version"] == flatten.BLOB_VERSION
+    assert h["n_trees"] == 100 and h["n_groups"] == 4 and h["n_cat"] == 9 and h["n_num"] == 14
+    assert h["denom"] == 100.0 and h["total_bytes"] == len(flat.blob)
+    assert h["chunks_off"] % 256 == 0
+    assert [g["n_trees"] for g in h["groups"]] == [32, 32, 32, 4]
+    off = 0
+    for g in h["groups"]:
+        assert g["chunk_off"] == off and g["chunk_bytes"] == (g["n_slots"] + g["n_leaf_slots"]) * 256
+        off += g["chunk_bytes"]
+    assert off == h["chunks_bytes"] <= 227 * 1024  # the pinned 100 x depth-6 forest is shared-memory resident
+    assert (h["vocab"][:9] == [2, 7, 4, 10, 10, 10, 10, 9, 9]).all()
+    rt = flatten.FlatForest.load  # save / load round trip
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as d:
+        flat.save(os.path.join(d, "f.npz"))
+        assert rt(os.path.join(d, "f.npz")).blob == flat.blob
+
+
+def test_threshold_conversion_is_exact():
+    from databricks_kubernetes_mlops_poc_b200.flatten import floor_to_f32, strict_upper_f32
+
+    rng = np.random.default_rng(3)
+    t = np.concatenate([rng.normal(0, 1e4, 2000), rng.normal(0, 1e-3, 500), [0.0, -0.0, 0.5, 0.27500000596046448, 1e39, -1e39, 3.4028234e38]])
+    x = np.concatenate([rng.normal(0, 1e4, 3000).astype(np.float32), t.astype(np.float32, casting="unsafe")[np.isfinite(t.astype(np.float32))],
+                        np.float32([0.0, -0.0, 1e-45, -1e-45, 3.4e38, -3.4e38])])
+    f = floor_to_f32(t)
+    u = strict_upper_f32(t)
+    want = x[:, None].astype(np.float64) <= t[None, :]  # sklearn: float32 x vs float64 threshold
+    assert (want == (x[:, None] <= f[None, :])).all()
+    assert (want == (x[:, None] < u[None, :])).all()
+
+
+def test_malformed_blobs_are_rejected(rf100d6):
+    from databricks_kubernetes_mlops_poc_b200 import flatten
+    from databricks_kubernetes_mlops_poc_b200._cabi import B2FError
+    from databricks_kubernetes_mlops_poc_b200.engine import validate_blob
+
+    blob = flatten.flatten_pipeline(rf100d6).blob
+    h = flatten.parse_header(blob)
+    validate_blob(blob)
+    for mutate in (
+        lambda b: b.__setitem__(0, 0),  # magic
+        lambda b: b.__setitem__(8, 9),  # version
+        lambda b: b.__setitem__(slice(h["chunks_off"] + 4, h["chunks_off"] + 8), (0x00FFFFF0).to_bytes(4, "little")),  # child out of range
+        lambda b: b.__setitem__(slice(h["chunks_off"] + 4, h["chunks_off"] + 8), (31 << 27 | 1).to_bytes(4, "little")),  # row word 31
+    ):
+        bad = bytearray(blob)
+        mutate(bad)
+        with pytest.raises(B2FError):
+            validate_blob(bytes(bad))
+    with pytest.raises(B2FError):
+        validate_blob(blob[:-1])
+    with pytest.raises(B2FError):
+        validate_blob(b"short")
+
+
+def test_unsupported_models_are_refused(curated):
+    from sklearn.ensemble import RandomForestClassifier
+
+    from databricks_kubernetes_mlops_poc_b200 import flatten, training
+
+    pipe = training.make_pipeline("rf", n_estimators=3, max_depth=2, random_state=0)
+    y3 = (np.arange(500) % 3)
+    pipe.fit(curated[flatten_features()].iloc[:500], y3)  # 3 classes
+    with pytest.raises(NotImplementedError):
+        flatten.flatten_pipeline(pipe)
+    assert isinstance(pipe.named_steps["classifier"], RandomForestClassifier)
+
+
+def flatten_features():
+    from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES
+
+    return ALL_FEATURES
+
+
+# ----------------------------------------------------------------------------- encoder
+def test_encoder_matches_reference_lookup(curated, inference, adversarial, rf100d6):
+    from databricks_kubernetes_mlops_poc_b200 import flatten
+    from databricks_kubernetes_mlops_poc_b200.encode import RowEncoder
+    from oracle import treewalk as tw
+
+    flat = flatten.flatten_pipeline(rf100d6)
+    enc = RowEncoder(flat)
+    dump = tw.dump_pipeline(rf100d6)
+    for df in (curated.iloc[:800], inference, adversarial):
+        rows = enc.encode_frame(df)
+        codes, nums = tw.encode_frame(dump, df)
+        assert rows.shape == (len(df), 24) and rows.dtype == np.uint32
+        assert (rows.view(np.int32)[:, :9] == codes).all()
+        got = rows.view(np.float32)[:, 9:23]
+        want = nums.astype(np.float32)
+        assert ((got == want) | (np.isnan(got) & np.isnan(want))).all()
+        assert (rows[:, 23] == 0).all()
+        shuffled = df[list(reversed([c for c in df.columns]))]  # column order must not matter
+        assert (enc.encode_frame(shuffled) == rows).all()
+
+
+def test_encoder_errors(curated, rf100d6):
+    from databricks_kubernetes_mlops_poc_b200 import flatten
+    from databricks_kubernetes_mlops_poc_b200.encode import RowEncoder
+    from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES
+
+    enc = RowEncoder(flatten.flatten_pipeline(rf100d6))
+    df = curated[ALL_FEATURES].iloc[:3].copy()
+    for bad in (np.inf, -np.inf, 1e39):
+        d = df.copy()
+        d.loc[d.index[1], "bill_amount_3"] = bad
+        with pytest.raises(ValueError, match="infinity or a value too large"):
+            enc.encode_frame(d)
+    with pytest.raises(KeyError):
+        enc.encode_frame(df.drop(columns=["sex"]))
+    d = df.copy()
+    d["age"] = d["age"].astype(object)
+    d.loc[d.index[0], "age"] = "forty"
+    with pytest.raises((ValueError, TypeError)):
+        enc.encode_frame(d)
+    assert enc.encode_frame(df.iloc[:0]).shape == (0, 24)
+
+
+def test_schema_is_wire_compatible():
+    """Field names, order, types and defaults of the reference's pydantic models (app/model.py:8-70)."""
+    from databricks_kubernetes_mlops_poc_b200 import schema
+
+    fields = schema.LoanApplicant.model_fields
+    assert list(fields) == schema.ALL_FEATURES and len(fields) == 23
+    assert [fields[n].annotation for n in schema.CATEGORICAL_FEATURES] == [str] * 9
+    assert [fields[n].annotation for n in schema.NUMERIC_FEATURES] == [float] * 14
+    row = schema.LoanApplicant()
+    assert row.sex == "male" and row.repayment_status_5 == "no_delay" and row.age == 18000.0 and row.payment_amount_6 == 805.65
+    assert schema.LoanApplicant.model_validate({}).model_dump() == schema.sample_request()[0]
+    with pytest.raises(Exception):
+        schema.LoanApplicant.model_validate({"sex": 3})
+    out = schema.ModelOutput.model_validate(
+        {"predictions": [0.5], "outliers": [0], "feature_drift_batch": {n: 0.0 for n in schema.ALL_FEATURES}})
+    assert out.model_dump()["outliers"] == [0.0]
+    with pytest.raises(Exception):
+        schema.ModelOutput.model_validate({"predictions": [0.5], "outliers": [0], "feature_drift_batch": {"sex": 0.0}})

@@ -1,0 +1,91 @@
+"""HTTP surface with a stub scorer (CPU): status codes, schema, logging, cross-request batching.
+Mirrors the behaviours probed on the unmodified reference app."""
+
+import asyncio
+import json
+import logging
+
+import numpy as np
+import pytest
+from fastapi.testclient import TestClient
+
+
+class StubModel:
+    """Deterministic scorer standing in for the GPU model: P = (credit_limit mod 1000) / 1000."""
+
+    drift = None
+
+    def __init__(self, fail=False):
+        self.calls, self.fail = [], fail
+        self.replicas = [self]
+
+    def predict_proba1(self, df):
+        if self.fail:
+            raise RuntimeError("b2f_predict failed (rc=-2): CUDA error")
+        self.calls.append(len(df))
+        return (df["credit_limit"].to_numpy() % 1000) / 1000.0
+
+
+def _client(model):
+    from databricks_kubernetes_mlops_poc_b200.server import create_app
+
+    return TestClient(create_app(model=model), raise_server_exceptions=False)
+
+
+def test_predict_contract(caplog):
+    from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES, sample_request
+
+    m = StubModel()
+    with caplog.at_level(logging.INFO), _client(m) as c:
+        r = c.post("/predict", json=sample_request())  # the reference CI smoke test body
+        assert r.status_code == 200
+        body = r.json()
+        assert set(body) == {"predictions", "outliers", "feature_drift_batch"}
+        assert body["predictions"] == [0.0] and body["outliers"] == [0.0]  # int flags serialised as floats
+        assert list(body["feature_drift_batch"]) == ALL_FEATURES
+        r = c.post("/predict", json=[{"credit_limit": 1250.0}, {}, {"sex": "female", "credit_limit": 333}])
+        assert r.status_code == 200 and r.json()["predictions"] == [0.25, 0.0, 0.333]
+        assert c.post("/predict", json=[{}]).status_code == 200  # defaults make {} a valid row
+        assert c.post("/predict", json=[{"sex": 3}]).status_code == 422
+        assert c.post("/predict", json={"sex": "male"}).status_code == 422
+        assert c.post("/predict", json=[]).status_code == 500  # as the reference (empty DataFrame)
+        assert c.get("/").status_code == 200  # Swagger UI at the root
+    import time
+
+    time.sleep(0.2)  # log lines are produced off the request path
+    recs = [json.loads(r.getMessage()) for r in caplog.records if r.getMessage().startswith("{")]
+    kinds = [r["type"] for r in recs]
+    assert "InferenceData" in kinds and "ModelOutput" in kinds
+    inf = next(r for r in recs if r["type"] == "InferenceData")
+    assert inf["service_name"] == "credit-default-api" and len(inf["request_id"]) == 32
+    assert json.loads(inf["data"])[0]["sex"] == "male"  # data is a JSON *string* of records, as in the reference
+    out = next(r for r in recs if r["type"] == "ModelOutput" and r["request_id"] == inf["request_id"])
+    assert set(out["data"]) == {"predictions", "outliers", "feature_drift_batch"}
+
+
+def test_engine_failure_is_http_500():
+    with _client(StubModel(fail=True)) as c:
+        assert c.post("/predict", json=[{}]).status_code == 500
+
+
+def test_concurrent_requests_share_batches():
+    import pandas as pd
+
+    from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES, DEFAULTS
+    from databricks_kubernetes_mlops_poc_b200.server import MicroBatcher
+
+    m = StubModel()
+    mb = MicroBatcher([m], max_rows=4096, window_us=20000)
+
+    async def main():
+        frames = [pd.DataFrame([{**DEFAULTS, "credit_limit": float(1000 * i + j)} for j in range(3)])[ALL_FEATURES] for i in range(40)]
+        outs = await asyncio.gather(*[mb.score(f) for f in frames])
+        for i, o in enumerate(outs):
+            assert np.allclose(o, [0.0, 0.001, 0.002])
+        return len(outs)
+
+    try:
+        assert asyncio.run(main()) == 40
+    finally:
+        mb.close()
+    assert sum(m.calls) == 120 and len(m.calls) < 40  # requests were merged into fewer engine calls
