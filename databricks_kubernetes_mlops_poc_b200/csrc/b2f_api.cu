@@ -128,6 +128,7 @@ struct b2f_model {
     int walk_mode = B2F_WALK_GLOBAL;
     int smem_bytes = 0;
     int rows_per_warp_max = 2;
+    int64_t chunk_rows = B2F_CHUNK_ROWS;
     void *d_blob = nullptr;
     int64_t forest_bytes = 0;
     Slot slots[B2F_STREAMS];
@@ -262,6 +263,8 @@ static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
         CUDA_TRY((set_smem_attr<2, true, double>(m->smem_bytes)));
         CUDA_TRY((set_smem_attr<4, true, double>(m->smem_bytes)));
     }
+    const char *cr = getenv("B2F_CHUNK_ROWS"); /* tuning hook: rows per pipelined H2D/kernel/D2H chunk */
+    if (cr && atoll(cr) >= 1024) m->chunk_rows = atoll(cr);
     const char *rpw = getenv("B2F_ROWS_PER_WARP");
     m->rows_per_warp_max = 2;
     if (rpw) {
@@ -429,7 +432,7 @@ static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, void *p
     if (n == 0) return B2F_OK;
     if (!rows) return set_err(B2F_EINVAL, "rows is NULL");
     CUDA_TRY(cudaSetDevice(m->device));
-    int64_t chunk = B2F_CHUNK_ROWS;
+    int64_t chunk = m->chunk_rows;
     if (n <= chunk + chunk / 2) chunk = n; /* small batch: one H2D, one launch */
     const size_t psz = f64 ? sizeof(double) : sizeof(float);
     int c = 0;
