@@ -129,6 +129,7 @@ struct b2f_model {
     int smem_bytes = 0;
     int rows_per_warp_max = 2;
     int64_t chunk_rows = B2F_CHUNK_ROWS;
+    int zero_copy = 0;
     void *d_blob = nullptr;
     int64_t forest_bytes = 0;
     Slot slots[B2F_STREAMS];
@@ -265,6 +266,8 @@ static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
     }
     const char *cr = getenv("B2F_CHUNK_ROWS"); /* tuning hook: rows per pipelined H2D/kernel/D2H chunk */
     if (cr && atoll(cr) >= 1024) m->chunk_rows = atoll(cr);
+    const char *zc = getenv("B2F_ZERO_COPY");
+    if (zc) m->zero_copy = atoi(zc);
     const char *rpw = getenv("B2F_ROWS_PER_WARP");
     m->rows_per_warp_max = 2;
     if (rpw) {
@@ -363,7 +366,7 @@ extern "C" int b2f_model_info(const b2f_model *m, b2f_info *out) {
 /* ------------------------------------------------------------------ pinned memory */
 extern "C" void *b2f_pinned_alloc(size_t nbytes) {
     void *p = nullptr;
-    cudaError_t e = cudaHostAlloc(&p, nbytes ? nbytes : 1, cudaHostAllocPortable);
+    cudaError_t e = cudaHostAlloc(&p, nbytes ? nbytes : 1, cudaHostAllocPortable | cudaHostAllocMapped);
     if (e != cudaSuccess) {
         set_err(B2F_ENOMEM, "cudaHostAlloc(%zu) failed: %s", nbytes, cudaGetErrorString(e));
         return nullptr;
@@ -425,30 +428,84 @@ static int slot_reserve(b2f_model *m, Slot &sl, int64_t rows) {
     return B2F_OK;
 }
 
-/* enqueue the whole batch; on return used_mask tells which slot streams carry work */
+static bool host_is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+/* enqueue the whole batch; on return used_mask tells which slot streams carry work.
+ * B2F_TIMELINE=1 (debug): record an event after every operation and print the schedule to stderr. */
 static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, void *proba, int f64, int32_t *label, uint32_t *used_mask) {
     *used_mask = 0;
     if (n < 0) return set_err(B2F_EINVAL, "negative row count");
     if (n == 0) return B2F_OK;
     if (!rows) return set_err(B2F_EINVAL, "rows is NULL");
     CUDA_TRY(cudaSetDevice(m->device));
+    /* Zero-copy path: when every buffer is page-locked (b2f_pinned_alloc / cudaHostRegister), the kernel
+     * reads the rows and writes the results straight over PCIe -- H2D, walk and D2H fused into one
+     * launch, no copy-engine hand-offs.  mode 1: inputs only, mode 2: inputs and outputs. */
+    if (m->zero_copy > 0 && host_is_pinned(rows) && (m->zero_copy < 2 || ((!proba || host_is_pinned(proba)) && (!label || host_is_pinned(label))))) {
+        Slot &sl = m->slots[0];
+        if (m->zero_copy >= 2) {
+            int rc = launch_predict(m, sl.stream, rows, n, proba, f64, label);
+            if (rc) return rc;
+        } else {
+            int rc = slot_reserve(m, sl, n);
+            if (rc) return rc;
+            rc = launch_predict(m, sl.stream, rows, n, proba ? sl.d_proba : nullptr, f64, label ? sl.d_label : nullptr);
+            if (rc) return rc;
+            const size_t psz0 = f64 ? sizeof(double) : sizeof(float);
+            if (proba) CUDA_TRY(cudaMemcpyAsync(proba, sl.d_proba, (size_t)n * psz0, cudaMemcpyDeviceToHost, sl.stream));
+            if (label) CUDA_TRY(cudaMemcpyAsync(label, sl.d_label, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
+        }
+        *used_mask = 1u;
+        return B2F_OK;
+    }
     int64_t chunk = m->chunk_rows;
     if (n <= chunk + chunk / 2) chunk = n; /* small batch: one H2D, one launch */
     const size_t psz = f64 ? sizeof(double) : sizeof(float);
+    static const bool timeline = getenv("B2F_TIMELINE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t st) {
+        if (!timeline) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tev.push_back(e);
+    };
     int c = 0;
     for (int64_t off = 0; off < n; off += chunk, ++c) {
         const int64_t cnt = std::min(chunk, n - off);
         Slot &sl = m->slots[c % B2F_STREAMS];
         int rc = slot_reserve(m, sl, cnt);
         if (rc) return rc;
+        if (c == 0) mark(sl.stream);
         CUDA_TRY(cudaMemcpyAsync(sl.d_rows, static_cast<const uint8_t *>(rows) + (size_t)off * B2F_ROW_BYTES, (size_t)cnt * B2F_ROW_BYTES,
                                  cudaMemcpyHostToDevice, sl.stream));
+        mark(sl.stream);
         rc = launch_predict(m, sl.stream, sl.d_rows, cnt, proba ? sl.d_proba : nullptr, f64, label ? sl.d_label : nullptr);
         if (rc) return rc;
+        mark(sl.stream);
         if (proba)
             CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(proba) + (size_t)off * psz, sl.d_proba, (size_t)cnt * psz, cudaMemcpyDeviceToHost, sl.stream));
         if (label) CUDA_TRY(cudaMemcpyAsync(label + off, sl.d_label, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
+        mark(sl.stream);
         *used_mask |= 1u << (c % B2F_STREAMS);
+    }
+    if (timeline) {
+        cudaDeviceSynchronize();
+        fprintf(stderr, "[b2f timeline] n=%lld chunk=%lld :", (long long)n, (long long)chunk);
+        for (size_t i = 1; i < tev.size(); ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, tev[0], tev[i]);
+            fprintf(stderr, " %s%.1f", (i % 3 == 1) ? "| h2d " : (i % 3 == 2 ? "k " : "d2h "), ms * 1e3f);
+        }
+        fprintf(stderr, " (us)\n");
+        for (auto e : tev) cudaEventDestroy(e);
     }
     return B2F_OK;
 }
