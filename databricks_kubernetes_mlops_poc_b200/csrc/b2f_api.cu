@@ -24,6 +24,7 @@
 #include "feature_moments.cuh"
 #include "forest_blob.h"
 #include "forest_predict.cuh"
+#include "forest_predict_tile.cuh"
 
 #define B2F_VERSION_STR "b200forest 0.1.0 (sm_100a)"
 #define B2F_STREAMS 4
@@ -130,6 +131,14 @@ struct b2f_model {
     int rows_per_warp_max = 2;
     int64_t chunk_rows = B2F_CHUNK_ROWS;
     int zero_copy = 0;
+    /* tile kernel (large batches) */
+    bool tile_ok = false;
+    TParams tp;
+    void *d_tile_layout = nullptr;
+    TPiece *d_tile_pieces = nullptr;
+    int tile_smem_bytes = 0;
+    int64_t tile_min_rows = 32768;
+    int64_t tile_layout_bytes = 0;
     void *d_blob = nullptr;
     int64_t forest_bytes = 0;
     Slot slots[B2F_STREAMS];
@@ -216,6 +225,119 @@ static cudaError_t set_smem_attr(int bytes) {
     return cudaFuncSetAttribute(k_forest_predict<R, SMEM, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
+
+/* ------------------------------------------------------------------ tile layout (forest_predict_tile.cuh)
+ * Re-pack the interleaved blob tree-major: per tree its breadth-first nodes then its leaf payloads, trees in
+ * U-groups of 4 with a 48-byte descriptor, U-groups packed into pieces that fit a shared-memory ring slot. */
+struct TileTree {
+    std::vector<uint32_t> nodes; /* T, M pairs */
+    std::vector<double> leaves;
+    uint32_t depth = 0;
+};
+
+static bool extract_tree(const uint8_t *blob, const b2f_blob_header &h, const b2f_blob_group &gr, uint32_t lane, TileTree &out) {
+    const uint32_t *N = reinterpret_cast<const uint32_t *>(blob + h.chunks_off + gr.chunk_off);
+    const double *LV = reinterpret_cast<const double *>(blob + h.chunks_off + gr.chunk_off + (size_t)gr.n_slots * 256);
+    std::vector<uint32_t> depth_of(gr.n_slots, 0);
+    uint32_t reach = 0, max_leaf = 0, max_depth = 0;
+    for (uint32_t s = 0; s <= reach; ++s) {
+        const uint32_t t = N[(s * 32 + lane) * 2], m = N[(s * 32 + lane) * 2 + 1];
+        const uint32_t feat = m >> B2F_META_FEAT_SHIFT, first = m & B2F_META_SLOT_MASK;
+        const bool cat = (m & B2F_META_CAT) != 0;
+        if (first >= (1u << 20)) return false;
+        out.nodes.push_back(t);
+        out.nodes.push_back((first << B2F_TILE_CHILD_SHIFT) | (cat ? B2F_TILE_META_CAT : 0u) | feat);
+        if (first == s) { /* leaf */
+            max_leaf = std::max(max_leaf, t);
+            max_depth = std::max(max_depth, depth_of[s]);
+        } else {
+            reach = std::max(reach, first + 1);
+            depth_of[first] = depth_of[first + 1] = depth_of[s] + 1;
+        }
+    }
+    out.leaves.resize(max_leaf + 1);
+    for (uint32_t i = 0; i <= max_leaf; ++i) out.leaves[i] = LV[i * 32 + lane];
+    out.depth = max_depth;
+    return true;
+}
+
+static bool build_tile_layout(const uint8_t *blob, const b2f_blob_header &h, uint32_t avail_smem, std::vector<uint8_t> &layout,
+                              std::vector<TPiece> &pieces, uint32_t *slot_bytes, int *n_slots) {
+    const b2f_blob_group *gt = reinterpret_cast<const b2f_blob_group *>(blob + h.groups_off);
+    std::vector<TileTree> trees(h.n_trees);
+    for (uint32_t t = 0; t < h.n_trees; ++t)
+        if (!extract_tree(blob, h, gt[t / 32], t % 32, trees[t])) return false;
+    /* U-groups */
+    struct UG {
+        uint32_t first, count, bytes;
+    };
+    std::vector<UG> ugs;
+    uint64_t total = 0;
+    for (uint32_t t = 0; t < h.n_trees; t += B2F_TILE_U) {
+        UG u{t, std::min<uint32_t>(B2F_TILE_U, h.n_trees - t), (uint32_t)sizeof(TUGroup)};
+        for (uint32_t k = 0; k < B2F_TILE_U; ++k)
+            u.bytes += k < u.count ? (uint32_t)(trees[t + k].nodes.size() * 4 + trees[t + k].leaves.size() * 8) : 16u; /* stub: 1 node + 1 leaf */
+        ugs.push_back(u);
+        total += u.bytes;
+    }
+    /* piece size: resident if everything fits (<= 8 pieces), else ~32 KB pieces streamed through the ring */
+    const bool fits = total + 128 * B2F_TILE_MAX_SLOTS <= avail_smem;
+    uint32_t target = fits ? (uint32_t)((total + B2F_TILE_MAX_SLOTS - 1) / B2F_TILE_MAX_SLOTS) + 64 : 32u * 1024u;
+    layout.clear();
+    pieces.clear();
+    size_t i = 0;
+    uint32_t max_piece = 0;
+    while (i < ugs.size()) {
+        size_t j = i;
+        uint32_t bytes = 0;
+        while (j < ugs.size() && (j == i || bytes + ugs[j].bytes <= target)) bytes += ugs[j++].bytes;
+        /* emit piece [i, j) */
+        const uint32_t n_ug = (uint32_t)(j - i);
+        const size_t start = layout.size();
+        std::vector<uint8_t> buf((size_t)n_ug * sizeof(TUGroup));
+        for (uint32_t g = 0; g < n_ug; ++g) {
+            TUGroup d;
+            memset(&d, 0, sizeof(d));
+            for (uint32_t k = 0; k < B2F_TILE_U; ++k) {
+                while (buf.size() % 8) buf.push_back(0);
+                d.node_off[k] = (uint32_t)buf.size();
+                if (k < ugs[i + g].count) {
+                    const TileTree &tr = trees[ugs[i + g].first + k];
+                    const uint8_t *np = reinterpret_cast<const uint8_t *>(tr.nodes.data());
+                    buf.insert(buf.end(), np, np + tr.nodes.size() * 4);
+                    d.leaf_off[k] = (uint32_t)buf.size();
+                    const uint8_t *lp = reinterpret_cast<const uint8_t *>(tr.leaves.data());
+                    buf.insert(buf.end(), lp, lp + tr.leaves.size() * 8);
+                    d.depth = std::max(d.depth, tr.depth);
+                } else { /* stub tree: one self-looping leaf worth 0.0 */
+                    const uint32_t stub[2] = {0u, (0u << B2F_TILE_CHILD_SHIFT) | B2F_TILE_META_CAT | B2F_SENTINEL_WORD};
+                    const uint8_t *sp = reinterpret_cast<const uint8_t *>(stub);
+                    buf.insert(buf.end(), sp, sp + 8);
+                    d.leaf_off[k] = (uint32_t)buf.size();
+                    const double z = 0.0;
+                    const uint8_t *zp = reinterpret_cast<const uint8_t *>(&z);
+                    buf.insert(buf.end(), zp, zp + 8);
+                }
+            }
+            memcpy(buf.data() + (size_t)g * sizeof(TUGroup), &d, sizeof(d));
+        }
+        while (buf.size() % 128) buf.push_back(0);
+        layout.insert(layout.end(), buf.begin(), buf.end());
+        pieces.push_back(TPiece{(uint32_t)start, (uint32_t)buf.size(), n_ug, 0u});
+        max_piece = std::max<uint32_t>(max_piece, (uint32_t)buf.size());
+        i = j;
+    }
+    *slot_bytes = max_piece;
+    if ((size_t)max_piece * pieces.size() <= avail_smem && pieces.size() <= B2F_TILE_MAX_SLOTS) {
+        *n_slots = (int)pieces.size(); /* resident */
+    } else {
+        int s = (int)std::min<uint64_t>(B2F_TILE_MAX_SLOTS, avail_smem / max_piece);
+        if (s < 2) return false; /* a single U-group does not fit a ring slot: tile kernel not applicable */
+        *n_slots = s;
+    }
+    return true;
+}
+
 static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
     CUDA_TRY(cudaSetDevice(m->device));
     cudaDeviceProp prop;
@@ -275,6 +397,45 @@ static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
         if (v == 1 || v == 2 || v == 4) m->rows_per_warp_max = v;
     }
 
+    /* tile kernel: tree-major layout + shared-memory ring plan */
+    {
+        const char *kn = getenv("B2F_KERNEL"); /* "warp" | "tile" | unset = choose by batch size */
+        const char *tm = getenv("B2F_TILE_MIN_ROWS");
+        if (tm && atoll(tm) >= 0) m->tile_min_rows = atoll(tm);
+        if (kn && !strcmp(kn, "tile")) m->tile_min_rows = 1;
+        const uint32_t avail = (uint32_t)m->max_smem_optin - 1024u - B2F_TILE_WARPS * B2F_TILE_XS_BYTES;
+        std::vector<uint8_t> layout;
+        std::vector<TPiece> pieces;
+        uint32_t slot_bytes = 0;
+        int n_slots = 0;
+        if (!(kn && !strcmp(kn, "warp")) && build_tile_layout(blob, m->hdr, avail, layout, pieces, &slot_bytes, &n_slots)) {
+            CUDA_TRY(cudaMalloc(&m->d_tile_layout, layout.size()));
+            CUDA_TRY(cudaMemcpy(m->d_tile_layout, layout.data(), layout.size(), cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMalloc((void **)&m->d_tile_pieces, pieces.size() * sizeof(TPiece)));
+            CUDA_TRY(cudaMemcpy(m->d_tile_pieces, pieces.data(), pieces.size() * sizeof(TPiece), cudaMemcpyHostToDevice));
+            TParams &tp = m->tp;
+            memset(&tp, 0, sizeof(tp));
+            tp.layout = static_cast<const uint8_t *>(m->d_tile_layout);
+            tp.pieces = m->d_tile_pieces;
+            tp.n_pieces = (int)pieces.size();
+            tp.n_slots = n_slots;
+            tp.slot_bytes = slot_bytes;
+            tp.agg_mode = kp.agg_mode;
+            tp.n_cat = kp.n_cat;
+            tp.n_num = kp.n_num;
+            tp.init_raw = kp.init_raw;
+            tp.denom = kp.denom;
+            memcpy(tp.impute, kp.impute, sizeof(tp.impute));
+            m->tile_smem_bytes = B2F_TILE_WARPS * B2F_TILE_XS_BYTES + n_slots * (int)slot_bytes;
+            m->tile_layout_bytes = (int64_t)layout.size();
+            CUDA_TRY(cudaFuncSetAttribute(k_forest_predict_tile<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->tile_smem_bytes));
+            CUDA_TRY(cudaFuncSetAttribute(k_forest_predict_tile<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->tile_smem_bytes));
+            m->tile_ok = true;
+        } else if (kn && !strcmp(kn, "tile")) {
+            return set_err(B2F_EINVAL, "B2F_KERNEL=tile but the forest's trees do not fit the tile kernel's shared-memory ring");
+        }
+    }
+
     for (int s = 0; s < B2F_STREAMS; ++s) CUDA_TRY(cudaStreamCreateWithFlags(&m->slots[s].stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&m->compute, cudaStreamNonBlocking));
 
@@ -327,6 +488,8 @@ extern "C" void b2f_model_destroy(b2f_model *m) {
             if (e) cudaEventDestroy(e);
     if (m->compute) cudaStreamDestroy(m->compute);
     if (m->d_blob) cudaFree(m->d_blob);
+    if (m->d_tile_layout) cudaFree(m->d_tile_layout);
+    if (m->d_tile_pieces) cudaFree(m->d_tile_pieces);
     if (m->d_mom_rows) cudaFree(m->d_mom_rows);
     if (m->d_mom_partials) cudaFree(m->d_mom_partials);
     if (m->d_mom_ticket) cudaFree(m->d_mom_ticket);
@@ -390,6 +553,20 @@ static cudaError_t launch_one(const b2f_model *m, cudaStream_t st, const void *r
 
 static int launch_predict(b2f_model *m, cudaStream_t st, const void *rows_dev, int64_t n, void *proba_dev, int f64, int32_t *label_dev) {
     if (n <= 0) return B2F_OK;
+    if (m->tile_ok && n >= m->tile_min_rows) {
+        const int64_t n_tiles = (n + B2F_TILE_ROWS - 1) / B2F_TILE_ROWS;
+        const unsigned ctas = (unsigned)std::max<int64_t>(1, std::min<int64_t>(m->sm_count, n_tiles));
+        if (f64)
+            k_forest_predict_tile<double><<<ctas, B2F_TILE_THREADS, m->tile_smem_bytes, st>>>(m->tp, static_cast<const uint32_t *>(rows_dev), (long long)n,
+                                                                                             static_cast<double *>(proba_dev), label_dev);
+        else
+            k_forest_predict_tile<float><<<ctas, B2F_TILE_THREADS, m->tile_smem_bytes, st>>>(m->tp, static_cast<const uint32_t *>(rows_dev), (long long)n,
+                                                                                            static_cast<float *>(proba_dev), label_dev);
+        cudaError_t te = cudaGetLastError();
+        if (te != cudaSuccess) return set_err(B2F_ECUDA, "k_forest_predict_tile launch failed: %s", cudaGetErrorString(te));
+        m->launches++;
+        return B2F_OK;
+    }
     const int r = pick_rows_per_warp(m, n);
     const bool sm = m->walk_mode == B2F_WALK_SMEM;
     cudaError_t e;

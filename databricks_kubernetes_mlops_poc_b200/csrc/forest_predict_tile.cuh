@@ -1,0 +1,280 @@
+/*
+ * forest_predict_tile.cuh -- K1b: the large-batch form of the fused scoring kernel (sm_100a).
+ *
+ * Same arithmetic as k_forest_predict (forest_predict.cuh) -- it replaces
+ * `classifier.predict_proba(df[all_features])[:, 1]` (reference databricks/src/02-register-model.ipynb:335-337)
+ * -- with the opposite geometry:
+ *
+ *   k_forest_predict       one WARP per row, lane = tree.  Lowest latency (one row spreads over 32 lanes),
+ *                          used for small batches and for forests whose trees do not fit a shared-memory piece.
+ *   k_forest_predict_tile  one THREAD per row, a warp owns a TILE of 32 consecutive rows and walks the trees one
+ *                          U-group (4 trees) at a time, all lanes in the same trees.  Node loads are
+ *                          near-broadcast (the 32 lanes sit in the same breadth-first level of the same tree, a
+ *                          contiguous <= 256-byte run), there is no cross-lane reduction, no 32-tree quantisation,
+ *                          the float64 sum runs in tree order (exactly sklearn's order), row tiles are read with
+ *                          16-byte vector loads and results are written as coalesced 128-byte stores.
+ *
+ * Memory plan per CTA (persistent, 1 CTA/SM, W consumer warps + 1 producer warp):
+ *   xs[W][24][32]   the warp's 32 encoded rows, TRANSPOSED (word-major) so a per-lane dynamic feature index is
+ *                   one conflict-free LDS:  bank = lane.
+ *   ring[n_slots]   forest PIECES (whole U-groups of trees, tree-major nodes + leaf payloads) streamed by the
+ *                   producer warp with TMA bulk copies (cp.async.bulk + mbarrier complete_tx).  If the forest has
+ *                   no more pieces than slots it is loaded once and stays resident; otherwise the ring is
+ *                   recycled (full/empty mbarriers) and the forest streams through shared memory once per pass
+ *                   of W tiles while accumulators stay in registers.
+ *
+ * Node format here ("tile layout", built by the library from the forest blob at model creation):
+ *   T  as in forest_blob.h (t' | category code | leaf id)
+ *   M  bits 12..31 first-child index inside the tree, bits 9..11 zero, bit 8 categorical flag, bits 0..4 row word.
+ *      child byte offset = IMAD.HI(M, 2^23) = M >> 9  (bits 9..11 are zero, so this is index*8 exactly).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "forest_predict.cuh"
+
+#define B2F_TILE_ROWS 32
+#define B2F_TILE_U 4                 /* trees walked concurrently by one thread (independent chains) */
+#define B2F_TILE_WARPS 16            /* consumer warps per CTA */
+#define B2F_TILE_THREADS ((B2F_TILE_WARPS + 1) * 32)
+#define B2F_TILE_XS_BYTES (B2F_ROW_WORDS * 32 * 4) /* 3072 B per warp */
+#define B2F_TILE_MAX_SLOTS 8
+#define B2F_TILE_META_CAT 0x100u
+#define B2F_TILE_CHILD_SHIFT 12u
+
+/* one U-group descriptor inside a piece (offsets in bytes from the piece start) */
+struct TUGroup {
+    uint32_t node_off[B2F_TILE_U];
+    uint32_t leaf_off[B2F_TILE_U];
+    uint32_t depth; /* max depth of the U trees: walk iterations */
+    uint32_t pad[3];
+};
+static_assert(sizeof(TUGroup) == 48, "TUGroup size");
+
+struct TPiece {
+    uint32_t off;   /* bytes from the tile-layout base (128-byte aligned) */
+    uint32_t bytes; /* multiple of 128 */
+    uint32_t n_ug;
+    uint32_t pad;
+};
+
+struct TParams {
+    const uint8_t *layout;  /* device: pieces back to back */
+    const TPiece *pieces;   /* device: piece table */
+    int32_t n_pieces;
+    int32_t n_slots;
+    uint32_t slot_bytes;
+    int32_t agg_mode;
+    int32_t n_cat;
+    int32_t n_num;
+    double init_raw;
+    double denom;
+    float impute[24];
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+
+/* split decision, tile-layout flag position */
+__device__ __forceinline__ bool take_second_tile(uint32_t x, uint32_t t, uint32_t m) {
+    uint32_t c;
+    asm("{\n\t"
+        ".reg .pred pc, p1, p2;\n\t"
+        ".reg .b32 cbit;\n\t"
+        "and.b32 cbit, %3, 0x100;\n\t"
+        "setp.ne.u32 pc, cbit, 0;\n\t"
+        "setp.geu.and.f32 p1, %1, %2, !pc;\n\t"
+        "setp.eq.or.u32 p2, %4, %5, p1;\n\t"
+        "selp.u32 %0, 1, 0, p2;\n\t"
+        "}"
+        : "=r"(c)
+        : "f"(__uint_as_float(x)), "f"(__uint_as_float(t)), "r"(m), "r"(x), "r"(t));
+    return c != 0;
+}
+
+/* walk one U-group for this lane's row; values are added to acc in tree order */
+template <int D>
+__device__ __forceinline__ void tile_walk_ugroup(uint32_t piece_addr, uint32_t ug_addr, uint32_t xs_lane, int depth, double &acc) {
+    const uint4 no = *reinterpret_cast<const uint4 *>(__cvta_shared_to_generic(ug_addr));
+    const uint4 lo = *reinterpret_cast<const uint4 *>(__cvta_shared_to_generic(ug_addr + 16));
+    uint32_t base[B2F_TILE_U] = {piece_addr + no.x, piece_addr + no.y, piece_addr + no.z, piece_addr + no.w};
+    const uint32_t lbase[B2F_TILE_U] = {piece_addr + lo.x, piece_addr + lo.y, piece_addr + lo.z, piece_addr + lo.w};
+    uint32_t at[B2F_TILE_U];
+#pragma unroll
+    for (int u = 0; u < B2F_TILE_U; ++u) at[u] = base[u];
+
+    auto level = [&]() {
+#pragma unroll
+        for (int u = 0; u < B2F_TILE_U; ++u) {
+            const uint2 tm = lds64(at[u]);
+            const uint32_t x = lds32(xs_lane + ((tm.y & 31u) << 7)); /* xs[word][lane] */
+            const uint32_t c = take_second_tile(x, tm.x, tm.y) ? base[u] + 8u : base[u];
+            at[u] = __umulhi(tm.y, 1u << 23) + c; /* (M >> 9) = child index * 8 */
+        }
+    };
+    if constexpr (D > 0) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) level();
+    } else {
+#pragma unroll 2
+        for (int d = 0; d < depth; ++d) level();
+    }
+#pragma unroll
+    for (int u = 0; u < B2F_TILE_U; ++u) {
+        const uint32_t leaf_id = lds32(at[u]);
+        acc += lds_f64(lbase[u] + leaf_id * 8u);
+    }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(B2F_TILE_THREADS, 1)
+    k_forest_predict_tile(const __grid_constant__ TParams p, const uint32_t *__restrict__ rows, long long n,
+                          OutT *__restrict__ proba, int32_t *__restrict__ label) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[B2F_TILE_MAX_SLOTS];
+    __shared__ __align__(8) uint64_t empty_bar[B2F_TILE_MAX_SLOTS];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int n_pieces = p.n_pieces, n_slots = p.n_slots;
+    const bool resident = n_pieces <= n_slots;
+
+    uint8_t *xs_all = smem;                                        /* [W][24][32] words */
+    uint8_t *ring = smem + B2F_TILE_WARPS * B2F_TILE_XS_BYTES;     /* [n_slots][slot_bytes] */
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < n_slots; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], B2F_TILE_WARPS);
+        }
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    const long long n_tiles = (n + B2F_TILE_ROWS - 1) / B2F_TILE_ROWS;
+    const long long tiles_per_pass = (long long)gridDim.x * B2F_TILE_WARPS;
+    /* every warp of every CTA runs the same number of passes so the ring hand-shake stays in step;
+     * tiles are numbered CTA-minor so a small batch spreads over all SMs */
+    const long long n_pass = (n_tiles + tiles_per_pass - 1) / tiles_per_pass;
+
+    if (warp == B2F_TILE_WARPS) {
+        /* ===== producer warp: one lane streams forest pieces into the ring with TMA bulk copies ===== */
+        if (lane == 0) {
+            const long long fills = resident ? (n_pass > 0 ? n_pieces : 0) : n_pass * n_pieces;
+            for (long long f = 0; f < fills; ++f) {
+                const int piece = (int)(f % n_pieces);
+                const int slot = (int)(f % n_slots);
+                const long long j = f / n_slots; /* fill number of this slot */
+                if (j > 0) mbar_wait(&empty_bar[slot], (uint32_t)((j - 1) & 1));
+                const TPiece pc = p.pieces[piece];
+                mbar_arrive_expect_tx(&full_bar[slot], pc.bytes);
+                uint8_t *dst = ring + (size_t)slot * p.slot_bytes;
+                for (uint32_t o = 0; o < pc.bytes; o += B2F_BULK_PIECE) {
+                    const uint32_t part = min(B2F_BULK_PIECE, pc.bytes - o);
+                    tma_bulk_g2s(dst + o, p.layout + pc.off + o, part, &full_bar[slot]);
+                }
+            }
+        }
+        return;
+    }
+
+    /* ===== consumer warps ===== */
+    const uint32_t xs_warp = smem_addr(xs_all + warp * B2F_TILE_XS_BYTES);
+    const uint32_t xs_lane = xs_warp + lane * 4u;
+    const uint32_t ring_addr = smem_addr(ring);
+
+    for (long long pass = 0; pass < n_pass; ++pass) {
+        const long long tile = (pass * B2F_TILE_WARPS + warp) * gridDim.x + blockIdx.x;
+        const long long row = tile * B2F_TILE_ROWS + lane;
+        const bool live = tile < n_tiles && row < n;
+
+        /* ---- stage this lane's row: six 16-byte vector loads, impute, transpose into xs[word][lane] ---- */
+        __syncwarp();
+        {
+            uint32_t w[B2F_ROW_WORDS];
+            if (live) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(rows + row * B2F_ROW_WORDS);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const uint4 v = __ldg(src + k);
+                    w[4 * k + 0] = v.x, w[4 * k + 1] = v.y, w[4 * k + 2] = v.z, w[4 * k + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < B2F_ROW_WORDS; ++k) w[k] = B2F_SENTINEL_BITS;
+            }
+#pragma unroll
+            for (int k = 0; k < B2F_ROW_WORDS; ++k) {
+                uint32_t v = w[k];
+                if (k >= p.n_cat && k < p.n_cat + p.n_num && isnan(__uint_as_float(v))) v = __float_as_uint(p.impute[k]);
+                if (k >= (int)B2F_SENTINEL_WORD) v = B2F_SENTINEL_BITS;
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(xs_lane + k * 128u), "r"(v) : "memory");
+            }
+        }
+        __syncwarp();
+
+        /* GBDT: start from the init estimator's raw value and add trees in order -- sklearn's own order */
+        double acc = p.agg_mode == B2F_AGG_RF_MEAN ? 0.0 : p.init_raw;
+        for (int piece = 0; piece < n_pieces; ++piece) {
+            const long long f = resident ? piece : pass * n_pieces + piece;
+            const int slot = (int)(f % n_slots);
+            if (!resident || pass == 0) mbar_wait(&full_bar[slot], (uint32_t)((f / n_slots) & 1));
+            const uint32_t piece_addr = ring_addr + slot * p.slot_bytes;
+            const int n_ug = (int)p.pieces[piece].n_ug;
+            for (int g = 0; g < n_ug; ++g) {
+                const uint32_t ug_addr = piece_addr + g * (uint32_t)sizeof(TUGroup);
+                const int depth = (int)lds32(ug_addr + 32);
+                switch (depth) {
+                    case 1: tile_walk_ugroup<1>(piece_addr, ug_addr, xs_lane, 1, acc); break;
+                    case 2: tile_walk_ugroup<2>(piece_addr, ug_addr, xs_lane, 2, acc); break;
+                    case 3: tile_walk_ugroup<3>(piece_addr, ug_addr, xs_lane, 3, acc); break;
+                    case 4: tile_walk_ugroup<4>(piece_addr, ug_addr, xs_lane, 4, acc); break;
+                    case 5: tile_walk_ugroup<5>(piece_addr, ug_addr, xs_lane, 5, acc); break;
+                    case 6: tile_walk_ugroup<6>(piece_addr, ug_addr, xs_lane, 6, acc); break;
+                    case 7: tile_walk_ugroup<7>(piece_addr, ug_addr, xs_lane, 7, acc); break;
+                    case 8: tile_walk_ugroup<8>(piece_addr, ug_addr, xs_lane, 8, acc); break;
+                    default: tile_walk_ugroup<0>(piece_addr, ug_addr, xs_lane, depth, acc); break;
+                }
+            }
+            if (!resident) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[slot]);
+            }
+        }
+
+        /* ---- aggregate -> probability + label, one row per lane, coalesced stores ---- */
+        if (live) {
+            double p1;
+            int lab;
+            if (p.agg_mode == B2F_AGG_RF_MEAN) {
+                p1 = acc / p.denom;
+                lab = acc > (p.denom - acc);
+            } else {
+                const double raw = acc;
+                p1 = 1.0 / (1.0 + exp(-raw));
+                lab = raw >= 0.0;
+            }
+            if (proba) proba[row] = (OutT)p1;
+            if (label) label[row] = lab;
+        }
+    }
+}
