@@ -244,9 +244,9 @@ static bool extract_tree(const uint8_t *blob, const b2f_blob_header &h, const b2
         const uint32_t t = N[(s * 32 + lane) * 2], m = N[(s * 32 + lane) * 2 + 1];
         const uint32_t feat = m >> B2F_META_FEAT_SHIFT, first = m & B2F_META_SLOT_MASK;
         const bool cat = (m & B2F_META_CAT) != 0;
-        if (first >= (1u << 20)) return false;
+        if (first >= B2F_TILE_MAX_TREE_NODES) return false;
         out.nodes.push_back(t);
-        out.nodes.push_back((first << B2F_TILE_CHILD_SHIFT) | (cat ? B2F_TILE_META_CAT : 0u) | feat);
+        out.nodes.push_back((first << B2F_TILE_CHILD_SHIFT) | (cat ? B2F_TILE_META_CAT : 0u) | (feat << B2F_TILE_FEAT_SHIFT));
         if (first == s) { /* leaf */
             max_leaf = std::max(max_leaf, t);
             max_depth = std::max(max_depth, depth_of[s]);
@@ -310,7 +310,7 @@ static bool build_tile_layout(const uint8_t *blob, const b2f_blob_header &h, uin
                     buf.insert(buf.end(), lp, lp + tr.leaves.size() * 8);
                     d.depth = std::max(d.depth, tr.depth);
                 } else { /* stub tree: one self-looping leaf worth 0.0 */
-                    const uint32_t stub[2] = {0u, (0u << B2F_TILE_CHILD_SHIFT) | B2F_TILE_META_CAT | B2F_SENTINEL_WORD};
+                    const uint32_t stub[2] = {0u, (0u << B2F_TILE_CHILD_SHIFT) | B2F_TILE_META_CAT | (B2F_SENTINEL_WORD << B2F_TILE_FEAT_SHIFT)};
                     const uint8_t *sp = reinterpret_cast<const uint8_t *>(stub);
                     buf.insert(buf.end(), sp, sp + 8);
                     d.leaf_off[k] = (uint32_t)buf.size();
@@ -403,7 +403,7 @@ static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
         const char *tm = getenv("B2F_TILE_MIN_ROWS");
         if (tm && atoll(tm) >= 0) m->tile_min_rows = atoll(tm);
         if (kn && !strcmp(kn, "tile")) m->tile_min_rows = 1;
-        const uint32_t avail = (uint32_t)m->max_smem_optin - 1024u - B2F_TILE_WARPS * B2F_TILE_XS_BYTES;
+        const uint32_t avail = (uint32_t)m->max_smem_optin - 1024u - 4096u - B2F_TILE_WARPS * B2F_TILE_XS_BYTES;
         std::vector<uint8_t> layout;
         std::vector<TPiece> pieces;
         uint32_t slot_bytes = 0;
@@ -426,7 +426,7 @@ static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
             tp.init_raw = kp.init_raw;
             tp.denom = kp.denom;
             memcpy(tp.impute, kp.impute, sizeof(tp.impute));
-            m->tile_smem_bytes = B2F_TILE_WARPS * B2F_TILE_XS_BYTES + n_slots * (int)slot_bytes;
+            m->tile_smem_bytes = 4096 + B2F_TILE_WARPS * B2F_TILE_XS_BYTES + n_slots * (int)slot_bytes;
             m->tile_layout_bytes = (int64_t)layout.size();
             CUDA_TRY(cudaFuncSetAttribute(k_forest_predict_tile<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->tile_smem_bytes));
             CUDA_TRY(cudaFuncSetAttribute(k_forest_predict_tile<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->tile_smem_bytes));

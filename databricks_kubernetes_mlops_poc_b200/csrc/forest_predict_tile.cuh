@@ -25,8 +25,10 @@
  *
  * Node format here ("tile layout", built by the library from the forest blob at model creation):
  *   T  as in forest_blob.h (t' | category code | leaf id)
- *   M  bits 12..31 first-child index inside the tree, bits 9..11 zero, bit 8 categorical flag, bits 0..4 row word.
- *      child byte offset = IMAD.HI(M, 2^23) = M >> 9  (bits 9..11 are zero, so this is index*8 exactly).
+ *   M  bits 16..31 first-child index inside the tree, bits 13..15 zero, bit 12 categorical flag,
+ *      bits 7..11 row word index (i.e. bits 0..11 hold word*128, the byte offset of xs[word][0]).
+ *      child byte offset = M >> 13 (one LEA.HI; bits 13..15 are zero so this is index*8 exactly);
+ *      feature address   = xs_lane | (M & 0xF80) (one LOP3; each warp's xs block is 4 KB aligned).
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -38,10 +40,12 @@
 #define B2F_TILE_U 4                 /* trees walked concurrently by one thread (independent chains) */
 #define B2F_TILE_WARPS 16            /* consumer warps per CTA */
 #define B2F_TILE_THREADS ((B2F_TILE_WARPS + 1) * 32)
-#define B2F_TILE_XS_BYTES (B2F_ROW_WORDS * 32 * 4) /* 3072 B per warp */
+#define B2F_TILE_XS_BYTES 4096 /* per warp: 24 words x 32 lanes x 4 B = 3072 B, padded so the block is 4 KB aligned */
 #define B2F_TILE_MAX_SLOTS 8
-#define B2F_TILE_META_CAT 0x100u
-#define B2F_TILE_CHILD_SHIFT 12u
+#define B2F_TILE_META_CAT 0x1000u
+#define B2F_TILE_CHILD_SHIFT 16u
+#define B2F_TILE_FEAT_SHIFT 7u
+#define B2F_TILE_MAX_TREE_NODES 65536u
 
 /* one U-group descriptor inside a piece (offsets in bytes from the piece start) */
 struct TUGroup {
@@ -99,7 +103,7 @@ __device__ __forceinline__ bool take_second_tile(uint32_t x, uint32_t t, uint32_
     asm("{\n\t"
         ".reg .pred pc, p1, p2;\n\t"
         ".reg .b32 cbit;\n\t"
-        "and.b32 cbit, %3, 0x100;\n\t"
+        "and.b32 cbit, %3, 0x1000;\n\t"
         "setp.ne.u32 pc, cbit, 0;\n\t"
         "setp.geu.and.f32 p1, %1, %2, !pc;\n\t"
         "setp.eq.or.u32 p2, %4, %5, p1;\n\t"
@@ -125,9 +129,9 @@ __device__ __forceinline__ void tile_walk_ugroup(uint32_t piece_addr, uint32_t u
 #pragma unroll
         for (int u = 0; u < B2F_TILE_U; ++u) {
             const uint2 tm = lds64(at[u]);
-            const uint32_t x = lds32(xs_lane + ((tm.y & 31u) << 7)); /* xs[word][lane] */
+            const uint32_t x = lds32(xs_lane | (tm.y & 0xF80u)); /* xs[word][lane] */
             const uint32_t c = take_second_tile(x, tm.x, tm.y) ? base[u] + 8u : base[u];
-            at[u] = __umulhi(tm.y, 1u << 23) + c; /* (M >> 9) = child index * 8 */
+            at[u] = (tm.y >> 13) + c; /* child index * 8 */
         }
     };
     if constexpr (D > 0) {
@@ -157,8 +161,10 @@ __global__ void __launch_bounds__(B2F_TILE_THREADS, 1)
     const int n_pieces = p.n_pieces, n_slots = p.n_slots;
     const bool resident = n_pieces <= n_slots;
 
-    uint8_t *xs_all = smem;                                        /* [W][24][32] words */
-    uint8_t *ring = smem + B2F_TILE_WARPS * B2F_TILE_XS_BYTES;     /* [n_slots][slot_bytes] */
+    /* xs blocks must be 4 KB aligned in the shared window (the feature address is formed with OR) */
+    const uint32_t pad = (4096u - (smem_addr(smem) & 4095u)) & 4095u;
+    uint8_t *xs_all = smem + pad;                                  /* [W] x 4 KB: [24][32] words each */
+    uint8_t *ring = xs_all + B2F_TILE_WARPS * B2F_TILE_XS_BYTES;   /* [n_slots][slot_bytes] */
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < n_slots; ++s) {

@@ -22,11 +22,12 @@ def _engine(pipe, device=0):
     return ForestEngine(flat, device), RowEncoder(flat)
 
 
-def _check(pipe, frames, walk=None, rows_per_warp=None):
+def _check(pipe, frames, walk=None, rows_per_warp=None, kernel="warp"):
     from oracle import reference_pipeline as rp
 
-    old = {k: os.environ.get(k) for k in ("B2F_FORCE_WALK", "B2F_ROWS_PER_WARP")}
+    old = {k: os.environ.get(k) for k in ("B2F_FORCE_WALK", "B2F_ROWS_PER_WARP", "B2F_KERNEL")}
     try:
+        os.environ["B2F_KERNEL"] = kernel  # "warp": one warp per row; "tile": one thread per row (large-batch kernel)
         if walk:
             os.environ["B2F_FORCE_WALK"] = walk
         if rows_per_warp:
@@ -289,7 +290,7 @@ def test_http_end_to_end_and_load_model(curated, rf100d6, tmp_path):
     ref = ReferenceCustomModel(rf100d6, curated)
     os.environ["MODEL_DIRECTORY"] = str(tmp_path)
     try:
-        with TestClient(create_app(loader=load_model)) as c:
+        with TestClient(create_app(loader=load_model), raise_server_exceptions=False) as c:
             body = curated[ALL_FEATURES].iloc[:64].to_dict(orient="records")
             r = c.post("/predict", json=body)
             assert r.status_code == 200
@@ -304,3 +305,66 @@ def test_http_end_to_end_and_load_model(curated, rf100d6, tmp_path):
             assert c.post("/predict", json=[{"age": "old"}]).status_code == 422
     finally:
         os.environ.pop("MODEL_DIRECTORY", None)
+
+
+# ----------------------------------------------------------------------------- tile kernel (one thread per row)
+def test_tile_kernel_resident_rf100d6(curated, inference, adversarial, rf100d6):
+    """Forest resident in the shared-memory ring: all reference rows + edges, every batch-size edge."""
+    from oracle import reference_pipeline as rp
+
+    _check(rf100d6, [curated, inference, adversarial], kernel="tile")
+    want_p, want_l = rp.oracle_predict(rf100d6, curated)
+    os.environ["B2F_KERNEL"] = "tile"
+    try:
+        eng, enc = _engine(rf100d6)
+    finally:
+        os.environ.pop("B2F_KERNEL")
+    try:
+        rows = enc.encode_frame(curated)
+        for n in (1, 31, 32, 33, 511, 512, 513, 20000, 30000):
+            p, l = eng.predict_rows(rows[:n], np.float64)
+            assert np.abs(p - want_p[:n]).max() <= TOL64 and (l == want_l[:n]).all()
+    finally:
+        eng.close()
+
+
+def test_tile_kernel_streams_big_forest(curated, adversarial, rf500d8):
+    """160 480 nodes: the forest streams through the shared-memory ring (full/empty mbarriers), several passes."""
+    _check(rf500d8, [curated, adversarial], kernel="tile")
+
+
+def test_tile_kernel_gbdt_and_small_forests(curated, adversarial, gbdt_small):
+    from oracle import reference_pipeline as rp
+
+    _check(gbdt_small, [curated.iloc[:9000], adversarial], kernel="tile")
+    for params in (dict(n_estimators=1, max_depth=1, random_state=0), dict(n_estimators=5, max_depth=3, random_state=0),
+                   dict(n_estimators=37, max_depth=11, random_state=0)):
+        pipe = rp.fit_reference_pipeline(curated.iloc[:3000], params)
+        _check(pipe, [curated.iloc[3000:5000], adversarial], kernel="tile")
+
+
+def test_kernel_auto_selection_agrees(curated, rf100d6):
+    """Default engine: chunked host batches take the warp kernel, one big device-resident launch the tile
+    kernel; same answers (to float64 summation-order noise)."""
+    from databricks_kubernetes_mlops_poc_b200 import training
+
+    eng, enc = _engine(rf100d6)
+    try:
+        _, codes, nums = training.synth_arrays(curated, 70000, seed=11)
+        rows = enc.encode_arrays(codes, nums)
+        big_p, big_l = eng.predict_rows(rows, np.float64)
+        d_rows = eng.device_alloc(rows.nbytes)
+        d_p = eng.device_alloc(len(rows) * 8)
+        d_l = eng.device_alloc(len(rows) * 4)
+        eng.h2d(d_rows, rows)
+        eng.predict_device(d_rows, len(rows), d_p, True, d_l)  # one 70 000-row launch -> tile kernel
+        eng.sync()
+        p = np.empty(len(rows))
+        l = np.empty(len(rows), dtype=np.int32)
+        eng.d2h(p, d_p)
+        eng.d2h(l, d_l)
+        for d in (d_rows, d_p, d_l):
+            eng.device_free(d)
+        assert np.abs(p - big_p).max() <= 1e-14 and (l == big_l).all()
+    finally:
+        eng.close()
