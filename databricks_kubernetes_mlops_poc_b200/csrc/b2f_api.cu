@@ -401,8 +401,6 @@ static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
     {
         const char *kn = getenv("B2F_KERNEL"); /* "warp" | "tile" | unset = choose by batch size */
         const char *tm = getenv("B2F_TILE_MIN_ROWS");
-        if (tm && atoll(tm) >= 0) m->tile_min_rows = atoll(tm);
-        if (kn && !strcmp(kn, "tile")) m->tile_min_rows = 1;
         const uint32_t avail = (uint32_t)m->max_smem_optin - 1024u - 4096u - B2F_TILE_WARPS * B2F_TILE_XS_BYTES;
         std::vector<uint8_t> layout;
         std::vector<TPiece> pieces;
@@ -431,6 +429,11 @@ static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
             CUDA_TRY(cudaFuncSetAttribute(k_forest_predict_tile<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->tile_smem_bytes));
             CUDA_TRY(cudaFuncSetAttribute(k_forest_predict_tile<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->tile_smem_bytes));
             m->tile_ok = true;
+            /* crossover measured on B200 (tools/ksweep.py): a resident forest ties with the warp kernel from
+             * 65 536 rows up (and sums in sklearn's tree order); a streamed forest wins from ~24k rows */
+            m->tile_min_rows = (tp.n_pieces <= tp.n_slots) ? 65536 : 24576;
+            if (tm && atoll(tm) >= 0) m->tile_min_rows = atoll(tm);
+            if (kn && !strcmp(kn, "tile")) m->tile_min_rows = 1;
         } else if (kn && !strcmp(kn, "tile")) {
             return set_err(B2F_EINVAL, "B2F_KERNEL=tile but the forest's trees do not fit the tile kernel's shared-memory ring");
         }
