@@ -320,6 +320,11 @@ def run_b200(args, dist: Dist):
 
     # ---- inputs: POOL distinct batches per rank (rank-seeded), resident in HBM and in pinned host memory
     vocabs, codes, nums, rows = make_batches(base, enc, POOL, DATA_SEED + 1000 * dist.rank)
+    rows24 = rows
+    packed = args.rows == "packed64" and bool(info0["packed_ok"])
+    if packed:
+        rows = enc.pack_rows(rows24)  # 64-byte rows: one third fewer bytes to read / to push over PCIe
+    row_bytes = rows.shape[1] * 4
     n_pool = POOL * BATCH
     d_rows = eng.device_alloc(rows.nbytes)
     d_proba = eng.device_alloc(n_pool * 4)
@@ -335,11 +340,13 @@ def run_b200(args, dist: Dist):
     t_load0 = time.time()
 
     # ---- value: device-resident, K launches, CUDA events on the launching stream
-    eng.predict_stream_timed(d_rows, BATCH, POOL, d_proba, False, d_label, W)  # warm-up
+    eng.predict_stream_timed(d_rows, BATCH, POOL, d_proba, False, d_label, W, packed=packed)  # warm-up
     dist.barrier()
-    l0 = eng.info()["launches"]
-    ms_each, ms_total = eng.predict_stream_timed(d_rows, BATCH, POOL, d_proba, False, d_label, K)
+    inf_a = eng.info()
+    l0 = inf_a["launches"]
+    ms_each, ms_total = eng.predict_stream_timed(d_rows, BATCH, POOL, d_proba, False, d_label, K, packed=packed)
     launches_value = eng.info()["launches"] - l0
+    kernel_used = "k_forest_predict_tile (thread per row)" if eng.info()["launches_tile"] > 0 else "k_forest_predict (warp per row)"
     dist.barrier()
     ms_total_max = dist.max(ms_total)
     value = dist.world * BATCH * K / (ms_total_max * 1e-3)
@@ -381,13 +388,13 @@ def run_b200(args, dist: Dist):
         t1 = time.perf_counter()
         eng.h2d(d_rows, h_rows[:BATCH])
         tt.append(time.perf_counter() - t1)
-    h2d_gbs = BATCH * 96 / min(tt) / 1e9
+    h2d_gbs = BATCH * row_bytes / min(tt) / 1e9
 
     # ---- sustained phase (>= 1.5 s of back-to-back launches) so the clock sampler sees the kernel under load
     t_sus0 = time.time()
     sus_steps, sus_ms = 0, 0.0
     while time.time() - t_sus0 < args.sustain:
-        _, tot = eng.predict_stream_timed(d_rows, BATCH, POOL, d_proba, False, d_label, 2000)
+        _, tot = eng.predict_stream_timed(d_rows, BATCH, POOL, d_proba, False, d_label, 2000, packed=packed)
         sus_steps += 2000
         sus_ms += tot
     t_load1 = time.time()
@@ -397,7 +404,11 @@ def run_b200(args, dist: Dist):
     mom = None
     if not args.no_moments:
         n_mom = min(1_000_000 // dist.world, n_pool)
-        ms_m, local = eng.moments_device_timed(d_rows, n_mom, 20, False)
+        d_rows24 = d_rows
+        if packed:  # the moments kernel reads the 96-byte layout
+            d_rows24 = eng.device_alloc(rows24.nbytes)
+            eng.h2d(d_rows24, rows24)
+        ms_m, local = eng.moments_device_timed(d_rows24, n_mom, 20, False)
         if dist.world > 1:
             uid = dist.bcast_bytes(ForestEngine.comm_unique_id() if dist.rank == 0 else None)
             eng.comm_init_rank(dist.world, dist.rank, uid)
@@ -409,7 +420,9 @@ def run_b200(args, dist: Dist):
         else:
             merged, t_gather = local, 0.0
         # kernel-only roofline on the whole pool (>= 201 MB, larger than L2)
-        ms_big, _ = eng.moments_device_timed(d_rows, n_pool, 10, False)
+        ms_big, _ = eng.moments_device_timed(d_rows24, n_pool, 10, False)
+        if packed:
+            eng.device_free(d_rows24)
         peak, _ = measured_peak_gbs()
         mom = {
             "rows_total": n_mom * dist.world, "kernel_ms_per_rank": float(np.median(ms_m)),
@@ -456,14 +469,16 @@ def run_b200(args, dist: Dist):
             "model": args.model, "batch": BATCH, "parallelism": f"dp{dist.world} (rows sharded, forest replicated, no collective)",
             "l2": f"inputs rotate over {POOL} distinct batches ({POOL * BATCH * 96 / 1e6:.0f} MB > 126 MB L2)",
             "walk": info0["walk"], "smem_bytes": info0["smem_bytes"], "rows_per_warp": info0["rows_per_warp"],
+            "row_format": f"{row_bytes}-byte encoded rows" + (" (packed: 9 x 7-bit category fields + 14 float32)" if packed else ""),
+            "kernel": kernel_used,
         },
-        "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": BATCH * 96, "d2h_bytes_per_step": BATCH * 8,
+        "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": BATCH * row_bytes, "d2h_bytes_per_step": BATCH * 8,
                 "ms_per_step": 1e3 * e2e_s_max / K, "p50_ms": 1e3 * float(np.percentile(lat, 50)), "p99_ms": 1e3 * float(np.percentile(lat, 99)),
-                "api": "b2f_predict(host pinned rows) -> float32 proba + int32 label", "pcie_h2d_gbs_one_batch": h2d_gbs},
+                "api": f"b2f_predict_ex(host pinned {row_bytes}-byte rows) -> float32 proba + int32 label", "pcie_h2d_gbs_one_batch": h2d_gbs},
         "gpu_launches": int(launches_value),
         "gpu_launches_e2e": int(launches_e2e),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(args.model), "peak_source": peak_src, "kernel": "k_forest_predict",
+                     "traffic": ncu_traffic(args.model), "peak_source": peak_src, "kernel": kernel_used,
                      "alg_bytes_per_launch": ALG_BYTES_PER_ROW * BATCH, "avg_launch_ms": avg_launch_ms,
                      "min_launch_ms": float(np.min(ms_each))},
         "clocks": clocks,
@@ -489,6 +504,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="gbdt100d6", choices=sorted(MODELS))
     ap.add_argument("--sustain", type=float, default=1.5, help="seconds of back-to-back launches for the clock record")
+    ap.add_argument("--rows", default="packed64", choices=["packed64", "words24"], help="encoded row layout fed to the engine")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-moments", action="store_true")
     args = ap.parse_args()

@@ -18,6 +18,10 @@ import numpy as np
 
 ROW_WORDS = 24
 ROW_BYTES = 96
+PACKED_ROW_WORDS = 16
+PACKED_ROW_BYTES = 64
+ROWS_WORDS24 = 0
+ROWS_PACKED64 = 1
 MOMENT_VALUES = ROW_WORDS * 3
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -47,6 +51,12 @@ class Info(C.Structure):
         ("rows_per_warp", C.c_int32),
         ("forest_bytes", C.c_int64),
         ("launches", C.c_int64),
+        ("launches_tile", C.c_int64),
+        ("tile_min_rows", C.c_int64),
+        ("tile_ok", C.c_int32),
+        ("tile_resident", C.c_int32),
+        ("packed_ok", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -63,6 +73,20 @@ SIGNATURES = {
     "b2f_pinned_free": (None, [C.c_void_p]),
     "b2f_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "b2f_predict_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "b2f_predict_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "b2f_predict_async_ex": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_uint64)],
+    ),
+    "b2f_predict_multi_ex": (
+        C.c_int,
+        [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p],
+    ),
+    "b2f_predict_device_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "b2f_predict_stream_timed_ex": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p],
+    ),
     "b2f_predict_async": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_uint64)],

@@ -139,6 +139,8 @@ struct b2f_model {
     int tile_smem_bytes = 0;
     int64_t tile_min_rows = 32768;
     int64_t tile_layout_bytes = 0;
+    int64_t launches_tile = 0;
+    bool packed_ok = false;
     void *d_blob = nullptr;
     int64_t forest_bytes = 0;
     Slot slots[B2F_STREAMS];
@@ -222,7 +224,9 @@ extern "C" int b2f_blob_validate(const void *forest_blob, size_t nbytes) {
 
 template <int R, bool SMEM, typename OutT>
 static cudaError_t set_smem_attr(int bytes) {
-    return cudaFuncSetAttribute(k_forest_predict<R, SMEM, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaError_t e = cudaFuncSetAttribute(k_forest_predict<R, SMEM, false, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_forest_predict<R, SMEM, true, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 
@@ -370,6 +374,11 @@ static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
         kp.g[g].depth = gt[g].depth;
     }
 
+    /* the packed 64-byte row needs the credit-default shape: <= 9 categoricals of <= 126 categories, <= 14 numerics */
+    m->packed_ok = m->hdr.n_cat <= 9 && m->hdr.n_num <= 14;
+    for (uint32_t f = 0; f < m->hdr.n_cat; ++f)
+        if (m->hdr.vocab[f] > 126) m->packed_ok = false;
+
     /* shared-memory residency: whole forest + static barriers must fit the opt-in limit */
     const int64_t need = (int64_t)m->hdr.chunks_bytes;
     const char *force = getenv("B2F_FORCE_WALK"); /* "smem" | "global": test hook */
@@ -426,8 +435,10 @@ static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
             memcpy(tp.impute, kp.impute, sizeof(tp.impute));
             m->tile_smem_bytes = 4096 + B2F_TILE_WARPS * B2F_TILE_XS_BYTES + n_slots * (int)slot_bytes;
             m->tile_layout_bytes = (int64_t)layout.size();
-            CUDA_TRY(cudaFuncSetAttribute(k_forest_predict_tile<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->tile_smem_bytes));
-            CUDA_TRY(cudaFuncSetAttribute(k_forest_predict_tile<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->tile_smem_bytes));
+            CUDA_TRY(cudaFuncSetAttribute(k_forest_predict_tile<false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->tile_smem_bytes));
+            CUDA_TRY(cudaFuncSetAttribute(k_forest_predict_tile<false, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->tile_smem_bytes));
+            CUDA_TRY(cudaFuncSetAttribute(k_forest_predict_tile<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->tile_smem_bytes));
+            CUDA_TRY(cudaFuncSetAttribute(k_forest_predict_tile<true, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->tile_smem_bytes));
             m->tile_ok = true;
             /* crossover measured on B200 (tools/ksweep.py): a resident forest ties with the warp kernel from
              * 65 536 rows up (and sums in sklearn's tree order); a streamed forest wins from ~24k rows */
@@ -526,6 +537,11 @@ extern "C" int b2f_model_info(const b2f_model *m, b2f_info *out) {
     out->rows_per_warp = m->rows_per_warp_max;
     out->forest_bytes = m->forest_bytes;
     out->launches = m->launches;
+    out->launches_tile = m->launches_tile;
+    out->tile_min_rows = m->tile_min_rows;
+    out->tile_ok = m->tile_ok ? 1 : 0;
+    out->tile_resident = (m->tile_ok && m->tp.n_pieces <= m->tp.n_slots) ? 1 : 0;
+    out->packed_ok = m->packed_ok ? 1 : 0;
     return B2F_OK;
 }
 
@@ -544,40 +560,50 @@ extern "C" void b2f_pinned_free(void *p) {
 }
 
 /* ------------------------------------------------------------------ kernel launch */
-template <int R, bool SMEM, typename OutT>
+template <int R, bool SMEM, bool PACKED, typename OutT>
 static cudaError_t launch_one(const b2f_model *m, cudaStream_t st, const void *rows, int64_t n, void *proba, int32_t *label) {
     const int64_t n_batches = (n + R - 1) / R;
     int64_t ctas = std::min<int64_t>(m->sm_count, n_batches);
     if (ctas < 1) ctas = 1;
-    k_forest_predict<R, SMEM, OutT><<<(unsigned)ctas, B2F_PREDICT_THREADS, SMEM ? m->smem_bytes : 0, st>>>(
+    k_forest_predict<R, SMEM, PACKED, OutT><<<(unsigned)ctas, B2F_PREDICT_THREADS, SMEM ? m->smem_bytes : 0, st>>>(
         m->kp, static_cast<const uint32_t *>(rows), (long long)n, static_cast<OutT *>(proba), label);
     return cudaGetLastError();
 }
 
-static int launch_predict(b2f_model *m, cudaStream_t st, const void *rows_dev, int64_t n, void *proba_dev, int f64, int32_t *label_dev) {
+template <bool PACKED, typename OutT>
+static cudaError_t launch_tile(const b2f_model *m, cudaStream_t st, const void *rows, int64_t n, void *proba, int32_t *label) {
+    const int64_t n_tiles = (n + B2F_TILE_ROWS - 1) / B2F_TILE_ROWS;
+    const unsigned ctas = (unsigned)std::max<int64_t>(1, std::min<int64_t>(m->sm_count, n_tiles));
+    k_forest_predict_tile<PACKED, OutT><<<ctas, B2F_TILE_THREADS, m->tile_smem_bytes, st>>>(m->tp, static_cast<const uint32_t *>(rows), (long long)n,
+                                                                                           static_cast<OutT *>(proba), label);
+    return cudaGetLastError();
+}
+
+static int check_row_format(const b2f_model *m, int fmt) {
+    if (fmt == B2F_ROWS_WORDS24) return B2F_OK;
+    if (fmt != B2F_ROWS_PACKED64) return set_err(B2F_EINVAL, "unknown row format %d", fmt);
+    if (!m->packed_ok) return set_err(B2F_EINVAL, "this model's schema does not fit the packed 64-byte row (needs <= 9 categoricals with <= 126 categories, <= 14 numerics)");
+    return B2F_OK;
+}
+
+static int launch_predict(b2f_model *m, cudaStream_t st, const void *rows_dev, int64_t n, int fmt, void *proba_dev, int f64, int32_t *label_dev) {
     if (n <= 0) return B2F_OK;
+    const bool pk = fmt == B2F_ROWS_PACKED64;
+    cudaError_t e;
     if (m->tile_ok && n >= m->tile_min_rows) {
-        const int64_t n_tiles = (n + B2F_TILE_ROWS - 1) / B2F_TILE_ROWS;
-        const unsigned ctas = (unsigned)std::max<int64_t>(1, std::min<int64_t>(m->sm_count, n_tiles));
-        if (f64)
-            k_forest_predict_tile<double><<<ctas, B2F_TILE_THREADS, m->tile_smem_bytes, st>>>(m->tp, static_cast<const uint32_t *>(rows_dev), (long long)n,
-                                                                                             static_cast<double *>(proba_dev), label_dev);
-        else
-            k_forest_predict_tile<float><<<ctas, B2F_TILE_THREADS, m->tile_smem_bytes, st>>>(m->tp, static_cast<const uint32_t *>(rows_dev), (long long)n,
-                                                                                            static_cast<float *>(proba_dev), label_dev);
-        cudaError_t te = cudaGetLastError();
-        if (te != cudaSuccess) return set_err(B2F_ECUDA, "k_forest_predict_tile launch failed: %s", cudaGetErrorString(te));
+        e = pk ? (f64 ? launch_tile<true, double>(m, st, rows_dev, n, proba_dev, label_dev) : launch_tile<true, float>(m, st, rows_dev, n, proba_dev, label_dev))
+               : (f64 ? launch_tile<false, double>(m, st, rows_dev, n, proba_dev, label_dev) : launch_tile<false, float>(m, st, rows_dev, n, proba_dev, label_dev));
+        if (e != cudaSuccess) return set_err(B2F_ECUDA, "k_forest_predict_tile launch failed: %s", cudaGetErrorString(e));
         m->launches++;
+        m->launches_tile++;
         return B2F_OK;
     }
     const int r = pick_rows_per_warp(m, n);
     const bool sm = m->walk_mode == B2F_WALK_SMEM;
-    cudaError_t e;
-#define DISPATCH(RR)                                                                                         \
-    (sm ? (f64 ? launch_one<RR, true, double>(m, st, rows_dev, n, proba_dev, label_dev)                      \
-               : launch_one<RR, true, float>(m, st, rows_dev, n, proba_dev, label_dev))                      \
-        : (f64 ? launch_one<RR, false, double>(m, st, rows_dev, n, proba_dev, label_dev)                     \
-               : launch_one<RR, false, float>(m, st, rows_dev, n, proba_dev, label_dev)))
+#define DISPATCH_T(RR, SM, PK)                                                                                      \
+    (f64 ? launch_one<RR, SM, PK, double>(m, st, rows_dev, n, proba_dev, label_dev)                                  \
+         : launch_one<RR, SM, PK, float>(m, st, rows_dev, n, proba_dev, label_dev))
+#define DISPATCH(RR) (sm ? (pk ? DISPATCH_T(RR, true, true) : DISPATCH_T(RR, true, false)) : (pk ? DISPATCH_T(RR, false, true) : DISPATCH_T(RR, false, false)))
     if (r == 4)
         e = DISPATCH(4);
     else if (r == 2)
@@ -585,6 +611,7 @@ static int launch_predict(b2f_model *m, cudaStream_t st, const void *rows_dev, i
     else
         e = DISPATCH(1);
 #undef DISPATCH
+#undef DISPATCH_T
     if (e != cudaSuccess) return set_err(B2F_ECUDA, "k_forest_predict launch failed: %s", cudaGetErrorString(e));
     m->launches++;
     return B2F_OK;
@@ -619,11 +646,16 @@ static bool host_is_pinned(const void *p) {
 
 /* enqueue the whole batch; on return used_mask tells which slot streams carry work.
  * B2F_TIMELINE=1 (debug): record an event after every operation and print the schedule to stderr. */
-static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, void *proba, int f64, int32_t *label, uint32_t *used_mask) {
+static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, int fmt, void *proba, int f64, int32_t *label, uint32_t *used_mask) {
     *used_mask = 0;
     if (n < 0) return set_err(B2F_EINVAL, "negative row count");
     if (n == 0) return B2F_OK;
     if (!rows) return set_err(B2F_EINVAL, "rows is NULL");
+    {
+        int rcf = check_row_format(m, fmt);
+        if (rcf) return rcf;
+    }
+    const size_t row_bytes = fmt == B2F_ROWS_PACKED64 ? B2F_PACKED_ROW_BYTES : B2F_ROW_BYTES;
     CUDA_TRY(cudaSetDevice(m->device));
     /* Zero-copy path: when every buffer is page-locked (b2f_pinned_alloc / cudaHostRegister), the kernel
      * reads the rows and writes the results straight over PCIe -- H2D, walk and D2H fused into one
@@ -631,12 +663,12 @@ static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, void *p
     if (m->zero_copy > 0 && host_is_pinned(rows) && (m->zero_copy < 2 || ((!proba || host_is_pinned(proba)) && (!label || host_is_pinned(label))))) {
         Slot &sl = m->slots[0];
         if (m->zero_copy >= 2) {
-            int rc = launch_predict(m, sl.stream, rows, n, proba, f64, label);
+            int rc = launch_predict(m, sl.stream, rows, n, fmt, proba, f64, label);
             if (rc) return rc;
         } else {
             int rc = slot_reserve(m, sl, n);
             if (rc) return rc;
-            rc = launch_predict(m, sl.stream, rows, n, proba ? sl.d_proba : nullptr, f64, label ? sl.d_label : nullptr);
+            rc = launch_predict(m, sl.stream, rows, n, fmt, proba ? sl.d_proba : nullptr, f64, label ? sl.d_label : nullptr);
             if (rc) return rc;
             const size_t psz0 = f64 ? sizeof(double) : sizeof(float);
             if (proba) CUDA_TRY(cudaMemcpyAsync(proba, sl.d_proba, (size_t)n * psz0, cudaMemcpyDeviceToHost, sl.stream));
@@ -664,10 +696,10 @@ static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, void *p
         int rc = slot_reserve(m, sl, cnt);
         if (rc) return rc;
         if (c == 0) mark(sl.stream);
-        CUDA_TRY(cudaMemcpyAsync(sl.d_rows, static_cast<const uint8_t *>(rows) + (size_t)off * B2F_ROW_BYTES, (size_t)cnt * B2F_ROW_BYTES,
+        CUDA_TRY(cudaMemcpyAsync(sl.d_rows, static_cast<const uint8_t *>(rows) + (size_t)off * row_bytes, (size_t)cnt * row_bytes,
                                  cudaMemcpyHostToDevice, sl.stream));
         mark(sl.stream);
-        rc = launch_predict(m, sl.stream, sl.d_rows, cnt, proba ? sl.d_proba : nullptr, f64, label ? sl.d_label : nullptr);
+        rc = launch_predict(m, sl.stream, sl.d_rows, cnt, fmt, proba ? sl.d_proba : nullptr, f64, label ? sl.d_label : nullptr);
         if (rc) return rc;
         mark(sl.stream);
         if (proba)
@@ -696,23 +728,31 @@ static int sync_mask(b2f_model *m, uint32_t mask) {
     return B2F_OK;
 }
 
-static int predict_host(b2f_model *m, const void *rows, int64_t n, void *proba, int f64, int32_t *label) {
+static int predict_host(b2f_model *m, const void *rows, int64_t n, int fmt, void *proba, int f64, int32_t *label) {
     if (!m) return set_err(B2F_EINVAL, "model is NULL");
     uint32_t mask = 0;
-    int rc = enqueue_host_batch(m, rows, n, proba, f64, label, &mask);
+    int rc = enqueue_host_batch(m, rows, n, fmt, proba, f64, label, &mask);
     int rc2 = sync_mask(m, mask);
     return rc ? rc : rc2;
 }
 
 extern "C" int b2f_predict(b2f_model *m, const void *rows, int64_t n, float *proba1, int32_t *label) {
-    return predict_host(m, rows, n, proba1, 0, label);
+    return predict_host(m, rows, n, B2F_ROWS_WORDS24, proba1, 0, label);
 }
 extern "C" int b2f_predict_f64(b2f_model *m, const void *rows, int64_t n, double *proba1, int32_t *label) {
-    return predict_host(m, rows, n, proba1, 1, label);
+    return predict_host(m, rows, n, B2F_ROWS_WORDS24, proba1, 1, label);
+}
+extern "C" int b2f_predict_ex(b2f_model *m, const void *rows, int64_t n, int row_format, void *proba1, int proba_is_f64, int32_t *label) {
+    return predict_host(m, rows, n, row_format, proba1, proba_is_f64, label);
 }
 
 extern "C" int b2f_predict_async(b2f_model *m, const void *rows_pinned, int64_t n, void *proba1_pinned, int proba_is_f64,
                                  int32_t *label_pinned, b2f_ticket *ticket) {
+    return b2f_predict_async_ex(m, rows_pinned, n, B2F_ROWS_WORDS24, proba1_pinned, proba_is_f64, label_pinned, ticket);
+}
+
+extern "C" int b2f_predict_async_ex(b2f_model *m, const void *rows_pinned, int64_t n, int row_format, void *proba1_pinned, int proba_is_f64,
+                                    int32_t *label_pinned, b2f_ticket *ticket) {
     if (!m || !ticket) return set_err(B2F_EINVAL, "null argument");
     const uint64_t id = m->next_ticket++;
     TicketRec &t = m->tickets[id % B2F_TICKETS];
@@ -721,7 +761,7 @@ extern "C" int b2f_predict_async(b2f_model *m, const void *rows_pinned, int64_t 
             if (t.used_mask & (1u << s)) CUDA_TRY(cudaEventSynchronize(t.ev[s]));
     }
     uint32_t mask = 0;
-    int rc = enqueue_host_batch(m, rows_pinned, n, proba1_pinned, proba_is_f64, label_pinned, &mask);
+    int rc = enqueue_host_batch(m, rows_pinned, n, row_format, proba1_pinned, proba_is_f64, label_pinned, &mask);
     if (rc) {
         sync_mask(m, mask);
         return rc;
@@ -750,7 +790,13 @@ extern "C" int b2f_wait(b2f_model *m, b2f_ticket ticket) {
 }
 
 extern "C" int b2f_predict_multi(b2f_model **models, int n_models, const void *rows, int64_t n, void *proba1, int proba_is_f64, int32_t *label) {
+    return b2f_predict_multi_ex(models, n_models, rows, n, B2F_ROWS_WORDS24, proba1, proba_is_f64, label);
+}
+
+extern "C" int b2f_predict_multi_ex(b2f_model **models, int n_models, const void *rows, int64_t n, int row_format, void *proba1, int proba_is_f64,
+                                    int32_t *label) {
     if (!models || n_models <= 0) return set_err(B2F_EINVAL, "no models");
+    const size_t row_bytes = row_format == B2F_ROWS_PACKED64 ? B2F_PACKED_ROW_BYTES : B2F_ROW_BYTES;
     if (n < 0) return set_err(B2F_EINVAL, "negative row count");
     std::vector<uint32_t> masks(n_models, 0);
     const size_t psz = proba_is_f64 ? sizeof(double) : sizeof(float);
@@ -758,7 +804,7 @@ extern "C" int b2f_predict_multi(b2f_model **models, int n_models, const void *r
     for (int i = 0; i < n_models && rc == B2F_OK; ++i) {
         const int64_t lo = n * i / n_models, hi = n * (i + 1) / n_models;
         if (hi <= lo) continue;
-        rc = enqueue_host_batch(models[i], static_cast<const uint8_t *>(rows) + (size_t)lo * B2F_ROW_BYTES, hi - lo,
+        rc = enqueue_host_batch(models[i], static_cast<const uint8_t *>(rows) + (size_t)lo * row_bytes, hi - lo, row_format,
                                 proba1 ? static_cast<uint8_t *>(proba1) + (size_t)lo * psz : nullptr, proba_is_f64, label ? label + lo : nullptr,
                                 &masks[i]);
     }
@@ -800,9 +846,15 @@ extern "C" int b2f_copy_d2h(b2f_model *m, void *dst_host, const void *src_dev, s
     return B2F_OK;
 }
 extern "C" int b2f_predict_device(b2f_model *m, const void *rows_dev, int64_t n, void *proba1_dev, int proba_is_f64, int32_t *label_dev) {
+    return b2f_predict_device_ex(m, rows_dev, n, B2F_ROWS_WORDS24, proba1_dev, proba_is_f64, label_dev);
+}
+extern "C" int b2f_predict_device_ex(b2f_model *m, const void *rows_dev, int64_t n, int row_format, void *proba1_dev, int proba_is_f64,
+                                     int32_t *label_dev) {
     if (!m) return set_err(B2F_EINVAL, "model is NULL");
+    int rcf = check_row_format(m, row_format);
+    if (rcf) return rcf;
     CUDA_TRY(cudaSetDevice(m->device));
-    return launch_predict(m, m->compute, rows_dev, n, proba1_dev, proba_is_f64, label_dev);
+    return launch_predict(m, m->compute, rows_dev, n, row_format, proba1_dev, proba_is_f64, label_dev);
 }
 extern "C" int b2f_sync(b2f_model *m) {
     if (!m) return set_err(B2F_EINVAL, "model is NULL");
@@ -830,7 +882,7 @@ extern "C" int b2f_predict_device_timed(b2f_model *m, const void *rows_dev, int6
     for (int i = 0; i < iters && rc == B2F_OK; ++i) {
         if (flush_l2) CUDA_TRY(cudaMemsetAsync(m->d_flush, i & 0xff, B2F_FLUSH_BYTES, m->compute));
         CUDA_TRY(cudaEventRecord(ev[2 * i], m->compute));
-        rc = launch_predict(m, m->compute, rows_dev, n, proba1_dev, proba_is_f64, label_dev);
+        rc = launch_predict(m, m->compute, rows_dev, n, B2F_ROWS_WORDS24, proba1_dev, proba_is_f64, label_dev);
         CUDA_TRY(cudaEventRecord(ev[2 * i + 1], m->compute));
     }
     CUDA_TRY(cudaStreamSynchronize(m->compute));
@@ -844,7 +896,17 @@ extern "C" int b2f_predict_device_timed(b2f_model *m, const void *rows_dev, int6
  * Per-launch events and one region event pair, all on the launching stream. */
 extern "C" int b2f_predict_stream_timed(b2f_model *m, const void *rows_dev, int64_t n, int pool, void *proba1_dev, int proba_is_f64,
                                         int32_t *label_dev, int steps, float *ms_each, float *ms_total) {
+    return b2f_predict_stream_timed_ex(m, rows_dev, n, B2F_ROWS_WORDS24, pool, proba1_dev, proba_is_f64, label_dev, steps, ms_each, ms_total);
+}
+
+extern "C" int b2f_predict_stream_timed_ex(b2f_model *m, const void *rows_dev, int64_t n, int row_format, int pool, void *proba1_dev,
+                                           int proba_is_f64, int32_t *label_dev, int steps, float *ms_each, float *ms_total) {
     if (!m || steps <= 0 || pool <= 0 || !ms_total) return set_err(B2F_EINVAL, "bad argument");
+    {
+        int rcf = check_row_format(m, row_format);
+        if (rcf) return rcf;
+    }
+    const size_t row_bytes = row_format == B2F_ROWS_PACKED64 ? B2F_PACKED_ROW_BYTES : B2F_ROW_BYTES;
     CUDA_TRY(cudaSetDevice(m->device));
     std::vector<cudaEvent_t> ev(2 * (size_t)steps + 2);
     for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
@@ -854,7 +916,7 @@ extern "C" int b2f_predict_stream_timed(b2f_model *m, const void *rows_dev, int6
     for (int i = 0; i < steps && rc == B2F_OK; ++i) {
         const size_t b = (size_t)(i % pool);
         CUDA_TRY(cudaEventRecord(ev[2 * i], m->compute));
-        rc = launch_predict(m, m->compute, static_cast<const uint8_t *>(rows_dev) + b * (size_t)n * B2F_ROW_BYTES, n,
+        rc = launch_predict(m, m->compute, static_cast<const uint8_t *>(rows_dev) + b * (size_t)n * row_bytes, n, row_format,
                             proba1_dev ? static_cast<uint8_t *>(proba1_dev) + b * (size_t)n * psz : nullptr, proba_is_f64,
                             label_dev ? label_dev + b * (size_t)n : nullptr);
         CUDA_TRY(cudaEventRecord(ev[2 * i + 1], m->compute));

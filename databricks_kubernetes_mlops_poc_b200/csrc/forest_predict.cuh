@@ -28,6 +28,7 @@
 #define B2F_PREDICT_THREADS 1024
 #define B2F_PREDICT_WARPS (B2F_PREDICT_THREADS / 32)
 #define B2F_BULK_PIECE (32u * 1024u) /* bytes per cp.async.bulk */
+#define B2F_PACKED_ROW_WORDS 16
 
 struct KGroup {
     uint32_t chunk_off;
@@ -216,7 +217,7 @@ __device__ __forceinline__ void walk_group(typename AddrOf<SMEM>::type a_first, 
     }
 }
 
-template <int R, bool SMEM, typename OutT>
+template <int R, bool SMEM, bool PACKED, typename OutT>
 __global__ void __launch_bounds__(B2F_PREDICT_THREADS, 1)
     k_forest_predict(const __grid_constant__ KParams p, const uint32_t *__restrict__ rows, long long n,
                      OutT *__restrict__ proba, int32_t *__restrict__ label) {
@@ -269,9 +270,27 @@ __global__ void __launch_bounds__(B2F_PREDICT_THREADS, 1)
     const uint32_t lane8 = (uint32_t)lane * 8u; /* this lane's node inside a 256-byte slot */
     const addr_t origin_lane = (SMEM ? (addr_t)0 : (addr_t)reinterpret_cast<uint64_t>(p.chunks)) + lane8;
 
+    /* raw load of this lane's word of a row (decoded by unpack_row when the row is consumed):
+     * 96-byte rows: lane l < 23 holds word l;  packed 64-byte rows: lane l < 16 holds word l */
     auto load_row = [&](long long row) -> uint32_t {
         uint32_t v = B2F_SENTINEL_BITS;
-        if (row < n && lane < (int)B2F_SENTINEL_WORD) v = __ldg(rows + row * B2F_ROW_WORDS + lane);
+        if constexpr (PACKED) {
+            if (row < n && lane < B2F_PACKED_ROW_WORDS) v = __ldg(rows + row * B2F_PACKED_ROW_WORDS + lane);
+        } else {
+            if (row < n && lane < (int)B2F_SENTINEL_WORD) v = __ldg(rows + row * B2F_ROW_WORDS + lane);
+        }
+        return v;
+    };
+    /* -> one row word per lane: lanes 0..n_cat-1 category codes, then float32 numerics, sentinel above */
+    auto unpack_row = [&](uint32_t v) -> uint32_t {
+        if constexpr (PACKED) {
+            /* words 0..1: nine 7-bit fields (code + 1, 0 = unknown); words 2..15: the 14 numerics */
+            const uint32_t lo = __shfl_sync(0xffffffffu, v, 0), hi = __shfl_sync(0xffffffffu, v, 1);
+            const uint32_t num = __shfl_sync(0xffffffffu, v, (lane - 7) & 31);
+            const uint32_t field = (uint32_t)(((((unsigned long long)hi) << 32) | lo) >> (7 * (lane < 9 ? lane : 0))) & 0x7fu;
+            v = lane < 9 ? field - 1u : (lane < (int)B2F_SENTINEL_WORD ? num : B2F_SENTINEL_BITS);
+        }
+        if (lane_numeric && isnan(__uint_as_float(v))) v = impute_bits;
         return v;
     };
 
@@ -288,9 +307,7 @@ __global__ void __launch_bounds__(B2F_PREDICT_THREADS, 1)
         double acc[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            uint32_t v = wnext[r];
-            if (lane_numeric && isnan(__uint_as_float(v))) v = impute_bits;
-            w[r] = v;
+            w[r] = unpack_row(wnext[r]);
             acc[r] = 0.0;
         }
         /* prefetch the next batch's rows; the loads complete behind this batch's walk */

@@ -148,7 +148,7 @@ __device__ __forceinline__ void tile_walk_ugroup(uint32_t piece_addr, uint32_t u
     }
 }
 
-template <typename OutT>
+template <bool PACKED, typename OutT>
 __global__ void __launch_bounds__(B2F_TILE_THREADS, 1)
     k_forest_predict_tile(const __grid_constant__ TParams p, const uint32_t *__restrict__ rows, long long n,
                           OutT *__restrict__ proba, int32_t *__restrict__ label) {
@@ -217,16 +217,31 @@ __global__ void __launch_bounds__(B2F_TILE_THREADS, 1)
         __syncwarp();
         {
             uint32_t w[B2F_ROW_WORDS];
+#pragma unroll
+            for (int k = 0; k < B2F_ROW_WORDS; ++k) w[k] = B2F_SENTINEL_BITS;
             if (live) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(rows + row * B2F_ROW_WORDS);
+                if constexpr (PACKED) {
+                    /* 64-byte row: words 0..1 = nine 7-bit (code + 1) fields, words 2..15 = 14 numerics */
+                    const uint4 *src = reinterpret_cast<const uint4 *>(rows + row * B2F_PACKED_ROW_WORDS);
+                    uint32_t q[B2F_PACKED_ROW_WORDS];
 #pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    const uint4 v = __ldg(src + k);
-                    w[4 * k + 0] = v.x, w[4 * k + 1] = v.y, w[4 * k + 2] = v.z, w[4 * k + 3] = v.w;
+                    for (int k = 0; k < 4; ++k) {
+                        const uint4 v = __ldg(src + k);
+                        q[4 * k + 0] = v.x, q[4 * k + 1] = v.y, q[4 * k + 2] = v.z, q[4 * k + 3] = v.w;
+                    }
+                    const unsigned long long codes = (((unsigned long long)q[1]) << 32) | q[0];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) w[k] = ((uint32_t)(codes >> (7 * k)) & 0x7fu) - 1u;
+#pragma unroll
+                    for (int k = 0; k < 14; ++k) w[9 + k] = q[2 + k];
+                } else {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(rows + row * B2F_ROW_WORDS);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        const uint4 v = __ldg(src + k);
+                        w[4 * k + 0] = v.x, w[4 * k + 1] = v.y, w[4 * k + 2] = v.z, w[4 * k + 3] = v.w;
+                    }
                 }
-            } else {
-#pragma unroll
-                for (int k = 0; k < B2F_ROW_WORDS; ++k) w[k] = B2F_SENTINEL_BITS;
             }
 #pragma unroll
             for (int k = 0; k < B2F_ROW_WORDS; ++k) {

@@ -24,6 +24,8 @@ import pandas as pd
 
 from .flatten import ROW_WORDS, FlatForest
 
+PACKED_ROW_WORDS = 16  # B2F_ROWS_PACKED64: 64-byte rows (include/b2f.h)
+
 _F32_MAX = float(np.finfo(np.float32).max)
 
 
@@ -35,6 +37,8 @@ class RowEncoder:
         self.n_num = len(self.num_features)
         self._index = [pd.Index(list(v), dtype=object) for v in flat.categories]
         self._missing = list(flat.missing_codes) if flat.missing_codes else [-1] * self.n_cat
+        # packed 64-byte rows: nine 7-bit (code + 1) fields + 14 float32 numerics
+        self.packed_ok = self.n_cat <= 9 and self.n_num <= 14 and all(len(v) <= 126 for v in flat.categories)
 
     # ------------------------------------------------------------------ columns
     def encode_categorical(self, j: int, values) -> np.ndarray:
@@ -86,3 +90,28 @@ class RowEncoder:
         )
         out[:, self.n_cat + self.n_num :] = 0
         return out
+
+    # ------------------------------------------------------------------ packed 64-byte rows
+    def pack_rows(self, rows24: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """(N, 24) encoded rows -> (N, 16) packed rows (B2F_ROWS_PACKED64): one third fewer bytes over PCIe.
+        Lossless: code + 1 in 7 bits (0 = unknown), numerics untouched."""
+        if not self.packed_ok:
+            raise ValueError("schema does not fit the packed row (<= 9 categoricals of <= 126 categories, <= 14 numerics)")
+        n = rows24.shape[0]
+        if out is None:
+            out = np.zeros((n, PACKED_ROW_WORDS), dtype=np.uint32)
+        fields = (rows24.view(np.int32)[:, : self.n_cat].astype(np.int64) + 1).astype(np.uint64)
+        word = np.zeros(n, dtype=np.uint64)
+        for j in range(self.n_cat):
+            word |= fields[:, j] << np.uint64(7 * j)
+        out[:, 0] = (word & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        out[:, 1] = (word >> np.uint64(32)).astype(np.uint32)
+        out[:, 2 : 2 + self.n_num] = rows24[:, self.n_cat : self.n_cat + self.n_num]
+        out[:, 2 + self.n_num :] = 0
+        return out
+
+    def encode_frame_packed(self, df: pd.DataFrame, out: np.ndarray | None = None) -> np.ndarray:
+        return self.pack_rows(self.encode_frame(df), out=out)
+
+    def encode_arrays_packed(self, codes: np.ndarray, nums: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        return self.pack_rows(self.encode_arrays(codes, nums), out=out)

@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _cabi
-from ._cabi import MOMENT_VALUES, ROW_WORDS, B2FError, Info, PinnedBuffer, check, ptr
+from ._cabi import MOMENT_VALUES, PACKED_ROW_WORDS, ROW_WORDS, ROWS_PACKED64, ROWS_WORDS24, B2FError, Info, PinnedBuffer, check, ptr
 from .flatten import FlatForest
 
 
@@ -89,24 +89,22 @@ class ForestEngine:
     def predict_rows(self, rows: np.ndarray, proba_dtype=np.float64, want_label: bool = True, out_proba=None, out_label=None):
         """Encoded rows (N, 24) uint32 in host memory -> (proba1, label)."""
         rows = np.ascontiguousarray(rows)
-        if rows.dtype != np.uint32 or rows.ndim != 2 or rows.shape[1] != ROW_WORDS:
-            raise ValueError(f"rows must be uint32 (N, {ROW_WORDS})")
+        fmt = _row_format(rows)
         n = rows.shape[0]
         f64 = np.dtype(proba_dtype) == np.float64
         proba = out_proba if out_proba is not None else np.empty(n, dtype=np.float64 if f64 else np.float32)
         label = out_label if out_label is not None else (np.empty(n, dtype=np.int32) if want_label else None)
-        fn = self._lib.b2f_predict_f64 if f64 else self._lib.b2f_predict
-        check(fn(self._h, ptr(rows), n, ptr(proba), ptr(label)), "b2f_predict")
+        check(self._lib.b2f_predict_ex(self._h, ptr(rows), n, fmt, ptr(proba), int(f64), ptr(label)), "b2f_predict_ex")
         return proba, label
 
     def predict_rows_async(self, rows: np.ndarray, proba: np.ndarray, label: np.ndarray | None) -> int:
         """Pinned buffers in, ticket out; pair with wait()."""
         t = C.c_uint64(0)
         check(
-            self._lib.b2f_predict_async(
-                self._h, ptr(rows), rows.shape[0], ptr(proba), int(proba.dtype == np.float64), ptr(label), C.byref(t)
+            self._lib.b2f_predict_async_ex(
+                self._h, ptr(rows), rows.shape[0], _row_format(rows), ptr(proba), int(proba.dtype == np.float64), ptr(label), C.byref(t)
             ),
-            "b2f_predict_async",
+            "b2f_predict_async_ex",
         )
         return t.value
 
@@ -130,8 +128,11 @@ class ForestEngine:
     def d2h(self, a: np.ndarray, dptr: int) -> None:
         check(self._lib.b2f_copy_d2h(self._h, ptr(a), dptr, a.nbytes), "b2f_copy_d2h")
 
-    def predict_device(self, rows_dev: int, n: int, proba_dev: int, proba_is_f64: bool, label_dev: int) -> None:
-        check(self._lib.b2f_predict_device(self._h, rows_dev, n, proba_dev, int(proba_is_f64), label_dev), "b2f_predict_device")
+    def predict_device(self, rows_dev: int, n: int, proba_dev: int, proba_is_f64: bool, label_dev: int, packed: bool = False) -> None:
+        check(
+            self._lib.b2f_predict_device_ex(self._h, rows_dev, n, ROWS_PACKED64 if packed else ROWS_WORDS24, proba_dev, int(proba_is_f64), label_dev),
+            "b2f_predict_device_ex",
+        )
 
     def sync(self) -> None:
         check(self._lib.b2f_sync(self._h), "b2f_sync")
@@ -146,15 +147,16 @@ class ForestEngine:
         )
         return ms
 
-    def predict_stream_timed(self, rows_dev, n, pool, proba_dev, proba_is_f64, label_dev, steps: int):
+    def predict_stream_timed(self, rows_dev, n, pool, proba_dev, proba_is_f64, label_dev, steps: int, packed: bool = False):
         """``steps`` launches cycling over ``pool`` device-resident batches -> (ms_each, ms_total)."""
         ms = np.zeros(steps, dtype=np.float32)
         tot = C.c_float(0.0)
         check(
-            self._lib.b2f_predict_stream_timed(
-                self._h, rows_dev, n, pool, proba_dev, int(proba_is_f64), label_dev, steps, ptr(ms), C.byref(tot)
+            self._lib.b2f_predict_stream_timed_ex(
+                self._h, rows_dev, n, ROWS_PACKED64 if packed else ROWS_WORDS24, pool, proba_dev, int(proba_is_f64), label_dev, steps,
+                ptr(ms), C.byref(tot)
             ),
-            "b2f_predict_stream_timed",
+            "b2f_predict_stream_timed_ex",
         )
         return ms, float(tot.value)
 
@@ -195,6 +197,12 @@ class ForestEngine:
         return out.reshape(ROW_WORDS, 3)
 
 
+def _row_format(rows: np.ndarray) -> int:
+    if rows.dtype != np.uint32 or rows.ndim != 2 or rows.shape[1] not in (ROW_WORDS, PACKED_ROW_WORDS):
+        raise ValueError(f"rows must be uint32 (N, {ROW_WORDS}) or packed (N, {PACKED_ROW_WORDS})")
+    return ROWS_PACKED64 if rows.shape[1] == PACKED_ROW_WORDS else ROWS_WORDS24
+
+
 def moments_merge(parts: np.ndarray) -> np.ndarray:
     """Chan merge of k (24, 3) partials (host)."""
     parts = np.ascontiguousarray(parts, dtype=np.float64).reshape(-1, MOMENT_VALUES)
@@ -228,8 +236,8 @@ class EngineGroup:
         proba = out_proba if out_proba is not None else np.empty(n, dtype=np.float64 if f64 else np.float32)
         label = out_label if out_label is not None else np.empty(n, dtype=np.int32)
         check(
-            self._lib.b2f_predict_multi(self._handles, len(self.engines), ptr(rows), n, ptr(proba), int(f64), ptr(label)),
-            "b2f_predict_multi",
+            self._lib.b2f_predict_multi_ex(self._handles, len(self.engines), ptr(rows), n, _row_format(rows), ptr(proba), int(f64), ptr(label)),
+            "b2f_predict_multi_ex",
         )
         return proba, label
 

@@ -42,8 +42,15 @@ extern "C" {
 
 #define B2F_ROW_WORDS 24
 #define B2F_ROW_BYTES 96
+#define B2F_PACKED_ROW_BYTES 64
 #define B2F_MAX_TREES 1024
 #define B2F_MOMENT_WORDS 3 /* per feature: count, mean, M2 */
+
+/* row formats (the *_ex entry points take one; the plain entry points use B2F_ROWS_WORDS24) */
+#define B2F_ROWS_WORDS24 0  /* 24 x 32-bit words, 96 B (layout above) */
+#define B2F_ROWS_PACKED64 1 /* 16 x 32-bit words, 64 B: words 0..1 = nine 7-bit fields (category code + 1, 0 = unknown /
+                               missing), little-endian bit order, field j at bit 7j; words 2..15 = the 14 float32 numerics.
+                               One third fewer bytes over PCIe; needs <= 9 categoricals of <= 126 categories, <= 14 numerics. */
 
 /* error codes */
 #define B2F_OK 0
@@ -80,6 +87,12 @@ typedef struct b2f_info {
     int32_t rows_per_warp;  /* rows walked concurrently by one warp */
     int64_t forest_bytes;   /* bytes of the node + leaf arrays on the device */
     int64_t launches;       /* kernels launched by this handle so far (predict + moments) */
+    int64_t launches_tile;  /* ... of which the large-batch tile kernel */
+    int64_t tile_min_rows;  /* launches of at least this many rows take the tile kernel (if tile_ok) */
+    int32_t tile_ok;        /* the forest's trees fit the tile kernel's shared-memory ring */
+    int32_t tile_resident;  /* ... and the whole forest stays resident in it (no streaming) */
+    int32_t packed_ok;      /* B2F_ROWS_PACKED64 is accepted for this model */
+    int32_t reserved;
 } b2f_info;
 
 /* ---- library / device ------------------------------------------------------------------ */
@@ -110,16 +123,26 @@ void b2f_pinned_free(void *p);
 int b2f_predict(b2f_model *m, const void *rows, int64_t n, float *proba1, int32_t *label);
 int b2f_predict_f64(b2f_model *m, const void *rows, int64_t n, double *proba1, int32_t *label);
 
+/* same, with an explicit row format and output type */
+int b2f_predict_ex(b2f_model *m, const void *rows, int64_t n, int row_format, void *proba1,
+                   int proba_is_f64, int32_t *label);
+
 /* asynchronous form for the request-batching ring: buffers must be pinned and stay valid until
  * b2f_wait(ticket) returns.  proba_is_f64 selects double (1) or float (0) outputs. */
 int b2f_predict_async(b2f_model *m, const void *rows_pinned, int64_t n, void *proba1_pinned,
                       int proba_is_f64, int32_t *label_pinned, b2f_ticket *ticket);
+int b2f_predict_async_ex(b2f_model *m, const void *rows_pinned, int64_t n, int row_format,
+                         void *proba1_pinned, int proba_is_f64, int32_t *label_pinned,
+                         b2f_ticket *ticket);
 int b2f_wait(b2f_model *m, b2f_ticket ticket);
 
 /* one call over several GPUs: contiguous slices of the batch go round-robin to the models
  * (one per device); no inter-GPU traffic (rows are independent). */
 int b2f_predict_multi(b2f_model **models, int n_models, const void *rows, int64_t n, void *proba1,
                       int proba_is_f64, int32_t *label);
+
+int b2f_predict_multi_ex(b2f_model **models, int n_models, const void *rows, int64_t n, int row_format,
+                         void *proba1, int proba_is_f64, int32_t *label);
 
 /* ---- device-resident interface (measurement and callers that already hold rows in HBM) ----- */
 void *b2f_device_alloc(b2f_model *m, size_t nbytes);
@@ -129,6 +152,8 @@ int b2f_copy_d2h(b2f_model *m, void *dst_host, const void *src_dev, size_t nbyte
 /* enqueue one predict launch on the model's compute stream (asynchronous) */
 int b2f_predict_device(b2f_model *m, const void *rows_dev, int64_t n, void *proba1_dev,
                        int proba_is_f64, int32_t *label_dev);
+int b2f_predict_device_ex(b2f_model *m, const void *rows_dev, int64_t n, int row_format,
+                          void *proba1_dev, int proba_is_f64, int32_t *label_dev);
 int b2f_sync(b2f_model *m);
 /* run `iters` launches back to back, each bracketed by CUDA events on the launching stream;
  * ms_each[iters] receives each launch's device time.  flush_l2 != 0 writes a >L2-sized scratch
@@ -143,6 +168,10 @@ int b2f_predict_device_timed(b2f_model *m, const void *rows_dev, int64_t n, void
 int b2f_predict_stream_timed(b2f_model *m, const void *rows_dev, int64_t n, int pool, void *proba1_dev,
                              int proba_is_f64, int32_t *label_dev, int steps, float *ms_each,
                              float *ms_total);
+
+int b2f_predict_stream_timed_ex(b2f_model *m, const void *rows_dev, int64_t n, int row_format, int pool,
+                                void *proba1_dev, int proba_is_f64, int32_t *label_dev, int steps,
+                                float *ms_each, float *ms_total);
 
 /* ---- drift-monitor moments (BASELINE config 5; nearest reference call is
  *      self.drift.predict(...), 02-register-model.ipynb:338 -- no mean/var exists there) --------

@@ -368,3 +368,26 @@ def test_kernel_auto_selection_agrees(curated, rf100d6):
         assert np.abs(p - big_p).max() <= 1e-14 and (l == big_l).all()
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("kernel", ["warp", "tile"])
+def test_packed_rows_give_identical_results(curated, adversarial, rf100d6, gbdt_small, kernel):
+    """64-byte packed rows (one third fewer PCIe bytes) vs 96-byte rows: bit-identical outputs, both kernels."""
+    os.environ["B2F_KERNEL"] = kernel
+    try:
+        for pipe in (rf100d6, gbdt_small):
+            eng, enc = _engine(pipe)
+            try:
+                assert eng.info()["packed_ok"] == 1
+                for df in (curated.iloc[:20000], adversarial):
+                    a = enc.encode_frame(df)
+                    b = enc.pack_rows(a)
+                    pa, la = eng.predict_rows(a, np.float64)
+                    pb, lb = eng.predict_rows(b, np.float64)
+                    assert (pa == pb).all() and (la == lb).all()
+                    pb32, _ = eng.predict_rows(b, np.float32)
+                    assert (pb32 == pa.astype(np.float32)).all()
+            finally:
+                eng.close()
+    finally:
+        os.environ.pop("B2F_KERNEL")

@@ -234,3 +234,22 @@ def test_schema_is_wire_compatible():
     assert out.model_dump()["outliers"] == [0.0]
     with pytest.raises(Exception):
         schema.ModelOutput.model_validate({"predictions": [0.5], "outliers": [0], "feature_drift_batch": {"sex": 0.0}})
+
+
+def test_packed_rows_are_lossless(curated, adversarial, rf100d6):
+    """B2F_ROWS_PACKED64: nine 7-bit (code + 1) fields + 14 float32 -> unpacking gives back the 96-byte row."""
+    from databricks_kubernetes_mlops_poc_b200 import flatten
+    from databricks_kubernetes_mlops_poc_b200.encode import RowEncoder
+
+    enc = RowEncoder(flatten.flatten_pipeline(rf100d6))
+    assert enc.packed_ok
+    for df in (curated.iloc[:2000], adversarial):
+        rows = enc.encode_frame(df)
+        pk = enc.encode_frame_packed(df)
+        assert pk.shape == (len(df), 16) and pk.dtype == np.uint32
+        word = pk[:, 0].astype(np.uint64) | (pk[:, 1].astype(np.uint64) << np.uint64(32))
+        for j in range(9):
+            code = ((word >> np.uint64(7 * j)) & np.uint64(0x7F)).astype(np.int64) - 1
+            assert (code == rows.view(np.int32)[:, j]).all()
+        assert (pk[:, 2:16] == rows[:, 9:23]).all()  # numerics bit-identical (NaN payloads included)
+        assert (word >> np.uint64(63) == 0).all()
