@@ -332,8 +332,9 @@ def run_b200(args, dist: Dist):
     eng.h2d(d_rows, rows)
     h_rows = eng.pinned("bench_rows", rows.nbytes).view(np.uint32, rows.shape)
     h_rows[:] = rows
-    h_proba = eng.pinned("bench_proba", n_pool * 4).view(np.float32, (n_pool,))
-    h_label = eng.pinned("bench_label", n_pool * 4).view(np.int32, (n_pool,))
+    from databricks_kubernetes_mlops_poc_b200._cabi import SCORED_DTYPE
+
+    h_out = eng.pinned("bench_out", n_pool * 8).view(SCORED_DTYPE, (n_pool,))  # {float32 proba1, int32 label} per row
 
     sampler = ClockSampler(dist.local_rank)
     sampler.start()
@@ -364,8 +365,7 @@ def run_b200(args, dist: Dist):
     # ---- e2e: C-ABI call with host buffers, H2D + kernel + D2H every step, wall clock around synchronous calls
     for i in range(W):
         b = i % POOL
-        eng.predict_rows(h_rows[b * BATCH:(b + 1) * BATCH], np.float32, out_proba=h_proba[b * BATCH:(b + 1) * BATCH],
-                         out_label=h_label[b * BATCH:(b + 1) * BATCH])
+        eng.predict_pairs(h_rows[b * BATCH:(b + 1) * BATCH], out=h_out[b * BATCH:(b + 1) * BATCH])
     dist.barrier()
     lat = []
     l0 = eng.info()["launches"]
@@ -373,12 +373,16 @@ def run_b200(args, dist: Dist):
     for i in range(K):
         b = i % POOL
         t1 = time.perf_counter()
-        eng.predict_rows(h_rows[b * BATCH:(b + 1) * BATCH], np.float32, out_proba=h_proba[b * BATCH:(b + 1) * BATCH],
-                         out_label=h_label[b * BATCH:(b + 1) * BATCH])
+        eng.predict_pairs(h_rows[b * BATCH:(b + 1) * BATCH], out=h_out[b * BATCH:(b + 1) * BATCH])
         lat.append(time.perf_counter() - t1)
     e2e_s = time.perf_counter() - t0
     launches_e2e = eng.info()["launches"] - l0
     dist.barrier()
+    # the host-buffer path must return what the device-resident path computed for the same rows
+    got_dev = np.empty(n_pool, dtype=np.float32)
+    eng.d2h(got_dev, d_proba)
+    k_chk = min(K, POOL) * BATCH
+    e2e_parity = float(np.abs(h_out["proba1"][:k_chk].astype(np.float64) - got_dev[:k_chk]).max())
     e2e_s_max = dist.max(e2e_s)
     e2e_value = dist.world * BATCH * K / e2e_s_max
 
@@ -474,7 +478,8 @@ def run_b200(args, dist: Dist):
         },
         "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": BATCH * row_bytes, "d2h_bytes_per_step": BATCH * 8,
                 "ms_per_step": 1e3 * e2e_s_max / K, "p50_ms": 1e3 * float(np.percentile(lat, 50)), "p99_ms": 1e3 * float(np.percentile(lat, 99)),
-                "api": f"b2f_predict_ex(host pinned {row_bytes}-byte rows) -> float32 proba + int32 label", "pcie_h2d_gbs_one_batch": h2d_gbs},
+                "api": f"b2f_predict_pairs(host pinned {row_bytes}-byte rows) -> {{float32 proba, int32 label}} per row",
+                "parity_max_abs_dp_vs_device_path": e2e_parity, "pcie_h2d_gbs_one_batch": h2d_gbs},
         "gpu_launches": int(launches_value),
         "gpu_launches_e2e": int(launches_e2e),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

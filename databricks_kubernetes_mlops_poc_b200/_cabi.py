@@ -22,6 +22,7 @@ PACKED_ROW_WORDS = 16
 PACKED_ROW_BYTES = 64
 ROWS_WORDS24 = 0
 ROWS_PACKED64 = 1
+SCORED_DTYPE = np.dtype([("proba1", np.float32), ("label", np.int32)])  # b2f_scored
 MOMENT_VALUES = ROW_WORDS * 3
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -74,6 +75,7 @@ SIGNATURES = {
     "b2f_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "b2f_predict_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "b2f_predict_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "b2f_predict_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "b2f_predict_async_ex": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_uint64)],

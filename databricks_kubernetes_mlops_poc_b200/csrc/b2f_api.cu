@@ -131,6 +131,7 @@ struct b2f_model {
     int rows_per_warp_max = 2;
     int64_t chunk_rows = B2F_CHUNK_ROWS;
     int zero_copy = 0;
+    std::vector<int64_t> chunk_plan; /* per-chunk share of a batch in 1/1024ths */
     /* tile kernel (large batches) */
     bool tile_ok = false;
     TParams tp;
@@ -397,6 +398,15 @@ static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
     }
     const char *cr = getenv("B2F_CHUNK_ROWS"); /* tuning hook: rows per pipelined H2D/kernel/D2H chunk */
     if (cr && atoll(cr) >= 1024) m->chunk_rows = atoll(cr);
+    m->chunk_plan = {768}; /* measured best on B200 for 65 536-row batches: 3/4 of the batch, then the rest */
+    if (const char *pl = getenv("B2F_CHUNK_PLAN")) {
+        m->chunk_plan.clear();
+        for (const char *q = pl; *q;) {
+            m->chunk_plan.push_back(atoll(q));
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+    }
     const char *zc = getenv("B2F_ZERO_COPY");
     if (zc) m->zero_copy = atoi(zc);
     const char *rpw = getenv("B2F_ROWS_PER_WARP");
@@ -561,21 +571,21 @@ extern "C" void b2f_pinned_free(void *p) {
 
 /* ------------------------------------------------------------------ kernel launch */
 template <int R, bool SMEM, bool PACKED, typename OutT>
-static cudaError_t launch_one(const b2f_model *m, cudaStream_t st, const void *rows, int64_t n, void *proba, int32_t *label) {
+static cudaError_t launch_one(const b2f_model *m, cudaStream_t st, const void *rows, int64_t n, void *proba, int32_t *label, int ostride) {
     const int64_t n_batches = (n + R - 1) / R;
     int64_t ctas = std::min<int64_t>(m->sm_count, n_batches);
     if (ctas < 1) ctas = 1;
     k_forest_predict<R, SMEM, PACKED, OutT><<<(unsigned)ctas, B2F_PREDICT_THREADS, SMEM ? m->smem_bytes : 0, st>>>(
-        m->kp, static_cast<const uint32_t *>(rows), (long long)n, static_cast<OutT *>(proba), label);
+        m->kp, static_cast<const uint32_t *>(rows), (long long)n, static_cast<OutT *>(proba), label, ostride);
     return cudaGetLastError();
 }
 
 template <bool PACKED, typename OutT>
-static cudaError_t launch_tile(const b2f_model *m, cudaStream_t st, const void *rows, int64_t n, void *proba, int32_t *label) {
+static cudaError_t launch_tile(const b2f_model *m, cudaStream_t st, const void *rows, int64_t n, void *proba, int32_t *label, int ostride) {
     const int64_t n_tiles = (n + B2F_TILE_ROWS - 1) / B2F_TILE_ROWS;
     const unsigned ctas = (unsigned)std::max<int64_t>(1, std::min<int64_t>(m->sm_count, n_tiles));
     k_forest_predict_tile<PACKED, OutT><<<ctas, B2F_TILE_THREADS, m->tile_smem_bytes, st>>>(m->tp, static_cast<const uint32_t *>(rows), (long long)n,
-                                                                                           static_cast<OutT *>(proba), label);
+                                                                                           static_cast<OutT *>(proba), label, ostride);
     return cudaGetLastError();
 }
 
@@ -586,13 +596,14 @@ static int check_row_format(const b2f_model *m, int fmt) {
     return B2F_OK;
 }
 
-static int launch_predict(b2f_model *m, cudaStream_t st, const void *rows_dev, int64_t n, int fmt, void *proba_dev, int f64, int32_t *label_dev) {
+static int launch_predict(b2f_model *m, cudaStream_t st, const void *rows_dev, int64_t n, int fmt, void *proba_dev, int f64, int32_t *label_dev,
+                          int ostride = 1) {
     if (n <= 0) return B2F_OK;
     const bool pk = fmt == B2F_ROWS_PACKED64;
     cudaError_t e;
     if (m->tile_ok && n >= m->tile_min_rows) {
-        e = pk ? (f64 ? launch_tile<true, double>(m, st, rows_dev, n, proba_dev, label_dev) : launch_tile<true, float>(m, st, rows_dev, n, proba_dev, label_dev))
-               : (f64 ? launch_tile<false, double>(m, st, rows_dev, n, proba_dev, label_dev) : launch_tile<false, float>(m, st, rows_dev, n, proba_dev, label_dev));
+        e = pk ? (f64 ? launch_tile<true, double>(m, st, rows_dev, n, proba_dev, label_dev, ostride) : launch_tile<true, float>(m, st, rows_dev, n, proba_dev, label_dev, ostride))
+               : (f64 ? launch_tile<false, double>(m, st, rows_dev, n, proba_dev, label_dev, ostride) : launch_tile<false, float>(m, st, rows_dev, n, proba_dev, label_dev, ostride));
         if (e != cudaSuccess) return set_err(B2F_ECUDA, "k_forest_predict_tile launch failed: %s", cudaGetErrorString(e));
         m->launches++;
         m->launches_tile++;
@@ -601,8 +612,8 @@ static int launch_predict(b2f_model *m, cudaStream_t st, const void *rows_dev, i
     const int r = pick_rows_per_warp(m, n);
     const bool sm = m->walk_mode == B2F_WALK_SMEM;
 #define DISPATCH_T(RR, SM, PK)                                                                                      \
-    (f64 ? launch_one<RR, SM, PK, double>(m, st, rows_dev, n, proba_dev, label_dev)                                  \
-         : launch_one<RR, SM, PK, float>(m, st, rows_dev, n, proba_dev, label_dev))
+    (f64 ? launch_one<RR, SM, PK, double>(m, st, rows_dev, n, proba_dev, label_dev, ostride)                         \
+         : launch_one<RR, SM, PK, float>(m, st, rows_dev, n, proba_dev, label_dev, ostride))
 #define DISPATCH(RR) (sm ? (pk ? DISPATCH_T(RR, true, true) : DISPATCH_T(RR, true, false)) : (pk ? DISPATCH_T(RR, false, true) : DISPATCH_T(RR, false, false)))
     if (r == 4)
         e = DISPATCH(4);
@@ -660,7 +671,7 @@ static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, int fmt
     /* Zero-copy path: when every buffer is page-locked (b2f_pinned_alloc / cudaHostRegister), the kernel
      * reads the rows and writes the results straight over PCIe -- H2D, walk and D2H fused into one
      * launch, no copy-engine hand-offs.  mode 1: inputs only, mode 2: inputs and outputs. */
-    if (m->zero_copy > 0 && host_is_pinned(rows) && (m->zero_copy < 2 || ((!proba || host_is_pinned(proba)) && (!label || host_is_pinned(label))))) {
+    if (f64 != 2 && m->zero_copy > 0 && m->zero_copy < 3 && host_is_pinned(rows) && (m->zero_copy < 2 || ((!proba || host_is_pinned(proba)) && (!label || host_is_pinned(label))))) {
         Slot &sl = m->slots[0];
         if (m->zero_copy >= 2) {
             int rc = launch_predict(m, sl.stream, rows, n, fmt, proba, f64, label);
@@ -679,7 +690,7 @@ static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, int fmt
     }
     int64_t chunk = m->chunk_rows;
     if (n <= chunk + chunk / 2) chunk = n; /* small batch: one H2D, one launch */
-    const size_t psz = f64 ? sizeof(double) : sizeof(float);
+    const size_t psz = f64 == 1 ? sizeof(double) : sizeof(float);
     static const bool timeline = getenv("B2F_TIMELINE") != nullptr;
     std::vector<cudaEvent_t> tev;
     auto mark = [&](cudaStream_t st) {
@@ -689,9 +700,22 @@ static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, int fmt
         cudaEventRecord(e, st);
         tev.push_back(e);
     };
+    /* chunk schedule: equal chunks by default; a plan (B2F_CHUNK_PLAN="a,b,c": fractions of the batch in
+     * 1/1024ths, the last chunk takes the remainder) front-loads the copies so the un-overlapped tail --
+     * the last chunk's kernel and D2H -- is short */
+    const bool pairs = f64 == 2; /* proba points at {float proba; int32 label} records, label is ignored */
+    const bool zc_out = !pairs && m->zero_copy == 3 && (!proba || host_is_pinned(proba)) && (!label || host_is_pinned(label));
     int c = 0;
-    for (int64_t off = 0; off < n; off += chunk, ++c) {
-        const int64_t cnt = std::min(chunk, n - off);
+    for (int64_t off = 0; off < n; ++c) {
+        int64_t cnt = std::min(chunk, n - off);
+        if (!m->chunk_plan.empty() && chunk != n && n >= 2 * m->chunk_rows) {
+            cnt = (size_t)c < m->chunk_plan.size() ? std::max<int64_t>(1024, (n * m->chunk_plan[c] / 1024 + 1023) / 1024 * 1024) : n - off;
+            cnt = std::min(cnt, n - off);
+        }
+        struct Advance {
+            int64_t &o, d;
+            ~Advance() { o += d; }
+        } advance{off, cnt};
         Slot &sl = m->slots[c % B2F_STREAMS];
         int rc = slot_reserve(m, sl, cnt);
         if (rc) return rc;
@@ -699,12 +723,26 @@ static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, int fmt
         CUDA_TRY(cudaMemcpyAsync(sl.d_rows, static_cast<const uint8_t *>(rows) + (size_t)off * row_bytes, (size_t)cnt * row_bytes,
                                  cudaMemcpyHostToDevice, sl.stream));
         mark(sl.stream);
-        rc = launch_predict(m, sl.stream, sl.d_rows, cnt, fmt, proba ? sl.d_proba : nullptr, f64, label ? sl.d_label : nullptr);
+        /* results: the tile kernel stores one coalesced 128-byte line per warp and array, so with pinned
+         * outputs it can write them straight to host memory (no D2H copy, no copy-engine hand-off) */
+        const bool direct = zc_out && m->tile_ok && cnt >= m->tile_min_rows;
+        void *k_proba = !proba ? nullptr : (direct ? static_cast<uint8_t *>(proba) + (size_t)off * psz : sl.d_proba);
+        int32_t *k_label = !label ? nullptr : (direct ? label + off : sl.d_label);
+        if (pairs) { /* one interleaved device buffer, ONE D2H copy per chunk */
+            rc = launch_predict(m, sl.stream, sl.d_rows, cnt, fmt, sl.d_proba, 0, static_cast<int32_t *>(sl.d_proba) + 1, 2);
+            if (rc) return rc;
+            mark(sl.stream);
+            CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(proba) + (size_t)off * 8, sl.d_proba, (size_t)cnt * 8, cudaMemcpyDeviceToHost, sl.stream));
+            mark(sl.stream);
+            *used_mask |= 1u << (c % B2F_STREAMS);
+            continue;
+        }
+        rc = launch_predict(m, sl.stream, sl.d_rows, cnt, fmt, k_proba, f64, k_label);
         if (rc) return rc;
         mark(sl.stream);
-        if (proba)
+        if (proba && !direct)
             CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(proba) + (size_t)off * psz, sl.d_proba, (size_t)cnt * psz, cudaMemcpyDeviceToHost, sl.stream));
-        if (label) CUDA_TRY(cudaMemcpyAsync(label + off, sl.d_label, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
+        if (label && !direct) CUDA_TRY(cudaMemcpyAsync(label + off, sl.d_label, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
         mark(sl.stream);
         *used_mask |= 1u << (c % B2F_STREAMS);
     }
@@ -743,7 +781,11 @@ extern "C" int b2f_predict_f64(b2f_model *m, const void *rows, int64_t n, double
     return predict_host(m, rows, n, B2F_ROWS_WORDS24, proba1, 1, label);
 }
 extern "C" int b2f_predict_ex(b2f_model *m, const void *rows, int64_t n, int row_format, void *proba1, int proba_is_f64, int32_t *label) {
-    return predict_host(m, rows, n, row_format, proba1, proba_is_f64, label);
+    return predict_host(m, rows, n, row_format, proba1, proba_is_f64 ? 1 : 0, label);
+}
+extern "C" int b2f_predict_pairs(b2f_model *m, const void *rows, int64_t n, int row_format, b2f_scored *out) {
+    if (!out && n > 0) return set_err(B2F_EINVAL, "out is NULL");
+    return predict_host(m, rows, n, row_format, out, 2, nullptr);
 }
 
 extern "C" int b2f_predict_async(b2f_model *m, const void *rows_pinned, int64_t n, void *proba1_pinned, int proba_is_f64,

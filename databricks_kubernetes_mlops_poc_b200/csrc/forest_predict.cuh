@@ -166,7 +166,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 /* aggregate -> (probability, label) for one row per lane; rows < 0 are empty slots */
 template <typename OutT>
 __device__ __forceinline__ void finalize_store(const KParams &p, double s, long long row, OutT *__restrict__ proba,
-                                               int32_t *__restrict__ label) {
+                                               int32_t *__restrict__ label, int ostride) {
     if (row < 0) return;
     double p1;
     int lab;
@@ -178,8 +178,8 @@ __device__ __forceinline__ void finalize_store(const KParams &p, double s, long 
         p1 = 1.0 / (1.0 + exp(-raw)); /* expit */
         lab = raw >= 0.0;
     }
-    if (proba) proba[row] = (OutT)p1;
-    if (label) label[row] = lab;
+    if (proba) proba[row * ostride] = (OutT)p1; /* ostride 2: interleaved {float proba, int32 label} pairs */
+    if (label) label[row * ostride] = lab;
 }
 
 /* ---------------------------------------------------------------- the kernel */
@@ -220,7 +220,7 @@ __device__ __forceinline__ void walk_group(typename AddrOf<SMEM>::type a_first, 
 template <int R, bool SMEM, bool PACKED, typename OutT>
 __global__ void __launch_bounds__(B2F_PREDICT_THREADS, 1)
     k_forest_predict(const __grid_constant__ KParams p, const uint32_t *__restrict__ rows, long long n,
-                     OutT *__restrict__ proba, int32_t *__restrict__ label) {
+                     OutT *__restrict__ proba, int32_t *__restrict__ label, int ostride) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[B2F_MAX_GROUPS];
     /* per group: {node area, leaf area, depth}: shared-window addresses (SMEM) or byte offsets from
@@ -353,13 +353,13 @@ __global__ void __launch_bounds__(B2F_PREDICT_THREADS, 1)
                 pend_row = row < n ? row : -1;
             }
             if (++pend_n == 32) {
-                finalize_store(p, pend_sum, pend_row, proba, label);
+                finalize_store(p, pend_sum, pend_row, proba, label, ostride);
                 pend_n = 0;
                 pend_row = -1;
             }
         }
     }
-    if (pend_n > 0) finalize_store(p, pend_sum, pend_row, proba, label);
+    if (pend_n > 0) finalize_store(p, pend_sum, pend_row, proba, label, ostride);
 
     if constexpr (SMEM) {
         /* never retire a CTA while a bulk copy into its shared memory is still in flight */

@@ -151,7 +151,7 @@ __device__ __forceinline__ void tile_walk_ugroup(uint32_t piece_addr, uint32_t u
 template <bool PACKED, typename OutT>
 __global__ void __launch_bounds__(B2F_TILE_THREADS, 1)
     k_forest_predict_tile(const __grid_constant__ TParams p, const uint32_t *__restrict__ rows, long long n,
-                          OutT *__restrict__ proba, int32_t *__restrict__ label) {
+                          OutT *__restrict__ proba, int32_t *__restrict__ label, int ostride) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[B2F_TILE_MAX_SLOTS];
     __shared__ __align__(8) uint64_t empty_bar[B2F_TILE_MAX_SLOTS];
@@ -294,8 +294,8 @@ __global__ void __launch_bounds__(B2F_TILE_THREADS, 1)
                 p1 = 1.0 / (1.0 + exp(-raw));
                 lab = raw >= 0.0;
             }
-            if (proba) proba[row] = (OutT)p1;
-            if (label) label[row] = lab;
+            if (proba) proba[row * ostride] = (OutT)p1;
+            if (label) label[row * ostride] = lab;
         }
     }
 }

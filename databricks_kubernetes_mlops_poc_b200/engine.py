@@ -97,6 +97,15 @@ class ForestEngine:
         check(self._lib.b2f_predict_ex(self._h, ptr(rows), n, fmt, ptr(proba), int(f64), ptr(label)), "b2f_predict_ex")
         return proba, label
 
+    def predict_pairs(self, rows: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """Encoded rows -> structured array of (proba1 float32, label int32), one D2H copy per chunk."""
+        rows = np.ascontiguousarray(rows)
+        n = rows.shape[0]
+        if out is None:
+            out = np.empty(n, dtype=_cabi.SCORED_DTYPE)
+        check(self._lib.b2f_predict_pairs(self._h, ptr(rows), n, _row_format(rows), ptr(out)), "b2f_predict_pairs")
+        return out
+
     def predict_rows_async(self, rows: np.ndarray, proba: np.ndarray, label: np.ndarray | None) -> int:
         """Pinned buffers in, ticket out; pair with wait()."""
         t = C.c_uint64(0)

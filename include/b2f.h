@@ -72,6 +72,13 @@ extern "C" {
 typedef struct b2f_model b2f_model;
 typedef uint64_t b2f_ticket;
 
+/* one scored row, for b2f_predict_pairs: both results of a row side by side, so a chunk comes back in
+ * ONE device-to-host copy instead of two */
+typedef struct b2f_scored {
+    float proba1;  /* P(class 1) */
+    int32_t label; /* hard class label */
+} b2f_scored;
+
 typedef struct b2f_info {
     int32_t device;
     int32_t sm_count;
@@ -126,6 +133,9 @@ int b2f_predict_f64(b2f_model *m, const void *rows, int64_t n, double *proba1, i
 /* same, with an explicit row format and output type */
 int b2f_predict_ex(b2f_model *m, const void *rows, int64_t n, int row_format, void *proba1,
                    int proba_is_f64, int32_t *label);
+
+/* both outputs interleaved per row (one D2H copy per pipelined chunk) */
+int b2f_predict_pairs(b2f_model *m, const void *rows, int64_t n, int row_format, b2f_scored *out);
 
 /* asynchronous form for the request-batching ring: buffers must be pinned and stay valid until
  * b2f_wait(ticket) returns.  proba_is_f64 selects double (1) or float (0) outputs. */

@@ -391,3 +391,21 @@ def test_packed_rows_give_identical_results(curated, adversarial, rf100d6, gbdt_
                 eng.close()
     finally:
         os.environ.pop("B2F_KERNEL")
+
+
+def test_pairs_output_and_chunk_plan(curated, rf100d6):
+    """b2f_predict_pairs ({proba, label} interleaved, one D2H per chunk) == the two-array path, for batch
+    sizes on every side of the chunk-plan thresholds."""
+    from databricks_kubernetes_mlops_poc_b200 import training
+
+    eng, enc = _engine(rf100d6)
+    try:
+        _, codes, nums = training.synth_arrays(curated, 70001, seed=5)
+        rows = enc.encode_arrays_packed(codes, nums)
+        for n in (0, 1, 1000, 16384, 24576, 24577, 32767, 32768, 65536, 70001):
+            p, l = eng.predict_rows(rows[:n], np.float32)
+            out = eng.predict_pairs(rows[:n])
+            assert out.shape == (n,)
+            assert (out["proba1"] == p).all() and (out["label"] == l).all()
+    finally:
+        eng.close()
