@@ -285,9 +285,12 @@ static bool build_tile_layout(const uint8_t *blob, const b2f_blob_header &h, uin
         ugs.push_back(u);
         total += u.bytes;
     }
-    /* piece size: resident if everything fits (<= 8 pieces), else ~32 KB pieces streamed through the ring */
-    const bool fits = total + 128 * B2F_TILE_MAX_SLOTS <= avail_smem;
-    uint32_t target = fits ? (uint32_t)((total + B2F_TILE_MAX_SLOTS - 1) / B2F_TILE_MAX_SLOTS) + 64 : 32u * 1024u;
+    /* piece size: if everything fits the ring, cut it into at most B2F_TILE_MAX_SLOTS pieces (resident: loaded
+     * once per CTA, and walking starts when the first piece lands); otherwise ~32 KB pieces streamed through */
+    uint32_t max_ug = 0;
+    for (const UG &u : ugs) max_ug = std::max(max_ug, u.bytes);
+    const bool fits = total + (uint64_t)(max_ug + 128) * B2F_TILE_MAX_SLOTS <= avail_smem;
+    uint32_t target = fits ? (uint32_t)((total + B2F_TILE_MAX_SLOTS - 1) / B2F_TILE_MAX_SLOTS) + max_ug : 32u * 1024u;
     layout.clear();
     pieces.clear();
     size_t i = 0;
@@ -463,7 +466,8 @@ static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
     for (int s = 0; s < B2F_STREAMS; ++s) CUDA_TRY(cudaStreamCreateWithFlags(&m->slots[s].stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&m->compute, cudaStreamNonBlocking));
 
-    m->mom_blocks = m->sm_count * 3; /* one full wave: 3 CTAs of 384 threads per SM (registers / 40 KB smem) */
+    CUDA_TRY(cudaFuncSetAttribute(k_feature_moments, cudaFuncAttributeMaxDynamicSharedMemorySize, B2F_MOM_SMEM));
+    m->mom_blocks = m->sm_count * 3; /* one full wave: 3 CTAs (3-stage 72 KB ring each) per SM */
     CUDA_TRY(cudaMalloc(&m->d_mom_partials, (size_t)m->mom_blocks * B2F_MOM_VALUES * sizeof(double)));
     CUDA_TRY(cudaMalloc(&m->d_mom_ticket, sizeof(unsigned int)));
     CUDA_TRY(cudaMemset(m->d_mom_ticket, 0, sizeof(unsigned int)));
@@ -974,10 +978,13 @@ extern "C" int b2f_predict_stream_timed_ex(b2f_model *m, const void *rows_dev, i
 
 /* ------------------------------------------------------------------ moments */
 static int launch_moments(b2f_model *m, const void *rows_dev, int64_t n) {
-    int64_t blocks = std::min<int64_t>(m->mom_blocks, (n + B2F_MOM_ROWS_PER_BLOCK - 1) / B2F_MOM_ROWS_PER_BLOCK);
+    /* one CTA per 256-row slab up to a full wave of 3 CTAs per SM; small inputs get fewer CTAs so the
+     * fixed-order final reduction over block partials stays short */
+    const int64_t n_slabs = (n + B2F_MOM_SLAB_ROWS - 1) / B2F_MOM_SLAB_ROWS;
+    int64_t blocks = std::min<int64_t>(m->mom_blocks, std::max<int64_t>(std::min<int64_t>(n_slabs, m->sm_count), n_slabs / 4));
     if (blocks < 1) blocks = 1;
-    k_feature_moments<<<(unsigned)blocks, B2F_MOM_THREADS, 0, m->compute>>>(static_cast<const uint4 *>(rows_dev), (long long)n, (int)m->hdr.n_cat,
-                                                                           m->d_mom_partials, m->d_mom_ticket, m->d_mom_out);
+    k_feature_moments<<<(unsigned)blocks, B2F_MOM_THREADS, B2F_MOM_SMEM, m->compute>>>(static_cast<const uint4 *>(rows_dev), (long long)n,
+                                                                                     (int)m->hdr.n_cat, m->d_mom_partials, m->d_mom_ticket, m->d_mom_out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_err(B2F_ECUDA, "k_feature_moments launch failed: %s", cudaGetErrorString(e));
     m->launches++;

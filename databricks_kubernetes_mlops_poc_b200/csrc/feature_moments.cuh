@@ -6,13 +6,18 @@
  * (reference databricks/src/02-register-model.ipynb:338).  This is a pure HBM-bound streaming
  * reduction: 96 B read per row, 24*3 float64 written per launch.
  *
- * Mapping: a row is six 16-byte vectors; thread t reads vector t%6 of row t/6 of its slab, so a warp
- * reads 512 contiguous bytes per load (LDG.128, fully coalesced).  Each thread keeps shifted sums
- * sum(x-K), sum((x-K)^2) and a count for its four words in float64 (K = the word's value in row 0,
- * read by every thread; the shift removes the catastrophic cancellation of the raw sum-of-squares
- * form).  Block partials are reduced through shared memory in a fixed order, written to global
- * memory, and the last block to finish (atomic ticket) reduces the partials in a fixed order, so the
- * result is deterministic.  NaN values are skipped (count is per word).
+ * Structure: a TMA-fed shared-memory ring per CTA.  A producer warp streams 256-row slabs (24 KB,
+ * contiguous) with cp.async.bulk + mbarrier complete_tx into a 3-stage ring; 12 consumer warps read
+ * their 16-byte vector of each row from shared memory (thread t owns vector t%6 of rows t/6 + 64 i, so
+ * its four words -- and its accumulators -- never change).  Memory-level parallelism therefore comes
+ * from the ring (3 CTAs x 3 stages x 24 KB = 216 KB in flight per SM), not from registers: a first
+ * version that relied on unrolled LDG.128 got one or two loads in flight per warp from ptxas and
+ * stalled on the long scoreboard at 2.7 TB/s.
+ * Arithmetic: shifted float64 sums sum(x-K), sum((x-K)^2) and an integer count per word (K = the word's
+ * value in row 0; the shift removes the cancellation of the raw sum-of-squares form), branch-free (a
+ * NaN contributes d = 0, count 0).  Block partials are reduced through shared memory in a fixed order,
+ * written to global memory, and the last block to finish (atomic ticket) reduces the partials in a fixed
+ * order, so the result is deterministic.
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -20,69 +25,133 @@
 
 #include "../../include/b2f.h"
 
+#include "forest_predict.cuh" /* mbarrier / TMA helpers */
+
 #define B2F_MOM_ROWS_PER_BLOCK 64
-#define B2F_MOM_THREADS (B2F_MOM_ROWS_PER_BLOCK * 6)
+#define B2F_MOM_CONSUMERS (B2F_MOM_ROWS_PER_BLOCK * 6) /* 384 consumer threads = 12 warps */
+#define B2F_MOM_THREADS (B2F_MOM_CONSUMERS + 32)       /* + 1 producer warp */
 #define B2F_MOM_VALUES (B2F_ROW_WORDS * 3)
+#define B2F_MOM_SLAB_ROWS 256
+#define B2F_MOM_SLAB_BYTES (B2F_MOM_SLAB_ROWS * B2F_ROW_BYTES) /* 24 576 */
+#define B2F_MOM_STAGES 3
+#define B2F_MOM_SMEM (B2F_MOM_STAGES * B2F_MOM_SLAB_BYTES)     /* 73 728 B dynamic */
 
 __device__ __forceinline__ double mom_word_value(uint32_t w, int word, int n_cat) {
     return word < n_cat ? (double)(int32_t)w : (double)__uint_as_float(w);
 }
 
-__global__ void __launch_bounds__(B2F_MOM_THREADS)
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(B2F_MOM_THREADS, 3)
     k_feature_moments(const uint4 *__restrict__ rows, long long n, int n_cat, double *__restrict__ partials,
                       unsigned int *__restrict__ ticket, double *__restrict__ out) {
-    __shared__ double red[B2F_MOM_THREADS][12 + 1];
+    extern __shared__ __align__(128) uint8_t ring[]; /* B2F_MOM_STAGES slabs; reused as `red` at the end */
+    __shared__ __align__(8) uint64_t full_bar[B2F_MOM_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[B2F_MOM_STAGES];
     __shared__ double tot[B2F_MOM_VALUES];
+    __shared__ double tot_seg[4][B2F_MOM_VALUES];
     __shared__ bool is_last;
+    double(*red)[12 + 1] = reinterpret_cast<double(*)[12 + 1]>(ring); /* [384][13] doubles = 39 936 B */
 
-    const int q = threadIdx.x % 6;  /* which 16-byte vector of the row */
-    const int rr = threadIdx.x / 6; /* row within the slab */
-
-    /* pivot: row 0's values (NaN -> 0) */
-    double K[4];
-    {
-        const uint4 v0 = n > 0 ? __ldg(rows + q) : make_uint4(0, 0, 0, 0);
-        const uint32_t w0[4] = {v0.x, v0.y, v0.z, v0.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const double x = mom_word_value(w0[k], q * 4 + k, n_cat);
-            K[k] = (x == x) ? x : 0.0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < B2F_MOM_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], B2F_MOM_CONSUMERS / 32);
         }
-    }
-
-    double cnt[4] = {0, 0, 0, 0}, s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
-    const long long stride = (long long)gridDim.x * B2F_MOM_ROWS_PER_BLOCK;
-#pragma unroll 4
-    for (long long row = (long long)blockIdx.x * B2F_MOM_ROWS_PER_BLOCK + rr; row < n; row += stride) {
-        const uint4 v = __ldg(rows + row * 6 + q);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const double x = mom_word_value(w[k], q * 4 + k, n_cat);
-            if (x == x) {
-                const double d = x - K[k];
-                cnt[k] += 1.0;
-                s[k] += d;
-                ss[k] = fma(d, d, ss[k]);
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        red[threadIdx.x][k * 3 + 0] = cnt[k];
-        red[threadIdx.x][k * 3 + 1] = s[k];
-        red[threadIdx.x][k * 3 + 2] = ss[k];
+        fence_mbar_init();
+        fence_proxy_async();
     }
     __syncthreads();
 
-    /* 72 threads: (word, component) -> fixed-order sum over the 64 row lanes */
-    if (threadIdx.x < B2F_MOM_VALUES) {
-        const int word = threadIdx.x / 3, comp = threadIdx.x % 3;
+    const long long n_slabs = (n + B2F_MOM_SLAB_ROWS - 1) / B2F_MOM_SLAB_ROWS;
+    const long long my_slabs = blockIdx.x < n_slabs ? (n_slabs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == B2F_MOM_CONSUMERS / 32) {
+        /* ===== producer warp: one lane feeds the ring with TMA bulk copies ===== */
+        if (lane == 0) {
+            for (long long k = 0; k < my_slabs; ++k) {
+                const int st = (int)(k % B2F_MOM_STAGES);
+                const long long j = k / B2F_MOM_STAGES;
+                if (j > 0) mbar_wait(&empty_bar[st], (uint32_t)((j - 1) & 1));
+                const long long slab = blockIdx.x + k * gridDim.x;
+                const long long r0 = slab * B2F_MOM_SLAB_ROWS;
+                const uint32_t bytes = (uint32_t)(min((long long)B2F_MOM_SLAB_ROWS, n - r0) * B2F_ROW_BYTES);
+                mbar_arrive_expect_tx(&full_bar[st], bytes);
+                tma_bulk_g2s(ring + st * B2F_MOM_SLAB_BYTES, reinterpret_cast<const uint8_t *>(rows) + r0 * B2F_ROW_BYTES, bytes, &full_bar[st]);
+            }
+        }
+    } else {
+        /* ===== consumer warps ===== */
+        const int q = threadIdx.x % 6; /* which 16-byte vector of the row: fixed per thread */
+        double K[4];
+        {
+            const uint4 v0 = n > 0 ? __ldg(rows + q) : make_uint4(0, 0, 0, 0);
+            const uint32_t w0[4] = {v0.x, v0.y, v0.z, v0.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double x = mom_word_value(w0[k], q * 4 + k, n_cat);
+                K[k] = (x == x) ? x : 0.0;
+            }
+        }
+        unsigned int cnt[4] = {0, 0, 0, 0};
+        double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+        const bool is_cat[4] = {q * 4 + 0 < n_cat, q * 4 + 1 < n_cat, q * 4 + 2 < n_cat, q * 4 + 3 < n_cat};
+        for (long long k = 0; k < my_slabs; ++k) {
+            const int st = (int)(k % B2F_MOM_STAGES);
+            mbar_wait(&full_bar[st], (uint32_t)((k / B2F_MOM_STAGES) & 1));
+            const long long r0 = (blockIdx.x + k * gridDim.x) * B2F_MOM_SLAB_ROWS;
+            const int vecs = (int)(min((long long)B2F_MOM_SLAB_ROWS, n - r0) * 6);
+            const uint4 *slab = reinterpret_cast<const uint4 *>(ring + st * B2F_MOM_SLAB_BYTES);
+#pragma unroll
+            for (int i = 0; i < B2F_MOM_SLAB_ROWS * 6 / B2F_MOM_CONSUMERS; ++i) {
+                const int idx = i * B2F_MOM_CONSUMERS + threadIdx.x; /* idx % 6 == q */
+                if (idx < vecs) {
+                    const uint4 v = slab[idx];
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float xf = __uint_as_float(w[c]);
+                        const bool ok = is_cat[c] || (xf == xf);
+                        const double x = is_cat[c] ? (double)(int32_t)w[c] : (double)xf;
+                        const double d = ok ? x - K[c] : 0.0;
+                        cnt[c] += ok ? 1u : 0u;
+                        s[c] += d;
+                        ss[c] = fma(d, d, ss[c]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta(&empty_bar[st]);
+        }
+        /* `red` aliases the ring: every consumer must be done reading slabs before anyone overwrites it */
+        asm volatile("bar.sync 1, %0;" ::"n"(B2F_MOM_CONSUMERS) : "memory");
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            red[threadIdx.x][k * 3 + 0] = (double)cnt[k];
+            red[threadIdx.x][k * 3 + 1] = s[k];
+            red[threadIdx.x][k * 3 + 2] = ss[k];
+        }
+    }
+    __syncthreads();
+
+    /* (word, component) -> fixed-order sum over the 64 row lanes, in 4 segments of 16 so 288 threads
+     * share the latency-bound chain; the 4 segment sums are then added in order */
+    if (threadIdx.x < 4 * B2F_MOM_VALUES) {
+        const int v = threadIdx.x % B2F_MOM_VALUES, sg = threadIdx.x / B2F_MOM_VALUES;
+        const int word = v / 3, comp = v % 3;
         const int wq = word / 4, wk = word % 4;
         double a = 0.0;
-        for (int r = 0; r < B2F_MOM_ROWS_PER_BLOCK; ++r) a += red[r * 6 + wq][wk * 3 + comp];
-        partials[(size_t)blockIdx.x * B2F_MOM_VALUES + threadIdx.x] = a;
+#pragma unroll 4
+        for (int r = sg * 16; r < sg * 16 + 16; ++r) a += red[r * 6 + wq][wk * 3 + comp];
+        tot_seg[sg][v] = a;
     }
+    __syncthreads();
+    if (threadIdx.x < B2F_MOM_VALUES)
+        partials[(size_t)blockIdx.x * B2F_MOM_VALUES + threadIdx.x] =
+            ((tot_seg[0][threadIdx.x] + tot_seg[1][threadIdx.x]) + tot_seg[2][threadIdx.x]) + tot_seg[3][threadIdx.x];
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
