@@ -141,6 +141,8 @@ struct b2f_model {
     int64_t tile_min_rows = 32768;
     int64_t tile_layout_bytes = 0;
     int64_t launches_tile = 0;
+    int64_t launches_split = 0;
+    int64_t split_max_rows = 0;
     bool packed_ok = false;
     void *d_blob = nullptr;
     int64_t forest_bytes = 0;
@@ -346,6 +348,11 @@ static bool build_tile_layout(const uint8_t *blob, const b2f_blob_header &h, uin
     return true;
 }
 
+static bool kn_env_is(const char *v) {
+    const char *kn = getenv("B2F_KERNEL");
+    return kn && !strcmp(kn, v);
+}
+
 static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
     CUDA_TRY(cudaSetDevice(m->device));
     cudaDeviceProp prop;
@@ -412,6 +419,11 @@ static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
     }
     const char *zc = getenv("B2F_ZERO_COPY");
     if (zc) m->zero_copy = atoi(zc);
+    /* latency kernel: while rows x groups warps still fit about two waves of the chip */
+    m->split_max_rows = std::max<int64_t>(2, (int64_t)m->sm_count * 64 / std::max(1, (int)m->hdr.n_groups));
+    if (const char *sp = getenv("B2F_SPLIT_MAX_ROWS")) m->split_max_rows = atoll(sp);
+    if (kn_env_is("warp") || kn_env_is("tile")) m->split_max_rows = 0; /* tests pin one kernel */
+    if (kn_env_is("split")) m->split_max_rows = INT64_MAX;
     const char *rpw = getenv("B2F_ROWS_PER_WARP");
     m->rows_per_warp_max = 2;
     if (rpw) {
@@ -556,6 +568,8 @@ extern "C" int b2f_model_info(const b2f_model *m, b2f_info *out) {
     out->tile_ok = m->tile_ok ? 1 : 0;
     out->tile_resident = (m->tile_ok && m->tp.n_pieces <= m->tp.n_slots) ? 1 : 0;
     out->packed_ok = m->packed_ok ? 1 : 0;
+    out->launches_split = m->launches_split;
+    out->split_max_rows = m->split_max_rows;
     return B2F_OK;
 }
 
@@ -593,6 +607,15 @@ static cudaError_t launch_tile(const b2f_model *m, cudaStream_t st, const void *
     return cudaGetLastError();
 }
 
+template <bool PACKED, typename OutT>
+static cudaError_t launch_split(const b2f_model *m, cudaStream_t st, const void *rows, int64_t n, void *proba, int32_t *label, int ostride) {
+    constexpr int R = 2;
+    const unsigned ctas = (unsigned)((n + R - 1) / R);
+    k_forest_predict_split<R, PACKED, OutT><<<ctas, 32u * (unsigned)m->kp.n_groups, 0, st>>>(m->kp, static_cast<const uint32_t *>(rows), (long long)n,
+                                                                                            static_cast<OutT *>(proba), label, ostride);
+    return cudaGetLastError();
+}
+
 static int check_row_format(const b2f_model *m, int fmt) {
     if (fmt == B2F_ROWS_WORDS24) return B2F_OK;
     if (fmt != B2F_ROWS_PACKED64) return set_err(B2F_EINVAL, "unknown row format %d", fmt);
@@ -611,6 +634,14 @@ static int launch_predict(b2f_model *m, cudaStream_t st, const void *rows_dev, i
         if (e != cudaSuccess) return set_err(B2F_ECUDA, "k_forest_predict_tile launch failed: %s", cudaGetErrorString(e));
         m->launches++;
         m->launches_tile++;
+        return B2F_OK;
+    }
+    if (n <= m->split_max_rows) { /* a handful of rows: spread each row's tree groups over the warps of a CTA */
+        e = pk ? (f64 ? launch_split<true, double>(m, st, rows_dev, n, proba_dev, label_dev, ostride) : launch_split<true, float>(m, st, rows_dev, n, proba_dev, label_dev, ostride))
+               : (f64 ? launch_split<false, double>(m, st, rows_dev, n, proba_dev, label_dev, ostride) : launch_split<false, float>(m, st, rows_dev, n, proba_dev, label_dev, ostride));
+        if (e != cudaSuccess) return set_err(B2F_ECUDA, "k_forest_predict_split launch failed: %s", cudaGetErrorString(e));
+        m->launches++;
+        m->launches_split++;
         return B2F_OK;
     }
     const int r = pick_rows_per_warp(m, n);

@@ -367,3 +367,64 @@ __global__ void __launch_bounds__(B2F_PREDICT_THREADS, 1)
             if (!((ready >> g) & 1u)) mbar_wait(&bars[g], 0);
     }
 }
+
+
+/* ---------------------------------------------------------------- small batches: groups across warps
+ * k_forest_predict_split: the latency form of the warp-per-row kernel.  For a handful of rows the
+ * dependent chain -- groups x depth node visits per row -- is what the caller waits for, so the tree
+ * GROUPS of one row go to different warps of one CTA (blockDim = 32 * n_groups, one CTA per R rows):
+ * every warp walks one group straight from global memory / L2 (no shared-memory fill of a forest that a
+ * few rows would not amortise), lane sums are reduced with shuffles, the per-group sums meet in shared
+ * memory and are added in group order (deterministic), then finalised.  500 trees x depth 8: the chain
+ * drops from 16 x 9 dependent loads to 9. */
+template <int R, bool PACKED, typename OutT>
+__global__ void __launch_bounds__(1024, 1)
+    k_forest_predict_split(const __grid_constant__ KParams p, const uint32_t *__restrict__ rows, long long n,
+                           OutT *__restrict__ proba, int32_t *__restrict__ label, int ostride) {
+    __shared__ double part[B2F_MAX_GROUPS][R];
+    const int lane = threadIdx.x & 31;
+    const int g = threadIdx.x >> 5; /* this warp's tree group */
+    const long long b = blockIdx.x;
+    const bool lane_numeric = lane >= p.n_cat && lane < p.n_cat + p.n_num;
+    const uint32_t impute_bits = lane < 24 ? __float_as_uint(p.impute[lane]) : 0u;
+    const uint32_t lane8 = (uint32_t)lane * 8u;
+
+    uint32_t w[R];
+    double acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const long long row = b * R + r;
+        uint32_t v = B2F_SENTINEL_BITS;
+        if constexpr (PACKED) {
+            if (row < n && lane < B2F_PACKED_ROW_WORDS) v = __ldg(rows + row * B2F_PACKED_ROW_WORDS + lane);
+            const uint32_t lo = __shfl_sync(0xffffffffu, v, 0), hi = __shfl_sync(0xffffffffu, v, 1);
+            const uint32_t num = __shfl_sync(0xffffffffu, v, (lane - 7) & 31);
+            const uint32_t field = (uint32_t)(((((unsigned long long)hi) << 32) | lo) >> (7 * (lane < 9 ? lane : 0))) & 0x7fu;
+            v = row < n ? (lane < 9 ? field - 1u : (lane < (int)B2F_SENTINEL_WORD ? num : B2F_SENTINEL_BITS)) : B2F_SENTINEL_BITS;
+        } else {
+            if (row < n && lane < (int)B2F_SENTINEL_WORD) v = __ldg(rows + row * B2F_ROW_WORDS + lane);
+        }
+        if (lane_numeric && isnan(__uint_as_float(v))) v = impute_bits;
+        w[r] = v;
+        acc[r] = 0.0;
+    }
+    {
+        const KGroup gd = p.g[g];
+        const uint64_t nodes = reinterpret_cast<uint64_t>(p.chunks) + gd.chunk_off + lane8;
+        const uint64_t leaves = nodes + (uint64_t)gd.n_slots * B2F_NODE_STRIDE;
+        walk_group<R, false, 0>(nodes, leaves, (int)gd.depth, w, acc);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const double s = warp_sum(acc[r]);
+        if (lane == 0) part[g][r] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < R) {
+        const int r = threadIdx.x;
+        double s = 0.0;
+        for (int k = 0; k < p.n_groups; ++k) s += part[k][r]; /* group order: deterministic */
+        const long long row = b * R + r;
+        finalize_store(p, s, row < n ? row : -1, proba, label, ostride);
+    }
+}

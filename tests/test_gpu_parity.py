@@ -409,3 +409,29 @@ def test_pairs_output_and_chunk_plan(curated, rf100d6):
             assert (out["proba1"] == p).all() and (out["label"] == l).all()
     finally:
         eng.close()
+
+
+def test_split_kernel_small_batches(curated, adversarial, rf100d6, rf500d8, gbdt_small):
+    """The latency kernel (tree groups of a row across the warps of a CTA, walked from global memory)."""
+    from oracle import reference_pipeline as rp
+
+    for pipe in (rf100d6, rf500d8, gbdt_small):
+        _check(pipe, [curated.iloc[:777], adversarial], kernel="split")
+    for params in (dict(n_estimators=1, max_depth=1, random_state=0), dict(n_estimators=999, max_depth=3, random_state=0),
+                   dict(n_estimators=40, max_depth=20, random_state=0)):
+        pipe = rp.fit_reference_pipeline(curated.iloc[:2500], params)
+        _check(pipe, [curated.iloc[2500:2700], adversarial.iloc[:64]], kernel="split")
+    # default selection: tiny batches -> split kernel, and it agrees with the warp kernel
+    eng, enc = _engine(rf500d8)
+    try:
+        rows = enc.encode_frame(curated.iloc[:300])
+        want_p, want_l = rp.oracle_predict(rf500d8, curated.iloc[:300])
+        for n in (1, 2, 3, 16, 256, 300):
+            before = eng.info()["launches_split"]
+            p, l = eng.predict_rows(rows[:n], np.float64)
+            assert eng.info()["launches_split"] == before + 1
+            assert np.abs(p - want_p[:n]).max() <= TOL64 and (l == want_l[:n]).all()
+            out = eng.predict_pairs(enc.pack_rows(rows[:n]))
+            assert np.abs(out["proba1"] - want_p[:n]).max() <= TOL32 and (out["label"] == want_l[:n]).all()
+    finally:
+        eng.close()
