@@ -490,6 +490,8 @@ def run_b200(args, dist: Dist):
         "sustained_rows_per_s": sustained,
         "parity_max_abs_dp_vs_sklearn_2048rows": parity,
     }
+    if args.sweep and dist.rank == 0:
+        line["latency_sweep"] = latency_sweep(args, dist)
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if mom is not None:
@@ -501,6 +503,53 @@ def run_b200(args, dist: Dist):
         print(json.dumps(line))
 
 
+def latency_sweep(args, dist: Dist):
+    """BASELINE config 3: batch in {1, 16, 256, 4096, 65536}, 500-tree depth-8 model; p50 / p99 of the C-ABI
+    call (pinned host buffers, H2D + kernel + D2H inside) and of the plugin call model.predict(DataFrame) -> dict."""
+    from databricks_kubernetes_mlops_poc_b200 import flatten, training
+    from databricks_kubernetes_mlops_poc_b200._cabi import SCORED_DTYPE
+    from databricks_kubernetes_mlops_poc_b200.model import B200Model
+    from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES
+
+    name = args.sweep_model
+    pipe, base = get_pipeline(name, dist)
+    model = B200Model(flatten.flatten_pipeline(pipe), devices=[dist.local_rank])
+    eng, enc = model.engine, model.encoder
+    n_max = 65536
+    vocabs, codes, nums = training.synth_arrays(base, n_max, DATA_SEED + 1)
+    pk = eng.pinned("sweep_rows", n_max * 64).view(np.uint32, (n_max, 16))
+    enc.encode_arrays_packed(codes, nums, out=pk)
+    out = eng.pinned("sweep_out", n_max * 8).view(SCORED_DTYPE, (n_max,))
+    df_all = training.arrays_to_frame(vocabs, codes, nums)[ALL_FEATURES]
+    res = {}
+    for n in (1, 16, 256, 4096, 65536):
+        calls = 1000 if n <= 4096 else 200
+        for _ in range(20):
+            eng.predict_pairs(pk[:n], out=out[:n])
+        ts = np.empty(calls)
+        for i in range(calls):
+            t0 = time.perf_counter()
+            eng.predict_pairs(pk[:n], out=out[:n])
+            ts[i] = time.perf_counter() - t0
+        df = df_all.iloc[:n]
+        pcalls = 200 if n <= 4096 else 20
+        for _ in range(3):
+            model.predict(df)
+        tp = np.empty(pcalls)
+        for i in range(pcalls):
+            t0 = time.perf_counter()
+            model.predict(df)
+            tp[i] = time.perf_counter() - t0
+        res[str(n)] = {"c_abi_p50_us": 1e6 * float(np.percentile(ts, 50)), "c_abi_p99_us": 1e6 * float(np.percentile(ts, 99)),
+                       "predict_p50_us": 1e6 * float(np.percentile(tp, 50)), "predict_p99_us": 1e6 * float(np.percentile(tp, 99)),
+                       "calls": calls}
+    info = eng.info()
+    model.close()
+    return {"model": name, "walk": info["walk"], "tile_resident": info["tile_resident"], "split_max_rows": info["split_max_rows"],
+            "api": "C ABI: b2f_predict_pairs on pinned 64-byte rows; plugin: B200Model.predict(DataFrame) -> dict (drift detector off)",
+            "batches": res}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -510,6 +559,8 @@ def main():
     ap.add_argument("--model", default="gbdt100d6", choices=sorted(MODELS))
     ap.add_argument("--sustain", type=float, default=1.5, help="seconds of back-to-back launches for the clock record")
     ap.add_argument("--rows", default="packed64", choices=["packed64", "words24"], help="encoded row layout fed to the engine")
+    ap.add_argument("--sweep", action="store_true", help="add the config-3 latency sweep (500-tree depth-8 model)")
+    ap.add_argument("--sweep-model", default="rf500d8", choices=sorted(MODELS))
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-moments", action="store_true")
     args = ap.parse_args()
