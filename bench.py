@@ -37,6 +37,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# rank 0's stdout carries exactly ONE JSON line: keep NCCL's own banner / debug lines out of it
+os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/b2f_bench_nccl_%h_%p.log")
 
 BATCH = 65536
 POOL = 32  # distinct device-resident batches: 32 * 6.29 MB = 201 MB > 126 MB L2

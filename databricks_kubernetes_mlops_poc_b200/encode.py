@@ -22,6 +22,12 @@ from __future__ import annotations
 import numpy as np
 import pandas as pd
 
+try:  # Arrow's C++ hash lookup for the categorical columns; pandas fallback if absent
+    import pyarrow as pa
+    import pyarrow.compute as pc
+except ImportError:  # pragma: no cover
+    pa = pc = None
+
 from .flatten import ROW_WORDS, FlatForest
 
 PACKED_ROW_WORDS = 16  # B2F_ROWS_PACKED64: 64-byte rows (include/b2f.h)
@@ -36,13 +42,31 @@ class RowEncoder:
         self.n_cat = len(self.cat_features)
         self.n_num = len(self.num_features)
         self._index = [pd.Index(list(v), dtype=object) for v in flat.categories]
+        self._lut = [{c: i for i, c in enumerate(v)} for v in flat.categories]
+        self._colpos = {}  # column-order tuple -> positions of the model's features
+        self._pa_vocab = [pa.array(list(v), type=pa.string()) for v in flat.categories] if pa is not None else None
         self._missing = list(flat.missing_codes) if flat.missing_codes else [-1] * self.n_cat
         # packed 64-byte rows: nine 7-bit (code + 1) fields + 14 float32 numerics
         self.packed_ok = self.n_cat <= 9 and self.n_num <= 14 and all(len(v) <= 126 for v in flat.categories)
 
     # ------------------------------------------------------------------ columns
     def encode_categorical(self, j: int, values) -> np.ndarray:
-        """One categorical column (any array-like of str / None) -> int32 codes, -1 = unknown."""
+        """One categorical column (any array-like of str / None) -> int32 codes, -1 = unknown.
+        Arrow's ``index_in`` does the vocabulary lookup in C++ (zero-copy for pandas' Arrow-backed
+        string columns); non-string columns fall back to a pandas hash lookup."""
+        if pa is not None:
+            try:
+                arr = pa.array(values, from_pandas=True)
+                if pa.types.is_dictionary(arr.type):
+                    arr = arr.dictionary_decode()
+                if pa.types.is_string(arr.type) or pa.types.is_large_string(arr.type):
+                    idx = pc.index_in(arr, value_set=self._pa_vocab[j].cast(arr.type))
+                    codes = idx.fill_null(-1).to_numpy(zero_copy_only=False).astype(np.int32)
+                    if self._missing[j] >= 0 and arr.null_count:
+                        codes[arr.is_null().to_numpy(zero_copy_only=False)] = self._missing[j]
+                    return codes
+            except (pa.ArrowInvalid, pa.ArrowTypeError, pa.ArrowNotImplementedError):
+                pass
         arr = values if isinstance(values, (pd.Series, np.ndarray)) else np.asarray(values, dtype=object)
         codes = self._index[j].get_indexer(pd.Index(arr, dtype=object)).astype(np.int32)  # -1 = not in vocabulary
         if self._missing[j] >= 0:
@@ -58,6 +82,8 @@ class RowEncoder:
         return block64.astype(np.float32)
 
     # ------------------------------------------------------------------ frames
+    SMALL_BATCH = 128  # below this, per-column vectorised machinery costs more than a Python loop
+
     def encode_frame(self, df: pd.DataFrame, out: np.ndarray | None = None) -> np.ndarray:
         """DataFrame with (at least) the 23 named columns -> uint32 (N, 24) encoded rows."""
         n = len(df)
@@ -65,17 +91,41 @@ class RowEncoder:
             out = np.empty((n, ROW_WORDS), dtype=np.uint32)
         else:
             assert out.shape == (n, ROW_WORDS) and out.dtype == np.uint32
-        missing = [c for c in self.cat_features + self.num_features if c not in df.columns]
+        cols = df.columns
+        missing = [c for c in self.cat_features + self.num_features if c not in cols]
         if missing:
             raise KeyError(f"{missing} not in index")  # what df[self.all_features] raises
         as_i32 = out.view(np.int32)
-        for j, name in enumerate(self.cat_features):
-            as_i32[:, j] = self.encode_categorical(j, df[name])
-        if self.n_num:
-            block = np.empty((n, self.n_num), dtype=np.float64)
-            for k, name in enumerate(self.num_features):
-                block[:, k] = pd.to_numeric(df[name], errors="raise").to_numpy(dtype=np.float64, na_value=np.nan)
-            out.view(np.float32)[:, self.n_cat : self.n_cat + self.n_num] = self.cast_numeric(block)
+        if n <= self.SMALL_BATCH:
+            # small request: ONE object-array extraction of the whole frame (column selection alone costs
+            # pandas ~0.5 ms), then dictionary lookups / float() in Python
+            key = tuple(cols)
+            pos = self._colpos.get(key)
+            if pos is None:
+                pos = self._colpos[key] = [cols.get_loc(c) for c in self.cat_features + self.num_features]
+            recs = df.to_numpy(dtype=object)
+            nums = np.empty((n, self.n_num), dtype=np.float64)
+            for i in range(n):
+                rec = recs[i]
+                for j in range(self.n_cat):
+                    v = rec[pos[j]]
+                    as_i32[i, j] = self._lut[j].get(v, -1) if isinstance(v, str) else (self._missing[j] if (v is None or v != v) else -1)
+                for k in range(self.n_num):
+                    v = rec[pos[self.n_cat + k]]
+                    nums[i, k] = np.nan if v is None else float(v)  # float("abc") raises ValueError, as pd.to_numeric does
+            if self.n_num:
+                out.view(np.float32)[:, self.n_cat : self.n_cat + self.n_num] = self.cast_numeric(nums)
+        else:
+            for j, name in enumerate(self.cat_features):
+                as_i32[:, j] = self.encode_categorical(j, df[name])
+            if self.n_num:
+                try:
+                    block = df[self.num_features].to_numpy(dtype=np.float64, na_value=np.nan)
+                except (ValueError, TypeError):
+                    block = np.empty((n, self.n_num), dtype=np.float64)
+                    for k, name in enumerate(self.num_features):
+                        block[:, k] = pd.to_numeric(df[name], errors="raise").to_numpy(dtype=np.float64, na_value=np.nan)
+                out.view(np.float32)[:, self.n_cat : self.n_cat + self.n_num] = self.cast_numeric(block)
         out[:, self.n_cat + self.n_num :] = 0
         return out
 
