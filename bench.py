@@ -209,7 +209,8 @@ def ncu_traffic(model_name: str):
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(model_name, {}).get("dram_bytes_per_launch")
+            v = json.load(open(p)).get(model_name, {})
+            return v.get("dram_bytes_per_launch") if isinstance(v, dict) else None
         except Exception:
             return None
     return None
