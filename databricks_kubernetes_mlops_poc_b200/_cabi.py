@@ -57,7 +57,7 @@ class Info(C.Structure):
         ("tile_ok", C.c_int32),
         ("tile_resident", C.c_int32),
         ("packed_ok", C.c_int32),
-        ("reserved", C.c_int32),
+        ("tile_warps", C.c_int32),
         ("launches_split", C.c_int64),
         ("split_max_rows", C.c_int64),
     ]

@@ -138,6 +138,7 @@ struct b2f_model {
     void *d_tile_layout = nullptr;
     TPiece *d_tile_pieces = nullptr;
     int tile_smem_bytes = 0;
+    int tile_cwarps = B2F_TILE_WARPS_MIN;
     int64_t tile_min_rows = 32768;
     int64_t tile_layout_bytes = 0;
     int64_t launches_tile = 0;
@@ -435,12 +436,31 @@ static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
     {
         const char *kn = getenv("B2F_KERNEL"); /* "warp" | "tile" | unset = choose by batch size */
         const char *tm = getenv("B2F_TILE_MIN_ROWS");
-        const uint32_t avail = (uint32_t)m->max_smem_optin - 1024u - 4096u - B2F_TILE_WARPS * B2F_TILE_XS_BYTES;
         std::vector<uint8_t> layout;
         std::vector<TPiece> pieces;
         uint32_t slot_bytes = 0;
         int n_slots = 0;
-        if (!(kn && !strcmp(kn, "warp")) && build_tile_layout(blob, m->hdr, avail, layout, pieces, &slot_bytes, &n_slots)) {
+        bool ok = false;
+        /* most consumer warps for which the forest still stays resident; else 16 warps and a streamed forest */
+        int cwarps = B2F_TILE_WARPS_MIN;
+        if (!(kn && !strcmp(kn, "warp"))) {
+            if (const char *tw = getenv("B2F_TILE_WARPS")) {
+                cwarps = std::min(B2F_TILE_WARPS_MAX, std::max(1, atoi(tw)));
+                const uint32_t avail = (uint32_t)m->max_smem_optin - 1024u - 4096u - (uint32_t)cwarps * B2F_TILE_XS_BYTES;
+                ok = build_tile_layout(blob, m->hdr, avail, layout, pieces, &slot_bytes, &n_slots);
+            } else {
+                for (int w = B2F_TILE_WARPS_MAX; w >= B2F_TILE_WARPS_MIN && !ok; w -= 4) {
+                    const uint32_t avail = (uint32_t)m->max_smem_optin - 1024u - 4096u - (uint32_t)w * B2F_TILE_XS_BYTES;
+                    const bool built = build_tile_layout(blob, m->hdr, avail, layout, pieces, &slot_bytes, &n_slots);
+                    const bool res = built && (int)pieces.size() <= n_slots;
+                    if (built && (res || w == B2F_TILE_WARPS_MIN)) {
+                        ok = true;
+                        cwarps = w;
+                    }
+                }
+            }
+        }
+        if (ok) {
             CUDA_TRY(cudaMalloc(&m->d_tile_layout, layout.size()));
             CUDA_TRY(cudaMemcpy(m->d_tile_layout, layout.data(), layout.size(), cudaMemcpyHostToDevice));
             CUDA_TRY(cudaMalloc((void **)&m->d_tile_pieces, pieces.size() * sizeof(TPiece)));
@@ -458,7 +478,8 @@ static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
             tp.init_raw = kp.init_raw;
             tp.denom = kp.denom;
             memcpy(tp.impute, kp.impute, sizeof(tp.impute));
-            m->tile_smem_bytes = 4096 + B2F_TILE_WARPS * B2F_TILE_XS_BYTES + n_slots * (int)slot_bytes;
+            m->tile_cwarps = cwarps;
+            m->tile_smem_bytes = 4096 + cwarps * B2F_TILE_XS_BYTES + n_slots * (int)slot_bytes;
             m->tile_layout_bytes = (int64_t)layout.size();
             CUDA_TRY(cudaFuncSetAttribute(k_forest_predict_tile<false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->tile_smem_bytes));
             CUDA_TRY(cudaFuncSetAttribute(k_forest_predict_tile<false, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->tile_smem_bytes));
@@ -568,6 +589,7 @@ extern "C" int b2f_model_info(const b2f_model *m, b2f_info *out) {
     out->tile_ok = m->tile_ok ? 1 : 0;
     out->tile_resident = (m->tile_ok && m->tp.n_pieces <= m->tp.n_slots) ? 1 : 0;
     out->packed_ok = m->packed_ok ? 1 : 0;
+    out->tile_warps = m->tile_ok ? m->tile_cwarps : 0;
     out->launches_split = m->launches_split;
     out->split_max_rows = m->split_max_rows;
     return B2F_OK;
@@ -602,7 +624,7 @@ template <bool PACKED, typename OutT>
 static cudaError_t launch_tile(const b2f_model *m, cudaStream_t st, const void *rows, int64_t n, void *proba, int32_t *label, int ostride) {
     const int64_t n_tiles = (n + B2F_TILE_ROWS - 1) / B2F_TILE_ROWS;
     const unsigned ctas = (unsigned)std::max<int64_t>(1, std::min<int64_t>(m->sm_count, n_tiles));
-    k_forest_predict_tile<PACKED, OutT><<<ctas, B2F_TILE_THREADS, m->tile_smem_bytes, st>>>(m->tp, static_cast<const uint32_t *>(rows), (long long)n,
+    k_forest_predict_tile<PACKED, OutT><<<ctas, (unsigned)(m->tile_cwarps + 1) * 32u, m->tile_smem_bytes, st>>>(m->tp, static_cast<const uint32_t *>(rows), (long long)n,
                                                                                            static_cast<OutT *>(proba), label, ostride);
     return cudaGetLastError();
 }

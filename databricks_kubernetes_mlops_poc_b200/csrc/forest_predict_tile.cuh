@@ -14,7 +14,7 @@
  *                          the float64 sum runs in tree order (exactly sklearn's order), row tiles are read with
  *                          16-byte vector loads and results are written as coalesced 128-byte stores.
  *
- * Memory plan per CTA (persistent, 1 CTA/SM, W consumer warps + 1 producer warp):
+ * Memory plan per CTA (persistent, 1 CTA/SM, W = 16..24 consumer warps + 1 producer warp):
  *   xs[W][24][32]   the warp's 32 encoded rows, TRANSPOSED (word-major) so a per-lane dynamic feature index is
  *                   one conflict-free LDS:  bank = lane.
  *   ring[n_slots]   forest PIECES (whole U-groups of trees, tree-major nodes + leaf payloads) streamed by the
@@ -38,8 +38,9 @@
 
 #define B2F_TILE_ROWS 32
 #define B2F_TILE_U 4                 /* trees walked concurrently by one thread (independent chains) */
-#define B2F_TILE_WARPS 16            /* consumer warps per CTA */
-#define B2F_TILE_THREADS ((B2F_TILE_WARPS + 1) * 32)
+#define B2F_TILE_WARPS_MIN 16        /* consumer warps per CTA: 16 when the forest streams, up to 24 when it is */
+#define B2F_TILE_WARPS_MAX 24        /* resident and shared memory allows (more warps hide more smem latency) */
+#define B2F_TILE_THREADS_MAX ((B2F_TILE_WARPS_MAX + 1) * 32)
 #define B2F_TILE_XS_BYTES 4096 /* per warp: 24 words x 32 lanes x 4 B = 3072 B, padded so the block is 4 KB aligned */
 #define B2F_TILE_MAX_SLOTS 8
 #define B2F_TILE_META_CAT 0x1000u
@@ -149,7 +150,7 @@ __device__ __forceinline__ void tile_walk_ugroup(uint32_t piece_addr, uint32_t u
 }
 
 template <bool PACKED, typename OutT>
-__global__ void __launch_bounds__(B2F_TILE_THREADS, 1)
+__global__ void __launch_bounds__(B2F_TILE_THREADS_MAX, 1)
     k_forest_predict_tile(const __grid_constant__ TParams p, const uint32_t *__restrict__ rows, long long n,
                           OutT *__restrict__ proba, int32_t *__restrict__ label, int ostride) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -159,17 +160,18 @@ __global__ void __launch_bounds__(B2F_TILE_THREADS, 1)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int n_pieces = p.n_pieces, n_slots = p.n_slots;
+    const int n_cwarps = (int)(blockDim.x >> 5) - 1; /* consumer warps; the last warp is the producer */
     const bool resident = n_pieces <= n_slots;
 
     /* xs blocks must be 4 KB aligned in the shared window (the feature address is formed with OR) */
     const uint32_t pad = (4096u - (smem_addr(smem) & 4095u)) & 4095u;
     uint8_t *xs_all = smem + pad;                                  /* [W] x 4 KB: [24][32] words each */
-    uint8_t *ring = xs_all + B2F_TILE_WARPS * B2F_TILE_XS_BYTES;   /* [n_slots][slot_bytes] */
+    uint8_t *ring = xs_all + n_cwarps * B2F_TILE_XS_BYTES;         /* [n_slots][slot_bytes] */
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < n_slots; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], B2F_TILE_WARPS);
+            mbar_init(&empty_bar[s], n_cwarps);
         }
         fence_mbar_init();
         fence_proxy_async();
@@ -177,12 +179,12 @@ __global__ void __launch_bounds__(B2F_TILE_THREADS, 1)
     __syncthreads();
 
     const long long n_tiles = (n + B2F_TILE_ROWS - 1) / B2F_TILE_ROWS;
-    const long long tiles_per_pass = (long long)gridDim.x * B2F_TILE_WARPS;
+    const long long tiles_per_pass = (long long)gridDim.x * n_cwarps;
     /* every warp of every CTA runs the same number of passes so the ring hand-shake stays in step;
      * tiles are numbered CTA-minor so a small batch spreads over all SMs */
     const long long n_pass = (n_tiles + tiles_per_pass - 1) / tiles_per_pass;
 
-    if (warp == B2F_TILE_WARPS) {
+    if (warp == n_cwarps) {
         /* ===== producer warp: one lane streams forest pieces into the ring with TMA bulk copies ===== */
         if (lane == 0) {
             const long long fills = resident ? (n_pass > 0 ? n_pieces : 0) : n_pass * n_pieces;
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(B2F_TILE_THREADS, 1)
     const uint32_t ring_addr = smem_addr(ring);
 
     for (long long pass = 0; pass < n_pass; ++pass) {
-        const long long tile = (pass * B2F_TILE_WARPS + warp) * gridDim.x + blockIdx.x;
+        const long long tile = (pass * n_cwarps + warp) * gridDim.x + blockIdx.x;
         const long long row = tile * B2F_TILE_ROWS + lane;
         const bool live = tile < n_tiles && row < n;
 

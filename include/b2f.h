@@ -99,7 +99,7 @@ typedef struct b2f_info {
     int32_t tile_ok;        /* the forest's trees fit the tile kernel's shared-memory ring */
     int32_t tile_resident;  /* ... and the whole forest stays resident in it (no streaming) */
     int32_t packed_ok;      /* B2F_ROWS_PACKED64 is accepted for this model */
-    int32_t reserved;
+    int32_t tile_warps;     /* consumer warps per CTA of the tile kernel (16..24) */
     int64_t launches_split; /* ... of which the small-batch (groups-across-warps) kernel */
     int64_t split_max_rows; /* launches of at most this many rows take it */
 } b2f_info;
