@@ -8,7 +8,7 @@
  *   k_forest_predict       one WARP per row, lane = tree.  Lowest latency (one row spreads over 32 lanes),
  *                          used for small batches and for forests whose trees do not fit a shared-memory piece.
  *   k_forest_predict_tile  one THREAD per row, a warp owns a TILE of 32 consecutive rows and walks the trees one
- *                          U-group (4 trees) at a time, all lanes in the same trees.  Node loads are
+ *                          U-group (8 trees) at a time, all lanes in the same trees.  Node loads are
  *                          near-broadcast (the 32 lanes sit in the same breadth-first level of the same tree, a
  *                          contiguous <= 256-byte run), there is no cross-lane reduction, no 32-tree quantisation,
  *                          the float64 sum runs in tree order (exactly sklearn's order), row tiles are read with
@@ -37,7 +37,9 @@
 #include "forest_predict.cuh"
 
 #define B2F_TILE_ROWS 32
-#define B2F_TILE_U 4                 /* trees walked concurrently by one thread (independent chains) */
+#ifndef B2F_TILE_U
+#define B2F_TILE_U 8                 /* trees walked concurrently by one thread (independent chains) */
+#endif
 #define B2F_TILE_WARPS_MIN 16        /* consumer warps per CTA: 16 when the forest streams, up to 24 when it is */
 #define B2F_TILE_WARPS_MAX 24        /* resident and shared memory allows (more warps hide more smem latency) */
 #define B2F_TILE_THREADS_MAX ((B2F_TILE_WARPS_MAX + 1) * 32)
@@ -55,7 +57,7 @@ struct TUGroup {
     uint32_t depth; /* max depth of the U trees: walk iterations */
     uint32_t pad[3];
 };
-static_assert(sizeof(TUGroup) == 48, "TUGroup size");
+static_assert(sizeof(TUGroup) == 8 * B2F_TILE_U + 16 && sizeof(TUGroup) % 16 == 0, "TUGroup size");
 
 struct TPiece {
     uint32_t off;   /* bytes from the tile-layout base (128-byte aligned) */
@@ -118,10 +120,14 @@ __device__ __forceinline__ bool take_second_tile(uint32_t x, uint32_t t, uint32_
 /* walk one U-group for this lane's row; values are added to acc in tree order */
 template <int D>
 __device__ __forceinline__ void tile_walk_ugroup(uint32_t piece_addr, uint32_t ug_addr, uint32_t xs_lane, int depth, double &acc) {
-    const uint4 no = *reinterpret_cast<const uint4 *>(__cvta_shared_to_generic(ug_addr));
-    const uint4 lo = *reinterpret_cast<const uint4 *>(__cvta_shared_to_generic(ug_addr + 16));
-    uint32_t base[B2F_TILE_U] = {piece_addr + no.x, piece_addr + no.y, piece_addr + no.z, piece_addr + no.w};
-    const uint32_t lbase[B2F_TILE_U] = {piece_addr + lo.x, piece_addr + lo.y, piece_addr + lo.z, piece_addr + lo.w};
+    uint32_t base[B2F_TILE_U], lbase[B2F_TILE_U];
+#pragma unroll
+    for (int u = 0; u < B2F_TILE_U; u += 4) {
+        const uint4 no = *reinterpret_cast<const uint4 *>(__cvta_shared_to_generic(ug_addr + 4 * u));
+        const uint4 lo = *reinterpret_cast<const uint4 *>(__cvta_shared_to_generic(ug_addr + 4 * B2F_TILE_U + 4 * u));
+        base[u] = piece_addr + no.x, base[u + 1] = piece_addr + no.y, base[u + 2] = piece_addr + no.z, base[u + 3] = piece_addr + no.w;
+        lbase[u] = piece_addr + lo.x, lbase[u + 1] = piece_addr + lo.y, lbase[u + 2] = piece_addr + lo.z, lbase[u + 3] = piece_addr + lo.w;
+    }
     uint32_t at[B2F_TILE_U];
 #pragma unroll
     for (int u = 0; u < B2F_TILE_U; ++u) at[u] = base[u];
@@ -257,25 +263,28 @@ __global__ void __launch_bounds__(B2F_TILE_THREADS_MAX, 1)
 
         /* GBDT: start from the init estimator's raw value and add trees in order -- sklearn's own order */
         double acc = p.agg_mode == B2F_AGG_RF_MEAN ? 0.0 : p.init_raw;
+        const bool warp_live = tile < n_tiles; /* warp-uniform: a warp without a tile only keeps the ring protocol */
         for (int piece = 0; piece < n_pieces; ++piece) {
             const long long f = resident ? piece : pass * n_pieces + piece;
             const int slot = (int)(f % n_slots);
             if (!resident || pass == 0) mbar_wait(&full_bar[slot], (uint32_t)((f / n_slots) & 1));
-            const uint32_t piece_addr = ring_addr + slot * p.slot_bytes;
-            const int n_ug = (int)p.pieces[piece].n_ug;
-            for (int g = 0; g < n_ug; ++g) {
-                const uint32_t ug_addr = piece_addr + g * (uint32_t)sizeof(TUGroup);
-                const int depth = (int)lds32(ug_addr + 32);
-                switch (depth) {
-                    case 1: tile_walk_ugroup<1>(piece_addr, ug_addr, xs_lane, 1, acc); break;
-                    case 2: tile_walk_ugroup<2>(piece_addr, ug_addr, xs_lane, 2, acc); break;
-                    case 3: tile_walk_ugroup<3>(piece_addr, ug_addr, xs_lane, 3, acc); break;
-                    case 4: tile_walk_ugroup<4>(piece_addr, ug_addr, xs_lane, 4, acc); break;
-                    case 5: tile_walk_ugroup<5>(piece_addr, ug_addr, xs_lane, 5, acc); break;
-                    case 6: tile_walk_ugroup<6>(piece_addr, ug_addr, xs_lane, 6, acc); break;
-                    case 7: tile_walk_ugroup<7>(piece_addr, ug_addr, xs_lane, 7, acc); break;
-                    case 8: tile_walk_ugroup<8>(piece_addr, ug_addr, xs_lane, 8, acc); break;
-                    default: tile_walk_ugroup<0>(piece_addr, ug_addr, xs_lane, depth, acc); break;
+            if (warp_live) {
+                const uint32_t piece_addr = ring_addr + slot * p.slot_bytes;
+                const int n_ug = (int)p.pieces[piece].n_ug;
+                for (int g = 0; g < n_ug; ++g) {
+                    const uint32_t ug_addr = piece_addr + g * (uint32_t)sizeof(TUGroup);
+                    const int depth = (int)lds32(ug_addr + 8 * B2F_TILE_U);
+                    switch (depth) {
+                        case 1: tile_walk_ugroup<1>(piece_addr, ug_addr, xs_lane, 1, acc); break;
+                        case 2: tile_walk_ugroup<2>(piece_addr, ug_addr, xs_lane, 2, acc); break;
+                        case 3: tile_walk_ugroup<3>(piece_addr, ug_addr, xs_lane, 3, acc); break;
+                        case 4: tile_walk_ugroup<4>(piece_addr, ug_addr, xs_lane, 4, acc); break;
+                        case 5: tile_walk_ugroup<5>(piece_addr, ug_addr, xs_lane, 5, acc); break;
+                        case 6: tile_walk_ugroup<6>(piece_addr, ug_addr, xs_lane, 6, acc); break;
+                        case 7: tile_walk_ugroup<7>(piece_addr, ug_addr, xs_lane, 7, acc); break;
+                        case 8: tile_walk_ugroup<8>(piece_addr, ug_addr, xs_lane, 8, acc); break;
+                        default: tile_walk_ugroup<0>(piece_addr, ug_addr, xs_lane, depth, acc); break;
+                    }
                 }
             }
             if (!resident) {
