@@ -553,6 +553,110 @@ def latency_sweep(args, dist: Dist):
             "batches": res}
 
 
+def run_cfg1(args):
+    """BASELINE config 1: the reference's own CPU path on 1 000 rows of the reference's curated.csv (frozen copy
+    under tests/golden), single process, n_jobs=-1 as the reference sets it; classifier alone and the whole
+    CustomModel.predict restatement (classifier + drift + outliers).  No GPU involved."""
+    import sklearn
+
+    from oracle import datasets
+    from oracle import reference_pipeline as rp
+    from oracle.custom_model import ReferenceCustomModel
+
+    cur = datasets.load_curated()
+    df = cur[rp.FEATURES].iloc[:1000]
+    out = {"rows": 1000, "cores": os.cpu_count(), "sklearn": sklearn.__version__, "models": {}}
+    for name, params in rp.PINNED_RF.items():
+        pipe = rp.fit_reference_pipeline(cur, params)
+        ts = []
+        for _ in range(6):
+            t0 = time.perf_counter()
+            pipe.predict_proba(df)
+            ts.append(time.perf_counter() - t0)
+        ts = ts[1:]
+        entry = {"classifier_best_ms": 1e3 * min(ts), "classifier_median_ms": 1e3 * statistics.median(ts),
+                 "classifier_rows_per_s": 1000 / min(ts)}
+        if name == "rf100d6":
+            cm = ReferenceCustomModel(pipe, cur)
+            tt = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                cm.predict(None, df)
+                tt.append(time.perf_counter() - t0)
+            entry["custom_model_predict_best_ms"] = 1e3 * min(tt)
+        out["models"][name] = entry
+    print(json.dumps({"metric": "reference CPU predict() on 1k curated rows (config 1)", "impl": "reference", "unit": "ms", **out}))
+
+
+def run_stream(args):
+    """BASELINE config 4: ONE process deals a 10 M-row synthetic stream in 65 536-row batches round-robin over all
+    GPUs of the box (forest replicated, rows independent, no inter-GPU traffic) through the asynchronous C ABI
+    (b2f_predict_async_ex on a pinned ring, two batches in flight per GPU).  Reports aggregate and per-GPU rows/s."""
+    from databricks_kubernetes_mlops_poc_b200 import flatten, training
+    from databricks_kubernetes_mlops_poc_b200.encode import RowEncoder
+    from databricks_kubernetes_mlops_poc_b200.engine import ForestEngine, device_count
+    from databricks_kubernetes_mlops_poc_b200.sharding import round_robin_batches
+
+    solo = Dist(1, use_cuda=False, solo=True)
+    pipe, base = get_pipeline(args.model, solo)
+    flat = flatten.flatten_pipeline(pipe)
+    enc = RowEncoder(flat)
+    ngpu = min(args.gpus, device_count()) if args.gpus > 1 else device_count()
+    engines = [ForestEngine(flat, d) for d in range(ngpu)]
+    total = args.stream_rows
+    distinct = 64 * BATCH  # 4.2 M distinct rows (268 MB pinned), cycled to make the 10 M-row stream
+    vocabs, codes, nums = training.synth_arrays(base, distinct, DATA_SEED + 7)
+    host = engines[0].pinned("stream_rows", distinct * 64).view(np.uint32, (distinct, 16))
+    enc.encode_arrays_packed(codes, nums, out=host)
+    proba = engines[0].pinned("stream_proba", total * 4).view(np.float32, (total,))
+    label = engines[0].pinned("stream_label", total * 4).view(np.int32, (total,))
+    plan = list(round_robin_batches(total, BATCH, ngpu))
+
+    def pump():
+        inflight = [[] for _ in range(ngpu)]
+        rows_gpu = [0] * ngpu
+        for g, lo, hi in plan:
+            src = lo % distinct
+            if src + (hi - lo) > distinct:
+                src = 0
+            if len(inflight[g]) >= 2:
+                engines[g].wait(inflight[g].pop(0))
+            inflight[g].append(engines[g].predict_rows_async(host[src:src + hi - lo], proba[lo:hi], label[lo:hi]))
+            rows_gpu[g] += hi - lo
+        for g in range(ngpu):
+            for t in inflight[g]:
+                engines[g].wait(t)
+        return rows_gpu
+
+    pump()  # warm-up pass (allocations, first-touch)
+    sampler = ClockSampler(0)
+    sampler.start()
+    t0w = time.time()
+    t0 = time.perf_counter()
+    rows_gpu = pump()
+    dt = time.perf_counter() - t0
+    t1w = time.time()
+    sampler.stop()
+    # parity spot check on the last pass: 1 024 rows against sklearn
+    sel = np.arange(0, BATCH, 64)[:1024]
+    df = training.arrays_to_frame(vocabs, codes[sel], nums[sel])
+    want = pipe.predict_proba(df)[:, 1]
+    err = float(np.abs(proba[sel].astype(np.float64) - want).max())
+    launches = sum(e.info()["launches"] for e in engines)
+    for e in engines:
+        e.close()
+    print(json.dumps({
+        "metric": "rows/sec, 10M-row synthetic stream dealt round-robin over the GPUs of one box (config 4)", "unit": "rows/s",
+        "value": total / dt, "n_gpus": ngpu, "rows": total, "batch": BATCH, "seconds": dt, "per_gpu_rows_per_s": [r / dt for r in rows_gpu],
+        "higher_is_better": True, "scaling": "strong", "data": "synthetic", "dtype": "f32cmp+f64acc",
+        "config": {"workload": f"cfg4: {args.model}, {total} rows in {len(plan)} batches of {BATCH}, one process, async C ABI, 64-byte rows",
+                   "model": args.model, "parallelism": f"round-robin over {ngpu} GPUs, forest replicated, no collective"},
+        "e2e": {"value": total / dt, "unit": "rows/s", "h2d_bytes_per_step": BATCH * 64, "d2h_bytes_per_step": BATCH * 8},
+        "gpu_launches": int(launches // 2), "clocks": sampler.summary(t0w, t1w), "parity_max_abs_dp_vs_sklearn_1024rows": err,
+        "roofline_frac_of_n_gpu_hbm": (total / dt) * ALG_BYTES_PER_ROW / 1e9 / (measured_peak_gbs()[0] * ngpu),
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -566,8 +670,17 @@ def main():
     ap.add_argument("--sweep-model", default="rf500d8", choices=sorted(MODELS))
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-moments", action="store_true")
+    ap.add_argument("--cfg1", action="store_true", help="config 1: the reference CPU path on 1k curated rows (no GPU)")
+    ap.add_argument("--stream", action="store_true", help="config 4: one process, 10M-row stream round-robin over all GPUs")
+    ap.add_argument("--stream-rows", type=int, default=10_000_000)
     args = ap.parse_args()
 
+    if args.cfg1:
+        run_cfg1(args)
+        return
+    if args.stream:
+        run_stream(args)
+        return
     if args.impl == "reference":
         # under torchrun only rank 0 works; the other ranks exit 0 without joining anything
         if int(os.environ.get("RANK", "0")) == 0:
