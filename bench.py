@@ -37,8 +37,15 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# rank 0's stdout carries exactly ONE JSON line: keep NCCL's own banner / debug lines out of it
-os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/b2f_bench_nccl_%h_%p.log")
+# rank 0's stdout carries exactly ONE JSON line.  Libraries (NCCL's "NCCL version ..." banner, torchrun notices) write
+# to fd 1 directly, so fd 1 is pointed at stderr for the whole run and only the final line goes to the real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
 
 BATCH = 65536
 POOL = 32  # distinct device-resident batches: 32 * 6.29 MB = 201 MB > 126 MB L2
@@ -305,7 +312,7 @@ def run_reference(args, dist: Dist):
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_b200(args, dist: Dist):
@@ -503,7 +510,7 @@ def run_b200(args, dist: Dist):
         eng.device_free(d)
     eng.close()
     if dist.rank == 0:
-        print(json.dumps(line))
+        emit(line)
 
 
 def latency_sweep(args, dist: Dist):
@@ -585,7 +592,7 @@ def run_cfg1(args):
                 tt.append(time.perf_counter() - t0)
             entry["custom_model_predict_best_ms"] = 1e3 * min(tt)
         out["models"][name] = entry
-    print(json.dumps({"metric": "reference CPU predict() on 1k curated rows (config 1)", "impl": "reference", "unit": "ms", **out}))
+    emit({"metric": "reference CPU predict() on 1k curated rows (config 1)", "impl": "reference", "unit": "ms", **out})
 
 
 def run_stream(args):
@@ -601,7 +608,7 @@ def run_stream(args):
     pipe, base = get_pipeline(args.model, solo)
     flat = flatten.flatten_pipeline(pipe)
     enc = RowEncoder(flat)
-    ngpu = min(args.gpus, device_count()) if args.gpus > 1 else device_count()
+    ngpu = min(args.stream_gpus, device_count()) if args.stream_gpus > 0 else device_count()
     engines = [ForestEngine(flat, d) for d in range(ngpu)]
     total = args.stream_rows
     distinct = 64 * BATCH  # 4.2 M distinct rows (268 MB pinned), cycled to make the 10 M-row stream
@@ -611,32 +618,39 @@ def run_stream(args):
     proba = engines[0].pinned("stream_proba", total * 4).view(np.float32, (total,))
     label = engines[0].pinned("stream_label", total * 4).view(np.int32, (total,))
     plan = list(round_robin_batches(total, BATCH, ngpu))
+    per_gpu = [[(lo, hi) for g, lo, hi in plan if g == d] for d in range(ngpu)]
 
-    def pump():
-        inflight = [[] for _ in range(ngpu)]
-        rows_gpu = [0] * ngpu
-        for g, lo, hi in plan:
+    def pump_gpu(d):
+        """One host thread per GPU (ctypes releases the GIL inside every engine call)."""
+        eng, inflight, rows = engines[d], [], 0
+        for lo, hi in per_gpu[d]:
             src = lo % distinct
             if src + (hi - lo) > distinct:
                 src = 0
-            if len(inflight[g]) >= 2:
-                engines[g].wait(inflight[g].pop(0))
-            inflight[g].append(engines[g].predict_rows_async(host[src:src + hi - lo], proba[lo:hi], label[lo:hi]))
-            rows_gpu[g] += hi - lo
-        for g in range(ngpu):
-            for t in inflight[g]:
-                engines[g].wait(t)
-        return rows_gpu
+            if len(inflight) >= 2:
+                eng.wait(inflight.pop(0))
+            inflight.append(eng.predict_rows_async(host[src:src + hi - lo], proba[lo:hi], label[lo:hi]))
+            rows += hi - lo
+        for t in inflight:
+            eng.wait(t)
+        return rows
 
-    pump()  # warm-up pass (allocations, first-touch)
+    from concurrent.futures import ThreadPoolExecutor
+
+    pool = ThreadPoolExecutor(ngpu)
+    list(pool.map(pump_gpu, range(ngpu)))  # warm-up pass (allocations, first touch)
     sampler = ClockSampler(0)
     sampler.start()
     t0w = time.time()
     t0 = time.perf_counter()
-    rows_gpu = pump()
-    dt = time.perf_counter() - t0
+    passes = 0
+    while passes < 3 or time.perf_counter() - t0 < args.sustain:
+        rows_gpu = list(pool.map(pump_gpu, range(ngpu)))
+        passes += 1
+    dt = (time.perf_counter() - t0) / passes
     t1w = time.time()
     sampler.stop()
+    pool.shutdown()
     # parity spot check on the last pass: 1 024 rows against sklearn
     sel = np.arange(0, BATCH, 64)[:1024]
     df = training.arrays_to_frame(vocabs, codes[sel], nums[sel])
@@ -645,16 +659,18 @@ def run_stream(args):
     launches = sum(e.info()["launches"] for e in engines)
     for e in engines:
         e.close()
-    print(json.dumps({
+    emit({
         "metric": "rows/sec, 10M-row synthetic stream dealt round-robin over the GPUs of one box (config 4)", "unit": "rows/s",
         "value": total / dt, "n_gpus": ngpu, "rows": total, "batch": BATCH, "seconds": dt, "per_gpu_rows_per_s": [r / dt for r in rows_gpu],
         "higher_is_better": True, "scaling": "strong", "data": "synthetic", "dtype": "f32cmp+f64acc",
-        "config": {"workload": f"cfg4: {args.model}, {total} rows in {len(plan)} batches of {BATCH}, one process, async C ABI, 64-byte rows",
+        "config": {"workload": f"cfg4: {args.model}, {total} rows in {len(plan)} batches of {BATCH}, one process, one host thread per GPU, "
+                               f"async C ABI on a pinned ring (2 batches in flight per GPU), 64-byte rows",
                    "model": args.model, "parallelism": f"round-robin over {ngpu} GPUs, forest replicated, no collective"},
         "e2e": {"value": total / dt, "unit": "rows/s", "h2d_bytes_per_step": BATCH * 64, "d2h_bytes_per_step": BATCH * 8},
         "gpu_launches": int(launches // 2), "clocks": sampler.summary(t0w, t1w), "parity_max_abs_dp_vs_sklearn_1024rows": err,
         "roofline_frac_of_n_gpu_hbm": (total / dt) * ALG_BYTES_PER_ROW / 1e9 / (measured_peak_gbs()[0] * ngpu),
-    }))
+        "passes": passes,
+    })
 
 
 def main():
@@ -673,6 +689,7 @@ def main():
     ap.add_argument("--cfg1", action="store_true", help="config 1: the reference CPU path on 1k curated rows (no GPU)")
     ap.add_argument("--stream", action="store_true", help="config 4: one process, 10M-row stream round-robin over all GPUs")
     ap.add_argument("--stream-rows", type=int, default=10_000_000)
+    ap.add_argument("--stream-gpus", type=int, default=0, help="GPUs used by --stream (0 = all visible)")
     args = ap.parse_args()
 
     if args.cfg1:
