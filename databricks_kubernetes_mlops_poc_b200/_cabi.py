@@ -100,6 +100,10 @@ SIGNATURES = {
         C.c_int,
         [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p],
     ),
+    "b2f_predict_stream": (
+        C.c_int,
+        [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int],
+    ),
     "b2f_device_alloc": (C.c_void_p, [C.c_void_p, C.c_size_t]),
     "b2f_device_free": (None, [C.c_void_p, C.c_void_p]),
     "b2f_copy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),

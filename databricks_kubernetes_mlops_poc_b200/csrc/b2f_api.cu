@@ -17,6 +17,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <string>
+#include <thread>
 #include <new>
 #include <vector>
 
@@ -913,6 +915,51 @@ extern "C" int b2f_predict_multi_ex(b2f_model **models, int n_models, const void
         if (rc == B2F_OK) rc = rc2;
     }
     return rc;
+}
+
+/* Round-robin streaming over the GPUs of one box: batch b (rows [b*batch, (b+1)*batch)) goes to model b % n_models.
+ * One host thread per GPU submits that GPU's batches through the asynchronous ring (at most `inflight` batches in
+ * flight per GPU), so submission cost is paid in parallel; rows are independent, so there is no inter-GPU traffic. */
+extern "C" int b2f_predict_stream(b2f_model **models, int n_models, const void *rows, int64_t n, int64_t batch, int row_format, void *proba1,
+                                  int proba_is_f64, int32_t *label, int inflight) {
+    if (!models || n_models <= 0 || batch <= 0 || n < 0) return set_err(B2F_EINVAL, "bad argument");
+    if (inflight < 1) inflight = 1;
+    if (inflight > 8) inflight = 8;
+    const size_t row_bytes = row_format == B2F_ROWS_PACKED64 ? B2F_PACKED_ROW_BYTES : B2F_ROW_BYTES;
+    const size_t psz = proba_is_f64 ? sizeof(double) : sizeof(float);
+    const int64_t n_batches = (n + batch - 1) / batch;
+    std::vector<int> rcs(n_models, B2F_OK);
+    std::vector<std::string> msgs(n_models);
+    auto worker = [&](int d) {
+        b2f_model *m = models[d];
+        std::vector<b2f_ticket> ring;
+        int rc = B2F_OK;
+        for (int64_t b = d; b < n_batches && rc == B2F_OK; b += n_models) {
+            const int64_t lo = b * batch, cnt = std::min(batch, n - lo);
+            if ((int)ring.size() >= inflight) {
+                rc = b2f_wait(m, ring.front());
+                ring.erase(ring.begin());
+                if (rc) break;
+            }
+            b2f_ticket t = 0;
+            rc = b2f_predict_async_ex(m, static_cast<const uint8_t *>(rows) + (size_t)lo * row_bytes, cnt, row_format,
+                                      proba1 ? static_cast<uint8_t *>(proba1) + (size_t)lo * psz : nullptr, proba_is_f64, label ? label + lo : nullptr, &t);
+            if (rc == B2F_OK) ring.push_back(t);
+        }
+        for (b2f_ticket t : ring) {
+            int rc2 = b2f_wait(m, t);
+            if (rc == B2F_OK) rc = rc2;
+        }
+        rcs[d] = rc;
+        if (rc) msgs[d] = b2f_last_error(); /* the message is thread-local: carry it back */
+    };
+    std::vector<std::thread> threads;
+    for (int d = 1; d < n_models; ++d) threads.emplace_back(worker, d);
+    worker(0);
+    for (auto &t : threads) t.join();
+    for (int d = 0; d < n_models; ++d)
+        if (rcs[d]) return set_err(rcs[d], "GPU %d: %s", models[d]->device, msgs[d].c_str());
+    return B2F_OK;
 }
 
 /* ------------------------------------------------------------------ device-resident interface */

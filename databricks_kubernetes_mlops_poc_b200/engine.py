@@ -250,6 +250,17 @@ class EngineGroup:
         )
         return proba, label
 
+    def predict_stream(self, rows: np.ndarray, batch: int, out_proba: np.ndarray, out_label: np.ndarray | None, inflight: int = 2) -> None:
+        """Deal a long stream in ``batch``-row batches round-robin over the GPUs (one host thread per GPU inside
+        the C call, ``inflight`` batches in flight per GPU).  Buffers should be pinned."""
+        check(
+            self._lib.b2f_predict_stream(
+                self._handles, len(self.engines), ptr(rows), rows.shape[0], int(batch), _row_format(rows), ptr(out_proba),
+                int(out_proba.dtype == np.float64), ptr(out_label), int(inflight)
+            ),
+            "b2f_predict_stream",
+        )
+
     def moments(self, rows: np.ndarray) -> np.ndarray:
         rows = np.ascontiguousarray(rows)
         out = np.zeros(MOMENT_VALUES, dtype=np.float64)

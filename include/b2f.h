@@ -156,6 +156,11 @@ int b2f_predict_multi(b2f_model **models, int n_models, const void *rows, int64_
 int b2f_predict_multi_ex(b2f_model **models, int n_models, const void *rows, int64_t n, int row_format,
                          void *proba1, int proba_is_f64, int32_t *label);
 
+/* a long stream of rows in `batch`-row batches dealt round-robin: batch b -> models[b % n_models]; one host thread
+ * per GPU inside the call, at most `inflight` (1..8) batches in flight per GPU; buffers should be pinned */
+int b2f_predict_stream(b2f_model **models, int n_models, const void *rows, int64_t n, int64_t batch, int row_format,
+                       void *proba1, int proba_is_f64, int32_t *label, int inflight);
+
 /* ---- device-resident interface (measurement and callers that already hold rows in HBM) ----- */
 void *b2f_device_alloc(b2f_model *m, size_t nbytes);
 void b2f_device_free(b2f_model *m, void *dptr);

@@ -435,3 +435,26 @@ def test_split_kernel_small_batches(curated, adversarial, rf100d6, rf500d8, gbdt
             assert np.abs(out["proba1"] - want_p[:n]).max() <= TOL32 and (out["label"] == want_l[:n]).all()
     finally:
         eng.close()
+
+
+def test_stream_dealer(curated, rf100d6):
+    """b2f_predict_stream: batches dealt round-robin over the models (one host thread per GPU inside the call)."""
+    from databricks_kubernetes_mlops_poc_b200 import flatten, training
+    from databricks_kubernetes_mlops_poc_b200.encode import RowEncoder
+    from databricks_kubernetes_mlops_poc_b200.engine import EngineGroup, device_count
+
+    flat = flatten.flatten_pipeline(rf100d6)
+    enc = RowEncoder(flat)
+    grp = EngineGroup(flat, devices=list(range(min(2, device_count()))))
+    try:
+        n = 50_003
+        _, codes, nums = training.synth_arrays(curated, n, seed=9)
+        rows = enc.encode_arrays_packed(codes, nums)
+        want_p, want_l = grp.engines[0].predict_rows(rows, np.float32)
+        for batch, inflight in ((4096, 2), (65536, 1), (1000, 8)):
+            p = np.full(n, -1, dtype=np.float32)
+            l = np.full(n, -1, dtype=np.int32)
+            grp.predict_stream(rows, batch, p, l, inflight=inflight)
+            assert (p == want_p).all() and (l == want_l).all()
+    finally:
+        grp.close()
