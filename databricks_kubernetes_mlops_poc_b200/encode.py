@@ -45,7 +45,8 @@ class RowEncoder:
         self._lut = [{c: i for i, c in enumerate(v)} for v in flat.categories]
         self._colpos = {}  # column-order tuple -> positions of the model's features
         self._pa_vocab = [pa.array(list(v), type=pa.string()) for v in flat.categories] if pa is not None else None
-        self._missing = list(flat.missing_codes) if flat.missing_codes else [-1] * self.n_cat
+        self._missing = list(flat.missing_codes) if flat.missing_codes else [-1] * self.n_cat  # NaN -> imputer constant
+        self._none = list(flat.none_codes) if flat.none_codes else [-1] * self.n_cat  # None -> None category, if any
         # packed 64-byte rows: nine 7-bit (code + 1) fields + 14 float32 numerics
         self.packed_ok = self.n_cat <= 9 and self.n_num <= 14 and all(len(v) <= 126 for v in flat.categories)
 
@@ -62,16 +63,26 @@ class RowEncoder:
                 if pa.types.is_string(arr.type) or pa.types.is_large_string(arr.type):
                     idx = pc.index_in(arr, value_set=self._pa_vocab[j].cast(arr.type))
                     codes = idx.fill_null(-1).to_numpy(zero_copy_only=False).astype(np.int32)
-                    if self._missing[j] >= 0 and arr.null_count:
-                        codes[arr.is_null().to_numpy(zero_copy_only=False)] = self._missing[j]
+                    if arr.null_count and (self._missing[j] >= 0 or self._none[j] >= 0):
+                        codes[arr.is_null().to_numpy(zero_copy_only=False)] = self._null_codes(j, values)
                     return codes
             except (pa.ArrowInvalid, pa.ArrowTypeError, pa.ArrowNotImplementedError):
                 pass
         arr = values if isinstance(values, (pd.Series, np.ndarray)) else np.asarray(values, dtype=object)
         codes = self._index[j].get_indexer(pd.Index(arr, dtype=object)).astype(np.int32)  # -1 = not in vocabulary
-        if self._missing[j] >= 0:
-            codes[np.asarray(pd.isna(arr))] = self._missing[j]
+        if self._missing[j] >= 0 or self._none[j] >= 0:
+            isna = np.asarray(pd.isna(arr))
+            if isna.any():
+                codes[isna] = self._null_codes(j, arr)
         return codes
+
+    def _null_codes(self, j: int, values) -> np.ndarray:
+        """Codes for the null entries of a column: None -> the None category (if fit saw one), NaN -> the
+        imputer's constant category (if fit saw missing values); Arrow-backed columns only have one kind of null."""
+        obj = np.asarray(values, dtype=object)
+        nulls = obj[np.asarray(pd.isna(obj))]
+        is_none = np.fromiter((v is None for v in nulls), dtype=bool, count=len(nulls))
+        return np.where(is_none, self._none[j], self._missing[j]).astype(np.int32)
 
     @staticmethod
     def cast_numeric(block64: np.ndarray) -> np.ndarray:
@@ -109,7 +120,7 @@ class RowEncoder:
                 rec = recs[i]
                 for j in range(self.n_cat):
                     v = rec[pos[j]]
-                    as_i32[i, j] = self._lut[j].get(v, -1) if isinstance(v, str) else (self._missing[j] if (v is None or v != v) else -1)
+                    as_i32[i, j] = self._lut[j].get(v, -1) if isinstance(v, str) else (self._none[j] if v is None else (self._missing[j] if v != v else -1))
                 for k in range(self.n_num):
                     v = rec[pos[self.n_cat + k]]
                     nums[i, k] = np.nan if v is None else float(v)  # float("abc") raises ValueError, as pd.to_numeric does

@@ -61,7 +61,8 @@ class FlatForest:
     n_trees: int
     max_depth: int
     total_nodes: int
-    missing_codes: list = field(default_factory=list)  # per cat feature: code of "missing" or -1
+    missing_codes: list = field(default_factory=list)  # per cat feature: code NaN maps to (the imputer's "missing") or -1
+    none_codes: list = field(default_factory=list)  # per cat feature: code None maps to (a None category seen at fit) or -1
 
     @property
     def all_features(self):
@@ -78,6 +79,7 @@ class FlatForest:
             max_depth=self.max_depth,
             total_nodes=self.total_nodes,
             missing_codes=self.missing_codes,
+            none_codes=self.none_codes,
         )
         np.savez_compressed(path, blob=np.frombuffer(self.blob, dtype=np.uint8), meta=np.array(json.dumps(meta)))
 
@@ -200,7 +202,10 @@ def _describe_preprocessor(pre):
         raise NotImplementedError("OneHotEncoder must use handle_unknown='ignore' and drop=None")
     if len(cat_cols) + len(num_cols) > SENTINEL_WORD:
         raise NotImplementedError(f"at most {SENTINEL_WORD} raw features supported")
-    categories = [[str(c) for c in cats] for cats in ohe.categories_]
+    # a training column that held None / NaN gives OneHotEncoder a non-string category (sorted last); keep its
+    # position under a placeholder no request string can equal, and remember it for the encoder
+    NONE_TOKEN = "\x00<none>"
+    categories = [[c if isinstance(c, str) else NONE_TOKEN for c in cats] for cats in ohe.categories_]
     n_cat, n_num = len(cat_cols), len(num_cols)
     cat_slice = pre.output_indices_[cat_name]
     num_slice = pre.output_indices_[num_name]
@@ -218,15 +223,18 @@ def _describe_preprocessor(pre):
         col_word[num_slice.start + k] = n_cat + k
     medians = np.asarray(num_imputer.statistics_, dtype=np.float64)
     fill = getattr(cat_imputer, "fill_value", None) if cat_imputer is not None else None
+    # NaN is imputed to the constant `fill` ("missing") before encoding; None is left alone by SimpleImputer and
+    # only matches a None category seen at fit time
     missing_codes = [cats.index(fill) if (fill is not None and fill in cats) else -1 for cats in categories]
-    return cat_cols, num_cols, categories, medians, col_word, col_code, col_is_cat, missing_codes
+    none_codes = [cats.index(NONE_TOKEN) if NONE_TOKEN in cats else -1 for cats in categories]
+    return cat_cols, num_cols, categories, medians, col_word, col_code, col_is_cat, missing_codes, none_codes
 
 
 def flatten_pipeline(pipeline) -> FlatForest:
     """Fitted reference-style Pipeline -> FlatForest."""
     pre = pipeline.named_steps["preprocessor"]
     clf = pipeline.named_steps["classifier"]
-    cat_cols, num_cols, categories, medians, col_word, col_code, col_is_cat, missing_codes = _describe_preprocessor(pre)
+    cat_cols, num_cols, categories, medians, col_word, col_code, col_is_cat, missing_codes, none_codes = _describe_preprocessor(pre)
     n_cat, n_num = len(cat_cols), len(num_cols)
 
     kind = type(clf).__name__
@@ -339,6 +347,7 @@ def flatten_pipeline(pipeline) -> FlatForest:
         max_depth=int(max_depth),
         total_nodes=int(sum(len(m[0]) for m in flat)),
         missing_codes=missing_codes,
+        none_codes=none_codes,
     )
 
 

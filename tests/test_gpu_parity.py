@@ -458,3 +458,66 @@ def test_stream_dealer(curated, rf100d6):
             assert (p == want_p).all() and (l == want_l).all()
     finally:
         grp.close()
+
+
+def test_c_abi_error_paths(curated, rf100d6):
+    """Bad arguments come back as error codes with a message (-> RuntimeError in the shim -> HTTP 500), never a crash."""
+    import ctypes as C
+
+    from databricks_kubernetes_mlops_poc_b200 import _cabi, flatten
+    from databricks_kubernetes_mlops_poc_b200._cabi import B2FError
+    from databricks_kubernetes_mlops_poc_b200.engine import ForestEngine
+
+    lib = _cabi.load_library()
+    flat = flatten.flatten_pipeline(rf100d6)
+    buf = np.frombuffer(flat.blob, dtype=np.uint8)
+    assert not lib.b2f_model_create(_cabi.ptr(buf), buf.size, 99)  # no such device
+    assert b"device 99" in lib.b2f_last_error()
+    bad = bytearray(flat.blob)
+    bad[0] = 0
+    badbuf = np.frombuffer(bytes(bad), dtype=np.uint8)
+    assert not lib.b2f_model_create(_cabi.ptr(badbuf), badbuf.size, 0)
+    assert b"magic" in lib.b2f_last_error()
+    eng = ForestEngine(flat, 0)
+    try:
+        rows = np.zeros((4, 24), dtype=np.uint32)
+        out = np.zeros(4, dtype=np.float32)
+        assert lib.b2f_predict(eng.handle, None, 4, _cabi.ptr(out), None) < 0  # NULL rows
+        assert lib.b2f_predict(eng.handle, _cabi.ptr(rows), -1, _cabi.ptr(out), None) < 0  # negative n
+        assert lib.b2f_predict_ex(eng.handle, _cabi.ptr(rows), 4, 7, _cabi.ptr(out), 0, None) < 0  # unknown row format
+        assert lib.b2f_predict(None, _cabi.ptr(rows), 4, _cabi.ptr(out), None) < 0  # NULL model
+        with pytest.raises(ValueError):
+            eng.predict_rows(np.zeros((4, 23), dtype=np.uint32))
+        with pytest.raises(B2FError):
+            eng.moments_allgather(np.zeros((24, 3)))  # communicator not initialised
+        # still healthy afterwards
+        p, _ = eng.predict_rows(rows, np.float32)
+        assert p.shape == (4,) and np.isfinite(p).all()
+    finally:
+        eng.close()
+
+
+def test_load_model_from_mlflow_layout(curated, rf100d6, tmp_path):
+    """The reference's artefact directory: artifacts/classifier/model/model.pkl (02-register-model.ipynb:317-321)
+    -> load_model flattens the pickled sklearn Pipeline and caches the forest blob next to it."""
+    import joblib
+
+    from databricks_kubernetes_mlops_poc_b200 import load_model
+    from oracle import reference_pipeline as rp
+
+    d = tmp_path / "artifacts" / "classifier" / "model"
+    d.mkdir(parents=True)
+    joblib.dump(rf100d6, d / "model.pkl")
+    m = load_model(str(tmp_path))
+    try:
+        df = curated[rp.FEATURES].iloc[:300]
+        want_p, _ = rp.oracle_predict(rf100d6, df)
+        assert np.abs(np.asarray(m.predict(df)["predictions"]) - want_p).max() <= TOL64
+        assert (tmp_path / "forest.b2f.npz").exists()
+    finally:
+        m.close()
+    m2 = load_model(str(tmp_path))  # second load comes from the cached blob
+    try:
+        assert np.abs(m2.predict_proba1(df) - want_p).max() <= TOL64
+    finally:
+        m2.close()

@@ -253,3 +253,59 @@ def test_packed_rows_are_lossless(curated, adversarial, rf100d6):
             assert (code == rows.view(np.int32)[:, j]).all()
         assert (pk[:, 2:16] == rows[:, 9:23]).all()  # numerics bit-identical (NaN payloads included)
         assert (word >> np.uint64(63) == 0).all()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_forest_shapes_through_the_blob(curated, adversarial, seed):
+    """Property check over model shapes: random (n_trees, depth, criterion, training subset, GBDT / RF) ->
+    flatten -> blob validates -> kernel-semantics emulation == the library, labels exact."""
+    from oracle import reference_pipeline as rp
+
+    rng = np.random.default_rng(100 + seed)
+    n_trees = int(rng.choice([1, 2, 31, 32, 33, 65, 130]))
+    depth = int(rng.choice([1, 2, 3, 5, 9, 14]))
+    lo = int(rng.integers(0, 20000))
+    train = curated.iloc[lo : lo + int(rng.choice([200, 1500, 4000]))]
+    if seed % 3 == 2:
+        pipe = rp.fit_gbdt_pipeline(train, train[rp.TARGET].to_numpy(), dict(n_estimators=min(n_trees, 40), max_depth=min(depth, 5), random_state=seed))
+    else:
+        pipe = rp.make_classifier_pipeline(dict(n_estimators=n_trees, max_depth=depth, criterion=["gini", "entropy"][seed % 2], random_state=seed))
+        pipe.fit(train[rp.FEATURES], train[rp.TARGET].to_numpy())
+    probe = curated.iloc[25000:25400]
+    for df in (probe, adversarial.iloc[:200]):
+        (p, l), flat = _emulate(pipe, df)
+        want_p, want_l = rp.oracle_predict(pipe, df)
+        assert np.abs(p - want_p).max() < 1e-13 and (l == want_l).all()
+    assert flat.n_trees == len(pipe.named_steps["classifier"].estimators_)
+
+
+@pytest.mark.parametrize("hole", [None, np.nan])
+def test_training_vocabulary_with_missing_values(curated, hole):
+    """Missing values at FIT time change the vocabulary: NaN is imputed to the constant "missing"
+    (SimpleImputer, 01-train-model.ipynb:200) and becomes a real category; None is left alone by the imputer
+    and becomes OneHotEncoder's None category.  Requests must then map NaN / None / "missing" / unknown
+    exactly as the library does."""
+    from oracle import reference_pipeline as rp
+
+    train = curated.iloc[:3000].copy()
+    col = train["education"].astype(object)
+    col.iloc[::7] = hole
+    train["education"] = col
+    pipe = rp.make_classifier_pipeline(dict(n_estimators=20, max_depth=6, random_state=0))
+    pipe.fit(train[rp.FEATURES], train[rp.TARGET].to_numpy())
+    probe = curated.iloc[5000:5300].copy()
+    c2 = probe["education"].astype(object)
+    c2.iloc[::3] = None
+    c2.iloc[1::5] = np.nan
+    c2.iloc[2::9] = "missing"
+    c2.iloc[3::11] = "unheard_of"
+    probe["education"] = c2
+    (p, l), flat = _emulate(pipe, probe)
+    want_p, want_l = rp.oracle_predict(pipe, probe)
+    if hole is None:
+        assert flat.none_codes[1] >= 0 and flat.missing_codes[1] == -1
+    else:
+        assert "missing" in flat.categories[1] and flat.missing_codes[1] >= 0
+    assert np.abs(p - want_p).max() < 1e-13 and (l == want_l).all()
+    (p1, l1), _ = _emulate(pipe, probe.iloc[:40])  # small-request encoder path
+    assert np.abs(p1 - want_p[:40]).max() < 1e-13 and (l1 == want_l[:40]).all()
