@@ -153,6 +153,7 @@ struct b2f_model {
     cudaStream_t compute = nullptr; /* device-resident interface + moments */
     TicketRec tickets[B2F_TICKETS];
     uint64_t next_ticket = 1;
+    uint64_t next_slot = 0;
     /* moments */
     void *d_mom_rows = nullptr;
     int64_t mom_cap_rows = 0;
@@ -775,7 +776,10 @@ static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, int fmt
             int64_t &o, d;
             ~Advance() { o += d; }
         } advance{off, cnt};
-        Slot &sl = m->slots[c % B2F_STREAMS];
+        /* slots rotate ACROSS calls too, so with several batches in flight (async ring, stream dealer) the next
+         * batch's H2D does not wait for the previous batch's kernel to release the same staging buffer */
+        const int slot_idx = (int)((m->next_slot + (uint64_t)c) % B2F_STREAMS);
+        Slot &sl = m->slots[slot_idx];
         int rc = slot_reserve(m, sl, cnt);
         if (rc) return rc;
         if (c == 0) mark(sl.stream);
@@ -793,7 +797,7 @@ static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, int fmt
             mark(sl.stream);
             CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(proba) + (size_t)off * 8, sl.d_proba, (size_t)cnt * 8, cudaMemcpyDeviceToHost, sl.stream));
             mark(sl.stream);
-            *used_mask |= 1u << (c % B2F_STREAMS);
+            *used_mask |= 1u << slot_idx;
             continue;
         }
         rc = launch_predict(m, sl.stream, sl.d_rows, cnt, fmt, k_proba, f64, k_label);
@@ -803,8 +807,9 @@ static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, int fmt
             CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(proba) + (size_t)off * psz, sl.d_proba, (size_t)cnt * psz, cudaMemcpyDeviceToHost, sl.stream));
         if (label && !direct) CUDA_TRY(cudaMemcpyAsync(label + off, sl.d_label, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
         mark(sl.stream);
-        *used_mask |= 1u << (c % B2F_STREAMS);
+        *used_mask |= 1u << slot_idx;
     }
+    m->next_slot += (uint64_t)c;
     if (timeline) {
         cudaDeviceSynchronize();
         fprintf(stderr, "[b2f timeline] n=%lld chunk=%lld :", (long long)n, (long long)chunk);

@@ -117,6 +117,15 @@ class ForestEngine:
         )
         return t.value
 
+    def predict_pairs_async(self, rows: np.ndarray, out: np.ndarray) -> int:
+        """Asynchronous ``predict_pairs`` on pinned buffers (``out``: SCORED_DTYPE); pair with wait()."""
+        t = C.c_uint64(0)
+        check(
+            self._lib.b2f_predict_async_ex(self._h, ptr(rows), rows.shape[0], _row_format(rows), ptr(out), 2, None, C.byref(t)),
+            "b2f_predict_async_ex",
+        )
+        return t.value
+
     def wait(self, ticket: int) -> None:
         check(self._lib.b2f_wait(self._h, ticket), "b2f_wait")
 

@@ -143,6 +143,7 @@ int b2f_predict_pairs(b2f_model *m, const void *rows, int64_t n, int row_format,
  * b2f_wait(ticket) returns.  proba_is_f64 selects double (1) or float (0) outputs. */
 int b2f_predict_async(b2f_model *m, const void *rows_pinned, int64_t n, void *proba1_pinned,
                       int proba_is_f64, int32_t *label_pinned, b2f_ticket *ticket);
+/* proba_is_f64: 0 = float, 1 = double, 2 = proba1_pinned points at b2f_scored records (label_pinned ignored) */
 int b2f_predict_async_ex(b2f_model *m, const void *rows_pinned, int64_t n, int row_format,
                          void *proba1_pinned, int proba_is_f64, int32_t *label_pinned,
                          b2f_ticket *ticket);
