@@ -306,7 +306,7 @@ def run_reference(args, dist: Dist):
         "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * mean_t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32cmp+f64acc", "data": "synthetic",
         "config": {"workload": f"cfg2: {args.model} in the reference preprocessing, batch {BATCH} x 23 features", "batch": BATCH,
-                   "model": args.model, "rows_per_step": rows},
+                   "forest": args.model, "rows_per_step": rows},
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores if procs == 1 else procs, "kind": "reference", "sample": sample,
                          "host_cores": cores, "best": best},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -499,7 +499,7 @@ def run_b200(args, dist: Dist):
         "config": {
             "workload": f"cfg2: {args.model} ({info0['n_trees']} trees, depth {info0['max_depth']}, {flat.total_nodes} nodes) in the "
                         f"reference preprocessing, batch {BATCH} x 23 features, per GPU",
-            "model": args.model, "batch": BATCH, "parallelism": f"dp{dist.world} (rows sharded, forest replicated, no collective)",
+            "forest": args.model, "batch": BATCH, "parallelism": f"dp{dist.world} (rows sharded, forest replicated, no collective)",
             "l2": f"inputs rotate over {POOL} distinct batches ({POOL * BATCH * row_bytes / 1e6:.0f} MB > 126 MB L2)",
             "walk": info0["walk"], "smem_bytes": info0["smem_bytes"], "rows_per_warp": info0["rows_per_warp"],
             "row_format": f"{row_bytes}-byte encoded rows" + (" (packed: 9 x 7-bit category fields + 14 float32)" if packed else ""),
@@ -667,7 +667,7 @@ def run_stream(args):
         "higher_is_better": True, "scaling": "strong", "data": "synthetic", "dtype": "f32cmp+f64acc",
         "config": {"workload": f"cfg4: {args.model}, {total} rows in {len(plan)} batches of {BATCH}, one process, b2f_predict_stream (one host thread per "
                                f"GPU inside the C call, 2 batches in flight per GPU, pinned buffers), 64-byte rows",
-                   "model": args.model, "parallelism": f"round-robin over {ngpu} GPUs, forest replicated, no collective"},
+                   "forest": args.model, "parallelism": f"round-robin over {ngpu} GPUs, forest replicated, no collective"},
         "e2e": {"value": total / dt, "unit": "rows/s", "h2d_bytes_per_step": BATCH * 64, "d2h_bytes_per_step": BATCH * 8},
         "gpu_launches": int(launches // (passes + 1)), "clocks": sampler.summary(t0w, t1w), "parity_max_abs_dp_vs_sklearn_1024rows": err,
         "roofline_frac_of_n_gpu_hbm": (total / dt) * ALG_BYTES_PER_ROW / 1e9 / (measured_peak_gbs()[0] * ngpu),
