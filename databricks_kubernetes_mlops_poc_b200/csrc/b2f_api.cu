@@ -132,7 +132,6 @@ struct b2f_model {
     int smem_bytes = 0;
     int rows_per_warp_max = 2;
     int64_t chunk_rows = B2F_CHUNK_ROWS;
-    int zero_copy = 0;
     std::vector<int64_t> chunk_plan; /* per-chunk share of a batch in 1/1024ths */
     /* tile kernel (large batches) */
     bool tile_ok = false;
@@ -421,8 +420,6 @@ static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
             if (*q == ',') ++q;
         }
     }
-    const char *zc = getenv("B2F_ZERO_COPY");
-    if (zc) m->zero_copy = atoi(zc);
     /* latency kernel: while rows x groups warps still fit about two waves of the chip */
     m->split_max_rows = std::max<int64_t>(2, (int64_t)m->sm_count * 64 / std::max(1, (int)m->hdr.n_groups));
     if (const char *sp = getenv("B2F_SPLIT_MAX_ROWS")) m->split_max_rows = atoll(sp);
@@ -601,7 +598,7 @@ extern "C" int b2f_model_info(const b2f_model *m, b2f_info *out) {
 /* ------------------------------------------------------------------ pinned memory */
 extern "C" void *b2f_pinned_alloc(size_t nbytes) {
     void *p = nullptr;
-    cudaError_t e = cudaHostAlloc(&p, nbytes ? nbytes : 1, cudaHostAllocPortable | cudaHostAllocMapped);
+    cudaError_t e = cudaHostAlloc(&p, nbytes ? nbytes : 1, cudaHostAllocPortable);
     if (e != cudaSuccess) {
         set_err(B2F_ENOMEM, "cudaHostAlloc(%zu) failed: %s", nbytes, cudaGetErrorString(e));
         return nullptr;
@@ -706,15 +703,6 @@ static int slot_reserve(b2f_model *m, Slot &sl, int64_t rows) {
     return B2F_OK;
 }
 
-static bool host_is_pinned(const void *p) {
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    return at.type == cudaMemoryTypeHost;
-}
-
 /* enqueue the whole batch; on return used_mask tells which slot streams carry work.
  * B2F_TIMELINE=1 (debug): record an event after every operation and print the schedule to stderr. */
 static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, int fmt, void *proba, int f64, int32_t *label, uint32_t *used_mask) {
@@ -728,26 +716,6 @@ static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, int fmt
     }
     const size_t row_bytes = fmt == B2F_ROWS_PACKED64 ? B2F_PACKED_ROW_BYTES : B2F_ROW_BYTES;
     CUDA_TRY(cudaSetDevice(m->device));
-    /* Zero-copy path: when every buffer is page-locked (b2f_pinned_alloc / cudaHostRegister), the kernel
-     * reads the rows and writes the results straight over PCIe -- H2D, walk and D2H fused into one
-     * launch, no copy-engine hand-offs.  mode 1: inputs only, mode 2: inputs and outputs. */
-    if (f64 != 2 && m->zero_copy > 0 && m->zero_copy < 3 && host_is_pinned(rows) && (m->zero_copy < 2 || ((!proba || host_is_pinned(proba)) && (!label || host_is_pinned(label))))) {
-        Slot &sl = m->slots[0];
-        if (m->zero_copy >= 2) {
-            int rc = launch_predict(m, sl.stream, rows, n, fmt, proba, f64, label);
-            if (rc) return rc;
-        } else {
-            int rc = slot_reserve(m, sl, n);
-            if (rc) return rc;
-            rc = launch_predict(m, sl.stream, rows, n, fmt, proba ? sl.d_proba : nullptr, f64, label ? sl.d_label : nullptr);
-            if (rc) return rc;
-            const size_t psz0 = f64 ? sizeof(double) : sizeof(float);
-            if (proba) CUDA_TRY(cudaMemcpyAsync(proba, sl.d_proba, (size_t)n * psz0, cudaMemcpyDeviceToHost, sl.stream));
-            if (label) CUDA_TRY(cudaMemcpyAsync(label, sl.d_label, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
-        }
-        *used_mask = 1u;
-        return B2F_OK;
-    }
     int64_t chunk = m->chunk_rows;
     if (n <= chunk + chunk / 2) chunk = n; /* small batch: one H2D, one launch */
     const size_t psz = f64 == 1 ? sizeof(double) : sizeof(float);
@@ -764,7 +732,6 @@ static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, int fmt
      * 1/1024ths, the last chunk takes the remainder) front-loads the copies so the un-overlapped tail --
      * the last chunk's kernel and D2H -- is short */
     const bool pairs = f64 == 2; /* proba points at {float proba; int32 label} records, label is ignored */
-    const bool zc_out = !pairs && m->zero_copy == 3 && (!proba || host_is_pinned(proba)) && (!label || host_is_pinned(label));
     int c = 0;
     for (int64_t off = 0; off < n; ++c) {
         int64_t cnt = std::min(chunk, n - off);
@@ -786,11 +753,6 @@ static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, int fmt
         CUDA_TRY(cudaMemcpyAsync(sl.d_rows, static_cast<const uint8_t *>(rows) + (size_t)off * row_bytes, (size_t)cnt * row_bytes,
                                  cudaMemcpyHostToDevice, sl.stream));
         mark(sl.stream);
-        /* results: the tile kernel stores one coalesced 128-byte line per warp and array, so with pinned
-         * outputs it can write them straight to host memory (no D2H copy, no copy-engine hand-off) */
-        const bool direct = zc_out && m->tile_ok && cnt >= m->tile_min_rows;
-        void *k_proba = !proba ? nullptr : (direct ? static_cast<uint8_t *>(proba) + (size_t)off * psz : sl.d_proba);
-        int32_t *k_label = !label ? nullptr : (direct ? label + off : sl.d_label);
         if (pairs) { /* one interleaved device buffer, ONE D2H copy per chunk */
             rc = launch_predict(m, sl.stream, sl.d_rows, cnt, fmt, sl.d_proba, 0, static_cast<int32_t *>(sl.d_proba) + 1, 2);
             if (rc) return rc;
@@ -800,12 +762,12 @@ static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, int fmt
             *used_mask |= 1u << slot_idx;
             continue;
         }
-        rc = launch_predict(m, sl.stream, sl.d_rows, cnt, fmt, k_proba, f64, k_label);
+        rc = launch_predict(m, sl.stream, sl.d_rows, cnt, fmt, proba ? sl.d_proba : nullptr, f64, label ? sl.d_label : nullptr);
         if (rc) return rc;
         mark(sl.stream);
-        if (proba && !direct)
+        if (proba)
             CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(proba) + (size_t)off * psz, sl.d_proba, (size_t)cnt * psz, cudaMemcpyDeviceToHost, sl.stream));
-        if (label && !direct) CUDA_TRY(cudaMemcpyAsync(label + off, sl.d_label, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
+        if (label) CUDA_TRY(cudaMemcpyAsync(label + off, sl.d_label, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
         mark(sl.stream);
         *used_mask |= 1u << slot_idx;
     }
