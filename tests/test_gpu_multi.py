@@ -1,0 +1,63 @@
+"""Multi-GPU C-ABI paths (one process driving several handles).  Skipped on a single-GPU box; the driver's
+round-end `pytest -m gpu` runs on one GPU, `gpurun --gpus 2 -- pytest tests/test_gpu_multi.py -m gpu` covers this."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _need_two():
+    from databricks_kubernetes_mlops_poc_b200.engine import device_count
+
+    if device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+
+
+def test_predict_multi_and_stream_across_gpus(curated, rf100d6):
+    _need_two()
+    from databricks_kubernetes_mlops_poc_b200 import flatten, training
+    from databricks_kubernetes_mlops_poc_b200.encode import RowEncoder
+    from databricks_kubernetes_mlops_poc_b200.engine import EngineGroup, device_count
+    from oracle import reference_pipeline as rp
+
+    flat = flatten.flatten_pipeline(rf100d6)
+    enc = RowEncoder(flat)
+    grp = EngineGroup(flat, devices=list(range(device_count())))
+    try:
+        want_p, want_l = rp.oracle_predict(rf100d6, curated)
+        rows = enc.encode_frame(curated)
+        p, l = grp.predict_rows(rows)  # one batch sliced over all GPUs
+        assert np.abs(p - want_p).max() <= 1e-12 and (l == want_l).all()
+        pk = enc.pack_rows(rows)
+        p32 = np.full(len(rows), -1, dtype=np.float32)
+        l32 = np.full(len(rows), -1, dtype=np.int32)
+        grp.predict_stream(pk, 4096, p32, l32)  # batches dealt round-robin, a host thread per GPU
+        assert np.abs(p32 - want_p).max() <= 2e-7 and (l32 == want_l).all()
+        assert all(e.info()["launches"] > 0 for e in grp.engines)
+    finally:
+        grp.close()
+
+
+def test_moments_merge_over_nccl(curated, rf100d6):
+    """b2f_comm_init_all + b2f_moments_multi: per-GPU moments of row slices, 576-byte ncclAllGather, Chan merge."""
+    _need_two()
+    from databricks_kubernetes_mlops_poc_b200 import flatten, training
+    from databricks_kubernetes_mlops_poc_b200.encode import RowEncoder
+    from databricks_kubernetes_mlops_poc_b200.engine import EngineGroup, device_count
+
+    flat = flatten.flatten_pipeline(rf100d6)
+    enc = RowEncoder(flat)
+    _, codes, nums = training.synth_arrays(curated, 300_007, seed=21)
+    rows = enc.encode_arrays(codes, nums)
+    f = rows.view(np.float32)[:, 9:23].astype(np.float64)
+    for nccl in (False, True):
+        grp = EngineGroup(flat, devices=list(range(device_count())), nccl=nccl)
+        try:
+            got = grp.moments(rows)
+            assert (got[9:23, 0] == (~np.isnan(f)).sum(0)).all()
+            assert np.allclose(got[9:23, 1], np.nanmean(f, 0), rtol=1e-10)
+            assert np.allclose(got[9:23, 2] / got[9:23, 0], np.nanvar(f, 0), rtol=1e-9)
+            assert np.allclose(got[:9, 1], codes.mean(0), rtol=1e-12)
+        finally:
+            grp.close()
