@@ -63,6 +63,20 @@ class Info(C.Structure):
     ]
 
 
+class StrColumn(C.Structure):
+    """b2f_str_column: one Arrow string array handed to the native row encoder."""
+
+    _fields_ = [
+        ("offsets", C.c_void_p),
+        ("data", C.c_void_p),
+        ("validity", C.c_void_p),
+        ("offset", C.c_int64),
+        ("data_bytes", C.c_int64),
+        ("offsets_are_64", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); every symbol declared in include/b2f.h must appear here
 SIGNATURES = {
     "b2f_version": (C.c_char_p, []),
@@ -72,6 +86,12 @@ SIGNATURES = {
     "b2f_model_create": (C.c_void_p, [C.c_void_p, C.c_size_t, C.c_int]),
     "b2f_model_destroy": (None, [C.c_void_p]),
     "b2f_model_info": (C.c_int, [C.c_void_p, C.POINTER(Info)]),
+    "b2f_encoder_create": (C.c_void_p, [C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]),
+    "b2f_encoder_destroy": (None, [C.c_void_p]),
+    "b2f_encoder_encode": (
+        C.c_int,
+        [C.c_void_p, C.c_int64, C.POINTER(StrColumn), C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_void_p, C.c_int],
+    ),
     "b2f_pinned_alloc": (C.c_void_p, [C.c_size_t]),
     "b2f_pinned_free": (None, [C.c_void_p]),
     "b2f_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

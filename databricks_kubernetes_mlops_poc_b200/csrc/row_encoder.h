@@ -1,0 +1,159 @@
+/*
+ * row_encoder.h -- native host-side row encoder (no GPU involved; compiled into libb200forest.so).
+ *
+ * The host half of the "fused preprocess": what the reference does with pandas + sklearn's
+ * SimpleImputer(constant) / OneHotEncoder lookup before any arithmetic
+ * (reference app/main.py:54 `pd.DataFrame(data)`, databricks/src/01-train-model.ipynb:197-221).
+ * Input is columnar, exactly as pandas / Arrow hold it:
+ *   - categorical columns as Arrow string arrays (validity bitmap, int32 or int64 offsets, UTF-8 bytes),
+ *   - numeric columns as float64 arrays (pointer + element stride).
+ * Output is encoded rows in either layout of include/b2f.h, written straight into the caller's (pinned)
+ * staging buffer by a few host threads.  Semantics are those of databricks_kubernetes_mlops_poc_b200/encode.py
+ * (which remains the portable implementation and the one used for tiny requests):
+ *   string in the feature's vocabulary -> its index; unknown string -> -1; null -> the feature's "missing" code
+ *   (the imputer's constant, if it was a training category) else -1;  float64 -> float32 round-to-nearest, NaN kept
+ *   (the kernel imputes), +-inf or float32 overflow -> error (sklearn raises ValueError there).
+ */
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/b2f.h"
+
+struct EncEntry {
+    uint64_t prefix; /* first min(len, 8) bytes, zero padded */
+    uint32_t len;
+    int32_t code;
+};
+
+struct b2f_encoder {
+    int n_cat = 0, n_num = 0;
+    std::vector<std::vector<std::string>> vocab; /* per categorical feature, in code order */
+    std::vector<std::vector<EncEntry>> index;    /* same, as (length, 8-byte prefix) keys */
+    std::vector<int32_t> null_code;              /* per categorical feature: code of a null entry, or -1 */
+    bool packed_ok = false;
+};
+
+static inline uint64_t enc_prefix(const uint8_t *s, int64_t len) {
+    uint64_t p = 0;
+    memcpy(&p, s, (size_t)(len < 8 ? len : 8));
+    return p;
+}
+
+static inline int32_t enc_lookup(const b2f_encoder *e, int j, const uint8_t *s, int64_t len, bool can_read8) {
+    /* vocabularies here have <= a few dozen short entries: compare (length, first 8 bytes) as two integers and
+     * fall back to memcmp only for longer strings -- cheaper than hashing.  The prefix is one unaligned 8-byte load
+     * masked to the string's length whenever 8 bytes are readable (always, except at the very end of the buffer). */
+    uint64_t p;
+    if (can_read8) {
+        memcpy(&p, s, 8);
+        if (len < 8) p &= (len == 0 ? 0ull : (~0ull >> (64 - 8 * len)));
+    } else {
+        p = enc_prefix(s, len);
+    }
+    for (const EncEntry &en : e->index[j])
+        if (en.len == (uint32_t)len && en.prefix == p && (len <= 8 || memcmp(e->vocab[j][en.code].data() + 8, s + 8, (size_t)len - 8) == 0))
+            return en.code;
+    return -1;
+}
+
+static int enc_range(const b2f_encoder *e, int64_t lo, int64_t hi, const b2f_str_column *cats, const double *const *nums,
+                     const int64_t *num_strides, int row_format, uint32_t *out) {
+    const int nc = e->n_cat, nn = e->n_num;
+    const bool packed = row_format == B2F_ROWS_PACKED64;
+    const int words = packed ? 16 : B2F_ROW_WORDS;
+    int bad = 0;
+    for (int64_t i = lo; i < hi; ++i) {
+        int32_t codes[16];
+        for (int j = 0; j < nc; ++j) {
+            const b2f_str_column &c = cats[j];
+            const int64_t k = i + c.offset;
+            int32_t code;
+            if (c.validity && !((c.validity[k >> 3] >> (k & 7)) & 1)) {
+                code = e->null_code[j];
+            } else {
+                int64_t a, b;
+                if (c.offsets_are_64) {
+                    a = static_cast<const int64_t *>(c.offsets)[k], b = static_cast<const int64_t *>(c.offsets)[k + 1];
+                } else {
+                    a = static_cast<const int32_t *>(c.offsets)[k], b = static_cast<const int32_t *>(c.offsets)[k + 1];
+                }
+                code = enc_lookup(e, j, c.data + a, b - a, a + 8 <= c.data_bytes);
+            }
+            codes[j] = code;
+        }
+        uint32_t *row = out + (size_t)i * words;
+        uint32_t *numw;
+        if (packed) {
+            uint64_t w = 0;
+            for (int j = 0; j < nc; ++j) w |= (uint64_t)(uint32_t)(codes[j] + 1) << (7 * j);
+            row[0] = (uint32_t)w;
+            row[1] = (uint32_t)(w >> 32);
+            numw = row + 2;
+            for (int k = nn; k < 14; ++k) numw[k] = 0;
+        } else {
+            for (int j = 0; j < nc; ++j) row[j] = (uint32_t)codes[j];
+            numw = row + nc;
+            for (int k = nc + nn; k < B2F_ROW_WORDS; ++k) row[k] = 0;
+        }
+        for (int k = 0; k < nn; ++k) {
+            const double v = nums[k][i * num_strides[k]];
+            const float f = (float)v; /* round-to-nearest-even, as numpy astype(float32) */
+            if (!(v != v) && !isfinite(f)) bad = 1; /* inf, or a finite float64 that overflows float32 */
+            memcpy(&numw[k], &f, 4);
+        }
+    }
+    return bad;
+}
+
+extern "C" b2f_encoder *b2f_encoder_create(int n_cat, int n_num, const int32_t *vocab_counts, const char *vocab_bytes,
+                                           const int64_t *vocab_offsets, const int32_t *null_codes) {
+    if (n_cat < 0 || n_cat > 16 || n_num < 0 || n_cat + n_num > 23 || (n_cat > 0 && (!vocab_counts || !vocab_bytes || !vocab_offsets)))
+        return nullptr;
+    b2f_encoder *e = new b2f_encoder();
+    e->n_cat = n_cat;
+    e->n_num = n_num;
+    e->vocab.resize(n_cat);
+    e->null_code.assign(n_cat, -1);
+    int64_t s = 0;
+    e->packed_ok = n_cat <= 9 && n_num <= 14;
+    for (int j = 0; j < n_cat; ++j) {
+        for (int k = 0; k < vocab_counts[j]; ++k, ++s)
+            e->vocab[j].emplace_back(vocab_bytes + vocab_offsets[s], (size_t)(vocab_offsets[s + 1] - vocab_offsets[s]));
+        if (null_codes) e->null_code[j] = null_codes[j];
+        if (vocab_counts[j] > 126) e->packed_ok = false;
+        e->index.emplace_back();
+        for (int k = 0; k < vocab_counts[j]; ++k) {
+            const std::string &w = e->vocab[j][k];
+            e->index[j].push_back(EncEntry{enc_prefix(reinterpret_cast<const uint8_t *>(w.data()), (int64_t)w.size()), (uint32_t)w.size(), k});
+        }
+    }
+    return e;
+}
+
+extern "C" void b2f_encoder_destroy(b2f_encoder *e) { delete e; }
+
+extern "C" int b2f_encoder_encode(const b2f_encoder *e, int64_t n, const b2f_str_column *cat_cols, const double *const *num_cols,
+                                  const int64_t *num_strides, int row_format, void *rows_out, int threads) {
+    if (!e || n < 0 || !rows_out || (e->n_cat > 0 && !cat_cols) || (e->n_num > 0 && (!num_cols || !num_strides))) return B2F_EINVAL;
+    if (row_format != B2F_ROWS_WORDS24 && row_format != B2F_ROWS_PACKED64) return B2F_EINVAL;
+    if (row_format == B2F_ROWS_PACKED64 && !e->packed_ok) return B2F_EINVAL;
+    if (threads < 1) threads = 1;
+    threads = (int)std::min<int64_t>(threads, std::max<int64_t>(1, n / 4096));
+    uint32_t *out = static_cast<uint32_t *>(rows_out);
+    if (threads == 1) return enc_range(e, 0, n, cat_cols, num_cols, num_strides, row_format, out) ? B2F_ERANGE : B2F_OK;
+    std::vector<int> bad(threads, 0);
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t)
+        pool.emplace_back([&, t] { bad[t] = enc_range(e, n * t / threads, n * (t + 1) / threads, cat_cols, num_cols, num_strides, row_format, out); });
+    bad[0] = enc_range(e, 0, n / threads, cat_cols, num_cols, num_strides, row_format, out);
+    for (auto &th : pool) th.join();
+    for (int b : bad)
+        if (b) return B2F_ERANGE;
+    return B2F_OK;
+}

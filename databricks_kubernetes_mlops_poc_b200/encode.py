@@ -19,6 +19,9 @@ Reference behaviour being matched (``databricks/src/01-train-model.ipynb:195-221
 
 from __future__ import annotations
 
+import ctypes as C
+import os
+
 import numpy as np
 import pandas as pd
 
@@ -31,6 +34,7 @@ except ImportError:  # pragma: no cover
 from .flatten import ROW_WORDS, FlatForest
 
 PACKED_ROW_WORDS = 16  # B2F_ROWS_PACKED64: 64-byte rows (include/b2f.h)
+NATIVE_THREADS = max(1, min(16, (os.cpu_count() or 1)))
 
 _F32_MAX = float(np.finfo(np.float32).max)
 
@@ -49,6 +53,88 @@ class RowEncoder:
         self._none = list(flat.none_codes) if flat.none_codes else [-1] * self.n_cat  # None -> None category, if any
         # packed 64-byte rows: nine 7-bit (code + 1) fields + 14 float32 numerics
         self.packed_ok = self.n_cat <= 9 and self.n_num <= 14 and all(len(v) <= 126 for v in flat.categories)
+        self._native = None  # b2f_encoder*, created on first use (needs libb200forest.so, not a GPU)
+        self._native_failed = pa is None
+        self._categories = [list(v) for v in flat.categories]
+
+    # ------------------------------------------------------------------ native encoder (csrc/row_encoder.h)
+    def _native_handle(self):
+        if self._native is None and not self._native_failed:
+            try:
+                from . import _cabi
+
+                lib = _cabi.load_library()
+                blobs = [c.encode("utf-8") for v in self._categories for c in v]
+                offsets = np.zeros(len(blobs) + 1, dtype=np.int64)
+                np.cumsum([len(b) for b in blobs], out=offsets[1:])
+                counts = np.array([len(v) for v in self._categories], dtype=np.int32)
+                # a null entry: pandas' Arrow-backed strings cannot tell None from NaN; NaN semantics first
+                nulls = np.array([m if m >= 0 else n for m, n in zip(self._missing, self._none)], dtype=np.int32)
+                h = lib.b2f_encoder_create(self.n_cat, self.n_num, _cabi.ptr(counts), b"".join(blobs), _cabi.ptr(offsets), _cabi.ptr(nulls))
+                if not h:
+                    raise RuntimeError("b2f_encoder_create failed")
+                self._native, self._lib, self._cabi = h, lib, _cabi
+            except Exception:
+                self._native_failed = True
+        return self._native
+
+    def __del__(self):
+        try:
+            if self._native:
+                self._lib.b2f_encoder_destroy(self._native)
+        except Exception:
+            pass
+
+    def _encode_native(self, df: pd.DataFrame, out: np.ndarray, packed: bool) -> bool:
+        """Columnar fast path: Arrow string buffers + float64 columns -> rows, in C++ threads.  Returns False when
+        a column does not have the expected physical type (the caller then takes the portable path)."""
+        h = self._native_handle()
+        if h is None:
+            return False
+        n = len(df)
+        cols = (self._cabi.StrColumn * max(self.n_cat, 1))()
+        keep = []  # keep the Arrow arrays alive during the call
+        for j, name in enumerate(self.cat_features):
+            ser = df[name]
+            if ser.dtype == object:
+                # object columns can hold None and NaN side by side, which the library treats differently
+                # (None is not imputed); Arrow would merge them into one null -> portable path
+                return False
+            try:
+                arr = pa.array(ser, from_pandas=True)
+            except (pa.ArrowInvalid, pa.ArrowTypeError, pa.ArrowNotImplementedError):
+                return False
+            if isinstance(arr, pa.ChunkedArray):
+                arr = arr.combine_chunks()
+            if pa.types.is_dictionary(arr.type):
+                arr = arr.dictionary_decode()
+            if not (pa.types.is_string(arr.type) or pa.types.is_large_string(arr.type)):
+                return False
+            validity, offsets, data = arr.buffers()
+            keep.append((arr, validity, offsets, data))
+            cols[j].offsets = offsets.address
+            cols[j].data = data.address if data is not None else 0
+            cols[j].validity = validity.address if (validity is not None and arr.null_count) else 0
+            cols[j].offset = arr.offset
+            cols[j].data_bytes = data.size if data is not None else 0
+            cols[j].offsets_are_64 = 1 if pa.types.is_large_string(arr.type) else 0
+        ptrs = (C.c_void_p * max(self.n_num, 1))()
+        strides = np.ones(max(self.n_num, 1), dtype=np.int64)
+        for k, name in enumerate(self.num_features):
+            col = df[name].to_numpy()
+            if col.dtype != np.float64:
+                if col.dtype.kind not in "iuf":
+                    return False
+                col = col.astype(np.float64)
+            keep.append(col)
+            ptrs[k] = col.ctypes.data
+            strides[k] = col.strides[0] // 8 if n > 1 else 1
+        rc = self._lib.b2f_encoder_encode(h, n, cols, ptrs, self._cabi.ptr(strides), 1 if packed else 0, self._cabi.ptr(out), NATIVE_THREADS)
+        if rc == -7:
+            raise ValueError("Input X contains infinity or a value too large for dtype('float32').")
+        if rc != 0:
+            raise RuntimeError(f"b2f_encoder_encode failed (rc={rc})")
+        return True
 
     # ------------------------------------------------------------------ columns
     def encode_categorical(self, j: int, values) -> np.ndarray:
@@ -126,6 +212,8 @@ class RowEncoder:
                     nums[i, k] = np.nan if v is None else float(v)  # float("abc") raises ValueError, as pd.to_numeric does
             if self.n_num:
                 out.view(np.float32)[:, self.n_cat : self.n_cat + self.n_num] = self.cast_numeric(nums)
+        elif self._encode_native(df, out, packed=False):
+            return out
         else:
             for j, name in enumerate(self.cat_features):
                 as_i32[:, j] = self.encode_categorical(j, df[name])
@@ -172,6 +260,16 @@ class RowEncoder:
         return out
 
     def encode_frame_packed(self, df: pd.DataFrame, out: np.ndarray | None = None) -> np.ndarray:
+        """DataFrame -> (N, 16) packed rows; large frames go through the native encoder in one pass."""
+        n = len(df)
+        if n > self.SMALL_BATCH and self.packed_ok:
+            missing = [c for c in self.cat_features + self.num_features if c not in df.columns]
+            if missing:
+                raise KeyError(f"{missing} not in index")
+            if out is None:
+                out = np.empty((n, PACKED_ROW_WORDS), dtype=np.uint32)
+            if self._encode_native(df, out, packed=True):
+                return out
         return self.pack_rows(self.encode_frame(df), out=out)
 
     def encode_arrays_packed(self, codes: np.ndarray, nums: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:

@@ -78,9 +78,10 @@ class ForestEngine:
             self._pinned[tag] = b
         return b
 
-    def staging(self, n: int):
-        """(rows uint32 (n,24), proba f64 (n,), label i32 (n,)) views over pinned memory."""
-        rows = self.pinned("rows", n * ROW_WORDS * 4).view(np.uint32, (n, ROW_WORDS))
+    def staging(self, n: int, packed: bool = False):
+        """(rows uint32 (n,24) or packed (n,16), proba f64 (n,), label i32 (n,)) views over pinned memory."""
+        words = PACKED_ROW_WORDS if packed else ROW_WORDS
+        rows = self.pinned("rows", n * ROW_WORDS * 4).view(np.uint32, (n, words))
         proba = self.pinned("proba", n * 8).view(np.float64, (n,))
         label = self.pinned("label", n * 4).view(np.int32, (n,))
         return rows, proba, label

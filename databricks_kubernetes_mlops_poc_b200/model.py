@@ -73,8 +73,13 @@ class B200Model:
     # ------------------------------------------------------------------ scoring
     def _score(self, df: pd.DataFrame):
         n = len(df)
-        rows, proba, label = self.engine.staging(n)
-        self.encoder.encode_frame(df, out=rows)
+        # large requests travel as 64-byte packed rows (one third fewer PCIe bytes), encoded natively in one pass
+        packed = self.encoder.packed_ok and n > self.encoder.SMALL_BATCH
+        rows, proba, label = self.engine.staging(n, packed=packed)
+        if packed:
+            self.encoder.encode_frame_packed(df, out=rows)
+        else:
+            self.encoder.encode_frame(df, out=rows)
         if self.proba_dtype != np.float64:
             proba = proba.view(np.float32)[:n]
         target = self.group if self.group is not None else self.engine
@@ -116,8 +121,12 @@ class _Replica:
 
     def predict_proba1(self, df: pd.DataFrame) -> np.ndarray:
         n = len(df)
-        rows, proba, label = self.engine.staging(n)
-        self.encoder.encode_frame(df, out=rows)
+        packed = self.encoder.packed_ok and n > self.encoder.SMALL_BATCH
+        rows, proba, label = self.engine.staging(n, packed=packed)
+        if packed:
+            self.encoder.encode_frame_packed(df, out=rows)
+        else:
+            self.encoder.encode_frame(df, out=rows)
         self.engine.predict_rows(rows, proba_dtype=np.float64, want_label=False, out_proba=proba)
         return np.array(proba, dtype=np.float64)
 

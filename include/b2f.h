@@ -60,6 +60,7 @@ extern "C" {
 #define B2F_ENOMEM (-4)  /* host or device allocation failed */
 #define B2F_ENCCL (-5)   /* NCCL error or NCCL library not loadable */
 #define B2F_ESTATE (-6)  /* call not valid in this state (e.g. communicator not initialised) */
+#define B2F_ERANGE (-7)  /* a numeric input is infinite or overflows float32 (sklearn raises ValueError there) */
 
 /* aggregation modes stored in the forest blob */
 #define B2F_AGG_RF_MEAN 0       /* RandomForestClassifier.predict_proba: mean of leaf class fractions */
@@ -117,6 +118,30 @@ int b2f_blob_validate(const void *forest_blob, size_t nbytes);
 b2f_model *b2f_model_create(const void *forest_blob, size_t nbytes, int device); /* NULL on error */
 void b2f_model_destroy(b2f_model *m);
 int b2f_model_info(const b2f_model *m, b2f_info *out);
+
+/* ---- native host-side row encoder (no GPU involved): columnar request data -> encoded rows -----------------
+ * Replaces the pandas / sklearn lookup work in front of the arithmetic (reference app/main.py:54,
+ * databricks/src/01-train-model.ipynb:197-221).  Categorical columns come as Arrow string arrays, numeric columns as
+ * float64 arrays; rows are written (multi-threaded) straight into the caller's, normally pinned, staging buffer. */
+typedef struct b2f_str_column {
+    const void *offsets;     /* Arrow offsets buffer: int32[n+1] or int64[n+1] */
+    const uint8_t *data;     /* Arrow UTF-8 data buffer */
+    const uint8_t *validity; /* Arrow validity bitmap (bit set = present), or NULL when there are no nulls */
+    int64_t offset;          /* logical offset of the array inside its buffers (Arrow slice) */
+    int64_t data_bytes;      /* size of the data buffer in bytes */
+    int32_t offsets_are_64;  /* 1: large_string (int64 offsets), 0: string (int32 offsets) */
+    int32_t reserved;
+} b2f_str_column;
+typedef struct b2f_encoder b2f_encoder;
+/* vocabularies concatenated feature by feature: entry s spans vocab_bytes[vocab_offsets[s] .. vocab_offsets[s+1]);
+ * null_codes[j] = code a null entry of feature j gets (the imputer's constant category if fit saw one), or -1 */
+b2f_encoder *b2f_encoder_create(int n_cat, int n_num, const int32_t *vocab_counts, const char *vocab_bytes,
+                                const int64_t *vocab_offsets, const int32_t *null_codes);
+void b2f_encoder_destroy(b2f_encoder *e);
+/* num_cols[k] + i * num_strides[k] addresses row i of numeric column k (strides in elements).
+ * Returns B2F_ERANGE if a value is infinite / overflows float32 (rows_out is then unspecified). */
+int b2f_encoder_encode(const b2f_encoder *e, int64_t n, const b2f_str_column *cat_cols, const double *const *num_cols,
+                       const int64_t *num_strides, int row_format, void *rows_out, int threads);
 
 /* ---- pinned host memory for request batches (the batching ring lives in these) ------------- */
 void *b2f_pinned_alloc(size_t nbytes); /* NULL on error */

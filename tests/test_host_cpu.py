@@ -309,3 +309,52 @@ def test_training_vocabulary_with_missing_values(curated, hole):
     assert np.abs(p - want_p).max() < 1e-13 and (l == want_l).all()
     (p1, l1), _ = _emulate(pipe, probe.iloc[:40])  # small-request encoder path
     assert np.abs(p1 - want_p[:40]).max() < 1e-13 and (l1 == want_l[:40]).all()
+
+
+def test_native_encoder_matches_portable_encoder(curated, inference, rf100d6):
+    """csrc/row_encoder.h (Arrow string buffers + float64 columns -> rows, C++ threads) == encode.py's portable
+    path, for both row layouts, on sliced / reordered frames, nulls, unknown strings, integer numerics."""
+    import pandas as pd
+
+    from databricks_kubernetes_mlops_poc_b200 import flatten
+    from databricks_kubernetes_mlops_poc_b200.encode import RowEncoder
+    from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES
+
+    enc = RowEncoder(flatten.flatten_pipeline(rf100d6))
+    base = curated[ALL_FEATURES].iloc[:9000].copy()
+    rng = np.random.default_rng(4)
+    for name in ("education", "repayment_status_3"):
+        col = base[name].astype(object)
+        col[rng.random(len(base)) < 0.05] = "never_seen"
+        col[rng.random(len(base)) < 0.03] = None
+        base[name] = col.astype("str") if False else pd.array(col, dtype="str")  # Arrow-backed string column with nulls
+    base["age"] = base["age"].astype(np.int64)
+    num = base["bill_amount_2"].to_numpy(copy=True)
+    num[::17] = np.nan
+    base["bill_amount_2"] = num
+    frames = [base, base.iloc[1234:7777], base[list(reversed(ALL_FEATURES))], inference]
+    for df in frames:
+        assert len(df) > RowEncoder.SMALL_BATCH or df is inference
+        want = np.empty((len(df), 24), dtype=np.uint32)
+        enc2 = RowEncoder(flatten.flatten_pipeline(rf100d6))
+        enc2._native_failed = True  # portable path only
+        enc2.encode_frame(df, out=want)
+        got = np.zeros_like(want)
+        used = enc._encode_native(df, got, packed=False)
+        assert used, "native path should accept string-dtype columns"
+        assert (got == want).all()
+        pk = np.zeros((len(df), 16), dtype=np.uint32)
+        assert enc._encode_native(df, pk, packed=True)
+        assert (pk == enc2.pack_rows(want)).all()
+        assert (enc.encode_frame_packed(df) == pk).all() and (enc.encode_frame(df) == want).all()
+    bad = base.copy()
+    bad.loc[bad.index[5000], "payment_amount_1"] = np.inf
+    with pytest.raises(ValueError, match="infinity or a value too large"):
+        enc.encode_frame(bad)
+    bad.loc[bad.index[5000], "payment_amount_1"] = 1e39
+    with pytest.raises(ValueError, match="infinity or a value too large"):
+        enc.encode_frame_packed(bad)
+    obj = base.copy()
+    obj["sex"] = obj["sex"].astype(object)  # object columns take the portable path (None vs NaN semantics)
+    assert not enc._encode_native(obj, np.zeros((len(obj), 24), dtype=np.uint32), packed=False)
+    assert (enc.encode_frame(obj) == enc.encode_frame(base)).all()
