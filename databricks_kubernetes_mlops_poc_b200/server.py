@@ -49,7 +49,8 @@ def rows_to_frame(data) -> pd.DataFrame:
     """Validated request rows -> the 23 named columns, built column-wise."""
     cols = {}
     for name in CATEGORICAL_FEATURES:
-        cols[name] = np.array([getattr(r, name) for r in data], dtype=object)
+        # validated `str` fields: an Arrow-backed string column, which the native row encoder reads in place
+        cols[name] = pd.array([getattr(r, name) for r in data], dtype="str")
     for name in NUMERIC_FEATURES:
         cols[name] = np.array([getattr(r, name) for r in data], dtype=np.float64)
     return pd.DataFrame(cols, columns=ALL_FEATURES)
