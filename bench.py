@@ -469,6 +469,11 @@ def run_b200(args, dist: Dist):
     clocks = sampler.summary(t_load0, t_load1)
     info1 = eng.info()
 
+    # ---- K4: the reference's outlier detector as a second forest over the same rows (rank 0, N=1)
+    outl = None
+    if dist.rank == 0 and dist.world == 1 and not args.no_outliers:
+        outl = outlier_section(eng, enc, base, flat, d_rows, d_proba, d_label, h_rows, nums, K, W, packed)
+
     # ---- cpu baseline (rank 0, N=1 only): bounded sample = the same 65 536-row batch 0
     cpu = None
     if dist.rank == 0 and dist.world == 1 and not args.no_cpu:
@@ -526,11 +531,67 @@ def run_b200(args, dist: Dist):
         line["cpu_baseline"] = cpu
     if mom is not None:
         line["cfg5_moments"] = mom
+    if outl is not None:
+        line["outlier_forest"] = outl
     for d in (d_rows, d_proba, d_label):
         eng.device_free(d)
     eng.close()
     if dist.rank == 0:
         emit(line)
+
+
+def outlier_section(eng, enc, base, flat, d_rows, d_proba, d_label, h_rows, nums, K, W, packed):
+    """IsolationForest(100) fitted as the reference fits it (02-register-model.ipynb:232-233, on the curated table's 14
+    numerics): kernel-only rate of the isolation-forest walk on the resident pool, the end-to-end rate of
+    b2f_predict_full (classifier + outlier forest on ONE H2D copy of the rows, 24-byte records back), sklearn's own
+    decision_function on the host beside it, and a flag / score parity spot check."""
+    from sklearn.ensemble import IsolationForest
+
+    from databricks_kubernetes_mlops_poc_b200 import flatten
+    from databricks_kubernetes_mlops_poc_b200._cabi import SCORED_FULL_DTYPE
+    from databricks_kubernetes_mlops_poc_b200.engine import ForestEngine
+
+    thr = 0.0  # the reference's 0.95 can never fire (score <= 0.5); 0.0 exercises both outcomes
+    iso = IsolationForest(n_estimators=100, random_state=0).fit(base[list(flat.num_features)].to_numpy())
+    blob = flatten.flatten_isolation_forest(iso, len(flat.cat_features), len(flat.num_features), threshold=thr)
+    alone = ForestEngine(blob, eng.device)
+    alone.predict_stream_timed(d_rows, BATCH, POOL, d_proba, False, d_label, W, packed=packed)
+    ms_each, ms_total = alone.predict_stream_timed(d_rows, BATCH, POOL, d_proba, False, d_label, K, packed=packed)
+    got_s = np.empty(BATCH, dtype=np.float32)
+    got_f = np.empty(BATCH, dtype=np.int32)
+    alone.d2h(got_s, d_proba)
+    alone.d2h(got_f, d_label)
+    info = alone.info()
+    alone.close()
+    sel = np.arange(0, BATCH, BATCH // 2048)[:2048]
+    x = nums[:BATCH].astype(np.float64)
+    t0 = time.perf_counter()
+    want = -iso.decision_function(x[:16384])
+    cpu_s = time.perf_counter() - t0
+    want_sel = -iso.decision_function(x[sel])
+
+    eng.attach_outlier_forest(blob)
+    h_full = eng.pinned("bench_full", BATCH * POOL * 24).view(SCORED_FULL_DTYPE, (BATCH * POOL,))
+    for i in range(W):
+        b = i % POOL
+        eng.predict_full(h_rows[b * BATCH:(b + 1) * BATCH], out=h_full[b * BATCH:(b + 1) * BATCH])
+    t0 = time.perf_counter()
+    for i in range(K):
+        b = i % POOL
+        eng.predict_full(h_rows[b * BATCH:(b + 1) * BATCH], out=h_full[b * BATCH:(b + 1) * BATCH])
+    full_s = time.perf_counter() - t0
+    return {
+        "detector": "IsolationForest(n_estimators=100, max_samples=256) on the 14 numerics, score = -decision_function, flag = score > 0.0",
+        "trees": info["n_trees"], "max_depth": info["max_depth"], "walk": info["walk"],
+        "kernel_rows_per_s": BATCH * K / (ms_total * 1e-3), "kernel_avg_launch_ms": float(np.mean(ms_each)),
+        "e2e_full_rows_per_s": BATCH * K / full_s, "e2e_full_ms_per_step": 1e3 * full_s / K,
+        "e2e_api": "b2f_predict_full(host pinned rows) -> {f64 proba, i32 label, i32 is_outlier, f32 score} per row",
+        "d2h_bytes_per_step": BATCH * 24,
+        "cpu_sklearn_rows_per_s": 16384 / cpu_s, "cpu_sample": "IsolationForest.decision_function on 16384 rows, sklearn default threading",
+        "parity_max_abs_dscore_2048rows": float(np.abs(got_s[sel].astype(np.float64) - want_sel).max()),
+        "parity_flags_equal_2048rows": bool((got_f[sel] == (want_sel > thr)).all()),
+        "parity_full_vs_alone_flags_equal": bool((h_full["is_outlier"][:BATCH] == got_f).all()),
+    }
 
 
 def latency_sweep(args, dist: Dist):
@@ -688,6 +749,7 @@ def main():
     ap.add_argument("--sweep-model", default="rf500d8", choices=sorted(MODELS))
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-moments", action="store_true")
+    ap.add_argument("--no-outliers", action="store_true", help="skip the K4 outlier-forest section")
     ap.add_argument("--cfg1", action="store_true", help="config 1: the reference CPU path on 1k curated rows (no GPU)")
     ap.add_argument("--stream", action="store_true", help="config 4: one process, 10M-row stream round-robin over all GPUs")
     ap.add_argument("--stream-rows", type=int, default=10_000_000)

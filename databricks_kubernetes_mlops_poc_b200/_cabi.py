@@ -23,13 +23,16 @@ PACKED_ROW_BYTES = 64
 ROWS_WORDS24 = 0
 ROWS_PACKED64 = 1
 SCORED_DTYPE = np.dtype([("proba1", np.float32), ("label", np.int32)])  # b2f_scored
+SCORED_FULL_DTYPE = np.dtype(  # b2f_scored_full, 24 bytes
+    [("proba1", np.float64), ("label", np.int32), ("is_outlier", np.int32), ("outlier_score", np.float32), ("reserved", np.int32)]
+)
 MOMENT_VALUES = ROW_WORDS * 3
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "lib", "libb200forest.so")
 
 WALK_NAMES = {0: "smem", 1: "global"}
-AGG_NAMES = {0: "rf_mean", 1: "gbdt_logistic"}
+AGG_NAMES = {0: "rf_mean", 1: "gbdt_logistic", 2: "iforest"}
 
 
 class B2FError(RuntimeError):
@@ -60,6 +63,8 @@ class Info(C.Structure):
         ("tile_warps", C.c_int32),
         ("launches_split", C.c_int64),
         ("split_max_rows", C.c_int64),
+        ("outlier_trees", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -98,6 +103,8 @@ SIGNATURES = {
     "b2f_predict_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "b2f_predict_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "b2f_predict_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "b2f_model_attach_outlier_forest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "b2f_predict_full": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "b2f_predict_async_ex": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_uint64)],

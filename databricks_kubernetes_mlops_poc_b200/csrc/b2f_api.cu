@@ -12,6 +12,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <stdarg.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -112,7 +113,7 @@ static int nccl_load(void) {
 struct Slot {
     cudaStream_t stream = nullptr;
     void *d_rows = nullptr;
-    void *d_proba = nullptr; /* sized for double */
+    void *d_proba = nullptr; /* 24 B per row: double, {float, int32} pairs or b2f_scored_full records */
     int32_t *d_label = nullptr;
     int64_t cap_rows = 0;
 };
@@ -149,6 +150,8 @@ struct b2f_model {
     bool packed_ok = false;
     void *d_blob = nullptr;
     int64_t forest_bytes = 0;
+    b2f_model *outlier = nullptr; /* attached isolation forest (b2f_model_attach_outlier_forest): a child handle on the
+                                     same device whose kernels are launched on this handle's streams and rows */
     Slot slots[B2F_STREAMS];
     cudaStream_t compute = nullptr; /* device-resident interface + moments */
     TicketRec tickets[B2F_TICKETS];
@@ -180,7 +183,7 @@ static int validate_blob(const uint8_t *blob, size_t nbytes, b2f_blob_header *hd
     if (h.version != B2F_BLOB_VERSION) return set_err(B2F_EINVAL, "forest blob: version %u, expected %u", h.version, B2F_BLOB_VERSION);
     if (h.header_bytes != B2F_BLOB_HEADER_BYTES || h.row_words != B2F_ROW_WORDS)
         return set_err(B2F_EINVAL, "forest blob: header_bytes=%u row_words=%u unsupported", h.header_bytes, h.row_words);
-    if (h.agg_mode != B2F_AGG_RF_MEAN && h.agg_mode != B2F_AGG_GBDT_LOGISTIC)
+    if (h.agg_mode != B2F_AGG_RF_MEAN && h.agg_mode != B2F_AGG_GBDT_LOGISTIC && h.agg_mode != B2F_AGG_IFOREST)
         return set_err(B2F_EINVAL, "forest blob: unknown agg_mode %u", h.agg_mode);
     if (h.n_trees == 0 || h.n_trees > B2F_MAX_TREES) return set_err(B2F_EINVAL, "forest blob: n_trees=%u out of range [1,%d]", h.n_trees, B2F_MAX_TREES);
     if (h.n_groups != (h.n_trees + 31) / 32) return set_err(B2F_EINVAL, "forest blob: n_groups=%u inconsistent with n_trees=%u", h.n_groups, h.n_trees);
@@ -379,6 +382,7 @@ static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
     kp.n_num = (int)m->hdr.n_num;
     kp.init_raw = m->hdr.init_raw;
     kp.denom = m->hdr.denom;
+    kp.threshold = m->hdr.threshold;
     memcpy(kp.impute, m->hdr.impute, sizeof(kp.impute));
     const b2f_blob_group *gt = reinterpret_cast<const b2f_blob_group *>(blob + m->hdr.groups_off);
     for (uint32_t g = 0; g < m->hdr.n_groups; ++g) {
@@ -478,6 +482,7 @@ static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
             tp.n_num = kp.n_num;
             tp.init_raw = kp.init_raw;
             tp.denom = kp.denom;
+            tp.threshold = kp.threshold;
             memcpy(tp.impute, kp.impute, sizeof(tp.impute));
             m->tile_cwarps = cwarps;
             m->tile_smem_bytes = 4096 + cwarps * B2F_TILE_XS_BYTES + n_slots * (int)slot_bytes;
@@ -537,6 +542,7 @@ extern "C" void b2f_model_destroy(b2f_model *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     cudaDeviceSynchronize();
+    if (m->outlier) b2f_model_destroy(m->outlier);
     if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
     for (int s = 0; s < B2F_STREAMS; ++s) {
         Slot &sl = m->slots[s];
@@ -584,8 +590,8 @@ extern "C" int b2f_model_info(const b2f_model *m, b2f_info *out) {
     out->block_threads = B2F_PREDICT_THREADS;
     out->rows_per_warp = m->rows_per_warp_max;
     out->forest_bytes = m->forest_bytes;
-    out->launches = m->launches;
-    out->launches_tile = m->launches_tile;
+    out->launches = m->launches + (m->outlier ? m->outlier->launches : 0);
+    out->launches_tile = m->launches_tile + (m->outlier ? m->outlier->launches_tile : 0);
     out->tile_min_rows = m->tile_min_rows;
     out->tile_ok = m->tile_ok ? 1 : 0;
     out->tile_resident = (m->tile_ok && m->tp.n_pieces <= m->tp.n_slots) ? 1 : 0;
@@ -593,6 +599,7 @@ extern "C" int b2f_model_info(const b2f_model *m, b2f_info *out) {
     out->tile_warps = m->tile_ok ? m->tile_cwarps : 0;
     out->launches_split = m->launches_split;
     out->split_max_rows = m->split_max_rows;
+    out->outlier_trees = m->outlier ? (int)m->outlier->hdr.n_trees : 0;
     return B2F_OK;
 }
 
@@ -698,7 +705,7 @@ static int slot_reserve(b2f_model *m, Slot &sl, int64_t rows) {
     sl.cap_rows = 0;
     int64_t cap = std::max<int64_t>(rows, 1024);
     CUDA_TRY(cudaMalloc(&sl.d_rows, (size_t)cap * B2F_ROW_BYTES));
-    CUDA_TRY(cudaMalloc(&sl.d_proba, (size_t)cap * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&sl.d_proba, (size_t)cap * sizeof(b2f_scored_full)));
     CUDA_TRY(cudaMalloc((void **)&sl.d_label, (size_t)cap * sizeof(int32_t)));
     sl.cap_rows = cap;
     return B2F_OK;
@@ -733,6 +740,9 @@ static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, int fmt
      * 1/1024ths, the last chunk takes the remainder) front-loads the copies so the un-overlapped tail --
      * the last chunk's kernel and D2H -- is short */
     const bool pairs = f64 == 2; /* proba points at {float proba; int32 label} records, label is ignored */
+    const bool full = f64 == 3;  /* proba points at b2f_scored_full records */
+    if (full && !m->outlier) return set_err(B2F_ESTATE, "no outlier forest attached (b2f_model_attach_outlier_forest)");
+    if ((pairs || full) && !proba) return set_err(B2F_EINVAL, "out is NULL");
     int c = 0;
     for (int64_t off = 0; off < n; ++c) {
         int64_t cnt = std::min(chunk, n - off);
@@ -754,6 +764,22 @@ static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, int fmt
         CUDA_TRY(cudaMemcpyAsync(sl.d_rows, static_cast<const uint8_t *>(rows) + (size_t)off * row_bytes, (size_t)cnt * row_bytes,
                                  cudaMemcpyHostToDevice, sl.stream));
         mark(sl.stream);
+        if (full) { /* classifier, then the outlier forest, on the same device rows; 24-byte records, ONE D2H copy */
+            static_assert(sizeof(b2f_scored_full) == 24 && offsetof(b2f_scored_full, label) == 8 && offsetof(b2f_scored_full, is_outlier) == 12 &&
+                              offsetof(b2f_scored_full, outlier_score) == 16,
+                          "b2f_scored_full layout");
+            uint8_t *rec = static_cast<uint8_t *>(sl.d_proba);
+            rc = launch_predict(m, sl.stream, sl.d_rows, cnt, fmt, rec, 1, reinterpret_cast<int32_t *>(rec + 8), B2F_OSTRIDE(3, 6));
+            if (rc) return rc;
+            rc = launch_predict(m->outlier, sl.stream, sl.d_rows, cnt, fmt, rec + 16, 0, reinterpret_cast<int32_t *>(rec + 12), B2F_OSTRIDE(6, 6));
+            if (rc) return rc;
+            mark(sl.stream);
+            CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(proba) + (size_t)off * sizeof(b2f_scored_full), sl.d_proba,
+                                     (size_t)cnt * sizeof(b2f_scored_full), cudaMemcpyDeviceToHost, sl.stream));
+            mark(sl.stream);
+            *used_mask |= 1u << slot_idx;
+            continue;
+        }
         if (pairs) { /* one interleaved device buffer, ONE D2H copy per chunk */
             rc = launch_predict(m, sl.stream, sl.d_rows, cnt, fmt, sl.d_proba, 0, static_cast<int32_t *>(sl.d_proba) + 1, 2);
             if (rc) return rc;
@@ -815,6 +841,30 @@ extern "C" int b2f_predict_pairs(b2f_model *m, const void *rows, int64_t n, int 
     return predict_host(m, rows, n, row_format, out, 2, nullptr);
 }
 
+extern "C" int b2f_model_attach_outlier_forest(b2f_model *m, const void *forest_blob, size_t nbytes) {
+    if (!m) return set_err(B2F_EINVAL, "model is NULL");
+    b2f_blob_header h;
+    int rc = validate_blob(static_cast<const uint8_t *>(forest_blob), nbytes, &h);
+    if (rc) return rc;
+    if (h.agg_mode != B2F_AGG_IFOREST) return set_err(B2F_EINVAL, "outlier forest: agg_mode %u is not B2F_AGG_IFOREST", h.agg_mode);
+    if (h.n_cat != m->hdr.n_cat || h.n_num != m->hdr.n_num)
+        return set_err(B2F_EINVAL, "outlier forest: row schema (%u categorical, %u numeric) differs from the model's (%u, %u)", h.n_cat, h.n_num,
+                       m->hdr.n_cat, m->hdr.n_num);
+    b2f_model *child = b2f_model_create(forest_blob, nbytes, m->device);
+    if (!child) return B2F_ECUDA; /* message set by b2f_model_create */
+    CUDA_TRY(cudaSetDevice(m->device));
+    if (m->outlier) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        b2f_model_destroy(m->outlier);
+    }
+    m->outlier = child;
+    return B2F_OK;
+}
+
+extern "C" int b2f_predict_full(b2f_model *m, const void *rows, int64_t n, int row_format, b2f_scored_full *out) {
+    return predict_host(m, rows, n, row_format, out, 3, nullptr);
+}
+
 extern "C" int b2f_predict_async(b2f_model *m, const void *rows_pinned, int64_t n, void *proba1_pinned, int proba_is_f64,
                                  int32_t *label_pinned, b2f_ticket *ticket) {
     return b2f_predict_async_ex(m, rows_pinned, n, B2F_ROWS_WORDS24, proba1_pinned, proba_is_f64, label_pinned, ticket);
@@ -868,7 +918,8 @@ extern "C" int b2f_predict_multi_ex(b2f_model **models, int n_models, const void
     const size_t row_bytes = row_format == B2F_ROWS_PACKED64 ? B2F_PACKED_ROW_BYTES : B2F_ROW_BYTES;
     if (n < 0) return set_err(B2F_EINVAL, "negative row count");
     std::vector<uint32_t> masks(n_models, 0);
-    const size_t psz = proba_is_f64 ? sizeof(double) : sizeof(float);
+    /* 0 = float, 1 = double, 2 = b2f_scored records, 3 = b2f_scored_full records */
+    const size_t psz = proba_is_f64 == 3 ? sizeof(b2f_scored_full) : (proba_is_f64 ? sizeof(double) : sizeof(float));
     int rc = B2F_OK;
     for (int i = 0; i < n_models && rc == B2F_OK; ++i) {
         const int64_t lo = n * i / n_models, hi = n * (i + 1) / n_models;

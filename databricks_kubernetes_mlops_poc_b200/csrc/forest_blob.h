@@ -1,5 +1,5 @@
 /*
- * forest_blob.h -- on-disk / in-HBM layout of a flattened forest ("forest blob", version 1).
+ * forest_blob.h -- on-disk / in-HBM layout of a flattened forest ("forest blob", version 2).
  *
  * Written by databricks_kubernetes_mlops_poc_b200/flatten.py from a fitted sklearn Pipeline
  * (the model artefact the reference serves: artifacts/classifier/model/model.pkl, reference
@@ -13,8 +13,9 @@
  * One group chunk, contiguous and 256-byte granular (so a chunk is one TMA bulk copy):
  *     N  : {uint32 T, uint32 M}[n_slots][32]   one 8-byte node per (slot, tree): a single 64-bit
  *                                              shared-memory load per visit, bank-conflict free
- *     LV : float64[n_leaf_slots][32]           leaf payload: RF class-1 fraction, or GBDT
- *                                              learning_rate*value
+ *     LV : float64[n_leaf_slots][32]           leaf payload: RF class-1 fraction, GBDT
+ *                                              learning_rate*value, or isolation-forest path length
+ *                                              depth(leaf) + c(n_node_samples)
  *   T  threshold word: float32 t' = nextup(floor32(threshold)) for a numeric split, int32 category
  *      code for a one-hot split, leaf_id (row of the leaf's payload in LV) for a leaf
  *   M  meta word: bits 27..31 row word index, bit 26 = categorical test, bits 0..23 = slot of the
@@ -59,15 +60,16 @@ typedef struct b2f_blob_header {
     uint32_t n_num;
     uint32_t max_depth;
     uint32_t reserved0;
-    double init_raw; /* GBDT: raw prediction of the init estimator; RF: 0 */
-    double denom;    /* RF: n_trees (proba = sum / denom); GBDT: 1 */
+    double init_raw; /* GBDT: raw prediction of the init estimator; RF: 0; isolation forest: offset_ */
+    double denom;    /* RF: n_trees (proba = sum / denom); GBDT: 1; isolation forest: n_trees * c(max_samples) */
     uint64_t groups_off;
     uint64_t chunks_off;
     uint64_t chunks_bytes;
     uint64_t total_bytes;
     float impute[24];  /* per row word: replacement for NaN (numeric words), float32(median) */
     int32_t vocab[24]; /* per row word: vocabulary size (categorical words), else 0 */
-    uint8_t pad[B2F_BLOB_HEADER_BYTES - 96 - 192];
+    double threshold;  /* isolation forest: is_outlier = score > threshold; other modes: 0 */
+    uint8_t pad[B2F_BLOB_HEADER_BYTES - 96 - 192 - 8];
 } b2f_blob_header;
 
 typedef struct b2f_blob_group {

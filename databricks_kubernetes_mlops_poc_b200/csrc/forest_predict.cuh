@@ -46,6 +46,7 @@ struct KParams {
     int32_t n_num;
     double init_raw;
     double denom;
+    double threshold; /* isolation forest: is_outlier = score > threshold */
     float impute[24];
     KGroup g[B2F_MAX_GROUPS];
 };
@@ -163,6 +164,33 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+/* sum of leaf payloads -> (score, label); shared by all predict kernels.
+ *   RF       : p1 = s / n_trees, label = argmax (class 1 iff p1 > p0)        (sklearn: proba /= n_estimators)
+ *   GBDT     : p1 = expit(init + s), label = raw >= 0
+ *   IFOREST  : score = 2^(-s / (n_trees * c(max_samples))) + offset_, flag = score > threshold
+ *              (sklearn IsolationForest: -decision_function; alibi-detect IForest.predict,
+ *              reference databricks/src/02-register-model.ipynb:232-233,339,344) */
+__device__ __forceinline__ void aggregate(int agg_mode, double init_raw, double denom, double threshold, double s, double &p1, int &lab) {
+    if (agg_mode == B2F_AGG_RF_MEAN) {
+        p1 = s / denom;
+        lab = s > (denom - s);
+    } else if (agg_mode == B2F_AGG_GBDT_LOGISTIC) {
+        const double raw = init_raw + s;
+        p1 = 1.0 / (1.0 + exp(-raw)); /* expit */
+        lab = raw >= 0.0;
+    } else {
+        p1 = exp2(-(s / denom)) + init_raw;
+        lab = p1 > threshold;
+    }
+}
+
+/* Output strides travel in one int: low 16 bits = stride of `proba` in OutT elements, high 16 bits = stride of
+ * `label` in int32 elements (0: same as proba's).  1 = two plain arrays; 2 = interleaved {float, int32} pairs
+ * (b2f_scored); B2F_OSTRIDE(3, 6) / B2F_OSTRIDE(6, 6) = the double / float fields of a 24-byte b2f_scored_full. */
+#define B2F_OSTRIDE(ps, ls) ((ps) | ((ls) << 16))
+__device__ __forceinline__ int ostride_p(int o) { return o & 0xffff; }
+__device__ __forceinline__ int ostride_l(int o) { return (o >> 16) ? (o >> 16) : (o & 0xffff); }
+
 /* aggregate -> (probability, label) for one row per lane; rows < 0 are empty slots */
 template <typename OutT>
 __device__ __forceinline__ void finalize_store(const KParams &p, double s, long long row, OutT *__restrict__ proba,
@@ -170,16 +198,9 @@ __device__ __forceinline__ void finalize_store(const KParams &p, double s, long 
     if (row < 0) return;
     double p1;
     int lab;
-    if (p.agg_mode == B2F_AGG_RF_MEAN) {
-        p1 = s / p.denom;            /* sklearn: proba /= n_estimators */
-        lab = s > (p.denom - s);     /* argmax: class 1 iff p1 > p0 */
-    } else {
-        const double raw = p.init_raw + s;
-        p1 = 1.0 / (1.0 + exp(-raw)); /* expit */
-        lab = raw >= 0.0;
-    }
-    if (proba) proba[row * ostride] = (OutT)p1; /* ostride 2: interleaved {float proba, int32 label} pairs */
-    if (label) label[row * ostride] = lab;
+    aggregate(p.agg_mode, p.init_raw, p.denom, p.threshold, s, p1, lab);
+    if (proba) proba[row * ostride_p(ostride)] = (OutT)p1;
+    if (label) label[row * ostride_l(ostride)] = lab;
 }
 
 /* ---------------------------------------------------------------- the kernel */

@@ -77,6 +77,7 @@ struct TParams {
     int32_t n_num;
     double init_raw;
     double denom;
+    double threshold;
     float impute[24];
 };
 
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(B2F_TILE_THREADS_MAX, 1)
         __syncwarp();
 
         /* GBDT: start from the init estimator's raw value and add trees in order -- sklearn's own order */
-        double acc = p.agg_mode == B2F_AGG_RF_MEAN ? 0.0 : p.init_raw;
+        double acc = p.agg_mode == B2F_AGG_GBDT_LOGISTIC ? p.init_raw : 0.0;
         const bool warp_live = tile < n_tiles; /* warp-uniform: a warp without a tile only keeps the ring protocol */
         for (int piece = 0; piece < n_pieces; ++piece) {
             const long long f = resident ? piece : pass * n_pieces + piece;
@@ -297,16 +298,10 @@ __global__ void __launch_bounds__(B2F_TILE_THREADS_MAX, 1)
         if (live) {
             double p1;
             int lab;
-            if (p.agg_mode == B2F_AGG_RF_MEAN) {
-                p1 = acc / p.denom;
-                lab = acc > (p.denom - acc);
-            } else {
-                const double raw = acc;
-                p1 = 1.0 / (1.0 + exp(-raw));
-                lab = raw >= 0.0;
-            }
-            if (proba) proba[row * ostride] = (OutT)p1;
-            if (label) label[row * ostride] = lab;
+            /* the GBDT init value is already in acc (added first, as sklearn does) */
+            aggregate(p.agg_mode, p.agg_mode == B2F_AGG_GBDT_LOGISTIC ? 0.0 : p.init_raw, p.denom, p.threshold, acc, p1, lab);
+            if (proba) proba[row * ostride_p(ostride)] = (OutT)p1;
+            if (label) label[row * ostride_l(ostride)] = lab;
         }
     }
 }

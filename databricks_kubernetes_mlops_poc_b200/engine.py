@@ -30,11 +30,12 @@ def validate_blob(blob: bytes) -> None:
 
 
 class ForestEngine:
-    def __init__(self, flat: FlatForest, device: int = 0):
+    def __init__(self, flat: FlatForest | bytes, device: int = 0):
+        """``flat``: a FlatForest (classifier) or raw forest-blob bytes (e.g. an isolation forest on its own)."""
         self._lib = _cabi.load_library()
         self.flat = flat
         self.device = int(device)
-        buf = np.frombuffer(flat.blob, dtype=np.uint8)
+        buf = np.frombuffer(flat.blob if isinstance(flat, FlatForest) else flat, dtype=np.uint8)
         self._h = self._lib.b2f_model_create(ptr(buf), buf.size, self.device)
         if not self._h:
             raise B2FError(f"b2f_model_create(device={device}) failed: {_cabi.last_error()}")
@@ -82,9 +83,13 @@ class ForestEngine:
         """(rows uint32 (n,24) or packed (n,16), proba f64 (n,), label i32 (n,)) views over pinned memory."""
         words = PACKED_ROW_WORDS if packed else ROW_WORDS
         rows = self.pinned("rows", n * ROW_WORDS * 4).view(np.uint32, (n, words))
-        proba = self.pinned("proba", n * 8).view(np.float64, (n,))
+        proba = self.pinned("proba", n * 24).view(np.float64, (n,))  # 24 B per row: also holds b2f_scored_full records
         label = self.pinned("label", n * 4).view(np.int32, (n,))
         return rows, proba, label
+
+    def staging_full(self, n: int) -> np.ndarray:
+        """SCORED_FULL_DTYPE (n,) view over the pinned result buffer (shares storage with ``staging``'s proba)."""
+        return self.pinned("proba", n * 24).view(_cabi.SCORED_FULL_DTYPE, (n,))
 
     # ------------------------------------------------------------------ scoring (host buffers)
     def predict_rows(self, rows: np.ndarray, proba_dtype=np.float64, want_label: bool = True, out_proba=None, out_label=None):
@@ -105,6 +110,22 @@ class ForestEngine:
         if out is None:
             out = np.empty(n, dtype=_cabi.SCORED_DTYPE)
         check(self._lib.b2f_predict_pairs(self._h, ptr(rows), n, _row_format(rows), ptr(out)), "b2f_predict_pairs")
+        return out
+
+    # ------------------------------------------------------------------ classifier + outlier detector in one pass
+    def attach_outlier_forest(self, blob: bytes) -> None:
+        """Attach an isolation-forest blob (``flatten.flatten_isolation_forest``) evaluated on the same rows."""
+        buf = np.frombuffer(blob, dtype=np.uint8)
+        check(self._lib.b2f_model_attach_outlier_forest(self._h, ptr(buf), buf.size), "b2f_model_attach_outlier_forest")
+
+    def predict_full(self, rows: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """Encoded rows -> structured array (proba1, label, outlier_score, is_outlier): one H2D copy of the rows,
+        both forests walked on the GPU, one D2H copy per chunk."""
+        rows = np.ascontiguousarray(rows)
+        n = rows.shape[0]
+        if out is None:
+            out = np.empty(n, dtype=_cabi.SCORED_FULL_DTYPE)
+        check(self._lib.b2f_predict_full(self._h, ptr(rows), n, _row_format(rows), ptr(out)), "b2f_predict_full")
         return out
 
     def predict_rows_async(self, rows: np.ndarray, proba: np.ndarray, label: np.ndarray | None) -> int:
@@ -259,6 +280,21 @@ class EngineGroup:
             "b2f_predict_multi_ex",
         )
         return proba, label
+
+    def attach_outlier_forest(self, blob: bytes) -> None:
+        for e in self.engines:
+            e.attach_outlier_forest(blob)
+
+    def predict_full(self, rows: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        rows = np.ascontiguousarray(rows)
+        n = rows.shape[0]
+        if out is None:
+            out = np.empty(n, dtype=_cabi.SCORED_FULL_DTYPE)
+        check(
+            self._lib.b2f_predict_multi_ex(self._handles, len(self.engines), ptr(rows), n, _row_format(rows), ptr(out), 3, None),
+            "b2f_predict_multi_ex",
+        )
+        return out
 
     def predict_stream(self, rows: np.ndarray, batch: int, out_proba: np.ndarray, out_label: np.ndarray | None, inflight: int = 2) -> None:
         """Deal a long stream in ``batch``-row batches round-robin over the GPUs (one host thread per GPU inside

@@ -42,9 +42,10 @@ MAX_TREES = 1024
 HEADER_BYTES = 512
 AGG_RF_MEAN = 0
 AGG_GBDT_LOGISTIC = 1
+AGG_IFOREST = 2
 BLOB_VERSION = 2
 
-_HEADER_FMT = "<8s" + "I" * 10 + "dd" + "Q" * 4 + "24f" + "24i"  # 288 bytes, padded to 512
+_HEADER_FMT = "<8s" + "I" * 10 + "dd" + "Q" * 4 + "24f" + "24i" + "d"  # 296 bytes, padded to 512
 _GROUP_FMT = "<8I"
 
 
@@ -179,6 +180,135 @@ def _flatten_tree(tree, col_word, col_cat_code, col_is_cat, leaf_value):
     return T, M, LV, depth
 
 
+def _assemble_blob(flat, agg, init_raw, denom, n_cat, n_num, impute, vocab, threshold=0.0):
+    """Flattened trees ``[(T, M, LV, depth), ...]`` -> (blob bytes, max depth): groups of 32 interleaved trees."""
+    n_trees = len(flat)
+    if not (1 <= n_trees <= MAX_TREES):
+        raise NotImplementedError(f"n_trees={n_trees} outside [1, {MAX_TREES}]")
+    n_groups = (n_trees + GROUP_TREES - 1) // GROUP_TREES
+    groups, chunks, off = [], [], 0
+    for g in range(n_groups):
+        members = flat[g * GROUP_TREES : (g + 1) * GROUP_TREES]
+        n_slots = max(len(m[0]) for m in members)
+        n_leaf = max(len(m[2]) for m in members)
+        depth = max(m[3] for m in members)
+        N = np.empty((n_slots, GROUP_TREES, 2), dtype=np.uint32)  # [slot][tree] -> (T, M)
+        LV = np.zeros((n_leaf, GROUP_TREES), dtype=np.float64)
+        # unused slots / stub trees: self-looping leaf with payload row 0 (value 0.0 for stubs)
+        N[:, :, 0] = 0
+        N[:, :, 1] = np.arange(n_slots, dtype=np.uint32)[:, None] | np.uint32(META_CAT | (SENTINEL_WORD << META_FEAT_SHIFT))
+        for lane, (t, m, lv, _) in enumerate(members):
+            N[: len(t), lane, 0] = t
+            N[: len(m), lane, 1] = m
+            LV[: len(lv), lane] = lv
+        chunk = N.tobytes() + LV.tobytes()
+        assert len(chunk) == (n_slots + n_leaf) * 256
+        groups.append((off, len(chunk), n_slots, n_leaf, depth, len(members), 0, 0))
+        chunks.append(chunk)
+        off += len(chunk)
+
+    max_depth = max(m[3] for m in flat)
+    groups_off = HEADER_BYTES
+    chunks_off = (groups_off + 32 * n_groups + 255) // 256 * 256
+    total = chunks_off + off
+    header = struct.pack(
+        _HEADER_FMT,
+        b"B2FOREST",
+        BLOB_VERSION,
+        HEADER_BYTES,
+        agg,
+        n_trees,
+        n_groups,
+        ROW_WORDS,
+        n_cat,
+        n_num,
+        max_depth,
+        0,
+        init_raw,
+        denom,
+        groups_off,
+        chunks_off,
+        off,
+        total,
+        *np.asarray(impute, dtype=np.float32).tolist(),
+        *np.asarray(vocab, dtype=np.int32).tolist(),
+        float(threshold),
+    )
+    header = header + b"\0" * (HEADER_BYTES - len(header))
+    table = b"".join(struct.pack(_GROUP_FMT, *g) for g in groups)
+    pad = b"\0" * (chunks_off - groups_off - len(table))
+    blob = header + table + pad + b"".join(chunks)
+    assert len(blob) == total
+    return blob, int(max_depth)
+
+
+def _average_path_length(n):
+    """c(n): average path length of an unsuccessful BST search over n points (Liu et al. 2008, eq. 1), with
+    sklearn's conventions c(<=1) = 0, c(2) = 1 (``sklearn/ensemble/_iforest.py`` ``_average_path_length``)."""
+    n = np.asarray(n, dtype=np.float64)
+    out = np.zeros(n.shape, dtype=np.float64)
+    out[n == 2] = 1.0
+    big = n > 2
+    out[big] = 2.0 * (np.log(n[big] - 1.0) + np.euler_gamma) - 2.0 * (n[big] - 1.0) / n[big]
+    return out
+
+
+def flatten_isolation_forest(detector, n_cat: int, n_num: int, vocab=None, threshold: float | None = None) -> bytes:
+    """Fitted outlier detector -> forest blob with ``agg_mode = AGG_IFOREST`` over the classifier's encoded rows.
+
+    ``detector`` is a fitted ``sklearn.ensemble.IsolationForest`` or an object carrying one as
+    ``.isolationforest`` plus ``.threshold`` (alibi-detect's ``IForest``; the reference builds
+    ``IForest(threshold=0.95).fit(df[NUMERIC_FEATURES].values)``, ``02-register-model.ipynb:232-233``, and calls
+    ``.predict(df[numeric_features].values)`` per request, ``:339,344``).  Feature k of the detector is numeric
+    feature k of the request, i.e. row word ``n_cat + k``.  What the GPU reproduces:
+
+    * ``score = -decision_function(X) = 2 ** (-sum_t h_t(x) / (n_trees * c(max_samples))) + offset_`` with
+      ``h_t(x) = depth(leaf) + c(n_node_samples[leaf])`` (``_iforest.py`` ``_compute_score_samples``);
+    * ``is_outlier = score > threshold``.
+
+    Splits compare float32 inputs with float64 thresholds exactly as the classifier's trees do.  NaN inputs are
+    outside the contract: the reference's pinned scikit-learn 1.1.1 (``app/requirements.txt:14``) rejects them in
+    ``IsolationForest.decision_function`` (ValueError -> HTTP 500) and ``B200Model`` does the same; newer sklearn
+    routes them by a per-node random ``missing_go_to_left`` flag that the 8-byte node does not carry (on the GPU a
+    NaN takes the second child at every split: the imputation table of this blob holds NaN).
+    """
+    iso = getattr(detector, "isolationforest", detector)
+    if type(iso).__name__ != "IsolationForest":
+        raise NotImplementedError(f"unsupported outlier detector {type(iso).__name__}")
+    if threshold is None:
+        threshold = getattr(detector, "threshold", None)
+    if threshold is None:
+        raise ValueError("an outlier threshold is required (alibi-detect IForest(threshold=...))")
+    if iso.n_features_in_ != n_num:
+        raise NotImplementedError(f"detector was fitted on {iso.n_features_in_} features, the request schema has {n_num} numerics")
+    if n_cat + n_num > SENTINEL_WORD:
+        raise NotImplementedError(f"at most {SENTINEL_WORD} raw features supported")
+    flat = []
+    for est, feats in zip(iso.estimators_, iso.estimators_features_):
+        tree = est.tree_
+        feats = np.asarray(feats, dtype=np.int64)
+        col_word = n_cat + feats  # the tree's local column j is detector feature feats[j]
+        none = np.zeros(col_word.shape[0], dtype=bool)
+        # h(leaf) = number of edges from the root + c(training points that ended in the leaf)
+        left, right = tree.children_left, tree.children_right
+        depth = np.zeros(tree.node_count, dtype=np.float64)
+        for i in range(tree.node_count):  # sklearn stores parents before children
+            if left[i] != -1:
+                depth[left[i]] = depth[right[i]] = depth[i] + 1.0
+        payload = depth + _average_path_length(tree.n_node_samples)
+        flat.append(_flatten_tree(tree, col_word, np.zeros_like(col_word), none, payload))
+    denom = float(len(flat)) * float(_average_path_length(np.array([iso._max_samples]))[0])
+    if not denom > 0.0:
+        raise NotImplementedError("isolation forest fitted on a single sample")
+    impute = np.zeros(ROW_WORDS, dtype=np.float32)
+    impute[n_cat : n_cat + n_num] = np.nan
+    v = np.zeros(ROW_WORDS, dtype=np.int32)
+    if vocab is not None:
+        v[:n_cat] = np.asarray(vocab, dtype=np.int32)[:n_cat]
+    blob, _ = _assemble_blob(flat, AGG_IFOREST, float(iso.offset_), denom, n_cat, n_num, impute, v, threshold=float(threshold))
+    return blob
+
+
 def _describe_preprocessor(pre):
     """ColumnTransformer of the reference shape -> column maps for its output matrix."""
     cat_cols, num_cols, ohe, num_imputer, cat_imputer = None, None, None, None, None
@@ -273,69 +403,14 @@ def flatten_pipeline(pipeline) -> FlatForest:
     else:
         raise NotImplementedError(f"unsupported classifier {kind}")
 
-    n_trees = len(trees)
-    if not (1 <= n_trees <= MAX_TREES):
-        raise NotImplementedError(f"n_trees={n_trees} outside [1, {MAX_TREES}]")
-
     flat = [_flatten_tree(t, col_word, col_code, col_is_cat, leaf_values(t)) for t in trees]
-    n_groups = (n_trees + GROUP_TREES - 1) // GROUP_TREES
-    groups, chunks, off = [], [], 0
-    for g in range(n_groups):
-        members = flat[g * GROUP_TREES : (g + 1) * GROUP_TREES]
-        n_slots = max(len(m[0]) for m in members)
-        n_leaf = max(len(m[2]) for m in members)
-        depth = max(m[3] for m in members)
-        N = np.empty((n_slots, GROUP_TREES, 2), dtype=np.uint32)  # [slot][tree] -> (T, M)
-        LV = np.zeros((n_leaf, GROUP_TREES), dtype=np.float64)
-        # unused slots / stub trees: self-looping leaf with payload row 0 (value 0.0 for stubs)
-        N[:, :, 0] = 0
-        N[:, :, 1] = np.arange(n_slots, dtype=np.uint32)[:, None] | np.uint32(META_CAT | (SENTINEL_WORD << META_FEAT_SHIFT))
-        for lane, (t, m, lv, _) in enumerate(members):
-            N[: len(t), lane, 0] = t
-            N[: len(m), lane, 1] = m
-            LV[: len(lv), lane] = lv
-        chunk = N.tobytes() + LV.tobytes()
-        assert len(chunk) == (n_slots + n_leaf) * 256
-        groups.append((off, len(chunk), n_slots, n_leaf, depth, len(members), 0, 0))
-        chunks.append(chunk)
-        off += len(chunk)
-
     impute = np.zeros(ROW_WORDS, dtype=np.float32)
     with np.errstate(over="ignore"):
         impute[n_cat : n_cat + n_num] = medians.astype(np.float32)
     vocab = np.zeros(ROW_WORDS, dtype=np.int32)
     vocab[:n_cat] = [len(c) for c in categories]
-    max_depth = max(m[3] for m in flat)
-    groups_off = HEADER_BYTES
-    chunks_off = (groups_off + 32 * n_groups + 255) // 256 * 256
-    total = chunks_off + off
-    header = struct.pack(
-        _HEADER_FMT,
-        b"B2FOREST",
-        BLOB_VERSION,
-        HEADER_BYTES,
-        agg,
-        n_trees,
-        n_groups,
-        ROW_WORDS,
-        n_cat,
-        n_num,
-        max_depth,
-        0,
-        init_raw,
-        denom,
-        groups_off,
-        chunks_off,
-        off,
-        total,
-        *impute.tolist(),
-        *vocab.tolist(),
-    )
-    header = header + b"\0" * (HEADER_BYTES - len(header))
-    table = b"".join(struct.pack(_GROUP_FMT, *g) for g in groups)
-    pad = b"\0" * (chunks_off - groups_off - len(table))
-    blob = header + table + pad + b"".join(chunks)
-    assert len(blob) == total
+    blob, max_depth = _assemble_blob(flat, agg, init_raw, denom, n_cat, n_num, impute, vocab)
+    n_trees = len(trees)
     return FlatForest(
         blob=blob,
         cat_features=[str(c) for c in cat_cols],
@@ -359,6 +434,7 @@ def parse_header(blob: bytes) -> dict:
     h = dict(zip(keys, f[:17]))
     h["impute"] = np.array(f[17:41], dtype=np.float32)
     h["vocab"] = np.array(f[41:65], dtype=np.int32)
+    h["threshold"] = f[65]
     gk = ["chunk_off", "chunk_bytes", "n_slots", "n_leaf_slots", "depth", "n_trees"]
     h["groups"] = [
         dict(zip(gk, struct.unpack_from(_GROUP_FMT, blob, h["groups_off"] + 32 * g)[:6])) for g in range(h["n_groups"])

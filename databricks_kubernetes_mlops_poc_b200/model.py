@@ -8,10 +8,12 @@ Plugin boundary being mirrored:
   ``{"predictions": [...], "outliers": [...], "feature_drift_batch": {23 names -> float}}``.
 
 ``predictions`` (the accelerated path) comes from the CUDA engine -- dictionary-encode on
-the host into pinned memory, H2D, fused kernel, D2H -- with no CPU fallback.  ``feature_drift_batch``
-and ``outliers`` ("next" rows) complete the response schema: drift through the
-optional CPU detector in ``drift.py``, outliers as the constant 0 the reference provably returns
-(its ``IForest(threshold=0.95)`` compares a score bounded by 0.5 with 0.95).
+the host into pinned memory, H2D, fused kernel, D2H -- with no CPU fallback.  ``outliers``
+comes from the same pass when an outlier forest is attached: the isolation forest is a second forest
+blob walked by the same kernels over the same rows in HBM (``b2f_predict_full``); without one it is the
+constant 0 the reference provably returns (its ``IForest(threshold=0.95)`` compares a score bounded by
+0.5 with 0.95).  ``feature_drift_batch`` (a "next" row) completes the
+response schema through the optional CPU detector in ``drift.py``.
 """
 
 from __future__ import annotations
@@ -23,15 +25,17 @@ import pandas as pd
 
 from .encode import RowEncoder
 from .engine import EngineGroup, ForestEngine
-from .flatten import FlatForest, flatten_pipeline
+from .flatten import FlatForest, flatten_isolation_forest, flatten_pipeline
 
 BLOB_FILE = "forest.b2f.npz"
+OUTLIER_BLOB_FILE = "outlier.b2f"
 DRIFT_FILE = "drift_reference.npz"
+OUTLIER_PICKLE = os.path.join("artifacts", "outlier.pkl")  # joblib.dump(outlier, ".../outlier.pkl"), 02-register-model.ipynb:264,326-328
 SKLEARN_PICKLE = os.path.join("artifacts", "classifier", "model", "model.pkl")  # MLflow layout, 02-register-model.ipynb:317-321
 
 
 class B200Model:
-    def __init__(self, flat: FlatForest, devices=None, drift=None, proba_dtype=np.float64):
+    def __init__(self, flat: FlatForest, devices=None, drift=None, proba_dtype=np.float64, outlier_blob: bytes | None = None):
         self.flat = flat
         self.all_features = flat.all_features
         self.categorical_features = list(flat.cat_features)
@@ -47,22 +51,33 @@ class B200Model:
         self.drift = drift
         self.proba_dtype = np.dtype(proba_dtype)
         self.classes = np.asarray(flat.classes)
+        self.outlier_blob = outlier_blob
+        if outlier_blob is not None:
+            (self.group if self.group is not None else self.engine).attach_outlier_forest(outlier_blob)
         # one scoring replica per GPU for the server's round-robin batcher (each has its own handle,
         # pinned staging and worker thread; the forest is replicated, rows are independent)
         engines = self.group.engines if self.group is not None else [self.engine]
-        self.replicas = [_Replica(self.encoder, e) for e in engines]
+        self.replicas = [_Replica(self.encoder, e, outlier_blob is not None, self.numeric_features) for e in engines]
 
     # ------------------------------------------------------------------ construction
     @classmethod
-    def from_pipeline(cls, pipeline, reference_frame: pd.DataFrame | None = None, **kw) -> "B200Model":
-        """Fitted sklearn Pipeline (the reference's model.pkl) -> model on the GPU."""
+    def from_pipeline(cls, pipeline, reference_frame: pd.DataFrame | None = None, outlier=None, **kw) -> "B200Model":
+        """Fitted sklearn Pipeline (the reference's model.pkl) -> model on the GPU.
+
+        ``outlier``: the reference's fitted outlier detector (an alibi-detect ``IForest`` or a bare sklearn
+        ``IsolationForest`` plus ``outlier_threshold=``), flattened into a second forest over the same rows."""
         flat = flatten_pipeline(pipeline)
         drift = None
         if reference_frame is not None:
             from .drift import TabularDriftCPU
 
             drift = TabularDriftCPU(reference_frame[flat.all_features], flat.cat_features)
-        return cls(flat, drift=drift, **kw)
+        threshold = kw.pop("outlier_threshold", None)
+        blob = None
+        if outlier is not None:
+            blob = flatten_isolation_forest(outlier, len(flat.cat_features), len(flat.num_features),
+                                            vocab=[len(c) for c in flat.categories], threshold=threshold)
+        return cls(flat, drift=drift, outlier_blob=blob, **kw)
 
     def close(self) -> None:
         if self.group is not None:
@@ -71,7 +86,8 @@ class B200Model:
             self.engine.close()
 
     # ------------------------------------------------------------------ scoring
-    def _score(self, df: pd.DataFrame):
+    def _score(self, df: pd.DataFrame, want_outliers: bool = False):
+        """-> (proba1, label, is_outlier or None); one H2D copy of the encoded rows whichever outputs are wanted."""
         n = len(df)
         # large requests travel as 64-byte packed rows (one third fewer PCIe bytes), encoded natively in one pass
         packed = self.encoder.packed_ok and n > self.encoder.SMALL_BATCH
@@ -80,11 +96,15 @@ class B200Model:
             self.encoder.encode_frame_packed(df, out=rows)
         else:
             self.encoder.encode_frame(df, out=rows)
+        target = self.group if self.group is not None else self.engine
+        if want_outliers and self.outlier_blob is not None:
+            _reject_nan(df, self.numeric_features)
+            rec = target.predict_full(rows, out=self.engine.staging_full(n))
+            return rec["proba1"], rec["label"], rec["is_outlier"]
         if self.proba_dtype != np.float64:
             proba = proba.view(np.float32)[:n]
-        target = self.group if self.group is not None else self.engine
         target.predict_rows(rows, proba_dtype=self.proba_dtype, out_proba=proba, out_label=label)
-        return proba, label
+        return proba, label, None
 
     def predict_proba1(self, df: pd.DataFrame) -> np.ndarray:
         """``classifier.predict_proba(df[all_features])[:, 1]`` (02-register-model.ipynb:335-337)."""
@@ -100,7 +120,7 @@ class B200Model:
         if len(df.columns) == 0:
             # the reference dies in df[self.all_features] on an empty request (-> HTTP 500)
             raise KeyError(f"None of {self.all_features} are in the [columns]")
-        proba, _ = self._score(df)
+        proba, _, flags = self._score(df, want_outliers=True)
         n = len(df)
         if self.drift is not None:
             drift_scores = self.drift.score(df[self.all_features])
@@ -108,38 +128,81 @@ class B200Model:
             drift_scores = [0.0] * len(self.all_features)
         return {
             "predictions": proba.tolist(),
-            "outliers": [0] * n,
+            "outliers": flags.tolist() if flags is not None else [0] * n,
             "feature_drift_batch": dict(zip(self.all_features, drift_scores)),
         }
+
+
+def _reject_nan(df: pd.DataFrame, numeric_features) -> None:
+    """The reference's outlier detector refuses NaN inputs: scikit-learn 1.1.1 (``app/requirements.txt:14``)
+    validates ``IsolationForest.decision_function``'s input with ``force_all_finite=True`` -> ValueError -> HTTP 500."""
+    for name in numeric_features:
+        if np.isnan(df[name].to_numpy(dtype=np.float64, copy=False)).any():
+            raise ValueError("Input X contains NaN.\nIsolationForest does not accept missing values encoded as NaN natively.")
 
 
 class _Replica:
     """One GPU's view of the model: encode into that engine's pinned staging and score there."""
 
-    def __init__(self, encoder: RowEncoder, engine: ForestEngine):
-        self.encoder, self.engine = encoder, engine
+    def __init__(self, encoder: RowEncoder, engine: ForestEngine, has_outlier: bool = False, numeric_features=()):
+        self.encoder, self.engine, self.has_outlier, self.numeric_features = encoder, engine, has_outlier, list(numeric_features)
 
-    def predict_proba1(self, df: pd.DataFrame) -> np.ndarray:
+    def score(self, df: pd.DataFrame):
+        """-> (proba1 float64 (n,), is_outlier int32 (n,) or None)."""
         n = len(df)
         packed = self.encoder.packed_ok and n > self.encoder.SMALL_BATCH
-        rows, proba, label = self.engine.staging(n, packed=packed)
+        rows, proba, _ = self.engine.staging(n, packed=packed)
         if packed:
             self.encoder.encode_frame_packed(df, out=rows)
         else:
             self.encoder.encode_frame(df, out=rows)
+        if self.has_outlier:
+            _reject_nan(df, self.numeric_features)
+            rec = self.engine.predict_full(rows, out=self.engine.staging_full(n))
+            return np.array(rec["proba1"], dtype=np.float64), np.array(rec["is_outlier"])
         self.engine.predict_rows(rows, proba_dtype=np.float64, want_label=False, out_proba=proba)
-        return np.array(proba, dtype=np.float64)
+        return np.array(proba, dtype=np.float64), None
+
+    def predict_proba1(self, df: pd.DataFrame) -> np.ndarray:
+        return self.score(df)[0]
 
 
 # ---------------------------------------------------------------------- loading
-def save_model_dir(path: str, flat: FlatForest, reference_frame: pd.DataFrame | None = None) -> None:
+def save_model_dir(path: str, flat: FlatForest, reference_frame: pd.DataFrame | None = None, outlier_blob: bytes | None = None) -> None:
     """Write the GPU-side artefact next to (or instead of) the MLflow pickles."""
     os.makedirs(path, exist_ok=True)
     flat.save(os.path.join(path, BLOB_FILE))
+    if outlier_blob is not None:
+        with open(os.path.join(path, OUTLIER_BLOB_FILE), "wb") as f:
+            f.write(outlier_blob)
     if reference_frame is not None:
         from .drift import TabularDriftCPU
 
         TabularDriftCPU(reference_frame[flat.all_features], flat.cat_features).save(os.path.join(path, DRIFT_FILE))
+
+
+def _load_outlier_blob(path: str, flat: FlatForest):
+    """Cached isolation-forest blob, else the reference's ``outlier.pkl`` (needs alibi-detect to unpickle)."""
+    cached = os.path.join(path, OUTLIER_BLOB_FILE)
+    if os.path.exists(cached):
+        with open(cached, "rb") as f:
+            return f.read()
+    pkl = os.path.join(path, OUTLIER_PICKLE)
+    if not os.path.exists(pkl):
+        return None
+    import joblib
+
+    try:
+        detector = joblib.load(pkl)
+    except ImportError:  # alibi-detect absent: `outliers` stays the constant 0 the reference's threshold produces anyway
+        return None
+    blob = flatten_isolation_forest(detector, len(flat.cat_features), len(flat.num_features), vocab=[len(c) for c in flat.categories])
+    try:
+        with open(cached, "wb") as f:
+            f.write(blob)
+    except OSError:
+        pass
+    return blob
 
 
 def load_model(path: str, devices=None, **kw) -> B200Model:
@@ -171,4 +234,5 @@ def load_model(path: str, devices=None, **kw) -> B200Model:
     if devices is None:
         env = os.environ.get("B200_DEVICES")
         devices = [int(d) for d in env.split(",")] if env else [0]
-    return B200Model(flat, devices=devices, drift=drift, **kw)
+    outlier_blob = _load_outlier_blob(path, flat) if os.environ.get("B200_OUTLIERS", "gpu") != "off" else None
+    return B200Model(flat, devices=devices, drift=drift, outlier_blob=outlier_blob, **kw)

@@ -64,7 +64,7 @@ class _Pending:
 
 
 class MicroBatcher:
-    """Cross-request batching in front of ``model.predict_proba1`` (one worker thread per model).
+    """Cross-request batching in front of a replica's ``score`` (one worker thread per model).
 
     ``models`` is a list (one per GPU); consecutive batches go round-robin over it."""
 
@@ -81,7 +81,8 @@ class MicroBatcher:
         for t in self._threads:
             t.start()
 
-    async def score(self, frame: pd.DataFrame) -> np.ndarray:
+    async def score(self, frame: pd.DataFrame):
+        """-> (proba1 (n,), is_outlier (n,) or None) for this request's rows."""
         loop = asyncio.get_running_loop()
         fut = loop.create_future()
         self.q.put(_Pending(frame, fut, loop))
@@ -121,12 +122,14 @@ class MicroBatcher:
                 return
             try:
                 frame = items[0].frame if len(items) == 1 else pd.concat([it.frame for it in items], ignore_index=True)
-                proba = model.predict_proba1(frame)  # encode -> pinned slot -> H2D -> kernel -> D2H
+                # encode -> pinned slot -> H2D -> classifier kernel (+ outlier-forest kernel) -> D2H
+                scorer = getattr(model, "score", None)
+                proba, flags = scorer(frame) if scorer is not None else (model.predict_proba1(frame), None)
                 self.batches += 1
                 self.rows += len(frame)
                 off = 0
                 for it in items:
-                    part = proba[off:off + it.n]
+                    part = (proba[off:off + it.n], None if flags is None else flags[off:off + it.n])
                     off += it.n
                     it.loop.call_soon_threadsafe(_resolve, it.future, part, None)
             except BaseException as e:  # surfaces as HTTP 500, like any model exception in the reference
@@ -186,7 +189,7 @@ def create_app(model=None, loader=None) -> FastAPI:
         request_id = uuid.uuid4().hex
         log_pool.submit(lambda: _log_record("InferenceData", request_id, input_df.to_json(orient="records")))
 
-        proba = await ml_models["_batcher"].score(input_df)
+        proba, flags = await ml_models["_batcher"].score(input_df)
         drift = getattr(m, "drift", None)
         if drift is not None:
             drift_scores = await asyncio.get_running_loop().run_in_executor(None, drift.score, input_df)
@@ -194,7 +197,7 @@ def create_app(model=None, loader=None) -> FastAPI:
             drift_scores = [0.0] * len(ALL_FEATURES)
         model_output = {
             "predictions": proba.tolist(),
-            "outliers": [0] * len(data),
+            "outliers": flags.tolist() if flags is not None else [0] * len(data),
             "feature_drift_batch": dict(zip(ALL_FEATURES, drift_scores)),
         }
         log_pool.submit(_log_record, "ModelOutput", request_id, model_output)

@@ -65,6 +65,8 @@ extern "C" {
 /* aggregation modes stored in the forest blob */
 #define B2F_AGG_RF_MEAN 0       /* RandomForestClassifier.predict_proba: mean of leaf class fractions */
 #define B2F_AGG_GBDT_LOGISTIC 1 /* binary GradientBoosting: expit(init + sum lr*leaf) */
+#define B2F_AGG_IFOREST 2       /* IsolationForest: score = 2^(-sum path length / (n_trees * c(max_samples))) + offset_,
+                                   flag = score > threshold (alibi-detect IForest: score = -decision_function) */
 
 /* walk modes chosen at model creation */
 #define B2F_WALK_SMEM 0   /* whole forest resident in shared memory (TMA bulk copy per CTA) */
@@ -79,6 +81,15 @@ typedef struct b2f_scored {
     float proba1;  /* P(class 1) */
     int32_t label; /* hard class label */
 } b2f_scored;
+
+/* one fully scored row, for b2f_predict_full: classifier and outlier detector evaluated on the same encoded row */
+typedef struct b2f_scored_full {
+    double proba1;       /* P(class 1), float64 as sklearn returns it */
+    int32_t label;       /* hard class label */
+    int32_t is_outlier;  /* outlier_score > threshold */
+    float outlier_score; /* isolation-forest score (alibi-detect `instance_score`) */
+    int32_t reserved;
+} b2f_scored_full;
 
 typedef struct b2f_info {
     int32_t device;
@@ -103,6 +114,8 @@ typedef struct b2f_info {
     int32_t tile_warps;     /* consumer warps per CTA of the tile kernel (16..24) */
     int64_t launches_split; /* ... of which the small-batch (groups-across-warps) kernel */
     int64_t split_max_rows; /* launches of at most this many rows take it */
+    int32_t outlier_trees;  /* trees of the attached outlier forest (0 = none attached) */
+    int32_t reserved;
 } b2f_info;
 
 /* ---- library / device ------------------------------------------------------------------ */
@@ -164,11 +177,23 @@ int b2f_predict_ex(b2f_model *m, const void *rows, int64_t n, int row_format, vo
 /* both outputs interleaved per row (one D2H copy per pipelined chunk) */
 int b2f_predict_pairs(b2f_model *m, const void *rows, int64_t n, int row_format, b2f_scored *out);
 
+/* ---- classifier + outlier detector in one pass: replaces, on top of the above,
+ *      `self.outliers.predict(df[numeric_features].values)` (02-register-model.ipynb:339,344; detector built at
+ *      :232-233 as alibi-detect IForest = sklearn IsolationForest, score = -decision_function, flag = score > threshold).
+ * The outlier forest is a second forest blob (agg_mode B2F_AGG_IFOREST) over the SAME encoded rows (its splits
+ * test the numeric row words); attach it once, then b2f_predict_full copies each chunk of rows to the GPU once,
+ * runs the classifier kernel and the isolation-forest kernel back to back on it and returns one 24-byte record
+ * per row in ONE device-to-host copy.  A forest blob with agg_mode B2F_AGG_IFOREST is also a valid model on its
+ * own (b2f_model_create): every predict entry point then returns (score, flag) in place of (proba1, label). */
+int b2f_model_attach_outlier_forest(b2f_model *m, const void *forest_blob, size_t nbytes);
+int b2f_predict_full(b2f_model *m, const void *rows, int64_t n, int row_format, b2f_scored_full *out);
+
 /* asynchronous form for the request-batching ring: buffers must be pinned and stay valid until
  * b2f_wait(ticket) returns.  proba_is_f64 selects double (1) or float (0) outputs. */
 int b2f_predict_async(b2f_model *m, const void *rows_pinned, int64_t n, void *proba1_pinned,
                       int proba_is_f64, int32_t *label_pinned, b2f_ticket *ticket);
-/* proba_is_f64: 0 = float, 1 = double, 2 = proba1_pinned points at b2f_scored records (label_pinned ignored) */
+/* proba_is_f64: 0 = float, 1 = double, 2 = proba1_pinned points at b2f_scored records (label_pinned ignored),
+ * 3 = proba1_pinned points at b2f_scored_full records (needs an attached outlier forest) */
 int b2f_predict_async_ex(b2f_model *m, const void *rows_pinned, int64_t n, int row_format,
                          void *proba1_pinned, int proba_is_f64, int32_t *label_pinned,
                          b2f_ticket *ticket);
@@ -179,6 +204,7 @@ int b2f_wait(b2f_model *m, b2f_ticket ticket);
 int b2f_predict_multi(b2f_model **models, int n_models, const void *rows, int64_t n, void *proba1,
                       int proba_is_f64, int32_t *label);
 
+/* proba_is_f64 as for b2f_predict_async_ex (2 / 3: proba1 points at b2f_scored / b2f_scored_full records) */
 int b2f_predict_multi_ex(b2f_model **models, int n_models, const void *rows, int64_t n, int row_format,
                          void *proba1, int proba_is_f64, int32_t *label);
 

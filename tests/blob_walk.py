@@ -49,5 +49,8 @@ def walk_blob(blob: bytes, rows: np.ndarray):
     s = v[:, 0]
     if h["agg_mode"] == 0:
         return s / h["denom"], (s > (h["denom"] - s)).astype(np.int32)
-    raw = h["init_raw"] + s
-    return 1.0 / (1.0 + np.exp(-raw)), (raw >= 0).astype(np.int32)
+    if h["agg_mode"] == 1:
+        raw = h["init_raw"] + s
+        return 1.0 / (1.0 + np.exp(-raw)), (raw >= 0).astype(np.int32)
+    score = np.exp2(-(s / h["denom"])) + h["init_raw"]  # isolation forest (aggregate() in forest_predict.cuh)
+    return score, (score > h["threshold"]).astype(np.int32)

@@ -103,6 +103,34 @@ def adversarial(curated, rf100d6):
     return pd.DataFrame(base)
 
 
+@pytest.fixture(scope="session")
+def iforest(curated):
+    """The reference's outlier detector, minus the alibi-detect wrapper (not installed): ``IForest(threshold=0.95)
+    .fit(df[NUMERIC_FEATURES].values)`` (02-register-model.ipynb:232-233) holds a default sklearn IsolationForest."""
+    from sklearn.ensemble import IsolationForest
+
+    from oracle import reference_pipeline as rp
+
+    return IsolationForest(n_estimators=100, random_state=0).fit(curated[rp.NUMERIC_FEATURES].to_numpy())
+
+
+@pytest.fixture(scope="session")
+def iforest_edges(curated, iforest):
+    """Rows whose numerics sit exactly on isolation-tree thresholds (and one float32 ulp either side); no NaN."""
+    from oracle import reference_pipeline as rp
+
+    rng = np.random.default_rng(11)
+    base = curated[rp.FEATURES].iloc[rng.integers(0, len(curated), 800)].reset_index(drop=True).copy()
+    for i in range(len(base)):
+        tree = iforest.estimators_[int(rng.integers(len(iforest.estimators_)))].tree_
+        node = int(rng.choice(np.nonzero(tree.children_left != -1)[0]))
+        t64 = float(tree.threshold[node])
+        t = np.float32(t64)
+        v = [t, np.nextafter(t, np.float32(np.inf)), np.nextafter(t, np.float32(-np.inf)), t64][i % 4]
+        base.loc[i, rp.NUMERIC_FEATURES[int(tree.feature[node])]] = float(v)
+    return base
+
+
 def has_gpu() -> bool:
     try:
         from databricks_kubernetes_mlops_poc_b200 import _cabi

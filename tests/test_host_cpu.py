@@ -91,6 +91,64 @@ def test_blob_semantics_match_oracle(curated, inference, adversarial, rf100d6, g
             assert np.abs(p - want_p).max() < 1e-14 and (l == want_l).all()
 
 
+def _iforest_rows(rf100d6, df):
+    from databricks_kubernetes_mlops_poc_b200 import flatten
+    from databricks_kubernetes_mlops_poc_b200.encode import RowEncoder
+
+    return RowEncoder(flatten.flatten_pipeline(rf100d6)).encode_frame(df)
+
+
+def test_isolation_forest_blob_matches_sklearn(curated, inference, iforest, iforest_edges, rf100d6):
+    """the outlier detector as a second forest blob over the classifier's encoded rows.
+    score = -decision_function (alibi-detect IForest.score), flag = score > threshold."""
+    from blob_walk import walk_blob
+    from oracle import reference_pipeline as rp
+
+    from databricks_kubernetes_mlops_poc_b200 import flatten
+    from databricks_kubernetes_mlops_poc_b200.engine import validate_blob
+
+    for thr in (0.95, 0.0, 0.04):
+        blob = flatten.flatten_isolation_forest(iforest, 9, 14, threshold=thr)
+        validate_blob(blob)
+        h = flatten.parse_header(blob)
+        assert h["agg_mode"] == flatten.AGG_IFOREST and h["n_trees"] == 100 and h["threshold"] == thr and h["init_raw"] == iforest.offset_
+        for df in (curated.iloc[:3000], inference, iforest_edges):
+            score, flag = walk_blob(blob, _iforest_rows(rf100d6, df))
+            want = -iforest.decision_function(df[rp.NUMERIC_FEATURES].to_numpy())
+            assert np.abs(score - want).max() < 1e-14
+            assert (flag == (want > thr)).all()
+            if thr == 0.95:
+                assert flag.sum() == 0  # the reference's threshold can never fire (score <= 0.5)
+            if thr == 0.0 and len(df) > 1000:
+                assert 0 < flag.sum() < len(df)
+
+
+@pytest.mark.parametrize("params", [dict(n_estimators=33, max_samples=64, random_state=1), dict(n_estimators=7, max_features=5, random_state=2),
+                                    dict(n_estimators=40, max_samples=0.5, bootstrap=True, random_state=3)])
+def test_isolation_forest_variants(curated, rf100d6, params):
+    """Feature sub-sampling (estimators_features_), bootstrap and other tree sizes; alibi-style wrapper object."""
+    from types import SimpleNamespace
+
+    from blob_walk import walk_blob
+    from sklearn.ensemble import IsolationForest
+
+    from oracle import reference_pipeline as rp
+
+    from databricks_kubernetes_mlops_poc_b200 import flatten
+
+    X = curated[rp.NUMERIC_FEATURES].to_numpy()
+    iso = IsolationForest(**params).fit(X[:5000])
+    blob = flatten.flatten_isolation_forest(SimpleNamespace(isolationforest=iso, threshold=0.01), 9, 14)
+    df = curated.iloc[5000:7000]
+    score, flag = walk_blob(blob, _iforest_rows(rf100d6, df))
+    want = -iso.decision_function(df[rp.NUMERIC_FEATURES].to_numpy())
+    assert np.abs(score - want).max() < 1e-14 and (flag == (want > 0.01)).all()
+    with pytest.raises(NotImplementedError):
+        flatten.flatten_isolation_forest(iso, 9, 13, threshold=0.5)  # schema mismatch
+    with pytest.raises(ValueError):
+        flatten.flatten_isolation_forest(iso, 9, 14)  # no threshold anywhere
+
+
 def test_blob_layout_invariants(rf100d6):
     from databricks_kubernetes_mlops_poc_b200 import flatten
 

@@ -63,6 +63,20 @@ def test_predict_contract(caplog):
     assert set(out["data"]) == {"predictions", "outliers", "feature_drift_batch"}
 
 
+def test_outlier_flags_pass_through():
+    """A replica with ``score`` (classifier + outlier forest in one pass) feeds the response's ``outliers``."""
+
+    class Scoring(StubModel):
+        def score(self, df):
+            x = df["credit_limit"].to_numpy()
+            return (x % 1000) / 1000.0, (x > 5000).astype(np.int32)
+
+    with _client(Scoring()) as c:
+        r = c.post("/predict", json=[{"credit_limit": 1250.0}, {"credit_limit": 9100.0}, {}])
+        assert r.status_code == 200
+        assert r.json()["predictions"] == [0.25, 0.1, 0.0] and r.json()["outliers"] == [0.0, 1.0, 1.0]  # {} = the schema defaults (credit_limit 18000)
+
+
 def test_engine_failure_is_http_500():
     with _client(StubModel(fail=True)) as c:
         assert c.post("/predict", json=[{}]).status_code == 500
@@ -81,7 +95,7 @@ def test_concurrent_requests_share_batches():
         frames = [pd.DataFrame([{**DEFAULTS, "credit_limit": float(1000 * i + j)} for j in range(3)])[ALL_FEATURES] for i in range(40)]
         outs = await asyncio.gather(*[mb.score(f) for f in frames])
         for i, o in enumerate(outs):
-            assert np.allclose(o, [0.0, 0.001, 0.002])
+            assert np.allclose(o[0], [0.0, 0.001, 0.002]) and o[1] is None
         return len(outs)
 
     try:
