@@ -157,6 +157,13 @@ SIGNATURES = {
     "b2f_comm_init_all": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "b2f_moments_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "b2f_moments_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "b2f_drift_create": (C.c_void_p, [C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "b2f_drift_destroy": (None, [C.c_void_p]),
+    "b2f_drift_score": (
+        C.c_int,
+        [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)],
+    ),
+    "b2f_drift_launches": (C.c_int64, [C.c_void_p]),
 }
 
 _lib = None

@@ -1300,3 +1300,6 @@ extern "C" int b2f_moments_multi(b2f_model **models, int n_models, const void *r
     b2f_moments_merge(parts.data(), n_models, out);
     return B2F_OK;
 }
+
+/* ------------------------------------------------------------------ batch drift detector (K3) */
+#include "drift_api.cuh"

@@ -1,0 +1,327 @@
+/*
+ * drift_stats.cuh -- K3: batch drift scores on the GPU.
+ *
+ * Replaces `self.drift.predict(df[self.all_features].values)` (reference databricks/src/02-register-model.ipynb:338;
+ * detector built at :224-229 as alibi-detect TabularDrift(x_ref, p_val=0.05, categories_per_feature={0..8: None})):
+ * per request, one p-value per feature of the batch against the 30 000-row reference table --
+ *   categorical: chi-squared test on the 2 x K table of reference / batch category counts (scipy chi2_contingency:
+ *                Pearson statistic, Yates correction when dof == 1, p = Q(dof/2, stat/2));
+ *   numeric    : two-sided two-sample Kolmogorov-Smirnov test, EXACT p-value (scipy ks_2samp(method="exact")).
+ * The reference re-sorts and re-counts its 30 000 reference rows on every request and then runs scipy's
+ * O(m * window) lattice-path recursion on one core; here the reference columns live pre-sorted in HBM and
+ *
+ *   k_drift_count   one thread per (feature, batch element): two binary searches of the element in the sorted
+ *                   reference column (a = #ref < x, b = #ref <= x) -> two histograms over reference positions;
+ *                   categorical elements -> a histogram over category codes.
+ *   k_drift_finish  one CTA per feature.
+ *     numeric : (1) prefix sums of the two histograms give #batch <= r_j and #batch < r_j at every reference point;
+ *               the K-S numerator  max_t |n*#{ref<=t} - m*#{batch<=t}|  is attained at a reference point or at the
+ *               left limit of one (both ECDFs are right-continuous steps), so it is an exact INTEGER;
+ *               (2) the exact p-value: the probability that a lattice path (0,0)->(m,n) leaves the band
+ *               |ng*i - mg*j| < h (Hodges 1958; the 1-p recursion of Viehmann 2021 that scipy's
+ *               _compute_outer_prob_inside_method runs column by column).  Cell (i,j) needs (i-1,j) and (i,j-1):
+ *               the CTA sweeps ANTI-DIAGONALS t = i + j, all in-band cells of a diagonal in parallel (one per
+ *               thread, values exchanged through a shared-memory ring indexed by j mod L), m + n steps instead
+ *               of m * window.
+ *     categorical: one thread forms the chi-squared statistic and the regularised upper incomplete gamma function.
+ *
+ * Everything is float64 / int64; results match scipy to ~1e-13 relative (the recursion multiplies by a correctly
+ * rounded 1/t where scipy divides by t).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#define B2F_DRIFT_THREADS 1024
+#define B2F_DRIFT_RING_MAX 4096 /* slots of the anti-diagonal ring (2 x 32 KB of shared memory) */
+#define B2F_DRIFT_MAX_CATS 512  /* categories per feature, reference + new ones of the batch */
+
+struct DriftParams {
+    int64_t n_ref;            /* reference rows m0 */
+    int64_t n;                /* batch rows */
+    int32_t n_num, n_cat;
+    const double *ref_sorted; /* [n_num][n_ref] ascending */
+    const double *x;          /* [n_num][n]  batch numerics, column-major */
+    const int32_t *codes;     /* [n_cat][n]  batch category codes, -1 = not a reference category */
+    uint32_t *hist_a;         /* [n_num][n_ref + 1]  #batch elements with (#ref <  x) == k */
+    uint32_t *hist_b;         /* [n_num][n_ref + 1]  #batch elements with (#ref <= x) == k */
+    uint32_t *nan_count;      /* [n_num] */
+    uint32_t *cat_hist;       /* [sum cat_sizes] batch counts per reference category */
+    const int32_t *cat_off;   /* [n_cat + 1] offsets into cat_hist / ref_counts */
+    const int64_t *ref_counts; /* [sum cat_sizes] */
+    const int32_t *new_off;   /* [n_cat + 1] offsets into new_counts (categories of the batch absent from the reference) */
+    const int64_t *new_counts;
+    double *p_val;            /* [n_cat + n_num]  categorical features first */
+    double *stat;             /* chi-squared statistic / K-S D */
+    int32_t *flags;           /* 0 ok; 1 = exact K-S not applicable (scipy switches to the asymptotic formula); 2 = NaN input */
+};
+
+/* ------------------------------------------------------------------ k_drift_count */
+__global__ void __launch_bounds__(256) k_drift_count(DriftParams p) {
+    const int64_t per = p.n;
+    const int64_t total = per * (p.n_num + p.n_cat);
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int f = (int)(idx / per);
+        const int64_t e = idx - (int64_t)f * per;
+        if (f < p.n_num) {
+            const double x = p.x[(int64_t)f * per + e];
+            if (x != x) {
+                atomicAdd(&p.nan_count[f], 1u);
+                continue;
+            }
+            const double *r = p.ref_sorted + (int64_t)f * p.n_ref;
+            int64_t lo = 0, hi = p.n_ref; /* a = first index with r[idx] >= x  == #ref < x */
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (__ldg(&r[mid]) < x) lo = mid + 1; else hi = mid;
+            }
+            const int64_t a = lo;
+            hi = p.n_ref;                 /* b = first index with r[idx] > x  == #ref <= x */
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (__ldg(&r[mid]) <= x) lo = mid + 1; else hi = mid;
+            }
+            atomicAdd(&p.hist_a[(int64_t)f * (p.n_ref + 1) + a], 1u);
+            atomicAdd(&p.hist_b[(int64_t)f * (p.n_ref + 1) + lo], 1u);
+        } else {
+            const int c = f - p.n_num;
+            const int32_t code = p.codes[(int64_t)c * per + e];
+            const int32_t size = p.cat_off[c + 1] - p.cat_off[c];
+            if (code >= 0 && code < size) atomicAdd(&p.cat_hist[p.cat_off[c] + code], 1u);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ chi-squared tail: Q(a, x) = Gamma(a, x) / Gamma(a) */
+__device__ inline double gamma_q(double a, double x) {
+    if (!(x > 0.0)) return 1.0;
+    if (x < a + 1.0) { /* series for P(a, x), Q = 1 - P */
+        double ap = a, sum = 1.0 / a, del = sum;
+        for (int it = 0; it < 100000; ++it) {
+            ap += 1.0;
+            del *= x / ap;
+            sum += del;
+            if (fabs(del) < fabs(sum) * 1e-17) break;
+        }
+        return 1.0 - sum * exp(-x + a * log(x) - lgamma(a));
+    }
+    /* modified Lentz continued fraction for Q(a, x) */
+    const double tiny = 1e-300;
+    double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, hcf = d;
+    for (int it = 1; it < 100000; ++it) {
+        const double an = -(double)it * ((double)it - a);
+        b += 2.0;
+        d = an * d + b;
+        if (fabs(d) < tiny) d = tiny;
+        c = b + an / c;
+        if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        const double del = d * c;
+        hcf *= del;
+        if (fabs(del - 1.0) < 1e-16) break;
+    }
+    return exp(-x + a * log(x) - lgamma(a)) * hcf;
+}
+
+/* scipy.stats.chi2_contingency on the 2 x K table (reference row, batch row): K = reference categories + new ones */
+__device__ inline void chi2_feature(const DriftParams &p, int c, double &stat, double &pv) {
+    const int k_ref = p.cat_off[c + 1] - p.cat_off[c];
+    const int k_new = p.new_off ? p.new_off[c + 1] - p.new_off[c] : 0;
+    const int K = k_ref + k_new;
+    double row0 = 0.0, row1 = 0.0;
+    for (int k = 0; k < K; ++k) {
+        row0 += k < k_ref ? (double)p.ref_counts[p.cat_off[c] + k] : 0.0;
+        row1 += k < k_ref ? (double)p.cat_hist[p.cat_off[c] + k] : (double)p.new_counts[p.new_off[c] + k - k_ref];
+    }
+    if (K < 2) { /* dof == 0 */
+        stat = 0.0;
+        pv = 1.0;
+        return;
+    }
+    const double tot = row0 + row1;
+    const bool yates = K == 2;
+    double s = 0.0;
+    for (int k = 0; k < K; ++k) {
+        const double o0 = k < k_ref ? (double)p.ref_counts[p.cat_off[c] + k] : 0.0;
+        const double o1 = k < k_ref ? (double)p.cat_hist[p.cat_off[c] + k] : (double)p.new_counts[p.new_off[c] + k - k_ref];
+        const double col = o0 + o1;
+        const double e0 = row0 * col / tot, e1 = row1 * col / tot;
+        double d0 = o0 - e0, d1 = o1 - e1;
+        if (yates) { /* observed moves towards expected by min(0.5, |diff|) */
+            d0 = d0 > 0 ? d0 - fmin(0.5, d0) : d0 + fmin(0.5, -d0);
+            d1 = d1 > 0 ? d1 - fmin(0.5, d1) : d1 + fmin(0.5, -d1);
+        }
+        s += d0 * d0 / e0 + d1 * d1 / e1;
+    }
+    stat = s;
+    pv = gamma_q(0.5 * (double)(K - 1), 0.5 * s);
+}
+
+/* ------------------------------------------------------------------ k_drift_finish */
+__device__ inline int64_t gcd64(int64_t a, int64_t b) {
+    while (b) {
+        const int64_t t = a % b;
+        a = b;
+        b = t;
+    }
+    return a;
+}
+
+/* One anti-diagonal cell.  P(i,j) = 1 outside the band or off the lattice, 0 on the first column inside the band,
+ * else (P(i-1,j)*i + P(i,j-1)*j) / (i+j). */
+__device__ __forceinline__ double drift_cell(int64_t i, int64_t j, int64_t m, int64_t n, int64_t mg, int64_t ng, int64_t h, double up, double left,
+                                             double rt) {
+    if (j < 0 || j > n || i < 0 || i > m) return 1.0;
+    int64_t dev = ng * i - mg * j;
+    if (dev < 0) dev = -dev;
+    if (dev >= h) return 1.0;
+    if (i == 0) return 0.0;
+    return (up * (double)i + left * (double)j) * rt;
+}
+
+extern __shared__ unsigned char drift_smem[];
+
+__global__ void __launch_bounds__(B2F_DRIFT_THREADS) k_drift_finish(DriftParams p) {
+    const int f = blockIdx.x;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (f >= p.n_num) { /* categorical feature: a few hundred flops, one thread */
+        if (tid == 0) {
+            const int c = f - p.n_num;
+            double s, pv;
+            chi2_feature(p, c, s, pv);
+            p.stat[c] = s;
+            p.p_val[c] = pv;
+            p.flags[c] = 0;
+        }
+        return;
+    }
+    const int out = p.n_cat + f;
+    __shared__ unsigned long long s_part_a[B2F_DRIFT_THREADS], s_part_b[B2F_DRIFT_THREADS];
+    __shared__ unsigned long long s_num;
+    __shared__ double s_result;
+
+    /* ---- (1) K-S numerator: max over reference points of |n*(#ref <= r) - m0*(#batch <= r)| and the left limits */
+    const int64_t m0 = p.n_ref, n0 = p.n;
+    const uint32_t *ha = p.hist_a + (int64_t)f * (m0 + 1);
+    const uint32_t *hb = p.hist_b + (int64_t)f * (m0 + 1);
+    const double *r = p.ref_sorted + (int64_t)f * m0;
+    const int64_t seg = (m0 + 1 + nt - 1) / nt;
+    const int64_t j0 = (int64_t)tid * seg, j1 = min(j0 + seg, m0 + 1);
+    unsigned long long sa = 0, sb = 0;
+    for (int64_t j = j0; j < j1; ++j) {
+        sa += ha[j];
+        sb += hb[j];
+    }
+    s_part_a[tid] = sa;
+    s_part_b[tid] = sb;
+    if (tid == 0) s_num = 0ull;
+    __syncthreads();
+    if (tid == 0) { /* exclusive scan of the per-thread partial sums */
+        unsigned long long ca = 0, cb = 0;
+        for (int k = 0; k < nt; ++k) {
+            const unsigned long long ta = s_part_a[k], tb = s_part_b[k];
+            s_part_a[k] = ca;
+            s_part_b[k] = cb;
+            ca += ta;
+            cb += tb;
+        }
+    }
+    __syncthreads();
+    {
+        int64_t cle = (int64_t)s_part_a[tid], clt = (int64_t)s_part_b[tid]; /* running #batch <= r_j, #batch < r_j */
+        int64_t best = 0;
+        for (int64_t j = j0; j < j1 && j < m0; ++j) {
+            cle += ha[j]; /* x <= r_j  <=>  (#ref < x) <= j */
+            clt += hb[j]; /* x <  r_j  <=>  (#ref <= x) <= j */
+            const double rj = r[j];
+            const bool first = j == 0 || r[j - 1] != rj;     /* #ref <  r_j == j     */
+            const bool last = j == m0 - 1 || r[j + 1] != rj; /* #ref <= r_j == j + 1 */
+            if (last) {
+                int64_t v = (j + 1) * n0 - cle * m0;
+                if (v < 0) v = -v;
+                best = max(best, v);
+            }
+            if (first) {
+                int64_t v = j * n0 - clt * m0;
+                if (v < 0) v = -v;
+                best = max(best, v);
+            }
+        }
+        atomicMax(&s_num, (unsigned long long)best);
+    }
+    __syncthreads();
+    const int64_t num = (int64_t)s_num;
+    const double dstat = (double)num / ((double)m0 * (double)n0);
+
+    /* ---- (2) exact two-sided p-value */
+    const int64_t g = gcd64(m0, n0);
+    const int64_t m = max(m0, n0), n = min(m0, n0); /* the recursion wants m >= n */
+    const int64_t mg = m / g, ng = n / g;
+    const int64_t h = num / g; /* == round(D * lcm(m, n)) */
+    int flag = 0;
+    if (p.nan_count[f] != 0) flag = 2;
+    else if ((double)(m0 / g) >= 2147483647.0 / (double)(n0 / g)) flag = 1; /* scipy: lcm too big -> asymptotic formula */
+    /* widest anti-diagonal of the band: in-band j satisfy |ng*t - (ng+mg)*j| < h */
+    const int64_t width = (2 * h) / (ng + mg) + 2;
+    int ring = 32;
+    while (ring < width + 3 && ring < B2F_DRIFT_RING_MAX) ring <<= 1;
+    const bool too_wide = width + 3 > ring; /* only when 2*en*D^2 > ~139: p < 1e-60, below float32 resolution */
+    if (tid == 0) {
+        p.stat[out] = dstat;
+        p.flags[out] = flag;
+        if (flag == 2) p.p_val[out] = nan("");
+        else if (flag == 1) p.p_val[out] = -1.0; /* caller applies kstwo.sf(D, round(m*n/(m+n))) */
+        else if (h == 0) p.p_val[out] = 1.0;
+        else if (too_wide) p.p_val[out] = 0.0;
+    }
+    if (flag != 0 || h == 0 || too_wide) return;
+
+    double *bufs = reinterpret_cast<double *>(drift_smem);
+    const int mask = ring - 1;
+    const int64_t T = m + n;
+    const int64_t den = ng + mg;
+    /* j_lo(t) = smallest j with den*j > ng*t - h (first in-band j of diagonal t); the ring covers [j_lo - 1, j_lo - 1 + ring) */
+    int64_t j_lo = -(h / den) - 1;
+    while (den * j_lo <= -h) ++j_lo;
+
+    if (ring == 32) {
+        /* one warp, one slot per lane, neighbours through shuffles */
+        if (tid >= 32) return;
+        double v = 1.0;
+        for (int64_t t = 0; t <= T; ++t) {
+            while (den * j_lo <= ng * t - h) ++j_lo;
+            const int64_t js = j_lo - 1;
+            const int64_t j = js + (int64_t)((tid - (int)js) & 31);
+            const double left = __shfl_sync(0xffffffffu, v, (tid + 31) & 31);
+            const double rt = t > 0 ? __drcp_rn((double)t) : 0.0;
+            v = drift_cell(t - j, j, m, n, mg, ng, h, v, left, rt);
+        }
+        const double res = __shfl_sync(0xffffffffu, v, (int)(n & 31));
+        if (tid == 0) p.p_val[out] = fmin(fmax(res, 0.0), 1.0);
+        return;
+    }
+
+    double *prev = bufs, *cur = bufs + ring;
+    for (int s = tid; s < ring; s += nt) prev[s] = 1.0;
+    __syncthreads();
+    if (tid >= ring) return; /* whole warps leave (ring is a multiple of 32): the rest synchronise on a named barrier */
+    const int active = min(nt, ring);
+    for (int64_t t = 0; t <= T; ++t) {
+        while (den * j_lo <= ng * t - h) ++j_lo;
+        const int64_t js = j_lo - 1;
+        const double rt = t > 0 ? __drcp_rn((double)t) : 0.0;
+        for (int s = tid; s < ring; s += active) {
+            const int64_t j = js + (int64_t)((s - (int)js) & mask);
+            cur[s] = drift_cell(t - j, j, m, n, mg, ng, h, prev[s], prev[(s - 1) & mask], rt);
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(active) : "memory");
+        double *tmp = prev;
+        prev = cur;
+        cur = tmp;
+    }
+    if (tid == 0) {
+        s_result = prev[(int)(n & mask)];
+        p.p_val[out] = fmin(fmax(s_result, 0.0), 1.0);
+    }
+}

@@ -12,8 +12,9 @@ the host into pinned memory, H2D, fused kernel, D2H -- with no CPU fallback.  ``
 comes from the same pass when an outlier forest is attached: the isolation forest is a second forest
 blob walked by the same kernels over the same rows in HBM (``b2f_predict_full``); without one it is the
 constant 0 the reference provably returns (its ``IForest(threshold=0.95)`` compares a score bounded by
-0.5 with 0.95).  ``feature_drift_batch`` (a "next" row) completes the
-response schema through the optional CPU detector in ``drift.py``.
+0.5 with 0.95).  ``feature_drift_batch`` comes from the GPU drift detector
+in ``drift.py`` (K3: the reference table resident in HBM, chi-squared and exact K-S p-values per request),
+when a reference table is supplied; without one every score is 0.0.
 """
 
 from __future__ import annotations
@@ -69,9 +70,10 @@ class B200Model:
         flat = flatten_pipeline(pipeline)
         drift = None
         if reference_frame is not None:
-            from .drift import TabularDriftCPU
+            from .drift import TabularDrift
 
-            drift = TabularDriftCPU(reference_frame[flat.all_features], flat.cat_features)
+            devices = kw.get("devices")
+            drift = TabularDrift(reference_frame[flat.all_features], flat.cat_features, device=devices[0] if devices else 0)
         threshold = kw.pop("outlier_threshold", None)
         blob = None
         if outlier is not None:
@@ -80,6 +82,8 @@ class B200Model:
         return cls(flat, drift=drift, outlier_blob=blob, **kw)
 
     def close(self) -> None:
+        if self.drift is not None:
+            self.drift.close()
         if self.group is not None:
             self.group.close()
         else:
@@ -176,9 +180,9 @@ def save_model_dir(path: str, flat: FlatForest, reference_frame: pd.DataFrame | 
         with open(os.path.join(path, OUTLIER_BLOB_FILE), "wb") as f:
             f.write(outlier_blob)
     if reference_frame is not None:
-        from .drift import TabularDriftCPU
+        from .drift import TabularDrift
 
-        TabularDriftCPU(reference_frame[flat.all_features], flat.cat_features).save(os.path.join(path, DRIFT_FILE))
+        TabularDrift(reference_frame[flat.all_features], flat.cat_features, device=None).save(os.path.join(path, DRIFT_FILE))
 
 
 def _load_outlier_blob(path: str, flat: FlatForest):
@@ -225,14 +229,14 @@ def load_model(path: str, devices=None, **kw) -> B200Model:
             flat.save(blob_path)
         except OSError:
             pass  # read-only image: keep the blob in memory only
-    drift = None
-    drift_path = os.path.join(path, DRIFT_FILE)
-    if os.path.exists(drift_path) and os.environ.get("B200_DRIFT", "cpu") != "off":
-        from .drift import TabularDriftCPU
-
-        drift = TabularDriftCPU.load(drift_path)
     if devices is None:
         env = os.environ.get("B200_DEVICES")
         devices = [int(d) for d in env.split(",")] if env else [0]
+    drift = None
+    drift_path = os.path.join(path, DRIFT_FILE)
+    if os.path.exists(drift_path) and os.environ.get("B200_DRIFT", "gpu") != "off":
+        from .drift import TabularDrift
+
+        drift = TabularDrift.load(drift_path, device=devices[0])
     outlier_blob = _load_outlier_blob(path, flat) if os.environ.get("B200_OUTLIERS", "gpu") != "off" else None
     return B200Model(flat, devices=devices, drift=drift, outlier_blob=outlier_blob, **kw)

@@ -213,6 +213,33 @@ int b2f_predict_multi_ex(b2f_model **models, int n_models, const void *rows, int
 int b2f_predict_stream(b2f_model **models, int n_models, const void *rows, int64_t n, int64_t batch, int row_format,
                        void *proba1, int proba_is_f64, int32_t *label, int inflight);
 
+/* ---- batch drift scores: replaces `self.drift.predict(df[self.all_features].values)` ---------------------------
+ *      (02-register-model.ipynb:338; detector built at :224-229 as alibi-detect TabularDrift(x_ref, p_val=0.05,
+ *      categories_per_feature={0..8: None}); the response carries 1 - p_val, :345-349).
+ * Per feature of the request batch against the reference table: categorical -> chi-squared test on the 2 x K table of
+ * category counts (scipy.stats.chi2_contingency), numeric -> two-sided two-sample Kolmogorov-Smirnov test with the
+ * EXACT p-value (scipy.stats.ks_2samp(method="exact")).  The reference table stays in HBM (numeric columns sorted,
+ * category counts); both the statistics and the exact lattice-path p-value recursion run on the GPU. */
+typedef struct b2f_drift b2f_drift;
+/* ref_sorted: n_num columns of n_ref float64 each, every column ascending (column-major);
+ * cat_sizes[c]: number of distinct reference categories of categorical feature c; ref_counts: their counts, concatenated */
+b2f_drift *b2f_drift_create(int device, int64_t n_ref, int n_num, const double *ref_sorted, int n_cat,
+                            const int32_t *cat_sizes, const int64_t *ref_counts); /* NULL on error */
+void b2f_drift_destroy(b2f_drift *d);
+/* num_cols: n_num x n float64, column-major (column k at num_cols + k*n); cat_codes: n_cat x n int32, column-major,
+ * code = index of the value among the feature's reference categories or -1 if it is not one of them.
+ * Values that are not reference categories form extra columns of the contingency table (alibi-detect counts over the
+ * union of reference and batch categories): new_offsets[n_cat + 1] / new_counts list their counts per feature
+ * (both NULL when every batch value is a reference category).
+ * Outputs, categorical features first then numeric ones: p_val (required), stat (chi-squared statistic / K-S D) and
+ * flags (0 = ok; 1 = scipy would switch to the asymptotic K-S formula (lcm of the sample sizes >= 2^31): p_val is -1 and
+ * the caller applies kstwo.sf(D, round(m*n/(m+n))); 2 = NaN in the batch column: p_val is NaN) may be NULL.
+ * device_ms (may be NULL): device time of the call (copies + kernels), from CUDA events. */
+int b2f_drift_score(b2f_drift *d, int64_t n, const double *num_cols, const int32_t *cat_codes,
+                    const int32_t *new_offsets, const int64_t *new_counts, double *p_val, double *stat,
+                    int32_t *flags, float *device_ms);
+int64_t b2f_drift_launches(const b2f_drift *d); /* kernels launched by this handle so far */
+
 /* ---- device-resident interface (measurement and callers that already hold rows in HBM) ----- */
 void *b2f_device_alloc(b2f_model *m, size_t nbytes);
 void b2f_device_free(b2f_model *m, void *dptr);

@@ -4,8 +4,9 @@ Follows ``databricks/src/02-register-model.ipynb:305-353``: ``predict`` builds a
 ``classifier.predict_proba(df[all_features])[:, 1]``, the drift detector's p-values and the outlier
 detector's flags, and returns the response dict.  mlflow and alibi-detect are not installed in this
 image: the classifier part is exact (the real sklearn pipeline); the drift part
-restates alibi-detect 0.12.0's ``TabularDrift`` with scipy (chi-squared on category counts, exact
-two-sample K-S on numerics, float32 p-values) and is therefore UNPINNED against the real package; the
+restates alibi-detect 0.12.0's ``TabularDrift`` with scipy (``oracle/drift.py``: chi-squared on category counts
+over the union of reference and batch categories, exact two-sample K-S on numerics, float32 p-values) and is
+therefore UNPINNED against the real package; the
 outlier part uses sklearn's IsolationForest the way alibi-detect's ``IForest`` does
 (``score = -decision_function``, ``is_outlier = score > threshold``) with the reference's threshold 0.95,
 which can never fire (the score is bounded by 0.5), so the flags are all 0.
@@ -15,7 +16,6 @@ from __future__ import annotations
 
 import numpy as np
 import pandas as pd
-from scipy import stats
 from sklearn.ensemble import IsolationForest
 
 from .reference_pipeline import CATEGORICAL_FEATURES, FEATURES, NUMERIC_FEATURES
@@ -30,7 +30,6 @@ class ReferenceCustomModel:
         self.classifier = classifier
         # 02-register-model.ipynb:224-229: TabularDrift(x_ref, p_val=.05, categories_per_feature={0..8: None})
         self.x_ref = reference_frame[self.all_features]
-        self.ref_cats = {c: np.unique(self.x_ref[c].astype(str)) for c in self.categorical_features}
         # 02-register-model.ipynb:232-233: IForest(threshold=0.95).fit(df[NUMERIC_FEATURES].values)
         self.threshold = 0.95
         self.iforest = IsolationForest(n_estimators=outlier_trees, random_state=0).fit(
@@ -38,18 +37,9 @@ class ReferenceCustomModel:
         )
 
     def drift_p_values(self, df: pd.DataFrame) -> np.ndarray:
-        p = np.zeros(len(self.all_features), dtype=np.float32)
-        for i, name in enumerate(self.all_features):
-            if name in self.ref_cats:
-                cats = self.ref_cats[name]
-                ref_counts = np.array([(self.x_ref[name].astype(str) == v).sum() for v in cats])
-                x_counts = np.array([(df[name].astype(str) == v).sum() for v in cats])
-                p[i] = stats.chi2_contingency(np.vstack((ref_counts, x_counts)))[1]
-            else:
-                p[i] = stats.ks_2samp(
-                    self.x_ref[name].to_numpy(dtype=float), df[name].to_numpy(dtype=float),
-                    alternative="two-sided", method="exact")[1]
-        return p
+        from .drift import tabular_drift_p_values
+
+        return tabular_drift_p_values(self.x_ref, df[self.all_features], self.categorical_features)
 
     def predict(self, context, model_input):
         df = pd.DataFrame(model_input)  # :332

@@ -1,0 +1,127 @@
+"""numpy emulation of the drift kernels' semantics (TEST INFRASTRUCTURE).
+
+Mirrors ``csrc/drift_stats.cuh`` step for step -- the two binary searches and histograms of ``k_drift_count``, the
+prefix-sum / tie-flag candidates of the K-S numerator, and the anti-diagonal ring sweep of the exact p-value with its
+"designated j per slot" indexing -- so the algorithm can be checked against scipy on a CPU-only box.  Nothing in the
+product imports it.
+"""
+
+import math
+
+import numpy as np
+
+RING_MAX = 4096
+
+
+def ks_numerator(ref_sorted: np.ndarray, x: np.ndarray) -> int:
+    m0, n0 = len(ref_sorted), len(x)
+    a = np.searchsorted(ref_sorted, x, side="left")   # #ref <  x
+    b = np.searchsorted(ref_sorted, x, side="right")  # #ref <= x
+    ha = np.bincount(a, minlength=m0 + 1).astype(np.int64)
+    hb = np.bincount(b, minlength=m0 + 1).astype(np.int64)
+    cle = np.cumsum(ha)[:m0]
+    clt = np.cumsum(hb)[:m0]
+    j = np.arange(m0, dtype=np.int64)
+    first = np.ones(m0, dtype=bool)
+    first[1:] = ref_sorted[1:] != ref_sorted[:-1]
+    last = np.ones(m0, dtype=bool)
+    last[:-1] = ref_sorted[1:] != ref_sorted[:-1]
+    v_last = np.abs((j + 1) * n0 - cle * m0)[last]
+    v_first = np.abs(j * n0 - clt * m0)[first]
+    return int(max(v_last.max(initial=0), v_first.max(initial=0)))
+
+
+def exact_p(m0: int, n0: int, num: int, force_ring: int | None = None):
+    """-> (p, flag): the ring sweep of k_drift_finish."""
+    g = math.gcd(m0, n0)
+    m, n = max(m0, n0), min(m0, n0)
+    mg, ng = m // g, n // g
+    h = num // g
+    if (m0 // g) >= 2147483647.0 / (n0 // g):
+        return -1.0, 1
+    width = (2 * h) // (ng + mg) + 2
+    ring = 32
+    while ring < width + 3 and ring < RING_MAX:
+        ring <<= 1
+    if force_ring:
+        ring = force_ring
+    if h == 0:
+        return 1.0, 0
+    if width + 3 > ring:
+        return 0.0, 0
+    mask = ring - 1
+    den = ng + mg
+    T = m + n
+    j_lo = -(h // den) - 1
+    while den * j_lo <= -h:
+        j_lo += 1
+    prev = np.ones(ring)
+    s = np.arange(ring, dtype=np.int64)
+    for t in range(T + 1):
+        while den * j_lo <= ng * t - h:
+            j_lo += 1
+        js = j_lo - 1
+        j = js + ((s - js) & mask)
+        i = t - j
+        up = prev
+        left = prev[(s - 1) & mask]
+        rt = 1.0 / t if t > 0 else 0.0
+        with np.errstate(invalid="ignore"):
+            val = (up * i + left * j) * rt
+        offl = (j < 0) | (j > n) | (i < 0) | (i > m) | (np.abs(ng * i - mg * j) >= h)
+        cur = np.where(offl, 1.0, np.where(i == 0, 0.0, val))
+        prev = cur
+    return float(min(max(prev[n & mask], 0.0), 1.0)), 0
+
+
+def gamma_q(a: float, x: float) -> float:
+    if not x > 0.0:
+        return 1.0
+    if x < a + 1.0:
+        ap, s = a, 1.0 / a
+        d = s
+        for _ in range(100000):
+            ap += 1.0
+            d *= x / ap
+            s += d
+            if abs(d) < abs(s) * 1e-17:
+                break
+        return 1.0 - s * math.exp(-x + a * math.log(x) - math.lgamma(a))
+    tiny = 1e-300
+    b = x + 1.0 - a
+    c = 1.0 / tiny
+    d = 1.0 / b
+    hcf = d
+    for it in range(1, 100000):
+        an = -it * (it - a)
+        b += 2.0
+        d = an * d + b
+        if abs(d) < tiny:
+            d = tiny
+        c = b + an / c
+        if abs(c) < tiny:
+            c = tiny
+        d = 1.0 / d
+        de = d * c
+        hcf *= de
+        if abs(de - 1.0) < 1e-16:
+            break
+    return math.exp(-x + a * math.log(x) - math.lgamma(a)) * hcf
+
+
+def chi2(ref_counts, batch_counts, new_counts=()):
+    o0 = np.concatenate((np.asarray(ref_counts, dtype=np.float64), np.zeros(len(new_counts))))
+    o1 = np.concatenate((np.asarray(batch_counts, dtype=np.float64), np.asarray(new_counts, dtype=np.float64)))
+    K = len(o0)
+    if K < 2:
+        return 0.0, 1.0
+    row0, row1 = o0.sum(), o1.sum()
+    tot = row0 + row1
+    col = o0 + o1
+    e0, e1 = row0 * col / tot, row1 * col / tot
+    d0, d1 = o0 - e0, o1 - e1
+    if K == 2:
+        d0 = np.where(d0 > 0, d0 - np.minimum(0.5, d0), d0 + np.minimum(0.5, -d0))
+        d1 = np.where(d1 > 0, d1 - np.minimum(0.5, d1), d1 + np.minimum(0.5, -d1))
+    s = float((d0 * d0 / e0 + d1 * d1 / e1).sum())
+    return s, gamma_q(0.5 * (K - 1), 0.5 * s)

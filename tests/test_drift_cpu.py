@@ -1,0 +1,120 @@
+"""Drift scores on a CPU-only box: the oracle restatement against the real scipy functions, and the numpy
+emulation of the kernels' algorithm (tests/drift_walk.py mirrors csrc/drift_stats.cuh) against the oracle."""
+
+import math
+
+import numpy as np
+import pytest
+from scipy import stats
+
+
+def _samples(rng, trial):
+    m = int(rng.integers(20, 500))
+    n = int(rng.integers(1, 250))
+    if trial % 5 == 0:
+        n = m  # equal sizes: scipy takes another formula (_compute_prob_outside_square), same probability
+    if trial % 7 == 0:
+        m, n = n + 5, m + 50  # batch larger than the reference
+    if trial % 2:  # heavy ties, as the integer-valued credit columns have
+        return np.sort(np.round(rng.normal(size=m) * 3) / 2), np.round(rng.normal(0.3, 1.2, size=n) * 3) / 2
+    return np.sort(rng.normal(size=m)), rng.normal(0.2 * (trial % 3), 1, size=n)
+
+
+def test_oracle_restatement_is_pinned_to_scipy():
+    """oracle/drift.py's plain restatement of scipy's exact K-S == the compiled scipy functions, bit for bit."""
+    from scipy.stats import _stats_pythran as sp
+
+    from oracle import drift as od
+
+    for m, n in [(50, 7), (30, 30), (64, 48), (300, 1), (300, 2), (1000, 37), (97, 100), (500, 125)]:
+        g = math.gcd(m, n)
+        lcm = m // g * n
+        for h in sorted({1, 2, 3, lcm // 50 + 1, lcm // 10 + 1, lcm // 3 + 1, lcm - 1, lcm}):
+            if 1 <= h <= lcm:
+                want = min(max(sp._compute_outer_prob_inside_method(m, n, g, h), 0.0), 1.0)
+                assert od.outer_prob_inside_method(m, n, g, h) == want
+    rng = np.random.default_rng(0)
+    for trial in range(40):
+        ref, x = _samples(rng, trial)
+        d, p = od.ks_2samp_exact(ref, x)
+        r = stats.ks_2samp(ref, x, alternative="two-sided", method="exact")
+        assert abs(d - r.statistic) < 1e-15
+        assert abs(p - r.pvalue) <= 1e-12 * max(r.pvalue, 1e-300) + 1e-300
+    for K in (2, 3, 7, 40):
+        a = rng.integers(1, 5000, K)
+        b = rng.integers(0, 30, K)
+        b[0] += 1
+        s, p = od.chi2_pvalue(a, b)
+        r = stats.chi2_contingency(np.vstack((a, b)))
+        assert abs(s - r[0]) <= 1e-12 * r[0] and abs(p - r[1]) <= 1e-12 * r[1]
+
+
+def test_kernel_algorithm_matches_scipy():
+    """The GPU formulation -- integer K-S numerator from two histograms over reference positions, anti-diagonal ring
+    sweep of the lattice-path recursion, chi-squared tail by series / continued fraction -- against scipy."""
+    import drift_walk as dw
+
+    from oracle import drift as od
+
+    rng = np.random.default_rng(1)
+    for trial in range(60):
+        ref, x = _samples(rng, trial)
+        m, n = len(ref), len(x)
+        num = dw.ks_numerator(ref, x)
+        assert num == od.ks_numerator(ref, x)
+        r = stats.ks_2samp(ref, x, alternative="two-sided", method="exact")
+        assert abs(num / (m * n) - r.statistic) < 1e-15
+        p, flag = dw.exact_p(m, n, num)
+        assert flag == 0 and abs(p - r.pvalue) <= 1e-12 * r.pvalue + 1e-300
+    # a wider ring than needed changes nothing; one too narrow is refused (p underflows float32 there anyway)
+    base = dw.exact_p(300, 40, 977)[0]
+    assert dw.exact_p(300, 40, 977, force_ring=64)[0] == base == dw.exact_p(300, 40, 977, force_ring=256)[0]
+    assert dw.exact_p(30000, 65536, 0)[0] == 1.0
+    assert dw.exact_p(30000, 99991, 12345)[1] == 1  # lcm >= 2^31: scipy switches to the asymptotic formula
+    for K in (1, 2, 3, 7, 40):
+        a = rng.integers(1, 5000, K)
+        b = rng.integers(0, 30, K)
+        b[0] += 1
+        if K >= 2:
+            s, p = dw.chi2(a, b)
+            r = stats.chi2_contingency(np.vstack((a, b)))
+            assert abs(s - r[0]) <= 1e-12 * r[0] and abs(p - r[1]) <= 1e-11 * r[1]
+        s, p = dw.chi2(a, b, [3, 1])  # two batch values outside the reference categories
+        r = stats.chi2_contingency(np.vstack((np.concatenate((a, [0, 0])), np.concatenate((b, [3, 1])))))
+        assert abs(s - r[0]) <= 1e-12 * r[0] and abs(p - r[1]) <= 1e-11 * r[1]
+
+
+@pytest.mark.parametrize("n", [1, 37, 1000])
+def test_kernel_algorithm_at_reference_size(curated, n):
+    """m = 30 000 (the curated table) against request-sized batches: 30 000 + n anti-diagonals."""
+    import drift_walk as dw
+
+    from oracle import reference_pipeline as rp
+
+    rng = np.random.default_rng(3)
+    name = rp.NUMERIC_FEATURES[5]
+    col = curated[name].to_numpy(float)
+    ref = np.sort(col)
+    x = col[rng.integers(0, len(col), n)] * (1.3 if n == 37 else 1.0)
+    r = stats.ks_2samp(ref, x, alternative="two-sided", method="exact")
+    num = dw.ks_numerator(ref, x)
+    p, flag = dw.exact_p(len(ref), n, num)
+    assert flag == 0 and abs(num / (len(ref) * n) - r.statistic) < 1e-15
+    assert abs(p - r.pvalue) <= 1e-11 * r.pvalue
+
+
+def test_drift_oracle_union_of_categories(curated):
+    """alibi-detect counts over the union of reference and batch categories: an unseen value adds a (0, k) column."""
+    from oracle import drift as od
+    from oracle import reference_pipeline as rp
+
+    ref = curated[rp.FEATURES]
+    batch = ref.iloc[:50].copy()
+    p0 = od.tabular_drift_p_values(ref, batch, rp.CATEGORICAL_FEATURES)
+    batch.iloc[3, batch.columns.get_loc("sex")] = "unseen_value"
+    p1 = od.tabular_drift_p_values(ref, batch, rp.CATEGORICAL_FEATURES)
+    i = rp.FEATURES.index("sex")
+    assert p1[i] < p0[i] and (np.delete(p1, i) == np.delete(p0, i)).all()
+    assert p0.dtype == np.float32 and ((0 <= p0) & (p0 <= 1)).all()
+    scores = od.drift_scores(ref, batch, rp.CATEGORICAL_FEATURES)
+    assert len(scores) == 23 and all(0.0 <= v <= 1.0 for v in scores)

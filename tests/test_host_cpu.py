@@ -45,6 +45,31 @@ def test_no_device_means_no_result(rf100d6):
         ForestEngine(flatten.flatten_pipeline(rf100d6), 0)
 
 
+def test_drift_detector_needs_the_device(curated, tmp_path):
+    """The drift detector has no CPU path either: reference statistics can be prepared and saved anywhere, scoring
+    (and opening a saved detector) needs the GPU."""
+    from conftest import has_gpu
+    from oracle import reference_pipeline as rp
+
+    from databricks_kubernetes_mlops_poc_b200._cabi import B2FError
+    from databricks_kubernetes_mlops_poc_b200.drift import TabularDrift
+
+    ref = curated[rp.FEATURES].iloc[:2000]
+    det = TabularDrift(ref, rp.CATEGORICAL_FEATURES, device=None)
+    assert det.features == rp.FEATURES and len(det.ref_sorted) == 14 and len(det.ref_cats) == 9
+    assert (np.diff(det.ref_sorted[rp.NUMERIC_FEATURES[0]]) >= 0).all()
+    assert int(det.ref_counts["sex"].sum()) == 2000
+    det.save(str(tmp_path / "d.npz"))
+    with pytest.raises(B2FError, match="no CPU fallback"):
+        det.statistics(ref.iloc[:5])
+    if has_gpu():
+        pytest.skip("GPU present")
+    with pytest.raises(B2FError, match="b2f_drift_create"):
+        TabularDrift(ref, rp.CATEGORICAL_FEATURES, device=0)
+    with pytest.raises(B2FError, match="b2f_drift_create"):
+        TabularDrift.load(str(tmp_path / "d.npz"), device=0)
+
+
 def test_missing_library_fails_loudly(tmp_path):
     from databricks_kubernetes_mlops_poc_b200 import _cabi
 
