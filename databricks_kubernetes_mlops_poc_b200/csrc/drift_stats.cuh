@@ -168,16 +168,123 @@ __device__ inline int64_t gcd64(int64_t a, int64_t b) {
     return a;
 }
 
-/* One anti-diagonal cell.  P(i,j) = 1 outside the band or off the lattice, 0 on the first column inside the band,
- * else (P(i-1,j)*i + P(i,j-1)*j) / (i+j). */
-__device__ __forceinline__ double drift_cell(int64_t i, int64_t j, int64_t m, int64_t n, int64_t mg, int64_t ng, int64_t h, double up, double left,
-                                             double rt) {
-    if (j < 0 || j > n || i < 0 || i > m) return 1.0;
-    int64_t dev = ng * i - mg * j;
-    if (dev < 0) dev = -dev;
-    if (dev >= h) return 1.0;
-    if (i == 0) return 0.0;
-    return (up * (double)i + left * (double)j) * rt;
+/* ---- the anti-diagonal sweep ----------------------------------------------------------------------------------
+ * P(i,j) = 1 outside the band |ng*i - mg*j| < h or off the lattice, 0 on the first column inside the band, else
+ * (P(i-1,j)*i + P(i,j-1)*j) / (i+j).  Diagonal t = i + j holds at most 2h/(ng+mg) + 1 in-band cells, consecutive in j.
+ * A ring of `ring` slots (power of two >= that + 3) covers j in [j_lo(t) - 1, j_lo(t) - 1 + ring), slot = j mod ring,
+ * where j_lo(t) is the first in-band j of the diagonal; the lowest covered cell is always outside the band (value 1),
+ * so when j_lo advances and a slot jumps from j to j + ring the value it leaves behind is exactly the value (1) its
+ * new cell's upper neighbour has.  Per step a slot therefore needs its own previous value ("up", a register) and
+ * the previous value of slot - 1 ("left": a shuffle inside a warp, shared memory across warps).
+ * All bookkeeping is incremental integer adds (dev = ng*i - mg*j grows by ng per step, edge tracks j_lo); the only
+ * floating-point work on the dependent chain is one FMA and one multiply by 1/t.  1/t comes from a per-warp batch:
+ * every 32 steps lane l divides once, 1/(t0 + l), and steps fetch their reciprocal with a shuffle. */
+struct SweepConst {
+    int64_t m, n, mg, ng, den, h, T;
+    int ring;
+};
+struct SlotState {
+    int64_t dev; /* ng*i - mg*j of the slot's current cell */
+    int32_t i, j;
+    double v;    /* value of the slot's cell on the previous diagonal */
+};
+
+__device__ __forceinline__ void slot_init(SlotState &st, int s, int64_t js0, const SweepConst &c) {
+    const int32_t j = (int32_t)js0 + ((s - (int32_t)js0) & (c.ring - 1));
+    st.j = j;
+    st.i = -j; /* t = 0 */
+    st.dev = -c.den * (int64_t)j;
+    st.v = 1.0;
+}
+__device__ __forceinline__ double slot_eval(const SlotState &st, double left, double rt, const SweepConst &c) {
+    int64_t a = st.dev < 0 ? -st.dev : st.dev;
+    const bool off = (st.j < 0) | ((int64_t)st.j > c.n) | (st.i < 0) | ((int64_t)st.i > c.m) | (a >= c.h);
+    const double val = fma(left, (double)st.j, st.v * (double)st.i) * rt;
+    return off ? 1.0 : (st.i == 0 ? 0.0 : val);
+}
+__device__ __forceinline__ void slot_advance(SlotState &st, bool adv, int32_t js_new, const SweepConst &c) {
+    st.i += 1;
+    st.dev += c.ng;
+    if (adv && st.j < js_new) { /* this slot held the lowest covered j: it now covers j + ring */
+        st.j += c.ring;
+        st.i -= c.ring;
+        st.dev -= c.den * (int64_t)c.ring;
+    }
+}
+
+/* ring == 32: one warp, one slot per lane, no shared memory */
+__device__ __forceinline__ double sweep_warp(const SweepConst &c, int lane) {
+    int64_t j_lo = -(c.h / c.den) - 1;
+    while (c.den * j_lo <= -c.h) ++j_lo;
+    int64_t edge = -c.h - c.den * j_lo; /* ng*t - h - den*j_lo < 0 */
+    int32_t js = (int32_t)j_lo - 1;
+    SlotState st;
+    slot_init(st, lane, js, c);
+    double r_mine = 0.0;
+    for (int64_t t = 0; t <= c.T; ++t) {
+        if ((t & 31) == 0) {
+            const double tl = (double)(t + lane);
+            r_mine = tl > 0.0 ? 1.0 / tl : 0.0;
+        }
+        const double rt = __shfl_sync(0xffffffffu, r_mine, (int)(t & 31));
+        const double left = __shfl_sync(0xffffffffu, st.v, (lane + 31) & 31);
+        st.v = slot_eval(st, left, rt, c);
+        edge += c.ng;
+        const bool adv = edge >= 0;
+        if (adv) {
+            edge -= c.den;
+            ++js;
+        }
+        slot_advance(st, adv, js, c);
+    }
+    return __shfl_sync(0xffffffffu, st.v, (int)(c.n & 31));
+}
+
+/* ring >= 64: `active` = min(ring, blockDim) threads, NS = ring / active slots each (slot = tid + k*active);
+ * "left" values travel through a double-buffered shared-memory ring, one named barrier per diagonal */
+template <int NS>
+__device__ __forceinline__ double sweep_block(const SweepConst &c, int tid, int active, double *buf0, double *buf1) {
+    const int mask = c.ring - 1;
+    int64_t j_lo = -(c.h / c.den) - 1;
+    while (c.den * j_lo <= -c.h) ++j_lo;
+    int64_t edge = -c.h - c.den * j_lo;
+    int32_t js = (int32_t)j_lo - 1;
+    SlotState st[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        slot_init(st[k], tid + k * active, js, c);
+        buf0[tid + k * active] = 1.0;
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(active) : "memory");
+    double *prev = buf0, *cur = buf1;
+    const int lane = tid & 31;
+    double r_mine = 0.0;
+    for (int64_t t = 0; t <= c.T; ++t) {
+        if ((t & 31) == 0) {
+            const double tl = (double)(t + lane);
+            r_mine = tl > 0.0 ? 1.0 / tl : 0.0;
+        }
+        const double rt = __shfl_sync(0xffffffffu, r_mine, (int)(t & 31));
+        edge += c.ng;
+        const bool adv = edge >= 0;
+        if (adv) {
+            edge -= c.den;
+            ++js;
+        }
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const int s = tid + k * active;
+            const double left = prev[(s - 1) & mask];
+            st[k].v = slot_eval(st[k], left, rt, c);
+            cur[s] = st[k].v;
+            slot_advance(st[k], adv, js, c);
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(active) : "memory");
+        double *tmp = prev;
+        prev = cur;
+        cur = tmp;
+    }
+    return prev[(int)(c.n & mask)]; /* written before the last barrier */
 }
 
 extern __shared__ unsigned char drift_smem[];
@@ -199,7 +306,6 @@ __global__ void __launch_bounds__(B2F_DRIFT_THREADS) k_drift_finish(DriftParams 
     const int out = p.n_cat + f;
     __shared__ unsigned long long s_part_a[B2F_DRIFT_THREADS], s_part_b[B2F_DRIFT_THREADS];
     __shared__ unsigned long long s_num;
-    __shared__ double s_result;
 
     /* ---- (1) K-S numerator: max over reference points of |n*(#ref <= r) - m0*(#batch <= r)| and the left limits */
     const int64_t m0 = p.n_ref, n0 = p.n;
@@ -277,51 +383,27 @@ __global__ void __launch_bounds__(B2F_DRIFT_THREADS) k_drift_finish(DriftParams 
     }
     if (flag != 0 || h == 0 || too_wide) return;
 
-    double *bufs = reinterpret_cast<double *>(drift_smem);
-    const int mask = ring - 1;
-    const int64_t T = m + n;
-    const int64_t den = ng + mg;
-    /* j_lo(t) = smallest j with den*j > ng*t - h (first in-band j of diagonal t); the ring covers [j_lo - 1, j_lo - 1 + ring) */
-    int64_t j_lo = -(h / den) - 1;
-    while (den * j_lo <= -h) ++j_lo;
-
+    SweepConst c;
+    c.m = m;
+    c.n = n;
+    c.mg = mg;
+    c.ng = ng;
+    c.den = ng + mg;
+    c.h = h;
+    c.T = m + n;
+    c.ring = ring;
+    double res;
     if (ring == 32) {
-        /* one warp, one slot per lane, neighbours through shuffles */
         if (tid >= 32) return;
-        double v = 1.0;
-        for (int64_t t = 0; t <= T; ++t) {
-            while (den * j_lo <= ng * t - h) ++j_lo;
-            const int64_t js = j_lo - 1;
-            const int64_t j = js + (int64_t)((tid - (int)js) & 31);
-            const double left = __shfl_sync(0xffffffffu, v, (tid + 31) & 31);
-            const double rt = t > 0 ? __drcp_rn((double)t) : 0.0;
-            v = drift_cell(t - j, j, m, n, mg, ng, h, v, left, rt);
-        }
-        const double res = __shfl_sync(0xffffffffu, v, (int)(n & 31));
-        if (tid == 0) p.p_val[out] = fmin(fmax(res, 0.0), 1.0);
-        return;
+        res = sweep_warp(c, tid);
+    } else {
+        if (tid >= ring) return; /* whole warps leave (ring is a multiple of 32); the rest meet on named barrier 1 */
+        const int active = min(nt, ring);
+        double *bufs = reinterpret_cast<double *>(drift_smem);
+        const int ns = ring / active;
+        if (ns == 1) res = sweep_block<1>(c, tid, active, bufs, bufs + ring);
+        else if (ns == 2) res = sweep_block<2>(c, tid, active, bufs, bufs + ring);
+        else res = sweep_block<4>(c, tid, active, bufs, bufs + ring);
     }
-
-    double *prev = bufs, *cur = bufs + ring;
-    for (int s = tid; s < ring; s += nt) prev[s] = 1.0;
-    __syncthreads();
-    if (tid >= ring) return; /* whole warps leave (ring is a multiple of 32): the rest synchronise on a named barrier */
-    const int active = min(nt, ring);
-    for (int64_t t = 0; t <= T; ++t) {
-        while (den * j_lo <= ng * t - h) ++j_lo;
-        const int64_t js = j_lo - 1;
-        const double rt = t > 0 ? __drcp_rn((double)t) : 0.0;
-        for (int s = tid; s < ring; s += active) {
-            const int64_t j = js + (int64_t)((s - (int)js) & mask);
-            cur[s] = drift_cell(t - j, j, m, n, mg, ng, h, prev[s], prev[(s - 1) & mask], rt);
-        }
-        asm volatile("bar.sync 1, %0;" ::"r"(active) : "memory");
-        double *tmp = prev;
-        prev = cur;
-        cur = tmp;
-    }
-    if (tid == 0) {
-        s_result = prev[(int)(n & mask)];
-        p.p_val[out] = fmin(fmax(s_result, 0.0), 1.0);
-    }
+    if (tid == 0) p.p_val[out] = fmin(fmax(res, 0.0), 1.0);
 }

@@ -31,7 +31,7 @@ def ks_numerator(ref_sorted: np.ndarray, x: np.ndarray) -> int:
     return int(max(v_last.max(initial=0), v_first.max(initial=0)))
 
 
-def exact_p(m0: int, n0: int, num: int, force_ring: int | None = None):
+def exact_p(m0: int, n0: int, num: int, force_ring: int | None = None, check_bookkeeping: bool = False):
     """-> (p, flag): the ring sweep of k_drift_finish."""
     g = math.gcd(m0, n0)
     m, n = max(m0, n0), min(m0, n0)
@@ -55,23 +55,38 @@ def exact_p(m0: int, n0: int, num: int, force_ring: int | None = None):
     j_lo = -(h // den) - 1
     while den * j_lo <= -h:
         j_lo += 1
-    prev = np.ones(ring)
+    # slot state kept INCREMENTALLY, as SlotState / slot_advance in the kernel do
     s = np.arange(ring, dtype=np.int64)
+    js = j_lo - 1
+    edge = -h - den * j_lo
+    j = js + ((s - js) & mask)
+    i = -j
+    dev = -den * j
+    v = np.ones(ring)
     for t in range(T + 1):
-        while den * j_lo <= ng * t - h:
-            j_lo += 1
-        js = j_lo - 1
-        j = js + ((s - js) & mask)
-        i = t - j
-        up = prev
-        left = prev[(s - 1) & mask]
+        if check_bookkeeping:  # the closed forms the increments must reproduce
+            jl = (ng * t - h) // den + 1
+            assert js == jl - 1
+            assert (j == js + ((s - js) & mask)).all() and (i == t - j).all() and (dev == ng * i - mg * j).all()
+        left = v[(s - 1) & mask]
         rt = 1.0 / t if t > 0 else 0.0
         with np.errstate(invalid="ignore"):
-            val = (up * i + left * j) * rt
-        offl = (j < 0) | (j > n) | (i < 0) | (i > m) | (np.abs(ng * i - mg * j) >= h)
-        cur = np.where(offl, 1.0, np.where(i == 0, 0.0, val))
-        prev = cur
-    return float(min(max(prev[n & mask], 0.0), 1.0)), 0
+            val = (left * j + v * i) * rt
+        offl = (j < 0) | (j > n) | (i < 0) | (i > m) | (np.abs(dev) >= h)
+        v = np.where(offl, 1.0, np.where(i == 0, 0.0, val))
+        edge += ng
+        adv = edge >= 0
+        if adv:
+            edge -= den
+            js += 1
+        i = i + 1
+        dev = dev + ng
+        if adv:
+            jump = j < js
+            j = np.where(jump, j + ring, j)
+            i = np.where(jump, i - ring, i)
+            dev = np.where(jump, dev - den * ring, dev)
+    return float(min(max(v[n & mask], 0.0), 1.0)), 0
 
 
 def gamma_q(a: float, x: float) -> float:

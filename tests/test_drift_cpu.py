@@ -64,7 +64,7 @@ def test_kernel_algorithm_matches_scipy():
         assert num == od.ks_numerator(ref, x)
         r = stats.ks_2samp(ref, x, alternative="two-sided", method="exact")
         assert abs(num / (m * n) - r.statistic) < 1e-15
-        p, flag = dw.exact_p(m, n, num)
+        p, flag = dw.exact_p(m, n, num, check_bookkeeping=True)
         assert flag == 0 and abs(p - r.pvalue) <= 1e-12 * r.pvalue + 1e-300
     # a wider ring than needed changes nothing; one too narrow is refused (p underflows float32 there anyway)
     base = dw.exact_p(300, 40, 977)[0]
