@@ -533,6 +533,8 @@ def run_b200(args, dist: Dist):
         line["cfg5_moments"] = mom
     if outl is not None:
         line["outlier_forest"] = outl
+    if dist.rank == 0 and dist.world == 1 and not args.no_drift:
+        line["drift_detector"] = drift_section(base, flat, dist.local_rank)
     for d in (d_rows, d_proba, d_label):
         eng.device_free(d)
     eng.close()
@@ -594,6 +596,41 @@ def outlier_section(eng, enc, base, flat, d_rows, d_proba, d_label, h_rows, nums
     }
 
 
+def drift_section(base, flat, device):
+    """K3: per-request drift scores against the 30 000-row reference table -- chi-squared on the 9
+    categoricals, exact two-sample K-S on the 14 numerics -- on the GPU, with the scipy path the reference runs
+    (restated in oracle/drift.py) timed on this box's host beside it for request-sized batches."""
+    from databricks_kubernetes_mlops_poc_b200.drift import TabularDrift
+    from oracle import drift as od
+
+    feats = flat.all_features
+    ref = base[feats]
+    det = TabularDrift(ref, flat.cat_features, device=device)
+    rng = np.random.default_rng(DATA_SEED + 7)
+    rows = []
+    for n in (1, 1000, 65536):
+        batch = ref.iloc[rng.integers(0, len(ref), n)].reset_index(drop=True)
+        got = det.p_values(batch)  # warm-up + parity sample
+        dev, wall = [], []
+        for _ in range(10 if n < 65536 else 3):
+            t0 = time.perf_counter()
+            det.statistics(batch)
+            wall.append(time.perf_counter() - t0)
+            dev.append(det.last_device_ms)
+        row = {"batch": n, "device_ms": float(np.median(dev)), "call_ms": 1e3 * float(np.median(wall))}
+        if n <= 1000:
+            t0 = time.perf_counter()
+            want = od.tabular_drift_p_values(ref, batch, flat.cat_features)
+            row["cpu_scipy_ms"] = 1e3 * (time.perf_counter() - t0)
+            row["parity_max_abs_dp"] = float(np.abs(got.astype(np.float64) - want.astype(np.float64)).max())
+        rows.append(row)
+    launches = det.launches
+    det.close()
+    return {"reference_rows": len(ref), "features": "9 categorical (chi-squared) + 14 numeric (exact two-sample K-S)",
+            "api": "b2f_drift_score (H2D of the batch columns + k_drift_count + k_drift_finish + D2H of 23 p-values)",
+            "gpu_launches": int(launches), "by_batch": rows}
+
+
 def latency_sweep(args, dist: Dist):
     """BASELINE config 3: batch in {1, 16, 256, 4096, 65536}, 500-tree depth-8 model; p50 / p99 of the C-ABI
     call (pinned host buffers, H2D + kernel + D2H inside) and of the plugin call model.predict(DataFrame) -> dict."""
@@ -636,8 +673,26 @@ def latency_sweep(args, dist: Dist):
                        "calls": calls}
     info = eng.info()
     model.close()
+    # the whole CustomModel.predict replacement: classifier + outlier forest (one pass) + drift detector, all on the GPU
+    from sklearn.ensemble import IsolationForest
+
+    iso = IsolationForest(n_estimators=100, random_state=0).fit(base[list(model.numeric_features)].to_numpy())
+    full = B200Model.from_pipeline(pipe, reference_frame=base, outlier=iso, outlier_threshold=0.95, devices=[dist.local_rank])
+    for n in (1, 16, 256, 4096):
+        df = df_all.iloc[:n]
+        for _ in range(3):
+            full.predict(df)
+        tp = np.empty(100)
+        for i in range(100):
+            t0 = time.perf_counter()
+            full.predict(df)
+            tp[i] = time.perf_counter() - t0
+        res[str(n)]["predict_full_p50_us"] = 1e6 * float(np.percentile(tp, 50))
+        res[str(n)]["predict_full_p99_us"] = 1e6 * float(np.percentile(tp, 99))
+    full.close()
     return {"model": name, "walk": info["walk"], "tile_resident": info["tile_resident"], "split_max_rows": info["split_max_rows"],
-            "api": "C ABI: b2f_predict_pairs on pinned 64-byte rows; plugin: B200Model.predict(DataFrame) -> dict (drift detector off)",
+            "api": "C ABI: b2f_predict_pairs on pinned 64-byte rows; plugin: B200Model.predict(DataFrame) -> dict, classifier only "
+                   "(predict_*) and with the outlier forest + drift detector attached (predict_full_*: the whole CustomModel.predict)",
             "batches": res}
 
 
@@ -750,6 +805,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-moments", action="store_true")
     ap.add_argument("--no-outliers", action="store_true", help="skip the K4 outlier-forest section")
+    ap.add_argument("--no-drift", action="store_true", help="skip the K3 drift-detector section")
     ap.add_argument("--cfg1", action="store_true", help="config 1: the reference CPU path on 1k curated rows (no GPU)")
     ap.add_argument("--stream", action="store_true", help="config 4: one process, 10M-row stream round-robin over all GPUs")
     ap.add_argument("--stream-rows", type=int, default=10_000_000)

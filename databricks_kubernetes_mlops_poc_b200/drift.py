@@ -49,26 +49,29 @@ class TabularDrift:
             cats, counts = np.unique(reference[name].astype(str).to_numpy(), return_counts=True)
             self.ref_cats[name] = cats
             self.ref_counts[name] = counts.astype(np.int64)
-        self._h = None
+        self._host_init()
         if device is not None:
             self._open(device)
 
     # ------------------------------------------------------------------ device state
+    def _host_init(self) -> None:
+        self._h = None
+        self._index = {name: {v: i for i, v in enumerate(self.ref_cats[name].tolist())} for name in self.cat_features}
+        # output position of every feature: the C ABI returns categorical features first, then numeric ones
+        order = self.cat_features + self.num_features
+        self._perm = np.array([order.index(f) for f in self.features], dtype=np.int64)
+        self.last_device_ms = 0.0
+
     def _open(self, device: int) -> None:
         self._lib = _cabi.load_library()
         self.device = int(device)
         self._lock = threading.Lock()
-        self._index = {name: {v: i for i, v in enumerate(self.ref_cats[name].tolist())} for name in self.cat_features}
         ref = np.ascontiguousarray(np.stack([self.ref_sorted[n] for n in self.num_features])) if self.num_features else np.zeros((0, self.n_ref))
         sizes = np.array([len(self.ref_cats[n]) for n in self.cat_features], dtype=np.int32)
         counts = np.concatenate([self.ref_counts[n] for n in self.cat_features]).astype(np.int64) if self.cat_features else np.zeros(0, np.int64)
         self._h = self._lib.b2f_drift_create(self.device, self.n_ref, len(self.num_features), ptr(ref), len(self.cat_features), ptr(sizes), ptr(counts))
         if not self._h:
             raise B2FError(f"b2f_drift_create(device={device}) failed: {_cabi.last_error()}")
-        # output position of every feature: the C ABI returns categorical features first, then numeric ones
-        order = self.cat_features + self.num_features
-        self._perm = np.array([order.index(f) for f in self.features], dtype=np.int64)
-        self.last_device_ms = 0.0
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -86,13 +89,11 @@ class TabularDrift:
         return int(self._lib.b2f_drift_launches(self._h))
 
     # ------------------------------------------------------------------ scoring
-    def statistics(self, batch: pd.DataFrame):
-        """-> (p float64, stat float64, flags int32), each in ``self.features`` order."""
+    def encode_batch(self, batch: pd.DataFrame):
+        """Host half of a request (no device needed): -> (x float64 (n_num, n), codes int32 (n_cat, n) with -1 for
+        values outside the reference categories, new_off int32 (n_cat + 1), new_counts int64 -- the counts of those
+        outside values, one entry per distinct value)."""
         n = len(batch)
-        if n < 1:
-            raise ValueError("Data passed to ks_2samp must not be empty")
-        if not self._h:
-            raise B2FError("drift detector has no device state (created with device=None or closed); there is no CPU fallback")
         nn, nc = len(self.num_features), len(self.cat_features)
         x = np.empty((nn, n), dtype=np.float64)
         for k, name in enumerate(self.num_features):
@@ -101,14 +102,40 @@ class TabularDrift:
         new_off = np.zeros(nc + 1, dtype=np.int32)
         new_counts = []
         for c, name in enumerate(self.cat_features):
-            vals = batch[name].astype(str).to_numpy()
             idx = self._index[name]
-            col = np.fromiter((idx.get(v, -1) for v in vals.tolist()), dtype=np.int32, count=n)
+            if n <= 128:  # request-sized batches: a Python loop beats the vectorised machinery
+                vals = batch[name].astype(str).tolist()
+                col = np.fromiter((idx.get(v, -1) for v in vals), dtype=np.int32, count=n)
+                unseen = {}
+                for v, k in zip(vals, col.tolist()):
+                    if k < 0:
+                        unseen[v] = unseen.get(v, 0) + 1
+            else:  # hash the column once, look up only its distinct values
+                inv, uniq = pd.factorize(batch[name], use_na_sentinel=False)
+                names = [str(u) for u in uniq]
+                mapped = np.fromiter((idx.get(v, -1) for v in names), dtype=np.int32, count=len(names))
+                col = mapped[inv]
+                unseen = {}
+                if (mapped < 0).any():
+                    cnt = np.bincount(inv, minlength=len(names))
+                    for v, k, q in zip(names, mapped.tolist(), cnt.tolist()):
+                        if k < 0:
+                            unseen[v] = unseen.get(v, 0) + q
             codes[c] = col
-            if (col < 0).any():  # values outside the reference categories: each distinct one is a column of its own
-                new_counts.extend(np.unique(vals[col < 0], return_counts=True)[1].tolist())
+            # values outside the reference categories: each distinct one is a column of its own in the contingency table
+            new_counts.extend(unseen[v] for v in sorted(unseen))
             new_off[c + 1] = len(new_counts)
-        newc = np.asarray(new_counts, dtype=np.int64)
+        return x, codes, new_off, np.asarray(new_counts, dtype=np.int64)
+
+    def statistics(self, batch: pd.DataFrame):
+        """-> (p float64, stat float64, flags int32), each in ``self.features`` order."""
+        n = len(batch)
+        if n < 1:
+            raise ValueError("Data passed to ks_2samp must not be empty")
+        if not self._h:
+            raise B2FError("drift detector has no device state (created with device=None or closed); there is no CPU fallback")
+        nn, nc = len(self.num_features), len(self.cat_features)
+        x, codes, new_off, newc = self.encode_batch(batch)
         F = nn + nc
         p, stat, flags = np.empty(F), np.empty(F), np.empty(F, dtype=np.int32)
         ms = C.c_float(0.0)
@@ -155,5 +182,6 @@ class TabularDrift:
             self.ref_cats = {k[len("cats__"):]: z[k] for k in z.files if k.startswith("cats__")}
             self.ref_counts = {k[len("counts__"):]: z[k] for k in z.files if k.startswith("counts__")}
         self.n_ref = int(meta.get("n_ref", len(next(iter(self.ref_sorted.values()))) if self.ref_sorted else 0))
+        self._host_init()
         self._open(device)
         return self

@@ -59,6 +59,21 @@ def test_drift_detector_needs_the_device(curated, tmp_path):
     assert det.features == rp.FEATURES and len(det.ref_sorted) == 14 and len(det.ref_cats) == 9
     assert (np.diff(det.ref_sorted[rp.NUMERIC_FEATURES[0]]) >= 0).all()
     assert int(det.ref_counts["sex"].sum()) == 2000
+    # host half of a request: category indices against the reference categories, counts of values outside them
+    big = curated[rp.FEATURES].iloc[2000:2600].copy().reset_index(drop=True)
+    big.loc[[5, 9, 11], "sex"] = ["zz_unseen", "aa_unseen", "zz_unseen"]
+    for batch in (big, big.iloc[:40]):  # vectorised path (n > 128) and request-sized path agree with the definition
+        x, codes, new_off, newc = det.encode_batch(batch)
+        assert x.shape == (14, len(batch)) and codes.shape == (9, len(batch))
+        for c, name in enumerate(det.cat_features):
+            vals = batch[name].astype(str).to_numpy()
+            cats = det.ref_cats[name].tolist()
+            want = np.array([cats.index(v) if v in cats else -1 for v in vals])
+            assert (codes[c] == want).all()
+            outside = sorted(set(vals[want < 0].tolist()))
+            assert newc[new_off[c]:new_off[c + 1]].tolist() == [int((vals == v).sum()) for v in outside]
+        assert (x[0] == batch[det.num_features[0]].to_numpy()).all()
+        assert new_off[-1] == len(newc) >= 2 and {1, 2} <= set(newc.tolist())
     det.save(str(tmp_path / "d.npz"))
     with pytest.raises(B2FError, match="no CPU fallback"):
         det.statistics(ref.iloc[:5])
