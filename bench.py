@@ -565,10 +565,12 @@ def outlier_section(eng, enc, base, flat, d_rows, d_proba, d_label, h_rows, nums
     alone.d2h(got_f, d_label)
     info = alone.info()
     alone.close()
-    sel = np.arange(0, BATCH, BATCH // 2048)[:2048]
     x = nums[:BATCH].astype(np.float64)
+    # parity sample: complete rows only -- the reference's detector refuses NaN (sklearn 1.1.1), the installed sklearn
+    # routes it by a per-node random flag, the kernel sends it to the second child (flatten_isolation_forest)
+    sel = np.nonzero(~np.isnan(x).any(axis=1))[0][:2048]
     t0 = time.perf_counter()
-    want = -iso.decision_function(x[:16384])
+    iso.decision_function(x[:16384])
     cpu_s = time.perf_counter() - t0
     want_sel = -iso.decision_function(x[sel])
 
@@ -590,8 +592,8 @@ def outlier_section(eng, enc, base, flat, d_rows, d_proba, d_label, h_rows, nums
         "e2e_api": "b2f_predict_full(host pinned rows) -> {f64 proba, i32 label, i32 is_outlier, f32 score} per row",
         "d2h_bytes_per_step": BATCH * 24,
         "cpu_sklearn_rows_per_s": 16384 / cpu_s, "cpu_sample": "IsolationForest.decision_function on 16384 rows, sklearn default threading",
-        "parity_max_abs_dscore_2048rows": float(np.abs(got_s[sel].astype(np.float64) - want_sel).max()),
-        "parity_flags_equal_2048rows": bool((got_f[sel] == (want_sel > thr)).all()),
+        "parity_max_abs_dscore_2048_complete_rows": float(np.abs(got_s[sel].astype(np.float64) - want_sel).max()),
+        "parity_flags_equal_2048_complete_rows": bool((got_f[sel] == (want_sel > thr)).all()),
         "parity_full_vs_alone_flags_equal": bool((h_full["is_outlier"][:BATCH] == got_f).all()),
     }
 
@@ -678,8 +680,12 @@ def latency_sweep(args, dist: Dist):
 
     iso = IsolationForest(n_estimators=100, random_state=0).fit(base[list(model.numeric_features)].to_numpy())
     full = B200Model.from_pipeline(pipe, reference_frame=base, outlier=iso, outlier_threshold=0.95, devices=[dist.local_rank])
+    # the reference's outlier detector refuses NaN numerics (sklearn 1.1.1 -> HTTP 500), so this leg scores complete rows
+    df_complete = df_all.iloc[:4096].copy()
+    for col in model.numeric_features:
+        df_complete[col] = df_complete[col].fillna(float(base[col].median()))
     for n in (1, 16, 256, 4096):
-        df = df_all.iloc[:n]
+        df = df_complete.iloc[:n]
         for _ in range(3):
             full.predict(df)
         tp = np.empty(100)
