@@ -176,91 +176,63 @@ __device__ inline int64_t gcd64(int64_t a, int64_t b) {
  * so when j_lo advances and a slot jumps from j to j + ring the value it leaves behind is exactly the value (1) its
  * new cell's upper neighbour has.  Per step a slot therefore needs its own previous value ("up", a register) and
  * the previous value of slot - 1 ("left": a shuffle inside a warp, shared memory across warps).
- * Bookkeeping is a 32-bit counter (edge, which tracks j_lo) and a per-slot validity interval in t; the only
+ * All bookkeeping is incremental integer adds (dev = ng*i - mg*j grows by ng per step, edge tracks j_lo); the only
  * floating-point work on the dependent chain is one FMA and one multiply by 1/t.  1/t comes from a per-warp batch:
  * every 32 steps lane l divides once, 1/(t0 + l), and steps fetch their reciprocal with a shuffle. */
 struct SweepConst {
     int64_t m, n, mg, ng, den, h, T;
     int ring;
 };
-/* A slot's cell (t - j, j) is on the lattice and inside the band exactly for t in [ta, tb] (empty if ta > tb):
- *   -h < ng*t - den*j < h   and   0 <= t - j <= m   and   0 <= j <= n.
- * The interval is recomputed only when the slot moves to another j (two integer divisions, rare); a step then costs
- * two 32-bit compares instead of 64-bit band arithmetic. */
 struct SlotState {
-    int32_t j, ta, tb;
-    double jd; /* (double) j */
-    double v;  /* value of the slot's cell on the previous diagonal */
+    int64_t dev; /* ng*i - mg*j of the slot's current cell */
+    int32_t i, j;
+    double v;    /* value of the slot's cell on the previous diagonal */
 };
 
-__device__ __forceinline__ void slot_interval(SlotState &st, const SweepConst &c) {
-    const int64_t j = st.j;
-    st.jd = (double)st.j;
-    if (j < 0 || j > c.n) {
-        st.ta = 1;
-        st.tb = 0;
-        return;
-    }
-    const int64_t a = c.den * j - c.h; /* need ng*t > a */
-    int64_t q = a / c.ng;
-    if (a % c.ng != 0 && a < 0) --q;   /* floor */
-    int64_t lo = q + 1;
-    const int64_t b = c.den * j + c.h; /* need ng*t < b, b > 0 */
-    int64_t hi = (b + c.ng - 1) / c.ng - 1;
-    lo = max(lo, j);
-    hi = min(hi, j + c.m);
-    if (lo > hi) {
-        st.ta = 1;
-        st.tb = 0;
-    } else {
-        st.ta = (int32_t)lo;
-        st.tb = (int32_t)hi;
-    }
-}
-__device__ __forceinline__ void slot_init(SlotState &st, int s, int32_t js0, const SweepConst &c) {
-    st.j = js0 + ((s - js0) & (c.ring - 1));
+__device__ __forceinline__ void slot_init(SlotState &st, int s, int64_t js0, const SweepConst &c) {
+    const int32_t j = (int32_t)js0 + ((s - (int32_t)js0) & (c.ring - 1));
+    st.j = j;
+    st.i = -j; /* t = 0 */
+    st.dev = -c.den * (int64_t)j;
     st.v = 1.0;
-    slot_interval(st, c);
 }
-__device__ __forceinline__ double slot_eval(const SlotState &st, int32_t t, double left, double rt) {
-    const bool off = (t < st.ta) | (t > st.tb);
-    const double val = fma(left, st.jd, st.v * (double)(t - st.j)) * rt;
-    return off ? 1.0 : (t == st.j ? 0.0 : val);
+__device__ __forceinline__ double slot_eval(const SlotState &st, double left, double rt, const SweepConst &c) {
+    int64_t a = st.dev < 0 ? -st.dev : st.dev;
+    const bool off = (st.j < 0) | ((int64_t)st.j > c.n) | (st.i < 0) | ((int64_t)st.i > c.m) | (a >= c.h);
+    const double val = fma(left, (double)st.j, st.v * (double)st.i) * rt;
+    return off ? 1.0 : (st.i == 0 ? 0.0 : val);
 }
 __device__ __forceinline__ void slot_advance(SlotState &st, bool adv, int32_t js_new, const SweepConst &c) {
+    st.i += 1;
+    st.dev += c.ng;
     if (adv && st.j < js_new) { /* this slot held the lowest covered j: it now covers j + ring */
         st.j += c.ring;
-        slot_interval(st, c);
+        st.i -= c.ring;
+        st.dev -= c.den * (int64_t)c.ring;
     }
-}
-/* first in-band j of diagonal 0 and the distance to the next advance: edge = ng*t - h - den*j_lo, in [-den, 0) */
-__device__ __forceinline__ void sweep_start(const SweepConst &c, int32_t &js, int32_t &edge) {
-    int64_t j_lo = -(c.h / c.den) - 1;
-    while (c.den * j_lo <= -c.h) ++j_lo;
-    js = (int32_t)j_lo - 1;
-    edge = (int32_t)(-c.h - c.den * j_lo);
 }
 
 /* ring == 32: one warp, one slot per lane, no shared memory */
 __device__ __forceinline__ double sweep_warp(const SweepConst &c, int lane) {
-    int32_t js, edge;
-    sweep_start(c, js, edge);
-    const int32_t ng = (int32_t)c.ng, den = (int32_t)c.den, T = (int32_t)c.T;
+    int64_t j_lo = -(c.h / c.den) - 1;
+    while (c.den * j_lo <= -c.h) ++j_lo;
+    int64_t edge = -c.h - c.den * j_lo; /* ng*t - h - den*j_lo < 0 */
+    int32_t js = (int32_t)j_lo - 1;
     SlotState st;
     slot_init(st, lane, js, c);
     double r_mine = 0.0;
-    for (int32_t t = 0; t <= T; ++t) {
+    for (int64_t t = 0; t <= c.T; ++t) {
         if ((t & 31) == 0) {
             const double tl = (double)(t + lane);
             r_mine = tl > 0.0 ? 1.0 / tl : 0.0;
         }
-        const double rt = __shfl_sync(0xffffffffu, r_mine, t & 31);
+        const double rt = __shfl_sync(0xffffffffu, r_mine, (int)(t & 31));
         const double left = __shfl_sync(0xffffffffu, st.v, (lane + 31) & 31);
-        st.v = slot_eval(st, t, left, rt);
-        edge += ng;
+        st.v = slot_eval(st, left, rt, c);
+        edge += c.ng;
         const bool adv = edge >= 0;
         if (adv) {
-            edge -= den;
+            edge -= c.den;
             ++js;
         }
         slot_advance(st, adv, js, c);
@@ -273,9 +245,10 @@ __device__ __forceinline__ double sweep_warp(const SweepConst &c, int lane) {
 template <int NS>
 __device__ __forceinline__ double sweep_block(const SweepConst &c, int tid, int active, double *buf0, double *buf1) {
     const int mask = c.ring - 1;
-    int32_t js, edge;
-    sweep_start(c, js, edge);
-    const int32_t ng = (int32_t)c.ng, den = (int32_t)c.den, T = (int32_t)c.T;
+    int64_t j_lo = -(c.h / c.den) - 1;
+    while (c.den * j_lo <= -c.h) ++j_lo;
+    int64_t edge = -c.h - c.den * j_lo;
+    int32_t js = (int32_t)j_lo - 1;
     SlotState st[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
@@ -286,23 +259,23 @@ __device__ __forceinline__ double sweep_block(const SweepConst &c, int tid, int 
     double *prev = buf0, *cur = buf1;
     const int lane = tid & 31;
     double r_mine = 0.0;
-    for (int32_t t = 0; t <= T; ++t) {
+    for (int64_t t = 0; t <= c.T; ++t) {
         if ((t & 31) == 0) {
             const double tl = (double)(t + lane);
             r_mine = tl > 0.0 ? 1.0 / tl : 0.0;
         }
-        const double rt = __shfl_sync(0xffffffffu, r_mine, t & 31);
-        edge += ng;
+        const double rt = __shfl_sync(0xffffffffu, r_mine, (int)(t & 31));
+        edge += c.ng;
         const bool adv = edge >= 0;
         if (adv) {
-            edge -= den;
+            edge -= c.den;
             ++js;
         }
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
             const int s = tid + k * active;
             const double left = prev[(s - 1) & mask];
-            st[k].v = slot_eval(st[k], t, left, rt);
+            st[k].v = slot_eval(st[k], left, rt, c);
             cur[s] = st[k].v;
             slot_advance(st[k], adv, js, c);
         }

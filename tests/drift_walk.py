@@ -55,43 +55,37 @@ def exact_p(m0: int, n0: int, num: int, force_ring: int | None = None, check_boo
     j_lo = -(h // den) - 1
     while den * j_lo <= -h:
         j_lo += 1
-    # slot state as SlotState / slot_interval / slot_advance keep it: the slot's j and the interval [ta, tb] of diagonals
-    # on which its cell (t - j, j) is on the lattice and inside the band
+    # slot state kept INCREMENTALLY, as SlotState / slot_advance in the kernel do
     s = np.arange(ring, dtype=np.int64)
     js = j_lo - 1
     edge = -h - den * j_lo
-    assert -den <= edge < 0
-
-    def interval(j):
-        ta = np.ones_like(j)
-        tb = np.zeros_like(j)
-        ok = (j >= 0) & (j <= n)
-        lo = np.maximum((den * j - h) // ng + 1, j)          # floor division: ng*t > den*j - h
-        hi = np.minimum(-((-(den * j + h)) // ng) - 1, j + m)  # ceil division:  ng*t < den*j + h
-        ok &= lo <= hi
-        return np.where(ok, lo, ta), np.where(ok, hi, tb)
-
     j = js + ((s - js) & mask)
-    ta, tb = interval(j)
+    i = -j
+    dev = -den * j
     v = np.ones(ring)
     for t in range(T + 1):
-        i = t - j
-        off = (t < ta) | (t > tb)
-        if check_bookkeeping:  # the closed forms the incremental state must reproduce
-            assert js == (ng * t - h) // den
-            assert (j == js + ((s - js) & mask)).all()
-            assert (off == ((j < 0) | (j > n) | (i < 0) | (i > m) | (np.abs(ng * i - mg * j) >= h))).all()
+        if check_bookkeeping:  # the closed forms the increments must reproduce
+            jl = (ng * t - h) // den + 1
+            assert js == jl - 1
+            assert (j == js + ((s - js) & mask)).all() and (i == t - j).all() and (dev == ng * i - mg * j).all()
         left = v[(s - 1) & mask]
         rt = 1.0 / t if t > 0 else 0.0
-        val = (left * j + v * i) * rt
-        v = np.where(off, 1.0, np.where(t == j, 0.0, val))
+        with np.errstate(invalid="ignore"):
+            val = (left * j + v * i) * rt
+        offl = (j < 0) | (j > n) | (i < 0) | (i > m) | (np.abs(dev) >= h)
+        v = np.where(offl, 1.0, np.where(i == 0, 0.0, val))
         edge += ng
-        if edge >= 0:
+        adv = edge >= 0
+        if adv:
             edge -= den
             js += 1
+        i = i + 1
+        dev = dev + ng
+        if adv:
             jump = j < js
             j = np.where(jump, j + ring, j)
-            ta, tb = interval(j)
+            i = np.where(jump, i - ring, i)
+            dev = np.where(jump, dev - den * ring, dev)
     return float(min(max(v[n & mask], 0.0), 1.0)), 0
 
 
