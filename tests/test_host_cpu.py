@@ -85,6 +85,28 @@ def test_drift_detector_needs_the_device(curated, tmp_path):
         TabularDrift.load(str(tmp_path / "d.npz"), device=0)
 
 
+def test_mlflow_shim_resolves_to_the_b200_loader(monkeypatch):
+    """with the shim directory on the path, the reference's `mlflow.pyfunc.load_model(dir)` call
+    (app/main.py:26-28) lands in this package's loader; the shim is opt-in by path and not imported otherwise."""
+    import importlib
+    import sys
+
+    import databricks_kubernetes_mlops_poc_b200 as pkg
+
+    shim = os.path.join(os.path.dirname(pkg.__file__), "shim")
+    monkeypatch.syspath_prepend(shim)
+    for name in [m for m in sys.modules if m == "mlflow" or m.startswith("mlflow.")]:
+        monkeypatch.delitem(sys.modules, name)
+    mlflow = importlib.import_module("mlflow")
+    assert mlflow.__file__.startswith(shim) and callable(mlflow.pyfunc.load_model)
+    seen = {}
+    monkeypatch.setattr(pkg, "load_model", lambda path: seen.setdefault("path", path) or "model")
+    mlflow.pyfunc.load_model("/models/credit_default")
+    assert seen["path"] == "/models/credit_default"
+    for name in [m for m in sys.modules if m == "mlflow" or m.startswith("mlflow.")]:
+        monkeypatch.delitem(sys.modules, name)
+
+
 def test_missing_library_fails_loudly(tmp_path):
     from databricks_kubernetes_mlops_poc_b200 import _cabi
 

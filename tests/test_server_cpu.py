@@ -103,3 +103,42 @@ def test_concurrent_requests_share_batches():
     finally:
         mb.close()
     assert sum(m.calls) == 120 and len(m.calls) < 40  # requests were merged into fewer engine calls
+
+
+REFERENCE_APP = "/root/reference/app"
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(REFERENCE_APP + "/main.py"), reason="reference checkout not present (GPU box)")
+def test_unmodified_reference_app_runs_on_the_shim(monkeypatch):
+    """the reference's own app/main.py, imported unmodified from /root/reference with the mlflow shim
+    ahead on the path, serves POST /predict from whatever `load_model` returns (a stub scorer here: no GPU)."""
+    import importlib
+    import os
+    import sys
+
+    import databricks_kubernetes_mlops_poc_b200 as pkg
+    from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES, sample_request
+
+    class Plugin:  # the plugin boundary: predict(DataFrame) -> dict (CustomModel.predict)
+        def predict(self, df):
+            if len(df.columns) == 0:
+                raise KeyError("no columns")  # what B200Model.predict (and the reference's CustomModel) do on []
+            n = len(df)
+            return {"predictions": [0.25] * n, "outliers": [0] * n, "feature_drift_batch": {k: 0.0 for k in ALL_FEATURES}}
+
+    monkeypatch.syspath_prepend(REFERENCE_APP)
+    monkeypatch.syspath_prepend(os.path.join(os.path.dirname(pkg.__file__), "shim"))
+    for name in [m for m in sys.modules if m in ("mlflow", "main", "model") or m.startswith("mlflow.")]:
+        monkeypatch.delitem(sys.modules, name)
+    monkeypatch.setattr(pkg, "load_model", lambda path: Plugin())
+    main = importlib.import_module("main")
+    try:
+        assert main.__file__.startswith(REFERENCE_APP)
+        with TestClient(main.app, raise_server_exceptions=False) as c:
+            r = c.post("/predict", json=sample_request())
+            assert r.status_code == 200 and r.json()["predictions"] == [0.25]
+            assert list(r.json()["feature_drift_batch"]) == ALL_FEATURES
+            assert c.post("/predict", json=[]).status_code == 500
+    finally:
+        for name in [m for m in sys.modules if m in ("mlflow", "main", "model") or m.startswith("mlflow.")]:
+            sys.modules.pop(name, None)
