@@ -62,21 +62,35 @@ class TabularDrift:
         self._perm = np.array([order.index(f) for f in self.features], dtype=np.int64)
         self.last_device_ms = 0.0
 
-    def _open(self, device: int) -> None:
+    def _open(self, device: int, handles: int | None = None) -> None:
+        """Upload the reference table.  ``handles`` (default ``B200_DRIFT_HANDLES`` or 4) independent device states,
+        each with its own stream and scratch, let that many requests be scored concurrently: one request occupies
+        one CTA per feature (23 of the 148 SMs), and the server scores every request's drift on its own thread."""
+        import os
+
         self._lib = _cabi.load_library()
         self.device = int(device)
-        self._lock = threading.Lock()
         ref = np.ascontiguousarray(np.stack([self.ref_sorted[n] for n in self.num_features])) if self.num_features else np.zeros((0, self.n_ref))
         sizes = np.array([len(self.ref_cats[n]) for n in self.cat_features], dtype=np.int32)
         counts = np.concatenate([self.ref_counts[n] for n in self.cat_features]).astype(np.int64) if self.cat_features else np.zeros(0, np.int64)
-        self._h = self._lib.b2f_drift_create(self.device, self.n_ref, len(self.num_features), ptr(ref), len(self.cat_features), ptr(sizes), ptr(counts))
-        if not self._h:
-            raise B2FError(f"b2f_drift_create(device={device}) failed: {_cabi.last_error()}")
+        k = max(1, int(handles if handles is not None else os.environ.get("B200_DRIFT_HANDLES", "4")))
+        self._handles, self._locks = [], []
+        for _ in range(k):
+            h = self._lib.b2f_drift_create(self.device, self.n_ref, len(self.num_features), ptr(ref), len(self.cat_features), ptr(sizes), ptr(counts))
+            if not h:
+                msg = _cabi.last_error()
+                self.close()
+                raise B2FError(f"b2f_drift_create(device={device}) failed: {msg}")
+            self._handles.append(h)
+            self._locks.append(threading.Lock())
+        self._h = self._handles[0]
+        self._next = 0
 
     def close(self) -> None:
-        if getattr(self, "_h", None):
-            self._lib.b2f_drift_destroy(self._h)
-            self._h = None
+        for h in getattr(self, "_handles", []):
+            self._lib.b2f_drift_destroy(h)
+        self._handles = []
+        self._h = None
 
     def __del__(self):
         try:
@@ -86,7 +100,7 @@ class TabularDrift:
 
     @property
     def launches(self) -> int:
-        return int(self._lib.b2f_drift_launches(self._h))
+        return sum(int(self._lib.b2f_drift_launches(h)) for h in self._handles)
 
     # ------------------------------------------------------------------ scoring
     def encode_batch(self, batch: pd.DataFrame):
@@ -139,10 +153,11 @@ class TabularDrift:
         F = nn + nc
         p, stat, flags = np.empty(F), np.empty(F), np.empty(F, dtype=np.int32)
         ms = C.c_float(0.0)
-        with self._lock:
+        k = self._next = (self._next + 1) % len(self._handles)  # round-robin; a benign race only skews the rotation
+        with self._locks[k]:
             check(
-                self._lib.b2f_drift_score(self._h, n, ptr(x), ptr(codes), ptr(new_off) if len(newc) else None, ptr(newc) if len(newc) else None,
-                                          ptr(p), ptr(stat), ptr(flags), C.byref(ms)),
+                self._lib.b2f_drift_score(self._handles[k], n, ptr(x), ptr(codes), ptr(new_off) if len(newc) else None,
+                                          ptr(newc) if len(newc) else None, ptr(p), ptr(stat), ptr(flags), C.byref(ms)),
                 "b2f_drift_score",
             )
         self.last_device_ms = float(ms.value)

@@ -61,3 +61,45 @@ def test_moments_merge_over_nccl(curated, rf100d6):
             assert np.allclose(got[:9, 1], codes.mean(0), rtol=1e-12)
         finally:
             grp.close()
+
+
+def test_full_model_across_gpus(curated, iforest, rf100d6):
+    """Classifier + outlier forest sliced over the GPUs (b2f_predict_multi_ex with b2f_scored_full records), the drift
+    detector on device 1, and concurrent drift requests over the detector's handle pool."""
+    _need_two()
+    from concurrent.futures import ThreadPoolExecutor
+    from types import SimpleNamespace
+
+    from oracle import drift as od
+    from oracle import reference_pipeline as rp
+
+    from databricks_kubernetes_mlops_poc_b200.drift import TabularDrift
+    from databricks_kubernetes_mlops_poc_b200.engine import device_count
+    from databricks_kubernetes_mlops_poc_b200.model import B200Model
+
+    ref = curated[rp.FEATURES]
+    m = B200Model.from_pipeline(rf100d6, outlier=SimpleNamespace(isolationforest=iforest, threshold=0.0), devices=list(range(device_count())))
+    try:
+        for df in (ref, ref.iloc[:3], ref.iloc[:1001]):
+            out = m.predict(df)
+            want_p, _ = rp.oracle_predict(rf100d6, df)
+            want_s = -iforest.decision_function(df[rp.NUMERIC_FEATURES].to_numpy())
+            assert np.abs(np.asarray(out["predictions"]) - want_p).max() <= 1e-12
+            assert out["outliers"] == (want_s > 0.0).astype(int).tolist()
+        assert all(e.info()["launches"] > 0 and e.info()["outlier_trees"] == 100 for e in m.group.engines)
+        for r in m.replicas:  # the server's per-GPU scoring path
+            proba, flags = r.score(ref.iloc[:500])
+            assert np.abs(proba - want_p[:500]).max() <= 1e-12 and (flags == (want_s[:500] > 0.0)).all()
+    finally:
+        m.close()
+    det = TabularDrift(ref, rp.CATEGORICAL_FEATURES, device=1)
+    try:
+        batches = [ref.iloc[100 * k: 100 * k + 64 + k].reset_index(drop=True) for k in range(12)]
+        want = [od.drift_scores(ref, b, rp.CATEGORICAL_FEATURES) for b in batches]
+        with ThreadPoolExecutor(max_workers=6) as pool:
+            got = list(pool.map(det.score, batches))
+        for g, w in zip(got, want):
+            assert np.abs(np.asarray(g) - np.asarray(w)).max() <= 1e-6
+        assert det.launches == 2 * len(batches)
+    finally:
+        det.close()
