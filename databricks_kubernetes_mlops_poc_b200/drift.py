@@ -118,7 +118,7 @@ class TabularDrift:
         for c, name in enumerate(self.cat_features):
             idx = self._index[name]
             if n <= 128:  # request-sized batches: a Python loop beats the vectorised machinery
-                vals = batch[name].astype(str).tolist()
+                vals = [v if type(v) is str else str(v) for v in batch[name].tolist()]
                 col = np.fromiter((idx.get(v, -1) for v in vals), dtype=np.int32, count=n)
                 unseen = {}
                 for v, k in zip(vals, col.tolist()):
