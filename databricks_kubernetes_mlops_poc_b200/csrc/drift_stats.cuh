@@ -176,39 +176,59 @@ __device__ inline int64_t gcd64(int64_t a, int64_t b) {
  * so when j_lo advances and a slot jumps from j to j + ring the value it leaves behind is exactly the value (1) its
  * new cell's upper neighbour has.  Per step a slot therefore needs its own previous value ("up", a register) and
  * the previous value of slot - 1 ("left": a shuffle inside a warp, shared memory across warps).
- * All bookkeeping is incremental integer adds (dev = ng*i - mg*j grows by ng per step, edge tracks j_lo); the only
- * floating-point work on the dependent chain is one FMA and one multiply by 1/t.  1/t comes from a per-warp batch:
+ * All bookkeeping is incremental adds (dev = ng*i - mg*j grows by ng per step, a 32-bit counter tracks j_lo); the
+ * only floating-point work on the dependent chain is one FMA and one multiply by 1/t.  1/t comes from a per-warp batch:
  * every 32 steps lane l divides once, 1/(t0 + l), and steps fetch their reciprocal with a shuffle. */
 struct SweepConst {
     int64_t m, n, mg, ng, den, h, T;
     int ring;
 };
+/* Slot bookkeeping lives in float64: every quantity is an integer below 2^53 (exact), a float64 add / compare is one
+ * instruction where the int64 form is two or three, and i and j are needed as float64 by the recurrence anyway. */
+struct SweepF {
+    double n, m, h, ng, ringd, den_ring;
+};
 struct SlotState {
-    int64_t dev; /* ng*i - mg*j of the slot's current cell */
-    int32_t i, j;
-    double v;    /* value of the slot's cell on the previous diagonal */
+    double dev; /* ng*i - mg*j of the slot's current cell */
+    double i, j;
+    double v;   /* value of the slot's cell on the previous diagonal */
+    int32_t jj; /* j as an integer, for the "lowest covered j" test */
 };
 
+__device__ __forceinline__ SweepF sweep_f(const SweepConst &c) {
+    SweepF f;
+    f.n = (double)c.n;
+    f.m = (double)c.m;
+    f.h = (double)c.h;
+    f.ng = (double)c.ng;
+    f.ringd = (double)c.ring;
+    f.den_ring = (double)(c.den * (int64_t)c.ring);
+    return f;
+}
 __device__ __forceinline__ void slot_init(SlotState &st, int s, int64_t js0, const SweepConst &c) {
     const int32_t j = (int32_t)js0 + ((s - (int32_t)js0) & (c.ring - 1));
-    st.j = j;
-    st.i = -j; /* t = 0 */
-    st.dev = -c.den * (int64_t)j;
+    st.jj = j;
+    st.j = (double)j;
+    st.i = -(double)j; /* t = 0 */
+    st.dev = -(double)(c.den * (int64_t)j);
     st.v = 1.0;
 }
-__device__ __forceinline__ double slot_eval(const SlotState &st, double left, double rt, const SweepConst &c) {
-    int64_t a = st.dev < 0 ? -st.dev : st.dev;
-    const bool off = (st.j < 0) | ((int64_t)st.j > c.n) | (st.i < 0) | ((int64_t)st.i > c.m) | (a >= c.h);
-    const double val = fma(left, (double)st.j, st.v * (double)st.i) * rt;
-    return off ? 1.0 : (st.i == 0 ? 0.0 : val);
+__device__ __forceinline__ double slot_eval(const SlotState &st, double left, double rt, const SweepF &f) {
+    const bool off = (st.j < 0.0) | (st.j > f.n) | (st.i < 0.0) | (st.i > f.m) | (fabs(st.dev) >= f.h);
+    /* blend instead of a chain of selects: the scale (1/t, or 0 off the band / on the first column) and the offset
+     * (1 off the band) do not depend on the neighbours, so only two FMAs sit on the dependent chain */
+    const double scale = (off | (st.i == 0.0)) ? 0.0 : rt;
+    const double offset = off ? 1.0 : 0.0;
+    return fma(fma(left, st.j, st.v * st.i), scale, offset);
 }
-__device__ __forceinline__ void slot_advance(SlotState &st, bool adv, int32_t js_new, const SweepConst &c) {
-    st.i += 1;
-    st.dev += c.ng;
-    if (adv && st.j < js_new) { /* this slot held the lowest covered j: it now covers j + ring */
-        st.j += c.ring;
-        st.i -= c.ring;
-        st.dev -= c.den * (int64_t)c.ring;
+__device__ __forceinline__ void slot_advance(SlotState &st, bool adv, int32_t js_new, int ring, const SweepF &f) {
+    st.i += 1.0;
+    st.dev += f.ng;
+    if (adv && st.jj < js_new) { /* this slot held the lowest covered j: it now covers j + ring */
+        st.jj += ring;
+        st.j += f.ringd;
+        st.i -= f.ringd;
+        st.dev -= f.den_ring;
     }
 }
 
@@ -216,26 +236,28 @@ __device__ __forceinline__ void slot_advance(SlotState &st, bool adv, int32_t js
 __device__ __forceinline__ double sweep_warp(const SweepConst &c, int lane) {
     int64_t j_lo = -(c.h / c.den) - 1;
     while (c.den * j_lo <= -c.h) ++j_lo;
-    int64_t edge = -c.h - c.den * j_lo; /* ng*t - h - den*j_lo < 0 */
+    int32_t edge = (int32_t)(-c.h - c.den * j_lo); /* ng*t - h - den*j_lo, in [-den, 0): den < 2^28 */
     int32_t js = (int32_t)j_lo - 1;
+    const int32_t ng = (int32_t)c.ng, den = (int32_t)c.den, T = (int32_t)c.T;
+    const SweepF f = sweep_f(c);
     SlotState st;
     slot_init(st, lane, js, c);
     double r_mine = 0.0;
-    for (int64_t t = 0; t <= c.T; ++t) {
+    for (int32_t t = 0; t <= T; ++t) {
         if ((t & 31) == 0) {
             const double tl = (double)(t + lane);
             r_mine = tl > 0.0 ? 1.0 / tl : 0.0;
         }
-        const double rt = __shfl_sync(0xffffffffu, r_mine, (int)(t & 31));
+        const double rt = __shfl_sync(0xffffffffu, r_mine, t & 31);
         const double left = __shfl_sync(0xffffffffu, st.v, (lane + 31) & 31);
-        st.v = slot_eval(st, left, rt, c);
-        edge += c.ng;
+        st.v = slot_eval(st, left, rt, f);
+        edge += ng;
         const bool adv = edge >= 0;
         if (adv) {
-            edge -= c.den;
+            edge -= den;
             ++js;
         }
-        slot_advance(st, adv, js, c);
+        slot_advance(st, adv, js, 32, f);
     }
     return __shfl_sync(0xffffffffu, st.v, (int)(c.n & 31));
 }
@@ -247,8 +269,10 @@ __device__ __forceinline__ double sweep_block(const SweepConst &c, int tid, int 
     const int mask = c.ring - 1;
     int64_t j_lo = -(c.h / c.den) - 1;
     while (c.den * j_lo <= -c.h) ++j_lo;
-    int64_t edge = -c.h - c.den * j_lo;
+    int32_t edge = (int32_t)(-c.h - c.den * j_lo);
     int32_t js = (int32_t)j_lo - 1;
+    const int32_t ng = (int32_t)c.ng, den = (int32_t)c.den, T = (int32_t)c.T;
+    const SweepF f = sweep_f(c);
     SlotState st[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
@@ -259,25 +283,25 @@ __device__ __forceinline__ double sweep_block(const SweepConst &c, int tid, int 
     double *prev = buf0, *cur = buf1;
     const int lane = tid & 31;
     double r_mine = 0.0;
-    for (int64_t t = 0; t <= c.T; ++t) {
+    for (int32_t t = 0; t <= T; ++t) {
         if ((t & 31) == 0) {
             const double tl = (double)(t + lane);
             r_mine = tl > 0.0 ? 1.0 / tl : 0.0;
         }
-        const double rt = __shfl_sync(0xffffffffu, r_mine, (int)(t & 31));
-        edge += c.ng;
+        const double rt = __shfl_sync(0xffffffffu, r_mine, t & 31);
+        edge += ng;
         const bool adv = edge >= 0;
         if (adv) {
-            edge -= c.den;
+            edge -= den;
             ++js;
         }
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
             const int s = tid + k * active;
             const double left = prev[(s - 1) & mask];
-            st[k].v = slot_eval(st[k], left, rt, c);
+            st[k].v = slot_eval(st[k], left, rt, f);
             cur[s] = st[k].v;
-            slot_advance(st[k], adv, js, c);
+            slot_advance(st[k], adv, js, c.ring, f);
         }
         asm volatile("bar.sync 1, %0;" ::"r"(active) : "memory");
         double *tmp = prev;
