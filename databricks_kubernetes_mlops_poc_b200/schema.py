@@ -12,7 +12,9 @@ batching loop here builds its columns directly and does not need that).
 
 from __future__ import annotations
 
-from pydantic import BaseModel, create_model
+from typing import TypedDict
+
+from pydantic import BaseModel, TypeAdapter, create_model
 
 # (name, default) in the order the model was trained on: categorical block, then numeric block
 # (reference 01-train-model.ipynb:126-158; defaults from app/model.py:12-34 -- including the
@@ -42,6 +44,16 @@ LoanApplicant = create_model(
     **{n: (float, d) for n, d in _NUMERIC},
 )
 LoanApplicant.__doc__ = "One applicant: 9 categorical strings then 14 numerics, every field defaulted."
+
+# The same row as a TypedDict: what the server validates request bodies into.  Same fields, types and coercion rules as
+# ``LoanApplicant`` (pydantic validates both with the same core schema per field); absent keys stay absent and take
+# ``DEFAULTS`` when the columns are built, so no per-row model object is constructed on the request path.
+LoanApplicantRow = TypedDict(
+    "LoanApplicantRow",
+    {**{n: str for n in CATEGORICAL_FEATURES}, **{n: float for n in NUMERIC_FEATURES}},
+    total=False,
+)
+REQUEST_ROWS = TypeAdapter(list[LoanApplicantRow])  # validate_json: JSON parsing + validation in one pass of pydantic-core
 
 FeatureBatchDrift = create_model("FeatureBatchDrift", **{n: (float, ...) for n in ALL_FEATURES})
 FeatureBatchDrift.__doc__ = "Per-feature drift score of the request batch (1 - p-value)."

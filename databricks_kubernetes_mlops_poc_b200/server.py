@@ -9,12 +9,15 @@ type errors are FastAPI's 422, anything raised while scoring is a 500, an empty 
 
 What is new sits between the reference's lines 54 and 72:
 
-* rows are turned into columns straight from the validated request (no ``pd.DataFrame(list_of_models)``);
+* the request body is parsed and validated in one pydantic-core pass into plain dicts (same field rules and 422
+  behaviour as ``list[LoanApplicant]``, no per-row model objects) and turned into columns directly (no
+  ``pd.DataFrame(list_of_models)``);
 * a micro-batcher collects concurrent requests for up to ``B200_BATCH_WINDOW_US`` microseconds (or
   ``B200_MAX_BATCH`` rows), dictionary-encodes them into one pinned staging slot, and scores the whole
-  slot with ONE engine call (H2D + fused kernel + D2H); batches are dealt round-robin to the GPUs listed
-  in ``B200_DEVICES`` -- the reference instead blocks its event loop per request (``async def`` calling
-  blocking code, ``app/main.py:43,72``), so requests are strictly serialised there;
+  slot with ONE engine call (H2D + classifier kernel + outlier-forest kernel + D2H); batches are dealt round-robin
+  to the GPUs listed in ``B200_DEVICES`` -- the reference instead blocks its event loop per request (``async def``
+  calling blocking code, ``app/main.py:43,72``), so requests are strictly serialised there;
+* the per-request drift scores (GPU, ``drift.py``) run concurrently with that on their own stream and thread;
 * the two JSON log lines are produced on a logging thread, off the request's critical path.
 """
 
@@ -34,9 +37,11 @@ from typing import AsyncGenerator
 
 import numpy as np
 import pandas as pd
-from fastapi import FastAPI
+from fastapi import FastAPI, Request
+from fastapi.exceptions import RequestValidationError
+from pydantic import ValidationError
 
-from .schema import ALL_FEATURES, CATEGORICAL_FEATURES, NUMERIC_FEATURES, LoanApplicant, ModelOutput
+from .schema import ALL_FEATURES, CATEGORICAL_FEATURES, DEFAULTS, NUMERIC_FEATURES, REQUEST_ROWS, LoanApplicant, ModelOutput
 
 ml_models: dict = {}
 
@@ -46,14 +51,36 @@ def _service_name() -> str:
 
 
 def rows_to_frame(data) -> pd.DataFrame:
-    """Validated request rows -> the 23 named columns, built column-wise."""
+    """Validated request rows -> the 23 named columns, built column-wise.  Rows are dicts (``LoanApplicantRow``: absent
+    keys take the schema defaults) or objects with the 23 attributes."""
     cols = {}
+    if len(data) and isinstance(data[0], dict):
+        for name in CATEGORICAL_FEATURES:
+            d = DEFAULTS[name]
+            # validated `str` fields: an Arrow-backed string column, which the native row encoder reads in place
+            cols[name] = pd.array([r.get(name, d) for r in data], dtype="str")
+        for name in NUMERIC_FEATURES:
+            d = DEFAULTS[name]
+            cols[name] = np.array([r.get(name, d) for r in data], dtype=np.float64)
+        return pd.DataFrame(cols, columns=ALL_FEATURES)
     for name in CATEGORICAL_FEATURES:
-        # validated `str` fields: an Arrow-backed string column, which the native row encoder reads in place
         cols[name] = pd.array([getattr(r, name) for r in data], dtype="str")
     for name in NUMERIC_FEATURES:
         cols[name] = np.array([getattr(r, name) for r in data], dtype=np.float64)
     return pd.DataFrame(cols, columns=ALL_FEATURES)
+
+
+def parse_request(raw: bytes) -> list:
+    """Request body -> validated rows, with FastAPI's own 422 behaviour (``RequestValidationError`` -> {"detail": [...]},
+    locations prefixed with "body") -- one pydantic-core pass over the bytes instead of json.loads + per-row models."""
+    try:
+        return REQUEST_ROWS.validate_json(raw)
+    except ValidationError as e:
+        raise RequestValidationError([{**err, "loc": ("body", *err["loc"])} for err in e.errors(include_url=False, include_context=False)])
+
+
+_REQUEST_SCHEMA = {"required": True, "content": {"application/json": {"schema": {
+    "title": "Data", "type": "array", "items": LoanApplicant.model_json_schema()}}}}
 
 
 class _Pending:
@@ -178,9 +205,10 @@ def create_app(model=None, loader=None) -> FastAPI:
 
     app = FastAPI(title=_service_name(), docs_url="/", lifespan=lifespan)
 
-    @app.post("/predict", response_model=ModelOutput)
-    async def predict(data: list[LoanApplicant]):
+    @app.post("/predict", response_model=ModelOutput, openapi_extra={"requestBody": _REQUEST_SCHEMA})
+    async def predict(request: Request):
         """Score a list of loan applicants: default probability, outlier flag, per-feature batch drift."""
+        data = parse_request(await request.body())  # list[LoanApplicant] semantics: 422 on a type error, defaults filled
         if len(data) == 0:
             # the reference's empty DataFrame has no columns and dies in df[self.all_features] -> HTTP 500
             raise KeyError(f"None of {ALL_FEATURES} are in the [columns]")
@@ -189,12 +217,14 @@ def create_app(model=None, loader=None) -> FastAPI:
         request_id = uuid.uuid4().hex
         log_pool.submit(lambda: _log_record("InferenceData", request_id, input_df.to_json(orient="records")))
 
-        proba, flags = await ml_models["_batcher"].score(input_df)
+        # the drift scores depend on this request's rows only (no cross-request batching): start them first, on their
+        # own device stream, and let them run while the batcher encodes and scores the rows
         drift = getattr(m, "drift", None)
-        if drift is not None:
-            drift_scores = await asyncio.get_running_loop().run_in_executor(None, drift.score, input_df)
-        else:
-            drift_scores = [0.0] * len(ALL_FEATURES)
+        pending = asyncio.get_running_loop().run_in_executor(None, drift.score, input_df) if drift is not None else None
+        try:
+            proba, flags = await ml_models["_batcher"].score(input_df)
+        finally:
+            drift_scores = (await pending) if pending is not None else [0.0] * len(ALL_FEATURES)
         model_output = {
             "predictions": proba.tolist(),
             "outliers": flags.tolist() if flags is not None else [0] * len(data),

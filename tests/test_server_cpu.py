@@ -142,3 +142,42 @@ def test_unmodified_reference_app_runs_on_the_shim(monkeypatch):
     finally:
         for name in [m for m in sys.modules if m in ("mlflow", "main", "model") or m.startswith("mlflow.")]:
             sys.modules.pop(name, None)
+
+
+def test_one_pass_request_parsing_equals_the_model_validation():
+    """parse_request (pydantic-core over the raw bytes into dict rows) accepts, rejects and coerces exactly like
+    FastAPI's `data: list[LoanApplicant]` (json.loads + one model per row), and the docs keep the request schema."""
+    from fastapi.exceptions import RequestValidationError
+    from pydantic import TypeAdapter, ValidationError
+
+    from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES, DEFAULTS, LoanApplicant
+    from databricks_kubernetes_mlops_poc_b200.server import create_app, parse_request, rows_to_frame
+
+    model_rows = TypeAdapter(list[LoanApplicant])
+    good = [
+        b"[]", b"[{}]", b'[{"sex": "female", "age": 41}]', b'[{"age": "41", "credit_limit": 5, "unknown_key": 1}]',
+        b'[{"bill_amount_1": 1e3, "education": ""}, {"payment_amount_6": -0.0}]', b'[{"age": true}]',
+    ]
+    for raw in good:
+        want = model_rows.validate_json(raw)
+        got = parse_request(raw)
+        assert len(got) == len(want)
+        if want:
+            a, b = rows_to_frame(got), rows_to_frame(want)
+            assert list(a.columns) == ALL_FEATURES and a.equals(b)
+    assert rows_to_frame(parse_request(b"[{}]")).iloc[0].to_dict() == DEFAULTS
+    bad = [b"", b"{", b'{"sex": "male"}', b'[{"sex": 3}]', b'[{"age": "old"}]', b"[1]", b'[{"age": null}]', b'[{"sex": null}]', b"null"]
+    for raw in bad:
+        with pytest.raises(ValidationError):
+            model_rows.validate_json(raw)
+        with pytest.raises(RequestValidationError) as ei:
+            parse_request(raw)
+        assert all(err["loc"][0] == "body" for err in ei.value.errors())
+    with _client(StubModel()) as c:
+        for raw in bad:
+            r = c.post("/predict", content=raw, headers={"content-type": "application/json"})
+            assert r.status_code == 422 and "detail" in r.json()
+        spec = c.get("/openapi.json").json()
+        body = spec["paths"]["/predict"]["post"]["requestBody"]["content"]["application/json"]["schema"]
+        assert body["type"] == "array" and list(body["items"]["properties"]) == ALL_FEATURES
+        assert body["items"]["properties"]["age"]["default"] == 18000.0
