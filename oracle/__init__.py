@@ -27,6 +27,11 @@ file).  The pins we build instead:
   compiled part of the algorithm (impute -> one-hot -> float32 cast -> tree walk
   -> float64 mean / GBDT sum + expit) independently and are checked against the
   library to <= 1e-15.
+* ``oracle.drift`` restates alibi-detect 0.12.0's ``TabularDrift.feature_score`` on top of the real scipy calls
+  (chi-squared over the union of categories, exact two-sample K-S) -- the oracle of the GPU drift detector -- and
+  restates scipy's own exact K-S recursion in plain Python, pinned bit for bit to the compiled scipy functions
+  (``tests/test_drift_cpu.py``).  alibi-detect itself is neither vendored nor installed: against it the drift path
+  is "parity unpinned".  The outlier detector's oracle is sklearn's ``IsolationForest`` itself.
 * ``tests/golden/make_golden.py`` freezes inputs + library outputs into
   ``tests/golden/*.npz`` so the GPU box (which has no ``/root/reference``) can
   re-fit, verify the re-fit reproduces the frozen outputs, and then check the
