@@ -118,3 +118,35 @@ def test_drift_oracle_union_of_categories(curated):
     assert p0.dtype == np.float32 and ((0 <= p0) & (p0 <= 1)).all()
     scores = od.drift_scores(ref, batch, rp.CATEGORICAL_FEATURES)
     assert len(scores) == 23 and all(0.0 <= v <= 1.0 for v in scores)
+
+
+def test_frozen_detector_outputs_are_reproduced(curated, inference, iforest):
+    """tests/golden/expected_detectors.npz (library outputs frozen by make_golden_detectors.py) == what the oracle
+    computes on this box: pins the scipy / sklearn behaviour the GPU tests compare against."""
+    import os
+
+    import scipy
+    import sklearn
+
+    from oracle import datasets
+    from oracle import drift as od
+    from oracle import reference_pipeline as rp
+
+    sys_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_golden_detectors", os.path.join(sys_path, "make_golden_detectors.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    exp = datasets.load_expected("detectors")
+    ref = curated[rp.FEATURES]
+    for key, batch in mg.drift_batches(curated, inference).items():
+        stat, p = mg.drift_reference_values(ref, batch)
+        assert np.abs(stat - exp[f"drift_stat_{key}"]).max() <= 1e-12 * np.abs(stat).max()
+        assert (np.abs(p - exp[f"drift_p_{key}"]) <= 1e-10 * exp[f"drift_p_{key}"] + 1e-300).all()
+        p32 = od.tabular_drift_p_values(ref, batch, rp.CATEGORICAL_FEATURES)
+        assert (p32 == p.astype(np.float32)).all()
+    if str(exp["sklearn_version"]) == sklearn.__version__:  # the isolation trees depend on the library's RNG stream
+        got = -iforest.decision_function(curated[rp.NUMERIC_FEATURES].iloc[:3000].to_numpy())
+        assert np.abs(got - exp["iforest_score_head3000"]).max() <= 1e-12
+    assert str(exp["scipy_version"]) and scipy.__version__

@@ -174,3 +174,28 @@ def test_model_predict_drift(curated, inference, rf100d6, tmp_path):
         assert np.abs(np.asarray(list(got.values())) - np.asarray(want)).max() <= 1e-6
     finally:
         m2.close()
+
+
+def test_drift_against_frozen_library_outputs(curated, inference):
+    """The GPU detector against tests/golden/expected_detectors.npz (scipy outputs frozen by make_golden_detectors.py)."""
+    import importlib.util
+    import os
+
+    from oracle import datasets
+    from oracle import reference_pipeline as rp
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden_detectors.py")
+    spec = importlib.util.spec_from_file_location("make_golden_detectors", here)
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    exp = datasets.load_expected("detectors")
+    det = _detector(curated)
+    try:
+        for key, batch in mg.drift_batches(curated, inference).items():
+            p, stat, flags = det.statistics(batch)
+            assert (flags == 0).all()
+            want_p, want_s = exp[f"drift_p_{key}"], exp[f"drift_stat_{key}"]
+            assert (np.abs(stat - want_s) <= 1e-10 * np.abs(want_s) + 4e-16).all(), key
+            assert (np.abs(p - want_p) <= RTOL * want_p + 1e-300).all(), key
+    finally:
+        det.close()

@@ -188,3 +188,29 @@ def test_model_predict_outliers(curated, inference, iforest, rf100d6, tmp_path):
         assert (tmp_path / "b" / "outlier.b2f").exists()
     finally:
         m3.close()
+
+
+def test_isolation_forest_against_frozen_library_outputs(curated, inference, iforest, rf100d6):
+    """The GPU walk against tests/golden/expected_detectors.npz (sklearn scores frozen by make_golden_detectors.py);
+    meaningful only when this box's sklearn grows the same isolation trees as the one that froze them."""
+    import sklearn
+
+    from oracle import datasets
+
+    from databricks_kubernetes_mlops_poc_b200 import flatten
+    from databricks_kubernetes_mlops_poc_b200.encode import RowEncoder
+    from databricks_kubernetes_mlops_poc_b200.engine import ForestEngine
+
+    exp = datasets.load_expected("detectors")
+    if str(exp["sklearn_version"]) != sklearn.__version__:
+        pytest.skip("frozen with another sklearn version")
+    head = curated.iloc[:3000]
+    assert np.abs(-iforest.decision_function(_num(head)) - exp["iforest_score_head3000"]).max() <= 1e-12
+    enc = RowEncoder(flatten.flatten_pipeline(rf100d6))
+    eng = ForestEngine(flatten.flatten_isolation_forest(iforest, 9, 14, threshold=0.0), 0)
+    try:
+        for df, key in ((head, "iforest_score_head3000"), (inference, "iforest_score_inference")):
+            s64, f64 = eng.predict_rows(enc.encode_frame(df), np.float64)
+            assert np.abs(s64 - exp[key]).max() <= TOL64 and (f64 == (exp[key] > 0.0)).all()
+    finally:
+        eng.close()
