@@ -242,7 +242,7 @@ static cudaError_t set_smem_attr(int bytes) {
 
 /* ------------------------------------------------------------------ tile layout (forest_predict_tile.cuh)
  * Re-pack the interleaved blob tree-major: per tree its breadth-first nodes then its leaf payloads, trees in
- * U-groups of 4 with a 48-byte descriptor, U-groups packed into pieces that fit a shared-memory ring slot. */
+ * U-groups of B2F_TILE_U (8) with an 80-byte descriptor, U-groups packed into pieces that fit a shared-memory ring slot. */
 struct TileTree {
     std::vector<uint32_t> nodes; /* T, M pairs */
     std::vector<double> leaves;
