@@ -118,7 +118,9 @@ class TabularDrift:
         for c, name in enumerate(self.cat_features):
             idx = self._index[name]
             if n <= 128:  # request-sized batches: a Python loop beats the vectorised machinery
-                vals = [v if type(v) is str else str(v) for v in batch[name].tolist()]
+                # missing values (None / NaN) are outside the reference's contract (alibi-detect's np.unique raises on
+                # them); both paths here count them as one category "nan"
+                vals = [v if type(v) is str else ("nan" if (v is None or v != v) else str(v)) for v in batch[name].tolist()]
                 col = np.fromiter((idx.get(v, -1) for v in vals), dtype=np.int32, count=n)
                 unseen = {}
                 for v, k in zip(vals, col.tolist()):
@@ -126,7 +128,7 @@ class TabularDrift:
                         unseen[v] = unseen.get(v, 0) + 1
             else:  # hash the column once, look up only its distinct values
                 inv, uniq = pd.factorize(batch[name], use_na_sentinel=False)
-                names = [str(u) for u in uniq]
+                names = [u if type(u) is str else ("nan" if (u is None or u != u) else str(u)) for u in uniq]
                 mapped = np.fromiter((idx.get(v, -1) for v in names), dtype=np.int32, count=len(names))
                 col = mapped[inv]
                 unseen = {}

@@ -74,6 +74,15 @@ def test_drift_detector_needs_the_device(curated, tmp_path):
             assert newc[new_off[c]:new_off[c + 1]].tolist() == [int((vals == v).sum()) for v in outside]
         assert (x[0] == batch[det.num_features[0]].to_numpy()).all()
         assert new_off[-1] == len(newc) >= 2 and {1, 2} <= set(newc.tolist())
+    # missing category values (outside the reference's contract) count as one category "nan" on both paths
+    holes = big.copy()
+    holes["education"] = holes["education"].astype(object)
+    holes.loc[[1, 2], "education"] = [None, np.nan]
+    c = det.cat_features.index("education")
+    for batch in (holes, holes.iloc[:20]):
+        _, codes, new_off, newc = det.encode_batch(batch)
+        assert (codes[c][[1, 2]] == -1).all() and 2 in newc[new_off[c]:new_off[c + 1]].tolist()
+        assert (codes[c][[0, 3]] == det.ref_cats["education"].tolist().index(batch["education"].iloc[0])).all()
     det.save(str(tmp_path / "d.npz"))
     with pytest.raises(B2FError, match="no CPU fallback"):
         det.statistics(ref.iloc[:5])
