@@ -406,6 +406,16 @@ __global__ void __launch_bounds__(B2F_DRIFT_THREADS) k_drift_finish(DriftParams 
         else if (too_wide) p.p_val[out] = 0.0;
     }
     if (flag != 0 || h == 0 || too_wide) return;
+    if (n == 1) {
+        /* single-row request (the common one): the m + 1 lattice paths -- one up-step after k right-steps, k = 0..m --
+         * are equally likely, and a path stays strictly inside |i - m*j| < h iff m - h < k < h: no sweep needed */
+        if (tid == 0) {
+            const int64_t lo = max(m - h + 1, (int64_t)0), hi = min(h - 1, m);
+            const int64_t inside = hi >= lo ? hi - lo + 1 : 0;
+            p.p_val[out] = (double)(m + 1 - inside) / (double)(m + 1);
+        }
+        return;
+    }
 
     SweepConst c;
     c.m = m;

@@ -49,6 +49,10 @@ def exact_p(m0: int, n0: int, num: int, force_ring: int | None = None, check_boo
         return 1.0, 0
     if width + 3 > ring:
         return 0.0, 0
+    if n == 1 and not force_ring:  # single-row request: closed form (m + 1 equally likely paths), as in the kernel
+        lo, hi = max(m - h + 1, 0), min(h - 1, m)
+        inside = hi - lo + 1 if hi >= lo else 0
+        return (m + 1 - inside) / (m + 1.0), 0
     mask = ring - 1
     den = ng + mg
     T = m + n

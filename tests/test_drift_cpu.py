@@ -66,6 +66,17 @@ def test_kernel_algorithm_matches_scipy():
         assert abs(num / (m * n) - r.statistic) < 1e-15
         p, flag = dw.exact_p(m, n, num, check_bookkeeping=True)
         assert flag == 0 and abs(p - r.pvalue) <= 1e-12 * r.pvalue + 1e-300
+    # single-row requests take a closed form instead of the sweep: both against scipy's recursion, every h
+    from scipy.stats import _stats_pythran as sp
+
+    for m in (1, 2, 3, 7, 30, 300):
+        for h in range(1, m + 1):
+            want = min(max(sp._compute_outer_prob_inside_method(m, 1, 1, h), 0.0), 1.0)
+            assert abs(dw.exact_p(m, 1, h)[0] - want) <= 1e-13 * want
+            assert abs(dw.exact_p(m, 1, h, force_ring=32)[0] - want) <= 1e-13 * want  # the sweep itself
+    for h in (1, 2, 14999, 15000, 15001, 29999, 30000):
+        want = min(max(sp._compute_outer_prob_inside_method(30000, 1, 1, h), 0.0), 1.0)
+        assert abs(dw.exact_p(30000, 1, h)[0] - want) <= 1e-12 * want
     # a wider ring than needed changes nothing; one too narrow is refused (p underflows float32 there anyway)
     base = dw.exact_p(300, 40, 977)[0]
     assert dw.exact_p(300, 40, 977, force_ring=64)[0] == base == dw.exact_p(300, 40, 977, force_ring=256)[0]
