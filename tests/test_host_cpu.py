@@ -195,7 +195,9 @@ def test_isolation_forest_blob_matches_sklearn(curated, inference, iforest, ifor
 
 
 @pytest.mark.parametrize("params", [dict(n_estimators=33, max_samples=64, random_state=1), dict(n_estimators=7, max_features=5, random_state=2),
-                                    dict(n_estimators=40, max_samples=0.5, bootstrap=True, random_state=3)])
+                                    dict(n_estimators=40, max_samples=0.5, bootstrap=True, random_state=3),
+                                    dict(n_estimators=1, max_samples=2, random_state=4), dict(n_estimators=65, max_samples=3, random_state=5),
+                                    dict(n_estimators=4, max_samples=4096, contamination=0.1, random_state=6)])
 def test_isolation_forest_variants(curated, rf100d6, params):
     """Feature sub-sampling (estimators_features_), bootstrap and other tree sizes; alibi-style wrapper object."""
     from types import SimpleNamespace
