@@ -157,6 +157,12 @@ SIGNATURES = {
     "b2f_comm_init_all": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "b2f_moments_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "b2f_moments_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "b2f_json_parser_create": (C.c_void_p, [C.c_int, C.c_int, C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]),
+    "b2f_json_parser_destroy": (None, [C.c_void_p]),
+    "b2f_json_parser_parse": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "b2f_json_parser_numeric": (C.POINTER(C.c_double), [C.c_void_p, C.c_int]),
+    "b2f_json_parser_str_offsets": (C.POINTER(C.c_int32), [C.c_void_p, C.c_int]),
+    "b2f_json_parser_str_data": (C.POINTER(C.c_uint8), [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
     "b2f_drift_create": (C.c_void_p, [C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "b2f_drift_destroy": (None, [C.c_void_p]),
     "b2f_drift_score": (

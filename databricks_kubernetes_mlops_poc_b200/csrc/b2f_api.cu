@@ -28,6 +28,7 @@
 #include "forest_blob.h"
 #include "forest_predict.cuh"
 #include "forest_predict_tile.cuh"
+#include "json_rows.h"
 #include "row_encoder.h"
 
 #define B2F_VERSION_STR "b200forest 0.1.0 (sm_100a)"

@@ -9,9 +9,10 @@ type errors are FastAPI's 422, anything raised while scoring is a 500, an empty 
 
 What is new sits between the reference's lines 54 and 72:
 
-* the request body is parsed and validated in one pydantic-core pass into plain dicts (same field rules and 422
-  behaviour as ``list[LoanApplicant]``, no per-row model objects) and turned into columns directly (no
-  ``pd.DataFrame(list_of_models)``);
+* a request body of the regular shape goes from bytes to the 23 columns in one pass of the native parser
+  (``ingest.py`` / ``csrc/json_rows.h``: float64 arrays + Arrow string buffers, no per-row Python objects); any other
+  body is validated by pydantic-core with the same field rules and 422 behaviour as ``list[LoanApplicant]`` (no
+  ``pd.DataFrame(list_of_models)`` either way);
 * a micro-batcher collects concurrent requests for up to ``B200_BATCH_WINDOW_US`` microseconds (or
   ``B200_MAX_BATCH`` rows), dictionary-encodes them into one pinned staging slot, and scores the whole
   slot with ONE engine call (H2D + classifier kernel + outlier-forest kernel + D2H); batches are dealt round-robin
@@ -38,10 +39,9 @@ from typing import AsyncGenerator
 import numpy as np
 import pandas as pd
 from fastapi import FastAPI, Request
-from fastapi.exceptions import RequestValidationError
-from pydantic import ValidationError
 
-from .schema import ALL_FEATURES, CATEGORICAL_FEATURES, DEFAULTS, NUMERIC_FEATURES, REQUEST_ROWS, LoanApplicant, ModelOutput
+from .ingest import NativeRequestParser, parse_rows, rows_to_frame  # noqa: F401  (rows_to_frame re-exported)
+from .schema import ALL_FEATURES, LoanApplicant, ModelOutput
 
 ml_models: dict = {}
 
@@ -50,33 +50,7 @@ def _service_name() -> str:
     return os.environ.get("SERVICE_NAME", "credit-default-api")
 
 
-def rows_to_frame(data) -> pd.DataFrame:
-    """Validated request rows -> the 23 named columns, built column-wise.  Rows are dicts (``LoanApplicantRow``: absent
-    keys take the schema defaults) or objects with the 23 attributes."""
-    cols = {}
-    if len(data) and isinstance(data[0], dict):
-        for name in CATEGORICAL_FEATURES:
-            d = DEFAULTS[name]
-            # validated `str` fields: an Arrow-backed string column, which the native row encoder reads in place
-            cols[name] = pd.array([r.get(name, d) for r in data], dtype="str")
-        for name in NUMERIC_FEATURES:
-            d = DEFAULTS[name]
-            cols[name] = np.array([r.get(name, d) for r in data], dtype=np.float64)
-        return pd.DataFrame(cols, columns=ALL_FEATURES)
-    for name in CATEGORICAL_FEATURES:
-        cols[name] = pd.array([getattr(r, name) for r in data], dtype="str")
-    for name in NUMERIC_FEATURES:
-        cols[name] = np.array([getattr(r, name) for r in data], dtype=np.float64)
-    return pd.DataFrame(cols, columns=ALL_FEATURES)
-
-
-def parse_request(raw: bytes) -> list:
-    """Request body -> validated rows, with FastAPI's own 422 behaviour (``RequestValidationError`` -> {"detail": [...]},
-    locations prefixed with "body") -- one pydantic-core pass over the bytes instead of json.loads + per-row models."""
-    try:
-        return REQUEST_ROWS.validate_json(raw)
-    except ValidationError as e:
-        raise RequestValidationError([{**err, "loc": ("body", *err["loc"])} for err in e.errors(include_url=False, include_context=False)])
+parse_request = parse_rows  # the general validator (pydantic-core over the raw bytes); see ingest.py
 
 
 _REQUEST_SCHEMA = {"required": True, "content": {"application/json": {"schema": {
@@ -181,6 +155,7 @@ def create_app(model=None, loader=None) -> FastAPI:
     """Build the app.  ``model``: an already-built B200Model (tests); otherwise ``loader`` (default
     ``databricks_kubernetes_mlops_poc_b200.load_model``) is called in ``lifespan`` on ``MODEL_DIRECTORY``."""
     log_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="b200-log")
+    parser = NativeRequestParser()
 
     @asynccontextmanager
     async def lifespan(app: FastAPI) -> AsyncGenerator[None, None]:
@@ -208,12 +183,13 @@ def create_app(model=None, loader=None) -> FastAPI:
     @app.post("/predict", response_model=ModelOutput, openapi_extra={"requestBody": _REQUEST_SCHEMA})
     async def predict(request: Request):
         """Score a list of loan applicants: default probability, outlier flag, per-feature batch drift."""
-        data = parse_request(await request.body())  # list[LoanApplicant] semantics: 422 on a type error, defaults filled
-        if len(data) == 0:
+        # list[LoanApplicant] semantics (422 on a type error, defaults filled): native one-pass parser for bodies of the
+        # regular shape, pydantic-core for everything else (ingest.py)
+        input_df = parser.frame(await request.body())
+        if len(input_df) == 0:
             # the reference's empty DataFrame has no columns and dies in df[self.all_features] -> HTTP 500
             raise KeyError(f"None of {ALL_FEATURES} are in the [columns]")
         m = ml_models["credit_default"]
-        input_df = rows_to_frame(data)
         request_id = uuid.uuid4().hex
         log_pool.submit(lambda: _log_record("InferenceData", request_id, input_df.to_json(orient="records")))
 
@@ -227,7 +203,7 @@ def create_app(model=None, loader=None) -> FastAPI:
             drift_scores = (await pending) if pending is not None else [0.0] * len(ALL_FEATURES)
         model_output = {
             "predictions": proba.tolist(),
-            "outliers": flags.tolist() if flags is not None else [0] * len(data),
+            "outliers": flags.tolist() if flags is not None else [0] * len(input_df),
             "feature_drift_batch": dict(zip(ALL_FEATURES, drift_scores)),
         }
         log_pool.submit(_log_record, "ModelOutput", request_id, model_output)

@@ -61,6 +61,7 @@ extern "C" {
 #define B2F_ENCCL (-5)   /* NCCL error or NCCL library not loadable */
 #define B2F_ESTATE (-6)  /* call not valid in this state (e.g. communicator not initialised) */
 #define B2F_ERANGE (-7)  /* a numeric input is infinite or overflows float32 (sklearn raises ValueError there) */
+#define B2F_EIRREGULAR (-8) /* b2f_json_parser_parse: the body is outside the fast path's grammar; use the general validator */
 
 /* aggregation modes stored in the forest blob */
 #define B2F_AGG_RF_MEAN 0       /* RandomForestClassifier.predict_proba: mean of leaf class fractions */
@@ -155,6 +156,25 @@ void b2f_encoder_destroy(b2f_encoder *e);
  * Returns B2F_ERANGE if a value is infinite / overflows float32 (rows_out is then unspecified). */
 int b2f_encoder_encode(const b2f_encoder *e, int64_t n, const b2f_str_column *cat_cols, const double *const *num_cols,
                        const int64_t *num_strides, int row_format, void *rows_out, int threads);
+
+/* ---- native request-body parser (no GPU involved): request BYTES -> the 23 columns in one pass -----------------
+ * Replaces json.loads + one LoanApplicant object per row + pd.DataFrame(rows) (reference app/main.py:42-54,
+ * app/model.py:8-34) for requests of the regular shape: a JSON array of objects whose keys are feature names,
+ * categorical values plain strings (printable ASCII, no escapes), numeric values plain JSON numbers.  Anything else
+ * (unknown / repeated keys, escapes, null, true, numbers in strings, malformed JSON ...) returns B2F_EIRREGULAR and the
+ * caller hands the same bytes to the general validator, which applies the reference's coercions and 422 rules.
+ * names: n_cat categorical then n_num numeric feature names, concatenated (name f = names[name_offsets[f] ..
+ * name_offsets[f+1])); defaults: what an absent key takes (app/model.py:12-34). */
+typedef struct b2f_json_parser b2f_json_parser;
+b2f_json_parser *b2f_json_parser_create(int n_cat, int n_num, const char *names, const int32_t *name_offsets,
+                                        const char *default_strs, const int32_t *default_str_offsets,
+                                        const double *default_nums); /* NULL on a bad argument */
+void b2f_json_parser_destroy(b2f_json_parser *p);
+/* number of rows (>= 0), B2F_EIRREGULAR, or B2F_EINVAL; the column buffers below stay valid until the next parse */
+int64_t b2f_json_parser_parse(b2f_json_parser *p, const char *body, int64_t len);
+const double *b2f_json_parser_numeric(const b2f_json_parser *p, int k);        /* n_rows float64 of numeric feature k */
+const int32_t *b2f_json_parser_str_offsets(const b2f_json_parser *p, int j);   /* n_rows + 1 Arrow offsets of categorical j */
+const uint8_t *b2f_json_parser_str_data(const b2f_json_parser *p, int j, int64_t *nbytes); /* its UTF-8 bytes */
 
 /* ---- pinned host memory for request batches (the batching ring lives in these) ------------- */
 void *b2f_pinned_alloc(size_t nbytes); /* NULL on error */

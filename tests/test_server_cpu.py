@@ -181,3 +181,133 @@ def test_one_pass_request_parsing_equals_the_model_validation():
         body = spec["paths"]["/predict"]["post"]["requestBody"]["content"]["application/json"]["schema"]
         assert body["type"] == "array" and list(body["items"]["properties"]) == ALL_FEATURES
         assert body["items"]["properties"]["age"]["default"] == 18000.0
+
+
+def _frames_identical(a, b):
+    from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES, CATEGORICAL_FEATURES
+
+    assert list(a.columns) == list(b.columns) == ALL_FEATURES and len(a) == len(b)
+    for name in ALL_FEATURES:
+        if name in CATEGORICAL_FEATURES:
+            assert a[name].tolist() == b[name].tolist(), name
+        else:  # bit patterns, so that -0.0 / 0.0 and the last ulp count
+            assert (a[name].to_numpy(np.float64).view(np.uint64) == b[name].to_numpy(np.float64).view(np.uint64)).all(), name
+
+
+def test_native_request_parser_equals_the_general_validator():
+    """ingest.NativeRequestParser (csrc/json_rows.h): for every body the fast path accepts the columns are identical to
+    the pydantic path's; everything else is declined (-> general validator -> same coercions / 422 as before)."""
+    from fastapi.exceptions import RequestValidationError
+
+    from databricks_kubernetes_mlops_poc_b200.ingest import NativeRequestParser, parse_rows, rows_to_frame
+    from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES, DEFAULTS, sample_request
+
+    p = NativeRequestParser(min_bytes=0)  # the service only takes this path for large bodies; here every body does
+    accepted = [
+        b"[]", b" [ ] ", b"[{}]", b"[{},{}]", json.dumps(sample_request()).encode(), json.dumps(sample_request(), indent=2).encode(),
+        b'[{"sex": "female", "age": 41}]', b'[{"age":41.5,"sex":"","education":"a b/c:d,e"}]',
+        b'[{"bill_amount_1": 1e3, "bill_amount_2": -1.5E-3, "bill_amount_3": 0, "bill_amount_4": -0, "bill_amount_5": -0.0, "bill_amount_6": 0.1}]',
+        b'[{"credit_limit": 123456789012345, "age": 1.7976931348623157e308, "payment_amount_1": 5e-324, "payment_amount_2": 2.2250738585072011e-308}]',
+        b'[{"credit_limit": 0.30000000000000004, "age": 9007199254740993.0, "payment_amount_3": 1.0000000000000002}]',
+        b'\n[\t{"sex"\r:\n"male" ,"age" : 1 }\n, {"age":2}]\n',
+    ]
+    for raw in accepted:
+        got = p.columns(raw)
+        assert got is not None, raw
+        rows = parse_rows(raw)
+        assert got[0] == len(rows)
+        if rows:
+            _frames_identical(p.frame(raw), rows_to_frame(rows))
+    assert p.frame(b"[{}]").iloc[0].to_dict() == DEFAULTS and len(p.frame(b"[]")) == 0
+    declined = [
+        b"", b"[", b"{", b'{"sex": "male"}', b"[1]", b"null", b'[{"sex": 3}]', b'[{"age": "41"}]', b'[{"age": "old"}]', b'[{"age": null}]',
+        b'[{"age": true}]', b'[{"unknown_key": 1}]', b'[{"age": 1, "age": 2}]', b'[{"sex": "a\\"b"}]', b'[{"sex": "caf\xc3\xa9"}]',
+        b'[{"sex": "x\\u0041"}]', b'[{"age": 01}]', b'[{"age": 1.}]', b'[{"age": .5}]', b'[{"age": +1}]', b'[{"age": 1e999}]', b'[{"age": NaN}]',
+        b'[{"age": Infinity}]', b'[{"age": 1234567890123456}]', b'[{"age": 1},]', b'[{"age": 1,}]', b'[{"age": 1}] x', b'[{"age" 1}]', b"[{]",
+        b'[{"sex": "a\tb"}]', b'[{"": 1}]', b"[[]]",
+    ]
+    for raw in declined:
+        assert p.columns(raw) is None, raw
+        try:  # ... and frame() then behaves exactly like the general path
+            want = parse_rows(raw)
+        except RequestValidationError:
+            with pytest.raises(RequestValidationError):
+                p.frame(raw)
+        else:
+            _frames_identical(p.frame(raw), rows_to_frame(want))
+    assert p.fast > 0 and p.general > 0
+    p.close()
+
+
+def test_native_request_parser_on_generated_bodies():
+    """Property test: random bodies built from the schema (random subsets of keys, random spacing, numbers printed in
+    several styles) -- whenever the fast path accepts, its columns equal the general validator's bit for bit."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from databricks_kubernetes_mlops_poc_b200.ingest import NativeRequestParser, parse_rows, rows_to_frame
+    from databricks_kubernetes_mlops_poc_b200.schema import CATEGORICAL_FEATURES, NUMERIC_FEATURES
+
+    p = NativeRequestParser(min_bytes=0)
+    ws = st.sampled_from(["", " ", "\n", "\t ", "  "])
+    number = st.one_of(
+        st.floats(allow_nan=False, allow_infinity=False).map(repr),
+        st.integers(-10**14, 10**14).map(str),
+        st.floats(-1e6, 1e6, allow_nan=False).map(lambda v: f"{v:.3f}"),
+        st.floats(allow_nan=False, allow_infinity=False).map(lambda v: f"{v:e}"),
+        st.sampled_from(["0", "-0", "0.0", "-0.0", "1E2", "1e+2", "1e-2", "5e-324", "1.7976931348623157e308"]),
+    )
+    text = st.text(alphabet=st.characters(min_codepoint=32, max_codepoint=126, exclude_characters='"\\'), max_size=12)
+
+    @st.composite
+    def body(draw):
+        rows = []
+        for _ in range(draw(st.integers(0, 4))):
+            keys = draw(st.lists(st.sampled_from(CATEGORICAL_FEATURES + NUMERIC_FEATURES), unique=True, max_size=23))
+            pairs = []
+            for k in keys:
+                v = '"' + draw(text) + '"' if k in CATEGORICAL_FEATURES else draw(number)
+                pairs.append(f'{draw(ws)}"{k}"{draw(ws)}:{draw(ws)}{v}{draw(ws)}')
+            rows.append("{" + ",".join(pairs) + (draw(ws) if not pairs else "") + "}")
+        return (draw(ws) + "[" + draw(ws) + (draw(ws) + "," + draw(ws)).join(rows) + draw(ws) + "]" + draw(ws)).encode()
+
+    accepted = [0]
+
+    @settings(max_examples=300, deadline=None)
+    @given(body())
+    def check(raw):
+        rows = parse_rows(raw)  # generated bodies are valid requests
+        got = p.columns(raw)
+        if got is not None:
+            accepted[0] += 1
+            assert got[0] == len(rows)
+            if rows:
+                _frames_identical(p.frame(raw), rows_to_frame(rows))
+
+    check()
+    assert accepted[0] > 100
+    p.close()
+
+
+def test_native_request_frames_encode_like_general_frames(curated, rf100d6):
+    """Bytes -> native parser -> DataFrame -> row encoder gives the same encoded rows as the pydantic path (1 000-row
+    body: large enough for the service to take the native parser and the native row encoder)."""
+    from databricks_kubernetes_mlops_poc_b200 import flatten
+    from databricks_kubernetes_mlops_poc_b200.encode import RowEncoder
+    from databricks_kubernetes_mlops_poc_b200.ingest import NATIVE_MIN_BYTES, NativeRequestParser, parse_rows, rows_to_frame
+    from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES
+
+    raw = json.dumps(curated[ALL_FEATURES].iloc[:1000].to_dict(orient="records")).encode()
+    assert len(raw) > NATIVE_MIN_BYTES
+    p = NativeRequestParser()
+    a = p.frame(raw)
+    assert p.fast == 1 and p.general == 0
+    b = rows_to_frame(parse_rows(raw))
+    _frames_identical(a, b)
+    enc = RowEncoder(flatten.flatten_pipeline(rf100d6))
+    assert (enc.encode_frame_packed(a) == enc.encode_frame_packed(b)).all()
+    assert (enc.encode_frame(a) == enc.encode_frame(curated[ALL_FEATURES].iloc[:1000])).all()
+    small = json.dumps(curated[ALL_FEATURES].iloc[:3].to_dict(orient="records")).encode()
+    p.frame(small)
+    assert p.general == 1  # small bodies stay on the general path
+    p.close()
