@@ -59,8 +59,16 @@ MODELS = {
     "rf500d8": ("rf", dict(n_estimators=500, max_depth=8, criterion="entropy", random_state=0)),
 }
 N_TRAIN = 20000
+# sklearn's GBDT fit is single-threaded: 500 x depth-8 on 20 000 rows takes minutes, so that model (config 3, latency sweep)
+# is fitted on fewer synthetic rows -- its trees are as deep and as many, which is what the sweep measures
+N_TRAIN_BY_MODEL = {"gbdt500d8": 4000}
 TRAIN_SEED = 20239
 DATA_SEED = 20240
+
+
+def workload_label(model: str) -> str:
+    """The same string in both arms' ``config.workload`` (the driver compares them)."""
+    return f"cfg2: {model} in the reference preprocessing, batch {BATCH} x 23 features per GPU"
 
 
 # ----------------------------------------------------------------------------- distributed plumbing
@@ -129,14 +137,15 @@ def get_pipeline(name: str, dist: Dist):
     kind, params = MODELS[name]
     cache_dir = os.environ.get("B2F_BENCH_CACHE", "/tmp/b2f_bench_cache")
     os.makedirs(cache_dir, exist_ok=True)
-    path = os.path.join(cache_dir, f"{name}_n{N_TRAIN}_s{TRAIN_SEED}_sk{sklearn.__version__}.joblib")
+    n_train = N_TRAIN_BY_MODEL.get(name, N_TRAIN)
+    path = os.path.join(cache_dir, f"{name}_n{n_train}_s{TRAIN_SEED}_sk{sklearn.__version__}.joblib")
     base = training.load_base_frame()
     if dist.rank == 0 and not os.path.exists(path):
         t0 = time.time()
-        pipe = training.fit_synthetic(kind, base, N_TRAIN, TRAIN_SEED, **params)
+        pipe = training.fit_synthetic(kind, base, n_train, TRAIN_SEED, **params)
         joblib.dump(pipe, path + ".tmp")
         os.replace(path + ".tmp", path)
-        print(f"[bench] fitted {name} on {N_TRAIN} synthetic rows in {time.time() - t0:.1f}s", file=sys.stderr)
+        print(f"[bench] fitted {name} on {n_train} synthetic rows in {time.time() - t0:.1f}s", file=sys.stderr)
     dist.barrier()
     return joblib.load(path), base
 
@@ -296,44 +305,56 @@ def run_reference(args, dist: Dist):
     if K * t_probe[0] > 120.0:
         rows = max(2048, int(BATCH * 120.0 / (K * t_probe[0])))
     best, med, times = cpu_reference_rate(pipe, df.iloc[:rows], K, procs)
-    mean_t = statistics.mean(times)
-    value = rows / mean_t
-    how = "n_jobs=-1 threads" if procs == 1 else f"{procs} forked processes, rows split evenly"
-    sample = (f"{len(times)} steps x {rows} rows of the {BATCH}-row cfg2 batch through sklearn {sklearn.__version__} "
-              f"Pipeline.predict_proba ({how}); mean step time")
+    med_t = statistics.median(times)  # median, not mean: one descheduled worker process must not move the number 3x
+    value = rows / med_t
+    how = "n_jobs=-1 threads" if procs == 1 else f"{procs} forked processes (pool created once), rows split evenly"
+    sample = (f"{len(times)} steps x {rows} rows of the {BATCH}-row cfg2 batch (a DataFrame of 9 string + 14 float columns) through sklearn "
+              f"{sklearn.__version__} Pipeline.predict_proba ({how}); median step time")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": len(times),
-        "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * mean_t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * med_t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32cmp+f64acc", "data": "synthetic",
-        "config": {"workload": f"cfg2: {args.model} in the reference preprocessing, batch {BATCH} x 23 features", "batch": BATCH,
-                   "forest": args.model, "rows_per_step": rows},
+        "config": {"workload": workload_label(args.model), "batch": BATCH, "forest": args.model, "rows_per_step": rows},
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores if procs == 1 else procs, "kind": "reference", "sample": sample,
-                         "host_cores": cores, "best": best},
-        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                         "host_cores": cores, "best": best, "mean": rows / statistics.mean(times)},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "api": "sklearn Pipeline.predict_proba(DataFrame) -> ndarray (what the reference's CustomModel.predict calls, 02-register-model.ipynb:335-337)"},
         "gpu_launches": 0,
     }
     emit(line)
 
 
+def host_thread_share(dist: Dist) -> int:
+    """Encoder threads for this rank: the physical cores of one socket shared by the ranks that sit on it."""
+    cores = os.cpu_count() or 2
+    per_node = max(1, cores // 2 // 2)  # two sockets, two hyper-threads per core on the B200 hosts
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(dist.world)))
+    ranks_per_node = max(1, (local_world + 1) // 2)
+    return int(os.environ.get("B200_HOST_THREADS", str(max(2, min(32, per_node // ranks_per_node)))))
+
+
 def run_b200(args, dist: Dist):
-    from databricks_kubernetes_mlops_poc_b200 import flatten, training
-    from databricks_kubernetes_mlops_poc_b200.encode import RowEncoder
+    from databricks_kubernetes_mlops_poc_b200 import _cabi, flatten, training
+    from databricks_kubernetes_mlops_poc_b200._cabi import SCORED_DTYPE
     from databricks_kubernetes_mlops_poc_b200.engine import ForestEngine
+    from databricks_kubernetes_mlops_poc_b200.model import B200Model
     from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES
 
     K, W = args.steps, max(args.warmup, 3)
     pipe, base = get_pipeline(args.model, dist)
     flat = flatten.flatten_pipeline(pipe)
-    enc = RowEncoder(flat)
-    eng = ForestEngine(flat, dist.local_rank)
+    model = B200Model(flat, devices=[dist.local_rank], host_threads=host_thread_share(dist))  # the plugin object (classifier only)
+    eng, enc = model.engine, model.encoder
     info0 = eng.info()
 
     # ---- inputs: POOL distinct batches per rank (rank-seeded), resident in HBM and in pinned host memory
-    vocabs, codes, nums, rows = make_batches(base, enc, POOL, DATA_SEED + 1000 * dist.rank)
-    rows24 = rows
-    packed = args.rows == "packed64" and bool(info0["packed_ok"])
-    if packed:
-        rows = enc.pack_rows(rows24)  # 64-byte rows: one third fewer bytes to read / to push over PCIe
+    vocabs, codes, nums, rows24 = make_batches(base, enc, POOL, DATA_SEED + 1000 * dist.rank)
+    if args.rows == "ranked" and info0["rank_ok"]:
+        fmt, rows, fmt_name = _cabi.ROWS_RANKED, enc.rank_rows(rows24), "ranked"  # 32-byte rows: ranks among the forest's split values
+    elif args.rows in ("ranked", "packed64") and info0["packed_ok"]:
+        fmt, rows, fmt_name = _cabi.ROWS_PACKED64, enc.pack_rows(rows24), "packed64"
+    else:
+        fmt, rows, fmt_name = _cabi.ROWS_WORDS24, rows24, "words24"
     row_bytes = rows.shape[1] * 4
     n_pool = POOL * BATCH
     d_rows = eng.device_alloc(rows.nbytes)
@@ -342,37 +363,41 @@ def run_b200(args, dist: Dist):
     eng.h2d(d_rows, rows)
     h_rows = eng.pinned("bench_rows", rows.nbytes).view(np.uint32, rows.shape)
     h_rows[:] = rows
-    from databricks_kubernetes_mlops_poc_b200._cabi import SCORED_DTYPE
-
     h_out = eng.pinned("bench_out", n_pool * 8).view(SCORED_DTYPE, (n_pool,))  # {float32 proba1, int32 label} per row
 
     sampler = ClockSampler(dist.local_rank)
     sampler.start()
     t_load0 = time.time()
 
-    # ---- value: device-resident, K launches, CUDA events on the launching stream
-    eng.predict_stream_timed(d_rows, BATCH, POOL, d_proba, False, d_label, W, packed=packed)  # warm-up
+    # ---- value: device-resident, K back-to-back launches, ONE CUDA-event pair around the region on the launching stream
+    #      (no events between launches: consecutive launches of the rank kernel overlap head and tail through programmatic
+    #      dependent launch, which an event record in between would serialise)
+    eng.predict_stream_timed(d_rows, BATCH, POOL, d_proba, False, d_label, W, fmt=fmt, per_launch=False)  # warm-up
     dist.barrier()
-    inf_a = eng.info()
-    l0 = inf_a["launches"]
-    ms_each, ms_total = eng.predict_stream_timed(d_rows, BATCH, POOL, d_proba, False, d_label, K, packed=packed)
+    l0 = eng.info()["launches"]
+    _, ms_total = eng.predict_stream_timed(d_rows, BATCH, POOL, d_proba, False, d_label, K, fmt=fmt, per_launch=False)
     launches_value = eng.info()["launches"] - l0
-    kernel_used = "k_forest_predict_tile (thread per row)" if eng.info()["launches_tile"] > 0 else "k_forest_predict (warp per row)"
     dist.barrier()
     ms_total_max = dist.max(ms_total)
     value = dist.world * BATCH * K / (ms_total_max * 1e-3)
+    inf1 = eng.info()
+    kernel_used = ("k_forest_predict_rank (thread per row, integer rank compares, 4-byte nodes)" if inf1["launches_rank"] > 0 else
+                   "k_forest_predict_tile (thread per row)" if inf1["launches_tile"] > 0 else "k_forest_predict (warp per row)")
+    # the same launches one at a time, each bracketed by its own event pair (no overlap between launches): the isolated launch time
+    iso_ms, _ = eng.predict_stream_timed(d_rows, BATCH, POOL, d_proba, False, d_label, min(K, 100), fmt=fmt, per_launch=True)
 
-    # ---- parity spot check inside the bench (GPU vs sklearn on 2 048 rows of batch 0), rank 0
-    parity = None
-    if dist.rank == 0:
-        got = np.empty(n_pool, dtype=np.float32)
-        eng.d2h(got, d_proba)
-        sel = np.arange(0, BATCH, BATCH // 2048)[:2048]
-        df = training.arrays_to_frame(vocabs, codes[sel], nums[sel])[ALL_FEATURES]
-        want = pipe.predict_proba(df)[:, 1]
-        parity = float(np.abs(got[sel].astype(np.float64) - want).max())
+    # ---- parity spot check inside the bench (GPU vs sklearn on 2 048 rows of this rank's batch 0), EVERY rank
+    got = np.empty(n_pool, dtype=np.float32)
+    eng.d2h(got, d_proba)
+    got_lab = np.empty(n_pool, dtype=np.int32)
+    eng.d2h(got_lab, d_label)
+    sel = np.arange(0, BATCH, BATCH // 2048)[:2048]
+    df_sel = training.arrays_to_frame(vocabs, codes[sel], nums[sel])[ALL_FEATURES]
+    want = pipe.predict_proba(df_sel)[:, 1]
+    parity = dist.max(float(np.abs(got[sel].astype(np.float64) - want).max()))
+    labels_equal = dist.max(0.0 if bool((got_lab[sel] == pipe.predict(df_sel)).all()) else 1.0) == 0.0
 
-    # ---- e2e: C-ABI call with host buffers, H2D + kernel + D2H every step, wall clock around synchronous calls
+    # ---- e2e at the C ABI: pre-encoded rows in pinned host memory, H2D + kernel + D2H every step, wall clock around synchronous calls
     for i in range(W):
         b = i % POOL
         eng.predict_pairs(h_rows[b * BATCH:(b + 1) * BATCH], out=h_out[b * BATCH:(b + 1) * BATCH])
@@ -385,19 +410,12 @@ def run_b200(args, dist: Dist):
         t1 = time.perf_counter()
         eng.predict_pairs(h_rows[b * BATCH:(b + 1) * BATCH], out=h_out[b * BATCH:(b + 1) * BATCH])
         lat.append(time.perf_counter() - t1)
-    e2e_s = time.perf_counter() - t0
-    launches_e2e = eng.info()["launches"] - l0
+    cabi_s = time.perf_counter() - t0
+    launches_cabi = eng.info()["launches"] - l0
     dist.barrier()
-    # the host-buffer path must return what the device-resident path computed for the same rows
-    got_dev = np.empty(n_pool, dtype=np.float32)
-    eng.d2h(got_dev, d_proba)
     k_chk = min(K, POOL) * BATCH
-    e2e_parity = float(np.abs(h_out["proba1"][:k_chk].astype(np.float64) - got_dev[:k_chk]).max())
-    e2e_s_max = dist.max(e2e_s)
-    e2e_value = dist.world * BATCH * K / e2e_s_max
-
-    # ---- the same e2e work with TWO batches in flight on the pinned ring (b2f_predict_async_ex / b2f_wait): the tail of
-    #      step i (last chunk's kernel + D2H) overlaps the H2D of step i+1.  Reported next to the synchronous number.
+    cabi_parity = float(np.abs(h_out["proba1"][:k_chk].astype(np.float64) - got[:k_chk]).max())  # host-buffer path == device path
+    cabi_value = dist.world * BATCH * K / dist.max(cabi_s)
     ring = []
     for i in range(W):
         b = i % POOL
@@ -415,7 +433,48 @@ def run_b200(args, dist: Dist):
     dist.barrier()
     pipe_value = dist.world * BATCH * K / dist.max(pipe_s)
 
-    # ---- PCIe probe: one batch, pinned host -> device, synchronous copy (the e2e floor is set by this)
+    # ---- e2e at the PLUGIN interface (the headline): B200Model.predict(DataFrame) -> dict, the call the reference makes at
+    #      app/main.py:72, on the same 65 536-row DataFrame of 9 string + 14 float columns the reference arm scores (rank 0;
+    #      other ranks: their own seed).  Inside every step: column buffers -> encode (host threads) -> H2D -> kernel -> D2H ->
+    #      Python lists.
+    if dist.rank == 0:
+        pv, pc, pn = training.synth_arrays(base, BATCH, DATA_SEED)
+    else:
+        pv, pc, pn = vocabs, codes[:BATCH], nums[:BATCH]
+    df0 = training.arrays_to_frame(pv, pc, pn)[ALL_FEATURES]
+    for _ in range(W):
+        out0 = model.predict(df0)
+    want0 = pipe.predict_proba(df0.iloc[sel])[:, 1]
+    plugin_parity = dist.max(float(np.abs(np.asarray(out0["predictions"])[sel] - want0).max()))
+    dist.barrier()
+    plat, stages = [], []
+    l0 = eng.info()["launches"]
+    t0 = time.perf_counter()
+    for _ in range(K):
+        t1 = time.perf_counter()
+        out0 = model.predict(df0)
+        plat.append(time.perf_counter() - t1)
+        stages.append(model.last_timing)
+    plugin_s = time.perf_counter() - t0
+    launches_plugin = eng.info()["launches"] - l0
+    dist.barrier()
+    plugin_value = dist.world * BATCH * K / dist.max(plugin_s)
+    st = [s for s in stages if s]
+    breakdown = None
+    if st:
+        breakdown = {"columns_ms": 1e3 * statistics.median(s["columns_s"] for s in st),
+                     "first_chunk_ms": 1e3 * statistics.median(s["first_chunk_s"] for s in st),
+                     "chunks_and_lists_ms": 1e3 * statistics.median(s["chunks_and_lists_s"] for s in st),
+                     "chunks": st[0]["chunks"], "host_threads": st[0]["threads"], "row_format": st[0]["row_format"]}
+        a = np.random.default_rng(0).random(BATCH)
+        tl = []
+        for _ in range(5):
+            t1 = time.perf_counter()
+            a.tolist()
+            tl.append(time.perf_counter() - t1)
+        breakdown["tolist_65536_float64_alone_ms"] = 1e3 * min(tl)
+
+    # ---- PCIe probe: one batch, pinned host -> device, synchronous copy (the C-ABI e2e floor is set by this)
     tt = []
     for _ in range(10):
         t1 = time.perf_counter()
@@ -427,7 +486,7 @@ def run_b200(args, dist: Dist):
     t_sus0 = time.time()
     sus_steps, sus_ms = 0, 0.0
     while time.time() - t_sus0 < args.sustain:
-        _, tot = eng.predict_stream_timed(d_rows, BATCH, POOL, d_proba, False, d_label, 2000, packed=packed)
+        _, tot = eng.predict_stream_timed(d_rows, BATCH, POOL, d_proba, False, d_label, 2000, fmt=fmt, per_launch=False)
         sus_steps += 2000
         sus_ms += tot
     t_load1 = time.time()
@@ -438,7 +497,7 @@ def run_b200(args, dist: Dist):
     if not args.no_moments:
         n_mom = min(1_000_000 // dist.world, n_pool)
         d_rows24 = d_rows
-        if packed:  # the moments kernel reads the 96-byte layout
+        if fmt != _cabi.ROWS_WORDS24:  # the moments kernel reads the 96-byte layout
             d_rows24 = eng.device_alloc(rows24.nbytes)
             eng.h2d(d_rows24, rows24)
         ms_m, local = eng.moments_device_timed(d_rows24, n_mom, 20, False)
@@ -452,9 +511,9 @@ def run_b200(args, dist: Dist):
             t_gather = time.perf_counter() - t0
         else:
             merged, t_gather = local, 0.0
-        # kernel-only roofline on the whole pool (>= 201 MB, larger than L2)
+        # kernel-only roofline on the whole pool (201 MB, larger than L2) and on a >= 1 GiB input
         ms_big, _ = eng.moments_device_timed(d_rows24, n_pool, 10, False)
-        if packed:
+        if d_rows24 != d_rows:
             eng.device_free(d_rows24)
         peak, _ = measured_peak_gbs()
         mom = {
@@ -464,69 +523,92 @@ def run_b200(args, dist: Dist):
             "kernel_frac_of_hbm_peak_201MB": MOM_BYTES_PER_ROW * n_pool / (float(np.median(ms_big)) * 1e-3) / 1e9 / peak,
             "count0": float(merged[9, 0]),
         }
+        if dist.rank == 0 and not args.no_gib:
+            n_gib = 11_200_000  # x 96 B = 1.075 GB of 96-byte rows (1.03 GB algorithmic at 92 B/row)
+            d_gib = eng.device_alloc(n_gib * 96)
+            reps = (n_gib + rows24.shape[0] - 1) // rows24.shape[0]
+            for r in range(reps):
+                cnt = min(rows24.shape[0], n_gib - r * rows24.shape[0])
+                eng.h2d(d_gib + r * rows24.shape[0] * 96, rows24[:cnt])
+            ms_gib, _ = eng.moments_device_timed(d_gib, n_gib, 10, False)
+            eng.device_free(d_gib)
+            mom["kernel_gbs_1GiB"] = MOM_BYTES_PER_ROW * n_gib / (float(np.median(ms_gib)) * 1e-3) / 1e9
+            mom["kernel_frac_of_hbm_peak_1GiB"] = mom["kernel_gbs_1GiB"] / peak
+            mom["rows_1GiB"] = n_gib
 
     sampler.stop()
     clocks = sampler.summary(t_load0, t_load1)
-    info1 = eng.info()
 
     # ---- K4: the reference's outlier detector as a second forest over the same rows (rank 0, N=1)
     outl = None
     if dist.rank == 0 and dist.world == 1 and not args.no_outliers:
-        outl = outlier_section(eng, enc, base, flat, d_rows, d_proba, d_label, h_rows, nums, K, W, packed)
+        pk = enc.pack_rows(rows24) if info0["packed_ok"] else rows24
+        d_pk = eng.device_alloc(pk.nbytes)
+        eng.h2d(d_pk, pk)
+        h_pk = eng.pinned("bench_rows_pk", pk.nbytes).view(np.uint32, pk.shape)
+        h_pk[:] = pk
+        outl = outlier_section(eng, enc, base, flat, d_pk, d_proba, d_label, h_pk, nums, K, W, bool(info0["packed_ok"]))
+        eng.device_free(d_pk)
 
-    # ---- cpu baseline (rank 0, N=1 only): bounded sample = the same 65 536-row batch 0
+    # ---- cpu baseline (rank 0, N=1 only): bounded sample = the same 65 536-row batch the plugin e2e scores
     cpu = None
     if dist.rank == 0 and dist.world == 1 and not args.no_cpu:
         import sklearn
 
         kind = MODELS[args.model][0]
         cores = os.cpu_count() or 1
-        df0 = training.arrays_to_frame(vocabs, codes[:BATCH], nums[:BATCH])[ALL_FEATURES]
         procs = 1 if kind == "rf" else min(cores, 64)
         best, med, times = cpu_reference_rate(pipe, df0, 5, procs)
         one_best, _, _ = cpu_reference_rate(pipe, df0.iloc[:16384], 2, 1) if procs > 1 else (best, None, None)
-        port = cpu_port_rate(pipe, codes[:BATCH], nums[:BATCH], 5)
+        port = cpu_port_rate(pipe, pc, pn, 5)
         cpu = {
             "value": med, "unit": "rows/s", "cores": cores if procs == 1 else procs, "kind": "reference",
-            "sample": (f"5 x batch 0 ({BATCH} rows) through sklearn {sklearn.__version__} Pipeline.predict_proba, "
+            "sample": (f"5 x the {BATCH}-row cfg2 DataFrame through sklearn {sklearn.__version__} Pipeline.predict_proba, "
                        f"{'n_jobs=-1 threads' if procs == 1 else str(procs) + ' forked processes'}; median"),
             "best": best, "single_process": one_best,
             "port_openmp_rows_per_s": port, "host_cores": cores,
         }
 
-    avg_launch_ms = float(np.mean(ms_each))
+    avg_launch_ms = ms_total_max / K  # the kernel is the only work of the timed region: region time / launches
     achieved = ALG_BYTES_PER_ROW * BATCH / (avg_launch_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak_gbs()
     line = {
         "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": dist.world, "steps": K, "warmup": W,
         "ms_per_step": ms_total_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32cmp+f64acc", "data": "synthetic",
+        "dtype": "u16 ranks + f64acc" if fmt == _cabi.ROWS_RANKED else "f32cmp+f64acc", "data": "synthetic",
         "config": {
-            "workload": f"cfg2: {args.model} ({info0['n_trees']} trees, depth {info0['max_depth']}, {flat.total_nodes} nodes) in the "
-                        f"reference preprocessing, batch {BATCH} x 23 features, per GPU",
-            "forest": args.model, "batch": BATCH, "parallelism": f"dp{dist.world} (rows sharded, forest replicated, no collective)",
-            "l2": f"inputs rotate over {POOL} distinct batches ({POOL * BATCH * row_bytes / 1e6:.0f} MB > 126 MB L2)",
-            "walk": info0["walk"], "smem_bytes": info0["smem_bytes"], "rows_per_warp": info0["rows_per_warp"],
-            "row_format": f"{row_bytes}-byte encoded rows" + (" (packed: 9 x 7-bit category fields + 14 float32)" if packed else ""),
+            "workload": workload_label(args.model),
+            "forest": args.model, "trees": info0["n_trees"], "depth": info0["max_depth"], "nodes": flat.total_nodes, "batch": BATCH,
+            "parallelism": f"dp{dist.world} (rows sharded, forest replicated, no collective)",
+            "l2": f"inputs rotate over {POOL} distinct batches ({POOL * BATCH * row_bytes / 1e6:.0f} MB of rows + {POOL * BATCH * 8 / 1e6:.0f} MB of results > 126 MB L2)",
+            "walk": info0["walk"], "row_format": f"{fmt_name}: {row_bytes}-byte encoded rows",
             "kernel": kernel_used,
         },
-        "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": BATCH * row_bytes, "d2h_bytes_per_step": BATCH * 8,
-                "ms_per_step": 1e3 * e2e_s_max / K, "p50_ms": 1e3 * float(np.percentile(lat, 50)), "p99_ms": 1e3 * float(np.percentile(lat, 99)),
-                "api": f"b2f_predict_pairs(host pinned {row_bytes}-byte rows) -> {{float32 proba, int32 label}} per row",
-                "parity_max_abs_dp_vs_device_path": e2e_parity,
-                "pipelined_2_in_flight": {"value": pipe_value, "unit": "rows/s", "api": "b2f_predict_async_ex + b2f_wait, two batches in flight"}, "pcie_h2d_gbs_one_batch": h2d_gbs},
+        "e2e": {"value": plugin_value, "unit": "rows/s", "h2d_bytes_per_step": BATCH * (info0["rank_row_bytes"] if info0["rank_ok"] else 64),
+                "d2h_bytes_per_step": BATCH * 8, "ms_per_step": 1e3 * dist.max(plugin_s) / K,
+                "p50_ms": 1e3 * float(np.percentile(plat, 50)), "p99_ms": 1e3 * float(np.percentile(plat, 99)),
+                "api": "B200Model.predict(DataFrame of 9 string + 14 float64 columns) -> {'predictions': list[float], 'outliers': list, "
+                       "'feature_drift_batch': dict}: the plugin call of reference app/main.py:72 (classifier only, like the reference arm)",
+                "breakdown": breakdown, "parity_max_abs_dp_vs_sklearn_2048rows": plugin_parity, "gpu_launches": int(launches_plugin)},
+        "e2e_c_abi": {"value": cabi_value, "unit": "rows/s", "h2d_bytes_per_step": BATCH * row_bytes, "d2h_bytes_per_step": BATCH * 8,
+                      "ms_per_step": 1e3 * dist.max(cabi_s) / K, "p50_ms": 1e3 * float(np.percentile(lat, 50)), "p99_ms": 1e3 * float(np.percentile(lat, 99)),
+                      "api": f"b2f_predict_pairs(pre-encoded {row_bytes}-byte rows in pinned host memory) -> {{float32 proba, int32 label}} per row",
+                      "parity_max_abs_dp_vs_device_path": cabi_parity, "gpu_launches": int(launches_cabi),
+                      "pipelined_2_in_flight": {"value": pipe_value, "unit": "rows/s", "api": "b2f_predict_async_ex + b2f_wait, two batches in flight"},
+                      "pcie_h2d_gbs_one_batch": h2d_gbs},
         "gpu_launches": int(launches_value),
-        "gpu_launches_e2e": int(launches_e2e),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(args.model), "peak_source": peak_src, "kernel": kernel_used,
                      "alg_bytes_per_launch": ALG_BYTES_PER_ROW * BATCH, "avg_launch_ms": avg_launch_ms,
-                     "min_launch_ms": float(np.min(ms_each))},
+                     "how": "timed region / launches (back-to-back launches overlap head and tail: programmatic dependent launch)",
+                     "isolated_launch_ms": float(np.mean(iso_ms)), "isolated_launch_min_ms": float(np.min(iso_ms)),
+                     "actual_bytes_per_launch": BATCH * (row_bytes + 8)},
         "clocks": clocks,
         "sustained_rows_per_s": sustained,
-        "parity_max_abs_dp_vs_sklearn_2048rows": parity,
+        "parity_max_abs_dp_vs_sklearn_2048rows_all_ranks": parity, "parity_labels_equal_all_ranks": labels_equal,
     }
-    if args.sweep and dist.rank == 0:
-        line["latency_sweep"] = latency_sweep(args, dist)
+    if dist.rank == 0 and not args.no_sweep:
+        line["latency_sweep"] = {m: latency_sweep(args, dist, m, full=args.sweep) for m in (["rf500d8", "gbdt500d8"] if not args.sweep_model else [args.sweep_model])}
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if mom is not None:
@@ -537,7 +619,12 @@ def run_b200(args, dist: Dist):
         line["drift_detector"] = drift_section(base, flat, dist.local_rank)
     for d in (d_rows, d_proba, d_label):
         eng.device_free(d)
-    eng.close()
+    model.close()
+    if dist.rank == 0 and dist.world == 1 and not args.no_stream:
+        from databricks_kubernetes_mlops_poc_b200.engine import device_count
+
+        if device_count() > 1:  # config 4 inside the default single-process run when the box shows several GPUs
+            line["cfg4_stream"] = stream_leg(args, pipe, base, flat, rows_total=args.stream_rows, sustain=1.0)
     if dist.rank == 0:
         emit(line)
 
@@ -633,17 +720,18 @@ def drift_section(base, flat, device):
             "gpu_launches": int(launches), "by_batch": rows}
 
 
-def latency_sweep(args, dist: Dist):
+def latency_sweep(args, dist: Dist, name: str, full: bool = False):
     """BASELINE config 3: batch in {1, 16, 256, 4096, 65536}, 500-tree depth-8 model; p50 / p99 of the C-ABI
-    call (pinned host buffers, H2D + kernel + D2H inside) and of the plugin call model.predict(DataFrame) -> dict."""
+    call (pinned host buffers, H2D + kernel + D2H inside) and of the plugin call model.predict(DataFrame) -> dict.
+    The default run takes a compact form of it (fewer calls per size); ``--sweep`` the 1000-call form and, for the
+    RandomForest, the whole CustomModel.predict (outlier forest + drift detector attached)."""
     from databricks_kubernetes_mlops_poc_b200 import flatten, training
     from databricks_kubernetes_mlops_poc_b200._cabi import SCORED_DTYPE
     from databricks_kubernetes_mlops_poc_b200.model import B200Model
     from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES
 
-    name = args.sweep_model
     pipe, base = get_pipeline(name, dist)
-    model = B200Model(flatten.flatten_pipeline(pipe), devices=[dist.local_rank])
+    model = B200Model(flatten.flatten_pipeline(pipe), devices=[dist.local_rank], host_threads=host_thread_share(dist))
     eng, enc = model.engine, model.encoder
     n_max = 65536
     vocabs, codes, nums = training.synth_arrays(base, n_max, DATA_SEED + 1)
@@ -651,9 +739,12 @@ def latency_sweep(args, dist: Dist):
     enc.encode_arrays_packed(codes, nums, out=pk)
     out = eng.pinned("sweep_out", n_max * 8).view(SCORED_DTYPE, (n_max,))
     df_all = training.arrays_to_frame(vocabs, codes, nums)[ALL_FEATURES]
+    # parity of the plugin call at every sweep size against the library (float64 outputs)
+    want_all = pipe.predict_proba(df_all.iloc[:4096])[:, 1]
     res = {}
+    parity = 0.0
     for n in (1, 16, 256, 4096, 65536):
-        calls = 1000 if n <= 4096 else 200
+        calls = (1000 if n <= 4096 else 200) if full else (200 if n <= 4096 else 50)
         for _ in range(20):
             eng.predict_pairs(pk[:n], out=out[:n])
         ts = np.empty(calls)
@@ -662,9 +753,11 @@ def latency_sweep(args, dist: Dist):
             eng.predict_pairs(pk[:n], out=out[:n])
             ts[i] = time.perf_counter() - t0
         df = df_all.iloc[:n]
-        pcalls = 200 if n <= 4096 else 20
+        pcalls = (200 if n <= 4096 else 20) if full else (50 if n <= 4096 else 20)
         for _ in range(3):
-            model.predict(df)
+            got = model.predict(df)
+        m = min(n, 4096)
+        parity = max(parity, float(np.abs(np.asarray(got["predictions"])[:m] - want_all[:m]).max()))
         tp = np.empty(pcalls)
         for i in range(pcalls):
             t0 = time.perf_counter()
@@ -672,33 +765,35 @@ def latency_sweep(args, dist: Dist):
             tp[i] = time.perf_counter() - t0
         res[str(n)] = {"c_abi_p50_us": 1e6 * float(np.percentile(ts, 50)), "c_abi_p99_us": 1e6 * float(np.percentile(ts, 99)),
                        "predict_p50_us": 1e6 * float(np.percentile(tp, 50)), "predict_p99_us": 1e6 * float(np.percentile(tp, 99)),
-                       "calls": calls}
+                       "calls": calls, "predict_calls": pcalls}
     info = eng.info()
     model.close()
-    # the whole CustomModel.predict replacement: classifier + outlier forest (one pass) + drift detector, all on the GPU
-    from sklearn.ensemble import IsolationForest
+    if full and MODELS[name][0] == "rf":
+        # the whole CustomModel.predict replacement: classifier + outlier forest (one pass) + drift detector, all on the GPU
+        from sklearn.ensemble import IsolationForest
 
-    iso = IsolationForest(n_estimators=100, random_state=0).fit(base[list(model.numeric_features)].to_numpy())
-    full = B200Model.from_pipeline(pipe, reference_frame=base, outlier=iso, outlier_threshold=0.95, devices=[dist.local_rank])
-    # the reference's outlier detector refuses NaN numerics (sklearn 1.1.1 -> HTTP 500), so this leg scores complete rows
-    df_complete = df_all.iloc[:4096].copy()
-    for col in model.numeric_features:
-        df_complete[col] = df_complete[col].fillna(float(base[col].median()))
-    for n in (1, 16, 256, 4096):
-        df = df_complete.iloc[:n]
-        for _ in range(3):
-            full.predict(df)
-        tp = np.empty(100)
-        for i in range(100):
-            t0 = time.perf_counter()
-            full.predict(df)
-            tp[i] = time.perf_counter() - t0
-        res[str(n)]["predict_full_p50_us"] = 1e6 * float(np.percentile(tp, 50))
-        res[str(n)]["predict_full_p99_us"] = 1e6 * float(np.percentile(tp, 99))
-    full.close()
-    return {"model": name, "walk": info["walk"], "tile_resident": info["tile_resident"], "split_max_rows": info["split_max_rows"],
+        iso = IsolationForest(n_estimators=100, random_state=0).fit(base[list(model.numeric_features)].to_numpy())
+        fullm = B200Model.from_pipeline(pipe, reference_frame=base, outlier=iso, outlier_threshold=0.95, devices=[dist.local_rank])
+        # the reference's outlier detector refuses NaN numerics (sklearn 1.1.1 -> HTTP 500), so this leg scores complete rows
+        df_complete = df_all.iloc[:4096].copy()
+        for col in model.numeric_features:
+            df_complete[col] = df_complete[col].fillna(float(base[col].median()))
+        for n in (1, 16, 256, 4096):
+            df = df_complete.iloc[:n]
+            for _ in range(3):
+                fullm.predict(df)
+            tp = np.empty(100)
+            for i in range(100):
+                t0 = time.perf_counter()
+                fullm.predict(df)
+                tp[i] = time.perf_counter() - t0
+            res[str(n)]["predict_full_p50_us"] = 1e6 * float(np.percentile(tp, 50))
+            res[str(n)]["predict_full_p99_us"] = 1e6 * float(np.percentile(tp, 99))
+        fullm.close()
+    return {"model": name, "walk": info["walk"], "tile_resident": info["tile_resident"], "rank_ok": info["rank_ok"], "split_max_rows": info["split_max_rows"],
+            "parity_max_abs_dp_vs_sklearn": parity,
             "api": "C ABI: b2f_predict_pairs on pinned 64-byte rows; plugin: B200Model.predict(DataFrame) -> dict, classifier only "
-                   "(predict_*) and with the outlier forest + drift detector attached (predict_full_*: the whole CustomModel.predict)",
+                   "(predict_*)" + ("; predict_full_*: with the outlier forest + drift detector attached (the whole CustomModel.predict)" if full else ""),
             "batches": res}
 
 
@@ -737,30 +832,30 @@ def run_cfg1(args):
     emit({"metric": "reference CPU predict() on 1k curated rows (config 1)", "impl": "reference", "unit": "ms", **out})
 
 
-def run_stream(args):
-    """BASELINE config 4: ONE process deals a 10 M-row synthetic stream in 65 536-row batches round-robin over all
-    GPUs of the box (forest replicated, rows independent, no inter-GPU traffic) through the asynchronous C ABI
-    (b2f_predict_async_ex on a pinned ring, two batches in flight per GPU).  Reports aggregate and per-GPU rows/s."""
-    from databricks_kubernetes_mlops_poc_b200 import flatten, training
+def stream_leg(args, pipe, base, flat, rows_total: int, sustain: float, ngpu: int = 0):
+    """BASELINE config 4: ONE process deals a synthetic stream in 65 536-row batches round-robin over all GPUs of the box
+    (forest replicated, rows independent, no inter-GPU traffic) through b2f_predict_stream (one host thread per GPU inside the C
+    call, two batches in flight per GPU, pinned buffers placed on each GPU's NUMA node by slices)."""
+    from databricks_kubernetes_mlops_poc_b200 import training
     from databricks_kubernetes_mlops_poc_b200.encode import RowEncoder
-    from databricks_kubernetes_mlops_poc_b200.engine import ForestEngine, device_count
+    from databricks_kubernetes_mlops_poc_b200.engine import EngineGroup, device_count
     from databricks_kubernetes_mlops_poc_b200.sharding import round_robin_batches
 
-    solo = Dist(1, use_cuda=False, solo=True)
-    pipe, base = get_pipeline(args.model, solo)
-    flat = flatten.flatten_pipeline(pipe)
     enc = RowEncoder(flat)
-    ngpu = min(args.stream_gpus, device_count()) if args.stream_gpus > 0 else device_count()
-    from databricks_kubernetes_mlops_poc_b200.engine import EngineGroup
-
+    ngpu = min(ngpu, device_count()) if ngpu > 0 else device_count()
     group = EngineGroup(flat, devices=list(range(ngpu)))
     engines = group.engines
-    total = args.stream_rows
+    total = rows_total
     vocabs, codes, nums = training.synth_arrays(base, total, DATA_SEED + 7)
-    host = engines[0].pinned("stream_rows", total * 64).view(np.uint32, (total, 16))
-    enc.encode_arrays_packed(codes, nums, out=host)
-    proba = engines[0].pinned("stream_proba", total * 4).view(np.float32, (total,))
-    label = engines[0].pinned("stream_label", total * 4).view(np.int32, (total,))
+    ranked = bool(engines[0].info()["rank_ok"])
+    rows24 = enc.encode_arrays(codes, nums)
+    enc_rows = enc.rank_rows(rows24) if ranked else enc.pack_rows(rows24)
+    words = enc_rows.shape[1]
+    # one pinned buffer each, striped by batch over the NUMA nodes of the GPUs the batches go to
+    host = group.pinned_striped(np.uint32, (total, words), BATCH)
+    host[:] = enc_rows
+    proba = group.pinned_striped(np.float32, (total,), BATCH)
+    label = group.pinned_striped(np.int32, (total,), BATCH)
     plan = list(round_robin_batches(total, BATCH, ngpu))
     rows_gpu = [sum(hi - lo for g, lo, hi in plan if g == d) for d in range(ngpu)]
 
@@ -770,31 +865,40 @@ def run_stream(args):
     t0w = time.time()
     t0 = time.perf_counter()
     passes = 0
-    while passes < 3 or time.perf_counter() - t0 < args.sustain:
+    while passes < 3 or time.perf_counter() - t0 < sustain:
         group.predict_stream(host, BATCH, proba, label)  # ONE C call: a host thread per GPU deals its batches
         passes += 1
     dt = (time.perf_counter() - t0) / passes
     t1w = time.time()
     sampler.stop()
     # parity spot check on the last pass: 1 024 rows against sklearn
-    sel = np.arange(0, BATCH, 64)[:1024]
+    sel = np.arange(0, min(total, BATCH), 64)[:1024]
     df = training.arrays_to_frame(vocabs, codes[sel], nums[sel])
     want = pipe.predict_proba(df)[:, 1]
     err = float(np.abs(proba[sel].astype(np.float64) - want).max())
     launches = sum(e.info()["launches"] for e in engines)
     group.close()
-    emit({
-        "metric": "rows/sec, 10M-row synthetic stream dealt round-robin over the GPUs of one box (config 4)", "unit": "rows/s",
+    return {
+        "metric": "rows/sec, synthetic stream dealt round-robin over the GPUs of one box by ONE process (config 4)", "unit": "rows/s",
         "value": total / dt, "n_gpus": ngpu, "rows": total, "batch": BATCH, "seconds": dt, "per_gpu_rows_per_s": [r / dt for r in rows_gpu],
-        "higher_is_better": True, "scaling": "strong", "data": "synthetic", "dtype": "f32cmp+f64acc",
+        "higher_is_better": True, "scaling": "strong", "data": "synthetic", "dtype": "u16 ranks + f64acc" if ranked else "f32cmp+f64acc",
         "config": {"workload": f"cfg4: {args.model}, {total} rows in {len(plan)} batches of {BATCH}, one process, b2f_predict_stream (one host thread per "
-                               f"GPU inside the C call, 2 batches in flight per GPU, pinned buffers), 64-byte rows",
+                               f"GPU inside the C call, 2 batches in flight per GPU, pinned buffers), {words * 4}-byte rows",
                    "forest": args.model, "parallelism": f"round-robin over {ngpu} GPUs, forest replicated, no collective"},
-        "e2e": {"value": total / dt, "unit": "rows/s", "h2d_bytes_per_step": BATCH * 64, "d2h_bytes_per_step": BATCH * 8},
+        "e2e": {"value": total / dt, "unit": "rows/s", "h2d_bytes_per_step": BATCH * words * 4, "d2h_bytes_per_step": BATCH * 8},
         "gpu_launches": int(launches // (passes + 1)), "clocks": sampler.summary(t0w, t1w), "parity_max_abs_dp_vs_sklearn_1024rows": err,
         "roofline_frac_of_n_gpu_hbm": (total / dt) * ALG_BYTES_PER_ROW / 1e9 / (measured_peak_gbs()[0] * ngpu),
         "passes": passes,
-    })
+    }
+
+
+def run_stream(args):
+    """--stream: config 4 on its own (10 M rows by default)."""
+    from databricks_kubernetes_mlops_poc_b200 import flatten
+
+    solo = Dist(1, use_cuda=False, solo=True)
+    pipe, base = get_pipeline(args.model, solo)
+    emit(stream_leg(args, pipe, base, flatten.flatten_pipeline(pipe), args.stream_rows, args.sustain, args.stream_gpus))
 
 
 def main():
@@ -805,9 +909,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="gbdt100d6", choices=sorted(MODELS))
     ap.add_argument("--sustain", type=float, default=1.5, help="seconds of back-to-back launches for the clock record")
-    ap.add_argument("--rows", default="packed64", choices=["packed64", "words24"], help="encoded row layout fed to the engine")
-    ap.add_argument("--sweep", action="store_true", help="add the config-3 latency sweep (500-tree depth-8 model)")
-    ap.add_argument("--sweep-model", default="rf500d8", choices=sorted(MODELS))
+    ap.add_argument("--rows", default="ranked", choices=["ranked", "packed64", "words24"], help="encoded row layout fed to the engine")
+    ap.add_argument("--sweep", action="store_true", help="config-3 latency sweep in its long form (1000 calls per size, whole CustomModel.predict leg)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the config-3 latency sweep")
+    ap.add_argument("--sweep-model", default=None, choices=sorted(MODELS), help="sweep this model only (default: rf500d8 and gbdt500d8)")
+    ap.add_argument("--no-stream", action="store_true", help="skip the config-4 stream leg (single-process runs on a multi-GPU box)")
+    ap.add_argument("--no-gib", action="store_true", help="skip the >= 1 GiB run of the moments kernel")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-moments", action="store_true")
     ap.add_argument("--no-outliers", action="store_true", help="skip the K4 outlier-forest section")
@@ -815,8 +922,11 @@ def main():
     ap.add_argument("--cfg1", action="store_true", help="config 1: the reference CPU path on 1k curated rows (no GPU)")
     ap.add_argument("--stream", action="store_true", help="config 4: one process, 10M-row stream round-robin over all GPUs")
     ap.add_argument("--stream-rows", type=int, default=10_000_000)
+    ap.add_argument("--quick", action="store_true", help="only the timed value / e2e legs (no sweep, stream, cpu baseline, outliers, drift)")
     ap.add_argument("--stream-gpus", type=int, default=0, help="GPUs used by --stream (0 = all visible)")
     args = ap.parse_args()
+    if args.quick:
+        args.no_sweep = args.no_stream = args.no_cpu = args.no_outliers = args.no_drift = args.no_gib = True
 
     if args.cfg1:
         run_cfg1(args)

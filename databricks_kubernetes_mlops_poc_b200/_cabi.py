@@ -22,6 +22,7 @@ PACKED_ROW_WORDS = 16
 PACKED_ROW_BYTES = 64
 ROWS_WORDS24 = 0
 ROWS_PACKED64 = 1
+ROWS_RANKED = 2
 SCORED_DTYPE = np.dtype([("proba1", np.float32), ("label", np.int32)])  # b2f_scored
 SCORED_FULL_DTYPE = np.dtype(  # b2f_scored_full, 24 bytes
     [("proba1", np.float64), ("label", np.int32), ("is_outlier", np.int32), ("outlier_score", np.float32), ("reserved", np.int32)]
@@ -64,7 +65,31 @@ class Info(C.Structure):
         ("launches_split", C.c_int64),
         ("split_max_rows", C.c_int64),
         ("outlier_trees", C.c_int32),
-        ("reserved", C.c_int32),
+        ("rank_ok", C.c_int32),
+        ("launches_rank", C.c_int64),
+        ("rank_smem_bytes", C.c_int32),
+        ("rank_row_bytes", C.c_int32),
+    ]
+
+
+class RankInfo(C.Structure):
+    """b2f_rank_info: the ranked row layout and the size of the forest's rank layout."""
+
+    _fields_ = [
+        ("ok", C.c_int32),
+        ("row_bytes", C.c_int32),
+        ("cat_bytes", C.c_int32),
+        ("n_cat", C.c_int32),
+        ("n_num", C.c_int32),
+        ("depth", C.c_int32),
+        ("n_trees", C.c_int32),
+        ("layout_bytes", C.c_int32),
+        ("cat_shift", C.c_int32 * 16),
+        ("cat_bits", C.c_int32 * 16),
+        ("n_thresholds", C.c_int32 * 24),
+        ("n_pairs", C.c_int32),
+        ("pairs", C.c_uint32 * 128),
+        ("why", C.c_char * 160),
     ]
 
 
@@ -91,6 +116,14 @@ SIGNATURES = {
     "b2f_model_create": (C.c_void_p, [C.c_void_p, C.c_size_t, C.c_int]),
     "b2f_model_destroy": (None, [C.c_void_p]),
     "b2f_model_info": (C.c_int, [C.c_void_p, C.POINTER(Info)]),
+    "b2f_ranker_create": (C.c_void_p, [C.c_void_p, C.c_size_t]),
+    "b2f_ranker_destroy": (None, [C.c_void_p]),
+    "b2f_ranker_info": (C.c_int, [C.c_void_p, C.POINTER(RankInfo)]),
+    "b2f_ranker_thresholds": (C.POINTER(C.c_float), [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]),
+    "b2f_ranker_layout": (C.c_void_p, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "b2f_ranker_rank_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int]),
+    "b2f_model_rank_info": (C.c_int, [C.c_void_p, C.POINTER(RankInfo)]),
+    "b2f_encoder_attach_ranker": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b2f_encoder_create": (C.c_void_p, [C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]),
     "b2f_encoder_destroy": (None, [C.c_void_p]),
     "b2f_encoder_encode": (
@@ -98,6 +131,16 @@ SIGNATURES = {
         [C.c_void_p, C.c_int64, C.POINTER(StrColumn), C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_void_p, C.c_int],
     ),
     "b2f_pinned_alloc": (C.c_void_p, [C.c_size_t]),
+    "b2f_pinned_alloc_near": (C.c_void_p, [C.c_int, C.c_size_t]),
+    "b2f_pinned_alloc_striped": (C.c_void_p, [C.POINTER(C.c_void_p), C.c_int, C.c_size_t, C.c_size_t]),
+    "b2f_pinned_free_striped": (None, [C.c_void_p]),
+    "b2f_scorer_create": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int]),
+    "b2f_scorer_destroy": (None, [C.c_void_p]),
+    "b2f_scorer_start": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(StrColumn), C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_int64]),
+    "b2f_scorer_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "b2f_scorer_results": (C.c_void_p, [C.c_void_p]),
+    "b2f_scorer_chunk_rows": (C.c_int64, [C.c_void_p]),
+    "b2f_scorer_threads": (C.c_int, [C.c_void_p]),
     "b2f_pinned_free": (None, [C.c_void_p]),
     "b2f_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "b2f_predict_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
@@ -215,10 +258,11 @@ def ptr(a) -> C.c_void_p:
 class PinnedBuffer:
     """A page-locked host allocation exposed as numpy views (the request ring lives in these)."""
 
-    def __init__(self, nbytes: int):
+    def __init__(self, nbytes: int, device: int | None = None):
+        """``device``: place the pages on that GPU's NUMA node (b2f_pinned_alloc_near)."""
         self._lib = load_library()
         self.nbytes = int(nbytes)
-        self.addr = self._lib.b2f_pinned_alloc(self.nbytes)
+        self.addr = self._lib.b2f_pinned_alloc(self.nbytes) if device is None else self._lib.b2f_pinned_alloc_near(int(device), self.nbytes)
         if not self.addr:
             raise B2FError(f"b2f_pinned_alloc({nbytes}) failed: {last_error()}")
         self._raw = (C.c_uint8 * self.nbytes).from_address(self.addr)

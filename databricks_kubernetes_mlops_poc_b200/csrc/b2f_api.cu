@@ -28,6 +28,8 @@
 #include "forest_blob.h"
 #include "forest_predict.cuh"
 #include "forest_predict_tile.cuh"
+#include "forest_predict_rank.cuh"
+#include "forest_rank.h"
 #include "json_rows.h"
 #include "row_encoder.h"
 
@@ -149,6 +151,14 @@ struct b2f_model {
     int64_t launches_split = 0;
     int64_t split_max_rows = 0;
     bool packed_ok = false;
+    /* rank kernel (B2F_ROWS_RANKED rows; forest resident in its 4-byte-node complete-tree layout) */
+    b2f_ranker rk;
+    bool rank_ok = false;
+    RParams rp;
+    void *d_rank_layout = nullptr;
+    int rank_smem_bytes = 0;
+    int rank_u = 4;
+    int64_t launches_rank = 0;
     void *d_blob = nullptr;
     int64_t forest_bytes = 0;
     b2f_model *outlier = nullptr; /* attached isolation forest (b2f_model_attach_outlier_forest): a child handle on the
@@ -231,6 +241,79 @@ static int validate_blob(const uint8_t *blob, size_t nbytes, b2f_blob_header *hd
 extern "C" int b2f_blob_validate(const void *forest_blob, size_t nbytes) {
     b2f_blob_header h;
     return validate_blob(static_cast<const uint8_t *>(forest_blob), nbytes, &h);
+}
+
+/* ------------------------------------------------------------------ ranked rows: host-side tables (forest_rank.h) */
+extern "C" b2f_ranker *b2f_ranker_create(const void *forest_blob, size_t nbytes) {
+    b2f_blob_header h;
+    if (validate_blob(static_cast<const uint8_t *>(forest_blob), nbytes, &h) != B2F_OK) return nullptr;
+    b2f_ranker *r = new (std::nothrow) b2f_ranker();
+    if (!r) {
+        set_err(B2F_ENOMEM, "out of host memory");
+        return nullptr;
+    }
+    ranker_build(r, static_cast<const uint8_t *>(forest_blob), h);
+    return r;
+}
+extern "C" void b2f_ranker_destroy(b2f_ranker *r) { delete r; }
+
+static void fill_rank_info(const b2f_ranker *r, bool ok, b2f_rank_info *out) {
+    memset(out, 0, sizeof(*out));
+    out->ok = ok ? 1 : 0;
+    out->row_bytes = r->row_bytes;
+    out->cat_bytes = r->cat_bytes;
+    out->n_cat = r->n_cat;
+    out->n_num = r->n_num;
+    out->depth = r->depth;
+    out->n_trees = r->n_trees;
+    out->layout_bytes = (int32_t)r->layout.size();
+    for (int j = 0; j < 16; ++j) {
+        out->cat_shift[j] = r->cat_shift[j];
+        out->cat_bits[j] = r->cat_bits[j];
+    }
+    for (size_t k = 0; k < r->thr.size() && k < 24; ++k) out->n_thresholds[k] = (int32_t)r->thr[k].size();
+    out->n_pairs = (int32_t)r->pairs.size();
+    for (size_t i = 0; i < r->pairs.size() && i < 128; ++i) out->pairs[i] = r->pairs[i];
+    snprintf(out->why, sizeof(out->why), "%s", r->why);
+}
+extern "C" int b2f_ranker_info(const b2f_ranker *r, b2f_rank_info *out) {
+    if (!r || !out) return set_err(B2F_EINVAL, "null argument");
+    fill_rank_info(r, r->ok, out);
+    return B2F_OK;
+}
+extern "C" const float *b2f_ranker_thresholds(const b2f_ranker *r, int k, int32_t *count) {
+    if (!r || k < 0 || k >= (int)r->thr.size()) {
+        if (count) *count = 0;
+        return nullptr;
+    }
+    if (count) *count = (int32_t)r->thr[k].size();
+    return r->thr[k].data();
+}
+extern "C" const void *b2f_ranker_layout(const b2f_ranker *r, int64_t *nbytes) {
+    if (!r || !r->ok) {
+        if (nbytes) *nbytes = 0;
+        return nullptr;
+    }
+    if (nbytes) *nbytes = (int64_t)r->layout.size();
+    return r->layout.data();
+}
+extern "C" int b2f_ranker_rank_rows(const b2f_ranker *r, const void *rows, int64_t n, int row_format, void *ranked_out, int threads) {
+    if (!r || n < 0 || (n > 0 && (!rows || !ranked_out))) return set_err(B2F_EINVAL, "bad argument");
+    if (!r->ok) return set_err(B2F_EINVAL, "no rank layout for this forest (%s)", r->why);
+    if (row_format != B2F_ROWS_WORDS24 && row_format != B2F_ROWS_PACKED64) return set_err(B2F_EINVAL, "rows must be B2F_ROWS_WORDS24 or B2F_ROWS_PACKED64");
+    if (row_format == B2F_ROWS_PACKED64 && !(r->n_cat == 9 && r->n_num <= 14)) return set_err(B2F_EINVAL, "schema does not fit the packed 64-byte row");
+    threads = (int)std::min<int64_t>(std::max(threads, 1), std::max<int64_t>(1, n / 4096));
+    const uint8_t *in = static_cast<const uint8_t *>(rows);
+    uint8_t *out = static_cast<uint8_t *>(ranked_out);
+    if (threads == 1) {
+        rank_rows_range(r, in, 0, n, row_format, out);
+        return B2F_OK;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back([=] { rank_rows_range(r, in, n * t / threads, n * (t + 1) / threads, row_format, out); });
+    rank_rows_range(r, in, 0, n / threads, row_format, out);
+    for (auto &th : pool) th.join();
+    return B2F_OK;
 }
 
 template <int R, bool SMEM, typename OutT>
@@ -356,6 +439,72 @@ static bool build_tile_layout(const uint8_t *blob, const b2f_blob_header &h, uin
     return true;
 }
 
+template <int D, int U, typename OutT>
+static cudaError_t rank_set_attr(int bytes) {
+    return cudaFuncSetAttribute(k_forest_predict_rank<D, U, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+template <int U>
+static cudaError_t rank_set_attr_all(int depth, int bytes) {
+    cudaError_t e = cudaSuccess;
+#define RK_ATTR(DD)                                                    \
+    case DD:                                                           \
+        e = rank_set_attr<DD, U, float>(bytes);                        \
+        if (e == cudaSuccess) e = rank_set_attr<DD, U, double>(bytes); \
+        break;
+    switch (depth) {
+        RK_ATTR(1) RK_ATTR(2) RK_ATTR(3) RK_ATTR(4) RK_ATTR(5) RK_ATTR(6) RK_ATTR(7) RK_ATTR(8)
+        default: e = cudaErrorInvalidValue;
+    }
+#undef RK_ATTR
+    return e;
+}
+
+static int rank_init(b2f_model *m, const uint8_t *blob) {
+    m->rank_ok = false;
+    ranker_build(&m->rk, blob, m->hdr);
+    if (!m->rk.ok) return B2F_OK; /* no rank layout for this forest: the other kernels serve it */
+    const char *off = getenv("B2F_RANK");
+    if (off && !strcmp(off, "0")) return B2F_OK;
+    const int64_t layout_bytes = (int64_t)m->rk.layout.size();
+    const int64_t fixed = B2F_RANK_XS_BYTES /* alignment slack */ + (int64_t)B2F_RANK_PARTIALS * 32 * 8 + layout_bytes + 256;
+    int max_tiles = (int)std::min<int64_t>(B2F_RANK_MAX_TILES, ((int64_t)m->max_smem_optin - fixed) / B2F_RANK_XS_BYTES);
+    if (const char *mt = getenv("B2F_RANK_MAX_TILES")) max_tiles = std::min(max_tiles, std::max(1, atoi(mt)));
+    if (max_tiles < 4) return B2F_OK; /* forest too large to stay resident next to a useful number of row tiles */
+    m->rank_u = 4;
+    if (const char *ru = getenv("B2F_RANK_U")) m->rank_u = atoi(ru) == 8 ? 8 : 4;
+    CUDA_TRY(cudaMalloc(&m->d_rank_layout, (size_t)layout_bytes));
+    CUDA_TRY(cudaMemcpy(m->d_rank_layout, m->rk.layout.data(), (size_t)layout_bytes, cudaMemcpyHostToDevice));
+    RParams &rp = m->rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.layout = static_cast<const uint8_t *>(m->d_rank_layout);
+    rp.layout_bytes = (uint32_t)layout_bytes;
+    rp.tree_stride = m->rk.tree_stride;
+    rp.n_trees_padded = m->rk.n_trees_padded;
+    rp.depth = m->rk.depth;
+    rp.agg_mode = (int)m->hdr.agg_mode;
+    rp.n_cat = m->rk.n_cat;
+    rp.n_num = m->rk.n_num;
+    rp.row_bytes = m->rk.row_bytes;
+    rp.cat_bytes = m->rk.cat_bytes;
+    rp.max_tiles = max_tiles;
+    rp.init_raw = m->hdr.init_raw;
+    rp.denom = m->hdr.denom;
+    rp.threshold = m->hdr.threshold;
+    rp.mul_two = 2u;
+    rp.mul_64k = 65536u;
+    rp.add_64k = 65535u;
+    rp.n_pairs = (int)m->rk.pairs.size();
+    if (rp.n_pairs > (int)(sizeof(rp.pair) / sizeof(rp.pair[0]))) return B2F_OK; /* more tested categories than the kernel's table holds */
+    for (int i = 0; i < rp.n_pairs; ++i) {
+        const uint32_t j = m->rk.pairs[i] >> 16, c = m->rk.pairs[i] & 0xFFFFu;
+        rp.pair[i] = (uint32_t)m->rk.cat_shift[j] | ((uint32_t)m->rk.cat_bits[j] << 8) | ((c + 1u) << 16);
+    }
+    m->rank_smem_bytes = (int)(B2F_RANK_XS_BYTES + (int64_t)max_tiles * B2F_RANK_XS_BYTES + (int64_t)B2F_RANK_PARTIALS * 32 * 8 + layout_bytes);
+    CUDA_TRY(m->rank_u == 8 ? rank_set_attr_all<8>(rp.depth, m->rank_smem_bytes) : rank_set_attr_all<4>(rp.depth, m->rank_smem_bytes));
+    m->rank_ok = true;
+    return B2F_OK;
+}
+
 static bool kn_env_is(const char *v) {
     const char *kn = getenv("B2F_KERNEL");
     return kn && !strcmp(kn, v);
@@ -394,8 +543,8 @@ static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
         kp.g[g].depth = gt[g].depth;
     }
 
-    /* the packed 64-byte row needs the credit-default shape: <= 9 categoricals of <= 126 categories, <= 14 numerics */
-    m->packed_ok = m->hdr.n_cat <= 9 && m->hdr.n_num <= 14;
+    /* the packed 64-byte row needs the credit-default shape: exactly 9 categoricals of <= 126 categories, <= 14 numerics */
+    m->packed_ok = m->hdr.n_cat == 9 && m->hdr.n_num <= 14; /* the kernels decode word L-7 / q[2+k] for exactly nine 7-bit fields */
     for (uint32_t f = 0; f < m->hdr.n_cat; ++f)
         if (m->hdr.vocab[f] > 126) m->packed_ok = false;
 
@@ -503,6 +652,12 @@ static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
         }
     }
 
+    /* rank kernel: 4-byte integer nodes, complete trees, rows as ranks (forest_rank.h); only while the layout stays resident */
+    {
+        int rc = rank_init(m, blob);
+        if (rc) return rc;
+    }
+
     for (int s = 0; s < B2F_STREAMS; ++s) CUDA_TRY(cudaStreamCreateWithFlags(&m->slots[s].stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&m->compute, cudaStreamNonBlocking));
 
@@ -559,6 +714,7 @@ extern "C" void b2f_model_destroy(b2f_model *m) {
     if (m->d_blob) cudaFree(m->d_blob);
     if (m->d_tile_layout) cudaFree(m->d_tile_layout);
     if (m->d_tile_pieces) cudaFree(m->d_tile_pieces);
+    if (m->d_rank_layout) cudaFree(m->d_rank_layout);
     if (m->d_mom_rows) cudaFree(m->d_mom_rows);
     if (m->d_mom_partials) cudaFree(m->d_mom_partials);
     if (m->d_mom_ticket) cudaFree(m->d_mom_ticket);
@@ -601,6 +757,17 @@ extern "C" int b2f_model_info(const b2f_model *m, b2f_info *out) {
     out->launches_split = m->launches_split;
     out->split_max_rows = m->split_max_rows;
     out->outlier_trees = m->outlier ? (int)m->outlier->hdr.n_trees : 0;
+    out->rank_ok = m->rank_ok ? 1 : 0;
+    out->launches_rank = m->launches_rank;
+    out->rank_smem_bytes = m->rank_ok ? m->rank_smem_bytes : 0;
+    out->rank_row_bytes = m->rk.row_bytes;
+    return B2F_OK;
+}
+
+extern "C" int b2f_model_rank_info(const b2f_model *m, b2f_rank_info *out) {
+    if (!m || !out) return set_err(B2F_EINVAL, "null argument");
+    fill_rank_info(&m->rk, m->rank_ok, out);
+    if (m->rk.ok && !m->rank_ok) snprintf(out->why, sizeof(out->why), "the rank layout (%zu bytes) does not stay resident in shared memory", m->rk.layout.size());
     return B2F_OK;
 }
 
@@ -647,10 +814,52 @@ static cudaError_t launch_split(const b2f_model *m, cudaStream_t st, const void 
     return cudaGetLastError();
 }
 
+/* the rank kernel goes out with programmatic stream serialization: back-to-back launches on one stream overlap the
+ * next launch's prologue (forest fill) with this launch's tail; the kernel orders its own global accesses with griddepcontrol.wait */
+template <int D, int U, typename OutT>
+static cudaError_t launch_rank_du(const b2f_model *m, cudaStream_t st, const void *rows, int64_t n, void *proba, int32_t *label, int ostride) {
+    const int64_t n_tiles = (n + 31) / 32;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>(m->sm_count, n_tiles)));
+    cfg.blockDim = dim3(B2F_RANK_THREADS);
+    cfg.dynamicSmemBytes = (size_t)m->rank_smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool no_pdl = getenv("B2F_NO_PDL") != nullptr;
+    cfg.attrs = attr;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, k_forest_predict_rank<D, U, OutT>, m->rp, static_cast<const uint8_t *>(rows), (long long)n,
+                              static_cast<OutT *>(proba), label, ostride);
+}
+template <typename OutT>
+static cudaError_t launch_rank(const b2f_model *m, cudaStream_t st, const void *rows, int64_t n, void *proba, int32_t *label, int ostride) {
+#define RK_CASE(DD)                                                                                         \
+    case DD:                                                                                                \
+        return m->rank_u == 8 ? launch_rank_du<DD, 8, OutT>(m, st, rows, n, proba, label, ostride)           \
+                              : launch_rank_du<DD, 4, OutT>(m, st, rows, n, proba, label, ostride);
+    switch (m->rp.depth) {
+        RK_CASE(1) RK_CASE(2) RK_CASE(3) RK_CASE(4) RK_CASE(5) RK_CASE(6) RK_CASE(7) RK_CASE(8)
+    }
+#undef RK_CASE
+    return cudaErrorInvalidValue;
+}
+
+static size_t row_bytes_of(const b2f_model *m, int fmt) {
+    return fmt == B2F_ROWS_RANKED ? (size_t)m->rk.row_bytes : (fmt == B2F_ROWS_PACKED64 ? B2F_PACKED_ROW_BYTES : B2F_ROW_BYTES);
+}
+
 static int check_row_format(const b2f_model *m, int fmt) {
     if (fmt == B2F_ROWS_WORDS24) return B2F_OK;
+    if (fmt == B2F_ROWS_RANKED) {
+        if (!m->rank_ok)
+            return set_err(B2F_EINVAL, "B2F_ROWS_RANKED is not available for this model (%s)",
+                           m->rk.ok ? "its rank layout does not stay resident in shared memory" : m->rk.why);
+        return B2F_OK;
+    }
     if (fmt != B2F_ROWS_PACKED64) return set_err(B2F_EINVAL, "unknown row format %d", fmt);
-    if (!m->packed_ok) return set_err(B2F_EINVAL, "this model's schema does not fit the packed 64-byte row (needs <= 9 categoricals with <= 126 categories, <= 14 numerics)");
+    if (!m->packed_ok) return set_err(B2F_EINVAL, "this model's schema does not fit the packed 64-byte row (needs exactly 9 categoricals with <= 126 categories, <= 14 numerics)");
     return B2F_OK;
 }
 
@@ -659,6 +868,13 @@ static int launch_predict(b2f_model *m, cudaStream_t st, const void *rows_dev, i
     if (n <= 0) return B2F_OK;
     const bool pk = fmt == B2F_ROWS_PACKED64;
     cudaError_t e;
+    if (fmt == B2F_ROWS_RANKED) { /* ranked rows have one kernel: integer compares on the resident rank layout */
+        e = f64 ? launch_rank<double>(m, st, rows_dev, n, proba_dev, label_dev, ostride) : launch_rank<float>(m, st, rows_dev, n, proba_dev, label_dev, ostride);
+        if (e != cudaSuccess) return set_err(B2F_ECUDA, "k_forest_predict_rank launch failed: %s", cudaGetErrorString(e));
+        m->launches++;
+        m->launches_rank++;
+        return B2F_OK;
+    }
     if (m->tile_ok && n >= m->tile_min_rows) {
         e = pk ? (f64 ? launch_tile<true, double>(m, st, rows_dev, n, proba_dev, label_dev, ostride) : launch_tile<true, float>(m, st, rows_dev, n, proba_dev, label_dev, ostride))
                : (f64 ? launch_tile<false, double>(m, st, rows_dev, n, proba_dev, label_dev, ostride) : launch_tile<false, float>(m, st, rows_dev, n, proba_dev, label_dev, ostride));
@@ -723,7 +939,7 @@ static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, int fmt
         int rcf = check_row_format(m, fmt);
         if (rcf) return rcf;
     }
-    const size_t row_bytes = fmt == B2F_ROWS_PACKED64 ? B2F_PACKED_ROW_BYTES : B2F_ROW_BYTES;
+    const size_t row_bytes = row_bytes_of(m, fmt);
     CUDA_TRY(cudaSetDevice(m->device));
     int64_t chunk = m->chunk_rows;
     if (n <= chunk + chunk / 2) chunk = n; /* small batch: one H2D, one launch */
@@ -743,6 +959,8 @@ static int enqueue_host_batch(b2f_model *m, const void *rows, int64_t n, int fmt
     const bool pairs = f64 == 2; /* proba points at {float proba; int32 label} records, label is ignored */
     const bool full = f64 == 3;  /* proba points at b2f_scored_full records */
     if (full && !m->outlier) return set_err(B2F_ESTATE, "no outlier forest attached (b2f_model_attach_outlier_forest)");
+    if (full && fmt == B2F_ROWS_RANKED)
+        return set_err(B2F_EINVAL, "b2f_predict_full takes float32 rows (B2F_ROWS_WORDS24 / B2F_ROWS_PACKED64): ranks are relative to ONE forest's split values");
     if ((pairs || full) && !proba) return set_err(B2F_EINVAL, "out is NULL");
     int c = 0;
     for (int64_t off = 0; off < n; ++c) {
@@ -874,6 +1092,8 @@ extern "C" int b2f_predict_async(b2f_model *m, const void *rows_pinned, int64_t 
 extern "C" int b2f_predict_async_ex(b2f_model *m, const void *rows_pinned, int64_t n, int row_format, void *proba1_pinned, int proba_is_f64,
                                     int32_t *label_pinned, b2f_ticket *ticket) {
     if (!m || !ticket) return set_err(B2F_EINVAL, "null argument");
+    if (proba_is_f64 < 0 || proba_is_f64 > 3) return set_err(B2F_EINVAL, "proba_is_f64 = %d: expected 0 (float), 1 (double), 2 (b2f_scored) or 3 (b2f_scored_full)", proba_is_f64);
+    if (proba_is_f64 >= 2 && n > 0 && !proba1_pinned) return set_err(B2F_EINVAL, "record output requested but the output pointer is NULL");
     const uint64_t id = m->next_ticket++;
     TicketRec &t = m->tickets[id % B2F_TICKETS];
     if (t.id != 0) { /* oldest ticket still outstanding in this ring position: retire it */
@@ -916,7 +1136,7 @@ extern "C" int b2f_predict_multi(b2f_model **models, int n_models, const void *r
 extern "C" int b2f_predict_multi_ex(b2f_model **models, int n_models, const void *rows, int64_t n, int row_format, void *proba1, int proba_is_f64,
                                     int32_t *label) {
     if (!models || n_models <= 0) return set_err(B2F_EINVAL, "no models");
-    const size_t row_bytes = row_format == B2F_ROWS_PACKED64 ? B2F_PACKED_ROW_BYTES : B2F_ROW_BYTES;
+    const size_t row_bytes = row_bytes_of(models[0], row_format);
     if (n < 0) return set_err(B2F_EINVAL, "negative row count");
     std::vector<uint32_t> masks(n_models, 0);
     /* 0 = float, 1 = double, 2 = b2f_scored records, 3 = b2f_scored_full records */
@@ -937,6 +1157,8 @@ extern "C" int b2f_predict_multi_ex(b2f_model **models, int n_models, const void
     return rc;
 }
 
+static void bind_thread_near(int device); /* scorer.h */
+
 /* Round-robin streaming over the GPUs of one box: batch b (rows [b*batch, (b+1)*batch)) goes to model b % n_models.
  * One host thread per GPU submits that GPU's batches through the asynchronous ring (at most `inflight` batches in
  * flight per GPU), so submission cost is paid in parallel; rows are independent, so there is no inter-GPU traffic. */
@@ -945,13 +1167,14 @@ extern "C" int b2f_predict_stream(b2f_model **models, int n_models, const void *
     if (!models || n_models <= 0 || batch <= 0 || n < 0) return set_err(B2F_EINVAL, "bad argument");
     if (inflight < 1) inflight = 1;
     if (inflight > 8) inflight = 8;
-    const size_t row_bytes = row_format == B2F_ROWS_PACKED64 ? B2F_PACKED_ROW_BYTES : B2F_ROW_BYTES;
+    const size_t row_bytes = row_bytes_of(models[0], row_format);
     const size_t psz = proba_is_f64 ? sizeof(double) : sizeof(float);
     const int64_t n_batches = (n + batch - 1) / batch;
     std::vector<int> rcs(n_models, B2F_OK);
     std::vector<std::string> msgs(n_models);
     auto worker = [&](int d) {
         b2f_model *m = models[d];
+        bind_thread_near(m->device); /* submit from the GPU's own NUMA node (scorer.h) */
         std::vector<b2f_ticket> ring;
         int rc = B2F_OK;
         for (int64_t b = d; b < n_batches && rc == B2F_OK; b += n_models) {
@@ -974,8 +1197,7 @@ extern "C" int b2f_predict_stream(b2f_model **models, int n_models, const void *
         if (rc) msgs[d] = b2f_last_error(); /* the message is thread-local: carry it back */
     };
     std::vector<std::thread> threads;
-    for (int d = 1; d < n_models; ++d) threads.emplace_back(worker, d);
-    worker(0);
+    for (int d = 0; d < n_models; ++d) threads.emplace_back(worker, d); /* every GPU its own thread: the caller's affinity is left alone */
     for (auto &t : threads) t.join();
     for (int d = 0; d < n_models; ++d)
         if (rcs[d]) return set_err(rcs[d], "GPU %d: %s", models[d]->device, msgs[d].c_str());
@@ -1072,26 +1294,30 @@ extern "C" int b2f_predict_stream_timed_ex(b2f_model *m, const void *rows_dev, i
         int rcf = check_row_format(m, row_format);
         if (rcf) return rcf;
     }
-    const size_t row_bytes = row_format == B2F_ROWS_PACKED64 ? B2F_PACKED_ROW_BYTES : B2F_ROW_BYTES;
+    const size_t row_bytes = row_bytes_of(m, row_format);
     CUDA_TRY(cudaSetDevice(m->device));
-    std::vector<cudaEvent_t> ev(2 * (size_t)steps + 2);
+    /* per-launch events only when the caller asks for per-launch times: an event record between two launches keeps
+     * them from overlapping (programmatic dependent launch of the rank kernel), so the region time is measured without */
+    const bool each = ms_each != nullptr;
+    std::vector<cudaEvent_t> ev(each ? 2 * (size_t)steps + 2 : 2);
     for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
     const size_t psz = proba_is_f64 ? sizeof(double) : sizeof(float);
+    const size_t i0 = ev.size() - 2, i1 = ev.size() - 1;
     int rc = B2F_OK;
-    CUDA_TRY(cudaEventRecord(ev[2 * steps], m->compute));
+    CUDA_TRY(cudaEventRecord(ev[i0], m->compute));
     for (int i = 0; i < steps && rc == B2F_OK; ++i) {
         const size_t b = (size_t)(i % pool);
-        CUDA_TRY(cudaEventRecord(ev[2 * i], m->compute));
+        if (each) CUDA_TRY(cudaEventRecord(ev[2 * i], m->compute));
         rc = launch_predict(m, m->compute, static_cast<const uint8_t *>(rows_dev) + b * (size_t)n * row_bytes, n, row_format,
                             proba1_dev ? static_cast<uint8_t *>(proba1_dev) + b * (size_t)n * psz : nullptr, proba_is_f64,
                             label_dev ? label_dev + b * (size_t)n : nullptr);
-        CUDA_TRY(cudaEventRecord(ev[2 * i + 1], m->compute));
+        if (each) CUDA_TRY(cudaEventRecord(ev[2 * i + 1], m->compute));
     }
-    CUDA_TRY(cudaEventRecord(ev[2 * steps + 1], m->compute));
+    CUDA_TRY(cudaEventRecord(ev[i1], m->compute));
     CUDA_TRY(cudaStreamSynchronize(m->compute));
-    if (ms_each)
+    if (each)
         for (int i = 0; i < steps; ++i) CUDA_TRY(cudaEventElapsedTime(&ms_each[i], ev[2 * i], ev[2 * i + 1]));
-    CUDA_TRY(cudaEventElapsedTime(ms_total, ev[2 * steps], ev[2 * steps + 1]));
+    CUDA_TRY(cudaEventElapsedTime(ms_total, ev[i0], ev[i1]));
     for (auto &e : ev) cudaEventDestroy(e);
     return rc;
 }
@@ -1301,6 +1527,9 @@ extern "C" int b2f_moments_multi(b2f_model **models, int n_models, const void *r
     b2f_moments_merge(parts.data(), n_models, out);
     return B2F_OK;
 }
+
+/* ------------------------------------------------------------------ columnar request pipeline (encode -> H2D -> kernel -> D2H per chunk) */
+#include "scorer.h"
 
 /* ------------------------------------------------------------------ batch drift detector (K3) */
 #include "drift_api.cuh"

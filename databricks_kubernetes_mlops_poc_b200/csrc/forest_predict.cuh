@@ -166,7 +166,9 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 /* sum of leaf payloads -> (score, label); shared by all predict kernels.
  *   RF       : p1 = s / n_trees, label = argmax (class 1 iff p1 > p0)        (sklearn: proba /= n_estimators)
- *   GBDT     : p1 = expit(init + s), label = raw >= 0
+ *   GBDT     : p1 = expit(init + s), label = raw >= 0   (sklearn >= 1.4 `_gb.py` predict: `raw_predictions >= 0`, the
+ *              library the oracle runs; the reference's pin 1.1.1 takes argmax([1-p, p]) and differs only on the exact
+ *              tie raw == 0, where it picks class 0.  The reference itself serves a RandomForest, never a GBDT.)
  *   IFOREST  : score = 2^(-s / (n_trees * c(max_samples))) + offset_, flag = score > threshold
  *              (sklearn IsolationForest: -decision_function; alibi-detect IForest.predict,
  *              reference databricks/src/02-register-model.ipynb:232-233,339,344) */

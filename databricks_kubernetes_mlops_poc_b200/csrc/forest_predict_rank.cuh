@@ -1,0 +1,232 @@
+/*
+ * forest_predict_rank.cuh -- K1c: the rank-quantised form of the fused scoring kernel (sm_100a), for forests that stay
+ * resident in shared memory.  Same arithmetic as k_forest_predict / k_forest_predict_tile -- it replaces
+ * `classifier.predict_proba(df[all_features])[:, 1]` (reference databricks/src/02-register-model.ipynb:335-337) -- on rows in
+ * the B2F_ROWS_RANKED format (forest_rank.h): every numeric feature arrives as its rank among the forest's split values and
+ * every tested (categorical feature, category) pair becomes a 0/1 value, so EVERY split is one unsigned integer compare
+ * "value[f] >= t" and a node is ONE 32-bit word (t << 16 | byte offset of value[f] in the tile's value block).
+ *
+ * Why (round-1 ncu, profiles/r01_ncu_tile.txt): the walk is bound by shared-memory wavefronts (LSU pipe, 1 per clock per SM).
+ * An 8-byte node costs two wavefronts per warp-level visit (LDS.64 is served half-warp by half-warp) plus a leaf-id load; here
+ *   - a node is 4 bytes: one wavefront, and at most 32 consecutive words per level up to depth 5 -> never a bank conflict;
+ *   - trees are COMPLETE in breadth-first order: child = 2i+1(+1), no child pointer, no leaf-id load -- after D levels the
+ *     path bits ARE the leaf index;
+ *   - per warp-level visit: LDS node, LOP3 (value address), LDS.U16 value, IMAD (value << 16 | 0xFFFF), ISETP, SEL, IMAD
+ *     (child address): 3 ops on the integer ALU pipe, 2 on the FMA pipe.  (The first version tested categorical nodes by
+ *     equality next to the numeric >=: 6 ALU-pipe ops per visit, and ncu showed that pipe -- one warp instruction per two
+ *     cycles per scheduler -- at 77 %, i.e. the bound; profiles/r02_ncu_rank_v1.txt.)
+ * and the machine is filled differently from the tile kernel (which left 60 % of its warps without a tile at 65 536 rows):
+ *   - one CTA per SM, 32 warps, ALL of them walk; the CTA owns a contiguous run of 32-row tiles (<= 16 per round);
+ *   - phase 1  all 1024 threads stage the CTA's rows into the per-tile value block xs[tile][f >> 1][lane][f & 1] (16-bit values,
+ *              TRANSPOSED: lane l's values sit in bank l, so the per-lane dynamic fetch of the walk is one conflict-free
+ *              LDS.U16), one lane per row and a share of the pseudo-features per thread, while one thread streams the forest
+ *              into shared memory with TMA bulk copies (cp.async.bulk + mbarrier complete_tx);
+ *   - phase 2  the round's work is tiles x tree groups (U trees per group, walked as U independent chains per thread); warp w
+ *              takes the contiguous share [w * units / 32, (w+1) * units / 32) -- balanced to one tree group whatever the batch
+ *              size -- and leaves one float64 partial per (warp, tile) it touched;
+ *   - phase 3  one thread per row adds that row's partials in warp order (fixed order: deterministic), aggregates
+ *              (RF mean | GBDT expit | isolation-forest score) and stores probability + label, coalesced.
+ *   - launched with programmatic stream serialization (PDL): `griddepcontrol.launch_dependents` is issued at entry so the next
+ *     launch's CTAs take over SMs as this launch's CTAs retire (its forest fill and row staging overlap this launch's tail);
+ *     `griddepcontrol.wait` sits before the first global access that could depend on the previous kernel.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "forest_predict.cuh"
+#include "forest_predict_tile.cuh"
+
+#define B2F_RANK_THREADS 1024
+#define B2F_RANK_WARPS 32
+#define B2F_RANK_MAX_TILES 16                       /* 32-row tiles per CTA per round */
+#define B2F_RANK_XS_BYTES 8192                      /* per tile: 64 words x 32 lanes x 4 B (128 16-bit values per lane), 8 KB aligned */
+#define B2F_RANK_PAIR_CHUNK 24                      /* categorical pseudo-features staged per work item */
+#define B2F_RANK_PARTIALS (B2F_RANK_WARPS + B2F_RANK_MAX_TILES)
+
+struct RParams {
+    const uint8_t *layout;   /* device: n_trees_padded complete trees, tree_stride bytes each */
+    uint32_t layout_bytes;   /* multiple of 16 */
+    uint32_t tree_stride;    /* 2^D * 12 */
+    int32_t n_trees_padded;  /* multiple of 8 */
+    int32_t depth;
+    int32_t agg_mode;
+    int32_t n_cat;
+    int32_t n_num;
+    int32_t row_bytes;       /* multiple of 8 */
+    int32_t cat_bytes;       /* 4 or 8 */
+    int32_t max_tiles;       /* tiles per round (<= B2F_RANK_MAX_TILES, what shared memory allows) */
+    double init_raw;
+    double denom;
+    double threshold;
+    uint32_t mul_two;        /* = 2, mul_64k = 65536, add_64k = 65535: multiplier / addend operands handed over as run-time values so */
+    uint32_t mul_64k;        /*   ptxas keeps the two multiply-adds of a node visit as IMAD (FMA pipe) instead of strength-reducing */
+    uint32_t add_64k;        /*   them to LEA / IADD3 on the integer ALU pipe, which is the pipe that bounds the walk */
+    int32_t n_pairs;         /* tested (categorical feature, category) pairs = pseudo-features n_num .. n_num + n_pairs - 1 */
+    uint32_t pair[128 - 4];  /* per pair: bit position of the feature's field | field width << 8 | (code + 1) << 16 */
+};
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint32_t v;
+    asm volatile("{ .reg .u16 h; ld.shared.u16 h, [%1]; cvt.u32.u16 %0, h; }" : "=r"(v) : "r"(a));
+    return v;
+}
+
+/* walk U consecutive trees (first tree at shared address t0) for this lane's row; payloads are added in tree order.
+ * A chain keeps the ABSOLUTE shared address a = B + 4i of its node (B = the tree's base): the child 2i+1 (+1) sits at
+ * 2a - B + 4 (+4), i.e. one SEL between the two per-tree constants (4 - B, 8 - B) and one multiply-add (FMA pipe). */
+template <int D, int U>
+__device__ __forceinline__ void rank_walk_group(uint32_t t0, uint32_t tree_stride, uint32_t xs_lane, uint32_t m2, uint32_t m64k, uint32_t a64k,
+                                                double &acc) {
+    uint32_t at[U], k4[U], k8[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        at[u] = t0 + u * tree_stride;
+        k4[u] = 4u - at[u];
+        k8[u] = 8u - at[u];
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t nw = lds32(at[u]);
+            const uint32_t v = lds_u16(xs_lane | (nw & 0x1F82u)); /* value[f] of this lane's row */
+            const uint32_t x = v * m64k + a64k;                   /* (v << 16 | 0xFFFF) >= node  <=>  v >= t   (IMAD) */
+            at[u] = at[u] * m2 + (x >= nw ? k8[u] : k4[u]);       /* IMAD */
+        }
+    }
+    /* a = B + 4 (2^D - 1 + leaf): payload at B + 4 * 2^D + 8 * leaf = 2a - B - 4 * 2^D + 8 = (a + a + k4) + (4 - 4 * 2^D) */
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc += lds_f64(at[u] + at[u] + k4[u] + 4u - (4u << D));
+}
+
+template <int D, int U, typename OutT>
+__global__ void __launch_bounds__(B2F_RANK_THREADS, 1)
+    k_forest_predict_rank(const __grid_constant__ RParams p, const uint8_t *__restrict__ rows, long long n, OutT *__restrict__ proba,
+                          int32_t *__restrict__ label, int ostride) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t forest_bar;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+
+    pdl_launch_dependents(); /* the next launch may start filling SMs as this one's CTAs retire */
+
+    /* shared-memory plan: [xs: max_tiles x 8 KB value blocks, 8 KB aligned][partials][forest] */
+    const uint32_t pad = (B2F_RANK_XS_BYTES - (smem_addr(smem) & (B2F_RANK_XS_BYTES - 1u))) & (B2F_RANK_XS_BYTES - 1u);
+    uint8_t *xs_all = smem + pad;
+    double *partial = reinterpret_cast<double *>(xs_all + (size_t)p.max_tiles * B2F_RANK_XS_BYTES);
+    uint8_t *forest = reinterpret_cast<uint8_t *>(partial + B2F_RANK_PARTIALS * 32);
+
+    if (tid == 0) {
+        mbar_init(&forest_bar, 1);
+        fence_mbar_init();
+        fence_proxy_async();
+        /* the forest is launch-invariant (never written by a kernel): safe to fetch before griddepcontrol.wait */
+        mbar_arrive_expect_tx(&forest_bar, p.layout_bytes);
+        for (uint32_t o = 0; o < p.layout_bytes; o += B2F_BULK_PIECE) {
+            const uint32_t part = min(B2F_BULK_PIECE, p.layout_bytes - o);
+            tma_bulk_g2s(forest + o, p.layout + o, part, &forest_bar);
+        }
+    }
+
+    /* this CTA's run of tiles (32-bit arithmetic: n < 2^31 rows) */
+    const uint32_t n_tiles = (uint32_t)((n + 31) >> 5);
+    const uint32_t tq = n_tiles / gridDim.x, tr = n_tiles % gridDim.x;
+    const uint32_t tile0 = blockIdx.x * tq + min(blockIdx.x, tr), cta_tiles = tq + (blockIdx.x < tr ? 1u : 0u);
+    const uint32_t n_rounds = (cta_tiles + (uint32_t)p.max_tiles - 1u) / (uint32_t)p.max_tiles;
+    const int groups = p.n_trees_padded / U; /* tree groups per tile */
+    const uint32_t forest_addr = smem_addr(forest);
+    const uint32_t xs_addr = smem_addr(xs_all);
+    bool forest_ready = false;
+
+    pdl_wait(); /* rows may have been produced by the previous kernel in the stream; outputs may still be read by it */
+
+    for (uint32_t round = 0; round < n_rounds; ++round) {
+        const uint32_t rt0 = cta_tiles * round / n_rounds, rt1 = cta_tiles * (round + 1u) / n_rounds;
+        const int T = (int)(rt1 - rt0);
+        const long long row0 = (long long)(tile0 + rt0) * 32;
+        const int n_rows = (int)min((long long)T * 32, n - row0);
+        if (round > 0) __syncthreads(); /* xs / partials of the previous round are free */
+
+        /* ---- phase 1: stage rows.  item = (part, row): consecutive lanes take consecutive rows, so every value store of a
+         *      warp goes to 32 different banks; part 0 writes the numeric ranks, parts 1.. a chunk of one-hot values each ---- */
+        {
+            const int n_parts = 1 + (p.n_pairs + B2F_RANK_PAIR_CHUNK - 1) / B2F_RANK_PAIR_CHUNK;
+            const int items = T * 32 * n_parts;
+            for (int it = tid; it < items; it += B2F_RANK_THREADS) {
+                const int part = it / (T * 32), r = it - part * (T * 32);
+                const uint32_t col = xs_addr + (uint32_t)(r >> 5) * B2F_RANK_XS_BYTES + (uint32_t)(r & 31) * 4u;
+                const bool live = r < n_rows;
+                const uint8_t *row = rows + (size_t)(row0 + (live ? r : 0)) * p.row_bytes;
+                if (part == 0) {
+                    const uint16_t *q = reinterpret_cast<const uint16_t *>(row + p.cat_bytes);
+                    for (int k = 0; k < p.n_num; ++k) {
+                        const uint16_t v = live ? __ldg(q + k) : (uint16_t)0;
+                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(col + (uint32_t)(k >> 1) * 128u + (uint32_t)(k & 1) * 2u), "h"(v) : "memory");
+                    }
+                } else {
+                    unsigned long long cw = 0ull;
+                    if (live) {
+                        cw = __ldg(reinterpret_cast<const uint32_t *>(row));
+                        if (p.cat_bytes == 8) cw |= (unsigned long long)__ldg(reinterpret_cast<const uint32_t *>(row) + 1) << 32;
+                    }
+                    const int i0 = (part - 1) * B2F_RANK_PAIR_CHUNK, i1 = min(p.n_pairs, i0 + B2F_RANK_PAIR_CHUNK);
+                    for (int i = i0; i < i1; ++i) {
+                        const uint32_t pr = p.pair[i];
+                        const uint32_t code1 = (uint32_t)(cw >> (pr & 0xFFu)) & ((1u << ((pr >> 8) & 0xFFu)) - 1u);
+                        const uint16_t v = (live && code1 == (pr >> 16)) ? (uint16_t)1 : (uint16_t)0;
+                        const uint32_t f = (uint32_t)(p.n_num + i);
+                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(col + (f >> 1) * 128u + (f & 1u) * 2u), "h"(v) : "memory");
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (!forest_ready) {
+            mbar_wait(&forest_bar, 0);
+            forest_ready = true;
+        }
+
+        /* ---- phase 2: walk.  units = T x groups, warp w takes [w * units / 32, (w + 1) * units / 32) ---- */
+        {
+            const int units = T * groups;
+            int u = warp * units / B2F_RANK_WARPS; /* units <= 16 tiles x 128 groups: 32-bit */
+            const int u_end = (warp + 1) * units / B2F_RANK_WARPS;
+            while (u < u_end) {
+                const int t = u / groups;
+                const int g_end = min(groups, u_end - t * groups);
+                const uint32_t xs_lane = xs_addr + (uint32_t)t * B2F_RANK_XS_BYTES + (uint32_t)lane * 4u;
+                double acc = 0.0;
+                for (int g = u - t * groups; g < g_end; ++g)
+                    rank_walk_group<D, U>(forest_addr + (uint32_t)(g * U) * p.tree_stride, p.tree_stride, xs_lane, p.mul_two, p.mul_64k, p.add_64k, acc);
+                partial[(warp + t) * 32 + lane] = acc; /* slot (warp + tile) is unique to this (warp, tile) segment */
+                u = t * groups + g_end;
+            }
+        }
+        __syncthreads();
+
+        /* ---- phase 3: one thread per row: partials in warp order -> aggregate -> store ---- */
+        for (int r = tid; r < n_rows; r += B2F_RANK_THREADS) {
+            const int t = r >> 5, ln = r & 31;
+            const int units = T * groups;
+            /* warps whose share meets tile t: first and last unit of the tile are t*groups and (t+1)*groups - 1 */
+            const int w_first = (int)(((uint32_t)(t * groups + 1) * B2F_RANK_WARPS + (uint32_t)units - 1u) / (uint32_t)units) - 1;
+            const int w_last = (int)(((uint32_t)((t + 1) * groups) * B2F_RANK_WARPS + (uint32_t)units - 1u) / (uint32_t)units) - 1;
+            double s = p.agg_mode == B2F_AGG_GBDT_LOGISTIC ? p.init_raw : 0.0;
+            for (int w = w_first; w <= w_last; ++w) /* warps whose share is empty (units < 32) wrote nothing */
+                if ((w + 1) * units / B2F_RANK_WARPS > w * units / B2F_RANK_WARPS) s += partial[(w + t) * 32 + ln];
+            double p1;
+            int lab;
+            aggregate(p.agg_mode, p.agg_mode == B2F_AGG_GBDT_LOGISTIC ? 0.0 : p.init_raw, p.denom, p.threshold, s, p1, lab);
+            const long long row = row0 + r;
+            if (proba) proba[row * ostride_p(ostride)] = (OutT)p1;
+            if (label) label[row * ostride_l(ostride)] = lab;
+        }
+    }
+    if (!forest_ready) mbar_wait(&forest_bar, 0); /* never retire a CTA while a bulk copy into its shared memory is in flight */
+}

@@ -146,8 +146,16 @@ extern "C" int64_t b2f_json_parser_parse(b2f_json_parser *p, const char *body, i
     using namespace jsonrows;
     if (!p || !body || len < 0) return B2F_EINVAL;
     const int nc = p->n_cat, nf = p->n_cat + p->n_num;
-    for (auto &v : p->num) v.clear();
+    /* clear() keeps capacity: after one huge body the column vectors would pin their peak size for the life of the
+     * service, so buffers far larger than this body can need (a row is >= 2 bytes of body) are released first */
+    const size_t keep_rows = (size_t)len / 2 + 1024;
+    for (auto &v : p->num) {
+        if (v.capacity() > 8 * keep_rows) std::vector<double>().swap(v);
+        v.clear();
+    }
     for (int j = 0; j < nc; ++j) {
+        if (p->str_off[j].capacity() > 8 * keep_rows) std::vector<int32_t>().swap(p->str_off[j]);
+        if (p->str_data[j].capacity() > 8 * (size_t)len + 65536) std::vector<uint8_t>().swap(p->str_data[j]);
         p->str_off[j].clear();
         p->str_off[j].push_back(0);
         p->str_data[j].clear();

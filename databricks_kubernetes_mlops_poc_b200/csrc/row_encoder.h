@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "../../include/b2f.h"
+#include "forest_rank.h"
 
 struct EncEntry {
     uint64_t prefix; /* first min(len, 8) bytes, zero padded */
@@ -37,6 +38,7 @@ struct b2f_encoder {
     std::vector<std::vector<EncEntry>> index;    /* same, as (length, 8-byte prefix) keys */
     std::vector<int32_t> null_code;              /* per categorical feature: code of a null entry, or -1 */
     bool packed_ok = false;
+    b2f_ranker *ranker = nullptr; /* copy of the forest's split-value tables (b2f_encoder_attach_ranker): B2F_ROWS_RANKED output */
 };
 
 static inline uint64_t enc_prefix(const uint8_t *s, int64_t len) {
@@ -62,31 +64,62 @@ static inline int32_t enc_lookup(const b2f_encoder *e, int j, const uint8_t *s, 
     return -1;
 }
 
+static inline int32_t enc_code(const b2f_encoder *e, int j, const b2f_str_column &c, int64_t i) {
+    const int64_t k = i + c.offset;
+    if (c.validity && !((c.validity[k >> 3] >> (k & 7)) & 1)) return e->null_code[j];
+    int64_t a, b;
+    if (c.offsets_are_64) {
+        a = static_cast<const int64_t *>(c.offsets)[k], b = static_cast<const int64_t *>(c.offsets)[k + 1];
+    } else {
+        a = static_cast<const int32_t *>(c.offsets)[k], b = static_cast<const int32_t *>(c.offsets)[k + 1];
+    }
+    return enc_lookup(e, j, c.data + a, b - a, a + 8 <= c.data_bytes);
+}
+
+/* ranked rows: blocks of B2F_RANK_BLOCK rows -- categorical block per row, float32 numerics transposed into a
+ * column-major scratch, then one SIMD rank pass per feature over the block (forest_rank.h / host_simd.cpp) */
+static int enc_range_ranked(const b2f_encoder *e, int64_t lo, int64_t hi, const b2f_str_column *cats, const double *const *nums,
+                            const int64_t *num_strides, uint8_t *out) {
+    const b2f_ranker *r = e->ranker;
+    const int nc = e->n_cat, nn = e->n_num;
+    int bad = 0;
+    float cols[24 * B2F_RANK_BLOCK];
+    int32_t codes[16];
+    for (int64_t b0 = lo; b0 < hi; b0 += B2F_RANK_BLOCK) {
+        const int64_t nb = std::min<int64_t>(B2F_RANK_BLOCK, hi - b0);
+        for (int64_t i = 0; i < nb; ++i) {
+            for (int j = 0; j < nc; ++j) {
+                const int32_t c = enc_code(e, j, cats[j], b0 + i);
+                codes[j] = c >= r->vocab[j] ? -1 : c;
+            }
+            rank_write_cats(r, codes, out + (size_t)(b0 + i) * r->row_bytes);
+        }
+        for (int k = 0; k < nn; ++k) {
+            const double *src = nums[k] + b0 * num_strides[k];
+            const int64_t st = num_strides[k];
+            float *dst = cols + (size_t)k * B2F_RANK_BLOCK;
+            for (int64_t i = 0; i < nb; ++i) {
+                const double v = src[i * st];
+                const float f = (float)v;
+                if (!(v != v) && !isfinite(f)) bad = 1;
+                dst[i] = f;
+            }
+        }
+        rank_block(r, cols, nb, out + (size_t)b0 * r->row_bytes);
+    }
+    return bad;
+}
+
 static int enc_range(const b2f_encoder *e, int64_t lo, int64_t hi, const b2f_str_column *cats, const double *const *nums,
                      const int64_t *num_strides, int row_format, uint32_t *out) {
+    if (row_format == B2F_ROWS_RANKED) return enc_range_ranked(e, lo, hi, cats, nums, num_strides, reinterpret_cast<uint8_t *>(out));
     const int nc = e->n_cat, nn = e->n_num;
     const bool packed = row_format == B2F_ROWS_PACKED64;
     const int words = packed ? 16 : B2F_ROW_WORDS;
     int bad = 0;
     for (int64_t i = lo; i < hi; ++i) {
         int32_t codes[16];
-        for (int j = 0; j < nc; ++j) {
-            const b2f_str_column &c = cats[j];
-            const int64_t k = i + c.offset;
-            int32_t code;
-            if (c.validity && !((c.validity[k >> 3] >> (k & 7)) & 1)) {
-                code = e->null_code[j];
-            } else {
-                int64_t a, b;
-                if (c.offsets_are_64) {
-                    a = static_cast<const int64_t *>(c.offsets)[k], b = static_cast<const int64_t *>(c.offsets)[k + 1];
-                } else {
-                    a = static_cast<const int32_t *>(c.offsets)[k], b = static_cast<const int32_t *>(c.offsets)[k + 1];
-                }
-                code = enc_lookup(e, j, c.data + a, b - a, a + 8 <= c.data_bytes);
-            }
-            codes[j] = code;
-        }
+        for (int j = 0; j < nc; ++j) codes[j] = enc_code(e, j, cats[j], i);
         uint32_t *row = out + (size_t)i * words;
         uint32_t *numw;
         if (packed) {
@@ -121,7 +154,7 @@ extern "C" b2f_encoder *b2f_encoder_create(int n_cat, int n_num, const int32_t *
     e->vocab.resize(n_cat);
     e->null_code.assign(n_cat, -1);
     int64_t s = 0;
-    e->packed_ok = n_cat <= 9 && n_num <= 14;
+    e->packed_ok = n_cat == 9 && n_num <= 14; /* the kernels' decode is fixed to nine 7-bit fields + numerics from word 2 */
     for (int j = 0; j < n_cat; ++j) {
         for (int k = 0; k < vocab_counts[j]; ++k, ++s)
             e->vocab[j].emplace_back(vocab_bytes + vocab_offsets[s], (size_t)(vocab_offsets[s + 1] - vocab_offsets[s]));
@@ -136,13 +169,27 @@ extern "C" b2f_encoder *b2f_encoder_create(int n_cat, int n_num, const int32_t *
     return e;
 }
 
-extern "C" void b2f_encoder_destroy(b2f_encoder *e) { delete e; }
+extern "C" void b2f_encoder_destroy(b2f_encoder *e) {
+    if (e) delete e->ranker;
+    delete e;
+}
+
+extern "C" int b2f_encoder_attach_ranker(b2f_encoder *e, const b2f_ranker *r) {
+    if (!e || !r || !r->ok || r->n_cat != e->n_cat || r->n_num != e->n_num) return B2F_EINVAL;
+    b2f_ranker *copy = new b2f_ranker(*r);
+    std::vector<uint8_t>().swap(copy->layout); /* the encoder only needs the tables */
+    ranker_fix_tabs(copy);                     /* the table views must point into the copy's own storage */
+    delete e->ranker;
+    e->ranker = copy;
+    return B2F_OK;
+}
 
 extern "C" int b2f_encoder_encode(const b2f_encoder *e, int64_t n, const b2f_str_column *cat_cols, const double *const *num_cols,
                                   const int64_t *num_strides, int row_format, void *rows_out, int threads) {
     if (!e || n < 0 || !rows_out || (e->n_cat > 0 && !cat_cols) || (e->n_num > 0 && (!num_cols || !num_strides))) return B2F_EINVAL;
-    if (row_format != B2F_ROWS_WORDS24 && row_format != B2F_ROWS_PACKED64) return B2F_EINVAL;
+    if (row_format != B2F_ROWS_WORDS24 && row_format != B2F_ROWS_PACKED64 && row_format != B2F_ROWS_RANKED) return B2F_EINVAL;
     if (row_format == B2F_ROWS_PACKED64 && !e->packed_ok) return B2F_EINVAL;
+    if (row_format == B2F_ROWS_RANKED && !e->ranker) return B2F_EINVAL;
     if (threads < 1) threads = 1;
     threads = (int)std::min<int64_t>(threads, std::max<int64_t>(1, n / 4096));
     uint32_t *out = static_cast<uint32_t *>(rows_out);

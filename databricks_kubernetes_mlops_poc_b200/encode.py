@@ -48,11 +48,15 @@ class RowEncoder:
         self._index = [pd.Index(list(v), dtype=object) for v in flat.categories]
         self._lut = [{c: i for i, c in enumerate(v)} for v in flat.categories]
         self._colpos = {}  # column-order tuple -> positions of the model's features
+        self._colpos_fast = {}  # id(columns Index) -> (Index, positions): the block-manager path of frame_columns
         self._pa_vocab = [pa.array(list(v), type=pa.string()) for v in flat.categories] if pa is not None else None
         self._missing = list(flat.missing_codes) if flat.missing_codes else [-1] * self.n_cat  # NaN -> imputer constant
         self._none = list(flat.none_codes) if flat.none_codes else [-1] * self.n_cat  # None -> None category, if any
         # packed 64-byte rows: nine 7-bit (code + 1) fields + 14 float32 numerics
-        self.packed_ok = self.n_cat <= 9 and self.n_num <= 14 and all(len(v) <= 126 for v in flat.categories)
+        self.packed_ok = self.n_cat == 9 and self.n_num <= 14 and all(len(v) <= 126 for v in flat.categories)
+        self._blob = flat.blob
+        self._ranker = None  # b2f_ranker*: the forest's split-value tables (ranked rows), created on first use
+        self._rank_info = None
         self._native = None  # b2f_encoder*, created on first use (needs libb200forest.so, not a GPU)
         self._native_failed = pa is None
         self._categories = [list(v) for v in flat.categories]
@@ -82,15 +86,154 @@ class RowEncoder:
         try:
             if self._native:
                 self._lib.b2f_encoder_destroy(self._native)
+            if self._ranker:
+                self._rk_lib.b2f_ranker_destroy(self._ranker)
         except Exception:
             pass
 
-    def _encode_native(self, df: pd.DataFrame, out: np.ndarray, packed: bool) -> bool:
+    # ------------------------------------------------------------------ ranked rows (csrc/forest_rank.h)
+    def rank_info(self):
+        """-> _cabi.RankInfo of this forest (``ok`` = 0 when it has no rank layout).  Needs the library, not a GPU."""
+        if self._rank_info is None:
+            from . import _cabi
+
+            lib = _cabi.load_library()
+            buf = np.frombuffer(self._blob, dtype=np.uint8)
+            h = lib.b2f_ranker_create(_cabi.ptr(buf), buf.size)
+            if not h:
+                raise _cabi.B2FError(f"b2f_ranker_create failed: {_cabi.last_error()}")
+            info = _cabi.RankInfo()
+            _cabi.check(lib.b2f_ranker_info(h, C.byref(info)), "b2f_ranker_info")
+            self._ranker, self._rk_lib, self._rank_info = h, lib, info
+        return self._rank_info
+
+    @property
+    def ranked_ok(self) -> bool:
+        return bool(self.rank_info().ok)
+
+    @property
+    def ranked_row_words(self) -> int:
+        return self.rank_info().row_bytes // 4
+
+    def rank_thresholds(self, k: int) -> np.ndarray:
+        """Sorted distinct float32 split values of numeric feature k."""
+        self.rank_info()
+        cnt = C.c_int32(0)
+        p = self._rk_lib.b2f_ranker_thresholds(self._ranker, k, C.byref(cnt))
+        return np.ctypeslib.as_array(p, shape=(cnt.value,)).copy() if cnt.value else np.zeros(0, dtype=np.float32)
+
+    def rank_layout(self) -> np.ndarray:
+        """The forest's rank layout (bytes the GPU kernel walks): complete trees of 4-byte nodes + float64 payloads."""
+        self.rank_info()
+        nb = C.c_int64(0)
+        p = self._rk_lib.b2f_ranker_layout(self._ranker, C.byref(nb))
+        return np.frombuffer((C.c_uint8 * nb.value).from_address(p), dtype=np.uint8).copy() if nb.value else np.zeros(0, dtype=np.uint8)
+
+    def rank_rows(self, rows: np.ndarray, out: np.ndarray | None = None, threads: int = NATIVE_THREADS) -> np.ndarray:
+        """Encoded rows (N, 24) / packed (N, 16) -> ranked rows (N, row_bytes / 4) uint32."""
+        from . import _cabi
+
+        info = self.rank_info()
+        if not info.ok:
+            raise ValueError(f"this forest has no rank layout: {info.why.decode()}")
+        rows = np.ascontiguousarray(rows)
+        n = rows.shape[0]
+        fmt = 1 if rows.shape[1] == PACKED_ROW_WORDS else 0
+        if out is None:
+            out = np.empty((n, info.row_bytes // 4), dtype=np.uint32)
+        _cabi.check(self._rk_lib.b2f_ranker_rank_rows(self._ranker, _cabi.ptr(rows), n, fmt, _cabi.ptr(out), threads), "b2f_ranker_rank_rows")
+        return out
+
+    def encode_frame_ranked(self, df: pd.DataFrame, out: np.ndarray | None = None) -> np.ndarray:
+        """DataFrame -> ranked rows in one native pass (large frames) or via the 96-byte rows (small / irregular ones)."""
+        n = len(df)
+        words = self.ranked_row_words
+        if out is None:
+            out = np.empty((n, words), dtype=np.uint32)
+        if n > self.SMALL_BATCH:
+            missing = [c for c in self.cat_features + self.num_features if c not in df.columns]
+            if missing:
+                raise KeyError(f"{missing} not in index")
+            if self._encode_native(df, out, fmt=2):
+                return out
+        return self.rank_rows(self.encode_frame(df), out=out)
+
+    def frame_columns(self, df: pd.DataFrame):
+        """The physical buffers behind the model's 23 columns of ``df``, as the native encoder / scorer take them:
+        -> (StrColumn array, float64 pointer array, strides, keep-alive list), or None when a column does not have the
+        expected physical type (object-dtype strings, non-numeric numerics ...: the portable path handles those).
+        Column lookup goes through the block manager (one ``get_indexer`` per distinct column index, then an array fetch per
+        column) -- ``df[name]`` builds a Series per column, which alone costs ~0.3 ms for 23 columns."""
+        if self._native_handle() is None:
+            return None
+        cols = df.columns
+        key = id(cols)
+        pos = self._colpos_fast.get(key)
+        if pos is None or pos[0] is not cols:
+            idx = cols.get_indexer(self.cat_features + self.num_features)
+            if (idx < 0).any():
+                missing = [c for c, i in zip(self.cat_features + self.num_features, idx) if i < 0]
+                raise KeyError(f"{missing} not in index")  # what df[self.all_features] raises
+            if len(self._colpos_fast) > 64:
+                self._colpos_fast.clear()
+            pos = self._colpos_fast[key] = (cols, [int(i) for i in idx])
+        pos = pos[1]
+        try:
+            fetch = df._mgr.iget_values
+        except AttributeError:  # pandas without this internal: public (slower) access
+            def fetch(i, _df=df):
+                return _df.iloc[:, i].array
+        n = len(df)
+        scol = (self._cabi.StrColumn * max(self.n_cat, 1))()
+        keep = []
+        for j in range(self.n_cat):
+            arr = fetch(pos[j])
+            pa_arr = getattr(arr, "_pa_array", None)
+            if pa_arr is None:
+                return None  # object-dtype strings (None and NaN are different things there) -> portable path
+            if isinstance(pa_arr, pa.ChunkedArray):
+                pa_arr = pa_arr.chunk(0) if pa_arr.num_chunks == 1 else pa_arr.combine_chunks()
+            t = pa_arr.type
+            large = pa.types.is_large_string(t)
+            if not (large or pa.types.is_string(t)):
+                return None
+            validity, offsets, data = pa_arr.buffers()
+            keep.append((pa_arr, validity, offsets, data))
+            c = scol[j]
+            c.offsets = offsets.address
+            c.data = data.address if data is not None else 0
+            c.validity = validity.address if (validity is not None and pa_arr.null_count) else 0
+            c.offset = pa_arr.offset
+            c.data_bytes = data.size if data is not None else 0
+            c.offsets_are_64 = 1 if large else 0
+        ptrs = (C.c_void_p * max(self.n_num, 1))()
+        strides = np.ones(max(self.n_num, 1), dtype=np.int64)
+        for k in range(self.n_num):
+            col = fetch(pos[self.n_cat + k])
+            if not isinstance(col, np.ndarray):
+                col = np.asarray(col)
+            if col.dtype != np.float64:
+                if col.dtype.kind not in "iuf":
+                    return None
+                col = col.astype(np.float64)
+            keep.append(col)
+            ptrs[k] = col.ctypes.data
+            strides[k] = col.strides[0] // 8 if n > 1 else 1
+        keep.append(strides)
+        return scol, ptrs, strides, keep
+
+    def _encode_native(self, df: pd.DataFrame, out: np.ndarray, packed: bool = False, fmt: int | None = None) -> bool:
         """Columnar fast path: Arrow string buffers + float64 columns -> rows, in C++ threads.  Returns False when
         a column does not have the expected physical type (the caller then takes the portable path)."""
         h = self._native_handle()
         if h is None:
             return False
+        if fmt is None:
+            fmt = 1 if packed else 0
+        if fmt == 2 and not getattr(self, "_ranker_attached", False):
+            if not self.rank_info().ok or self._lib.b2f_encoder_attach_ranker(h, self._ranker) != 0:
+                return False
+            self._ranker_attached = True
         n = len(df)
         cols = (self._cabi.StrColumn * max(self.n_cat, 1))()
         keep = []  # keep the Arrow arrays alive during the call
@@ -129,7 +272,7 @@ class RowEncoder:
             keep.append(col)
             ptrs[k] = col.ctypes.data
             strides[k] = col.strides[0] // 8 if n > 1 else 1
-        rc = self._lib.b2f_encoder_encode(h, n, cols, ptrs, self._cabi.ptr(strides), 1 if packed else 0, self._cabi.ptr(out), NATIVE_THREADS)
+        rc = self._lib.b2f_encoder_encode(h, n, cols, ptrs, self._cabi.ptr(strides), fmt, self._cabi.ptr(out), NATIVE_THREADS)
         if rc == -7:
             raise ValueError("Input X contains infinity or a value too large for dtype('float32').")
         if rc != 0:
@@ -245,7 +388,7 @@ class RowEncoder:
         """(N, 24) encoded rows -> (N, 16) packed rows (B2F_ROWS_PACKED64): one third fewer bytes over PCIe.
         Lossless: code + 1 in 7 bits (0 = unknown), numerics untouched."""
         if not self.packed_ok:
-            raise ValueError("schema does not fit the packed row (<= 9 categoricals of <= 126 categories, <= 14 numerics)")
+            raise ValueError("schema does not fit the packed row (exactly 9 categoricals of <= 126 categories, <= 14 numerics)")
         n = rows24.shape[0]
         if out is None:
             out = np.zeros((n, PACKED_ROW_WORDS), dtype=np.uint32)

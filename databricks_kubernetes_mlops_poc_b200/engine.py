@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _cabi
-from ._cabi import MOMENT_VALUES, PACKED_ROW_WORDS, ROW_WORDS, ROWS_PACKED64, ROWS_WORDS24, B2FError, Info, PinnedBuffer, check, ptr
+from ._cabi import MOMENT_VALUES, PACKED_ROW_WORDS, ROW_WORDS, ROWS_PACKED64, ROWS_RANKED, ROWS_WORDS24, B2FError, Info, PinnedBuffer, RankInfo, check, ptr
 from .flatten import FlatForest
 
 
@@ -68,6 +68,11 @@ class ForestEngine:
         d["agg"] = _cabi.AGG_NAMES.get(d["agg_mode"], "?")
         return d
 
+    def rank_info(self) -> RankInfo:
+        inf = RankInfo()
+        check(self._lib.b2f_model_rank_info(self._h, C.byref(inf)), "b2f_model_rank_info")
+        return inf
+
     # ------------------------------------------------------------------ pinned staging
     def pinned(self, tag: str, nbytes: int) -> PinnedBuffer:
         """A reusable page-locked buffer of at least nbytes (grown geometrically)."""
@@ -75,7 +80,7 @@ class ForestEngine:
         if b is None or b.nbytes < nbytes:
             if b is not None:
                 b.close()
-            b = PinnedBuffer(max(int(nbytes * 1.5), 1 << 16))
+            b = PinnedBuffer(max(int(nbytes * 1.5), 1 << 16), device=self.device)  # pages on the GPU's NUMA node
             self._pinned[tag] = b
         return b
 
@@ -111,6 +116,11 @@ class ForestEngine:
             out = np.empty(n, dtype=_cabi.SCORED_DTYPE)
         check(self._lib.b2f_predict_pairs(self._h, ptr(rows), n, _row_format(rows), ptr(out)), "b2f_predict_pairs")
         return out
+
+    # ------------------------------------------------------------------ columnar request pipeline (csrc/scorer.h)
+    def scorer(self, encoder, threads: int = 0):
+        """A ``Scorer`` bound to this engine and ``encoder`` (created once, reused for every request)."""
+        return Scorer(self, encoder, threads)
 
     # ------------------------------------------------------------------ classifier + outlier detector in one pass
     def attach_outlier_forest(self, blob: bytes) -> None:
@@ -168,9 +178,9 @@ class ForestEngine:
     def d2h(self, a: np.ndarray, dptr: int) -> None:
         check(self._lib.b2f_copy_d2h(self._h, ptr(a), dptr, a.nbytes), "b2f_copy_d2h")
 
-    def predict_device(self, rows_dev: int, n: int, proba_dev: int, proba_is_f64: bool, label_dev: int, packed: bool = False) -> None:
+    def predict_device(self, rows_dev: int, n: int, proba_dev: int, proba_is_f64: bool, label_dev: int, packed: bool = False, fmt: int | None = None) -> None:
         check(
-            self._lib.b2f_predict_device_ex(self._h, rows_dev, n, ROWS_PACKED64 if packed else ROWS_WORDS24, proba_dev, int(proba_is_f64), label_dev),
+            self._lib.b2f_predict_device_ex(self._h, rows_dev, n, fmt if fmt is not None else (ROWS_PACKED64 if packed else ROWS_WORDS24), proba_dev, int(proba_is_f64), label_dev),
             "b2f_predict_device_ex",
         )
 
@@ -187,15 +197,16 @@ class ForestEngine:
         )
         return ms
 
-    def predict_stream_timed(self, rows_dev, n, pool, proba_dev, proba_is_f64, label_dev, steps: int, packed: bool = False):
-        """``steps`` launches cycling over ``pool`` device-resident batches -> (ms_each, ms_total)."""
-        ms = np.zeros(steps, dtype=np.float32)
+    def predict_stream_timed(self, rows_dev, n, pool, proba_dev, proba_is_f64, label_dev, steps: int, packed: bool = False, fmt: int | None = None,
+                             per_launch: bool = True):
+        """``steps`` launches cycling over ``pool`` device-resident batches -> (ms_each or None, ms_total).
+        ``per_launch=False`` records no events between launches (back-to-back launches of the rank kernel then overlap)."""
+        ms = np.zeros(steps, dtype=np.float32) if per_launch else None
         tot = C.c_float(0.0)
+        if fmt is None:
+            fmt = ROWS_PACKED64 if packed else ROWS_WORDS24
         check(
-            self._lib.b2f_predict_stream_timed_ex(
-                self._h, rows_dev, n, ROWS_PACKED64 if packed else ROWS_WORDS24, pool, proba_dev, int(proba_is_f64), label_dev, steps,
-                ptr(ms), C.byref(tot)
-            ),
+            self._lib.b2f_predict_stream_timed_ex(self._h, rows_dev, n, fmt, pool, proba_dev, int(proba_is_f64), label_dev, steps, ptr(ms), C.byref(tot)),
             "b2f_predict_stream_timed_ex",
         )
         return ms, float(tot.value)
@@ -237,10 +248,76 @@ class ForestEngine:
         return out.reshape(ROW_WORDS, 3)
 
 
+class Scorer:
+    """Owner of a ``b2f_scorer*``: DataFrame columns -> encode (worker threads, pinned staging) -> H2D -> kernel -> D2H,
+    chunk by chunk (``csrc/scorer.h``).  One job at a time."""
+
+    def __init__(self, engine: "ForestEngine", encoder, threads: int = 0):
+        self._lib = engine._lib
+        self.engine, self.encoder = engine, encoder
+        h_enc = encoder._native_handle()
+        if h_enc is None:
+            raise B2FError("the native row encoder is not available")
+        self.fmt = ROWS_WORDS24
+        if encoder.ranked_ok and engine.info()["rank_ok"] and self._lib.b2f_encoder_attach_ranker(h_enc, encoder._ranker) == 0:
+            encoder._ranker_attached = True
+            self.fmt = ROWS_RANKED  # 32-byte ranked rows: half the PCIe bytes, integer-compare kernel
+        elif encoder.packed_ok:
+            self.fmt = ROWS_PACKED64
+        self._h = self._lib.b2f_scorer_create(engine.handle, h_enc, int(threads))
+        if not self._h:
+            raise B2FError(f"b2f_scorer_create failed: {_cabi.last_error()}")
+        self.threads = self._lib.b2f_scorer_threads(self._h)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.b2f_scorer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def start(self, n: int, columns, out_mode: int = 1, chunk_rows: int = 0, fmt: int | None = None) -> int:
+        """``columns``: what ``RowEncoder.frame_columns`` returned.  -> number of chunks."""
+        scol, ptrs, strides, _keep = columns
+        rc = self._lib.b2f_scorer_start(self._h, n, scol, ptrs, ptr(strides), self.fmt if fmt is None else fmt, out_mode, chunk_rows)
+        if rc == -7:
+            raise ValueError("Input X contains infinity or a value too large for dtype('float32').")
+        if rc < 0:
+            raise B2FError(f"b2f_scorer_start failed (rc={rc}): {_cabi.last_error()}")
+        self._n, self._mode = n, out_mode
+        self._chunk = self._lib.b2f_scorer_chunk_rows(self._h)
+        return rc
+
+    def wait(self, chunk: int) -> None:
+        rc = self._lib.b2f_scorer_wait(self._h, chunk)
+        if rc == -7:
+            raise ValueError("Input X contains infinity or a value too large for dtype('float32').")
+        check(rc, "b2f_scorer_wait")
+
+    def results(self) -> np.ndarray:
+        """View over the pinned result buffer of the current job (valid until the next ``start``)."""
+        dt = {0: np.dtype(np.float32), 1: np.dtype(np.float64), 3: _cabi.SCORED_FULL_DTYPE}[self._mode]
+        addr = self._lib.b2f_scorer_results(self._h)
+        buf = (C.c_uint8 * (self._n * dt.itemsize)).from_address(addr)
+        return np.frombuffer(buf, dtype=dt, count=self._n)
+
+    @property
+    def chunk_rows(self) -> int:
+        return self._chunk
+
+
 def _row_format(rows: np.ndarray) -> int:
-    if rows.dtype != np.uint32 or rows.ndim != 2 or rows.shape[1] not in (ROW_WORDS, PACKED_ROW_WORDS):
-        raise ValueError(f"rows must be uint32 (N, {ROW_WORDS}) or packed (N, {PACKED_ROW_WORDS})")
-    return ROWS_PACKED64 if rows.shape[1] == PACKED_ROW_WORDS else ROWS_WORDS24
+    """Row layout from the array shape: (N, 24) words, (N, 16) packed, any other width = ranked rows (2 .. 14 words:
+    4 or 8 bytes of categorical fields + one uint16 per numeric, never 16 or 24 words)."""
+    if rows.dtype != np.uint32 or rows.ndim != 2 or not (2 <= rows.shape[1] <= ROW_WORDS):
+        raise ValueError(f"rows must be uint32 (N, {ROW_WORDS}), packed (N, {PACKED_ROW_WORDS}) or ranked (N, row_bytes / 4)")
+    if rows.shape[1] == ROW_WORDS:
+        return ROWS_WORDS24
+    return ROWS_PACKED64 if rows.shape[1] == PACKED_ROW_WORDS else ROWS_RANKED
 
 
 def moments_merge(parts: np.ndarray) -> np.ndarray:
@@ -266,6 +343,9 @@ class EngineGroup:
             check(self._lib.b2f_comm_init_all(self._handles, len(self.engines)), "b2f_comm_init_all")
 
     def close(self) -> None:
+        for a in getattr(self, "_striped", []):
+            self._lib.b2f_pinned_free_striped(a)
+        self._striped = []
         for e in self.engines:
             e.close()
 
@@ -295,6 +375,18 @@ class EngineGroup:
             "b2f_predict_multi_ex",
         )
         return out
+
+    def pinned_striped(self, dtype, shape, stripe_rows: int) -> np.ndarray:
+        """A page-locked array whose row stripes (``stripe_rows`` rows each, dealt round-robin) sit on the NUMA node of the GPU
+        that will copy them (``b2f_pinned_alloc_striped``).  Kept alive by the group; freed in ``close``."""
+        dt = np.dtype(dtype)
+        row_bytes = dt.itemsize * int(np.prod(shape[1:])) if len(shape) > 1 else dt.itemsize
+        total = row_bytes * int(shape[0])
+        addr = self._lib.b2f_pinned_alloc_striped(self._handles, len(self.engines), stripe_rows * row_bytes, total)
+        if not addr:
+            raise B2FError(f"b2f_pinned_alloc_striped failed: {_cabi.last_error()}")
+        self._striped = getattr(self, "_striped", []) + [addr]
+        return np.frombuffer((C.c_uint8 * total).from_address(addr), dtype=dt).reshape(shape)
 
     def predict_stream(self, rows: np.ndarray, batch: int, out_proba: np.ndarray, out_label: np.ndarray | None, inflight: int = 2) -> None:
         """Deal a long stream in ``batch``-row batches round-robin over the GPUs (one host thread per GPU inside

@@ -40,7 +40,10 @@ def parse_rows(raw: bytes) -> list:
     try:
         return REQUEST_ROWS.validate_json(raw)
     except ValidationError as e:
-        raise RequestValidationError([{**err, "loc": ("body", *err["loc"])} for err in e.errors(include_url=False, include_context=False)])
+        # rows are validated as TypedDicts (no per-row model object); the one place that shows through is the error type of
+        # a non-object row, which list[LoanApplicant] reports as "model_type" -- rewritten so the 422 body is identical
+        raise RequestValidationError([{**err, "type": "model_type" if err["type"] == "dict_type" else err["type"], "loc": ("body", *err["loc"])}
+                                      for err in e.errors(include_url=False, include_context=False)])
 
 
 def rows_to_frame(data) -> pd.DataFrame:

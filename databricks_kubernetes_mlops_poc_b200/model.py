@@ -37,7 +37,7 @@ SKLEARN_PICKLE = os.path.join("artifacts", "classifier", "model", "model.pkl")  
 
 
 class B200Model:
-    def __init__(self, flat: FlatForest, devices=None, drift=None, proba_dtype=np.float64, outlier_blob: bytes | None = None):
+    def __init__(self, flat: FlatForest, devices=None, drift=None, proba_dtype=np.float64, outlier_blob: bytes | None = None, host_threads: int = 0):
         self.flat = flat
         self.all_features = flat.all_features
         self.categorical_features = list(flat.cat_features)
@@ -61,6 +61,11 @@ class B200Model:
         # pinned staging and worker thread; the forest is replicated, rows are independent)
         engines = self.group.engines if self.group is not None else [self.engine]
         self.replicas = [_Replica(self.encoder, e, outlier_blob is not None, self.numeric_features) for e in engines]
+        # the columnar request pipeline of the first GPU (csrc/scorer.h): created on first use
+        self._scorer = None
+        self.host_threads = int(os.environ.get("B200_HOST_THREADS", host_threads or 0))  # 0: half the CPUs of the GPU's NUMA node
+        self._scorer_failed = os.environ.get("B200_SCORER", "1") == "0"
+        self.last_timing = None  # seconds spent in the stages of the last large predict(): columns / first chunk / lists
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -84,6 +89,9 @@ class B200Model:
         return cls(flat, drift=drift, outlier_blob=blob, **kw)
 
     def close(self) -> None:
+        if self._scorer is not None:
+            self._scorer.close()
+            self._scorer = None
         if self._pool is not None:
             self._pool.shutdown(wait=True)
         if self.drift is not None:
@@ -122,22 +130,76 @@ class B200Model:
         """``pipeline.predict(df)`` (hard labels, 01-train-model.ipynb:290)."""
         return self.classes[np.array(self._score(df)[1])]
 
+    PIPELINE_MIN_ROWS = 2048  # from here up a request goes through the chunked columnar pipeline
+
+    def _pipeline(self, df: pd.DataFrame):
+        """Large requests on one GPU: the DataFrame's column buffers go to the native scorer in ONE call; chunks come back while
+        later chunks are still being encoded / copied / scored, and each chunk's Python floats are built as it lands.
+        -> (predictions list, outlier-flag list or None), or None when this request has to take the general path."""
+        if self._scorer_failed or self.group is not None or len(df) < self.PIPELINE_MIN_ROWS:
+            return None
+        import time
+
+        t0 = time.perf_counter()
+        if self._scorer is None:
+            try:
+                self._scorer = self.engine.scorer(self.encoder, self.host_threads)
+            except Exception:
+                self._scorer_failed = True
+                return None
+        cols = self.encoder.frame_columns(df)
+        if cols is None:
+            return None
+        sc = self._scorer
+        n = len(df)
+        full = self.outlier_blob is not None
+        if full:
+            _reject_nan(df, self.numeric_features)
+        t1 = time.perf_counter()
+        # classifier only: ranked rows (half the PCIe bytes); with the outlier forest on the same rows: packed float32 rows
+        n_chunks = sc.start(n, cols, out_mode=3 if full else 1, fmt=(1 if self.encoder.packed_ok else 0) if full else None)
+        out = sc.results()
+        step = sc.chunk_rows
+        preds, flags = [], ([] if full else None)
+        t_first = None
+        for c in range(n_chunks):
+            sc.wait(c)
+            if t_first is None:
+                t_first = time.perf_counter()
+            part = out[c * step:(c + 1) * step]
+            if full:
+                preds += part["proba1"].tolist()
+                flags += part["is_outlier"].tolist()
+            else:
+                preds += part.tolist()
+        t2 = time.perf_counter()
+        self.last_timing = {"columns_s": t1 - t0, "first_chunk_s": (t_first or t2) - t1, "chunks_and_lists_s": t2 - t1, "chunks": n_chunks,
+                            "threads": sc.threads, "row_format": sc.fmt if not full else 1}
+        return preds, flags
+
     def predict(self, model_input) -> dict:
         """Mirror of ``CustomModel.predict(context, model_input)`` (02-register-model.ipynb:330-353)."""
-        df = pd.DataFrame(model_input)
+        df = model_input if isinstance(model_input, pd.DataFrame) else pd.DataFrame(model_input)  # never mutated here
         if len(df.columns) == 0:
             # the reference dies in df[self.all_features] on an empty request (-> HTTP 500)
             raise KeyError(f"None of {self.all_features} are in the [columns]")
         # the drift sweep is ~2 ms of device time on its own stream: start it first, score the rows meanwhile
         pending = self._pool.submit(self.drift.score, df) if self.drift is not None else None
+        n = len(df)
         try:
-            proba, _, flags = self._score(df, want_outliers=True)
+            fast = self._pipeline(df)
+            if fast is not None:
+                preds, flags = fast
+                flags = flags if flags is not None else [0] * n
+            else:
+                proba, _, fl = self._score(df, want_outliers=True)
+                preds = proba.tolist()
+                flags = fl.tolist() if fl is not None else [0] * n
         finally:
             drift_scores = pending.result() if pending is not None else [0.0] * len(self.all_features)
-        n = len(df)
         return {
-            "predictions": proba.tolist(),
-            "outliers": flags.tolist() if flags is not None else [0] * n,
+            "predictions": preds,
+            "outliers": flags,
             "feature_drift_batch": dict(zip(self.all_features, drift_scores)),
         }
 

@@ -115,6 +115,20 @@ class MicroBatcher:
             rows += nxt.n
         return items
 
+    def _score_items(self, model, items):
+        """One engine call for the whole batch -> per-item (proba, flags) parts."""
+        frame = items[0].frame if len(items) == 1 else pd.concat([it.frame for it in items], ignore_index=True)
+        # encode -> pinned slot -> H2D -> classifier kernel (+ outlier-forest kernel) -> D2H
+        scorer = getattr(model, "score", None)
+        proba, flags = scorer(frame) if scorer is not None else (model.predict_proba1(frame), None)
+        self.batches += 1
+        self.rows += len(frame)
+        parts, off = [], 0
+        for it in items:
+            parts.append((proba[off:off + it.n], None if flags is None else flags[off:off + it.n]))
+            off += it.n
+        return parts
+
     def _run(self, idx: int) -> None:
         model = self.models[idx]
         while not self._stop:
@@ -122,20 +136,22 @@ class MicroBatcher:
             if items is None:
                 return
             try:
-                frame = items[0].frame if len(items) == 1 else pd.concat([it.frame for it in items], ignore_index=True)
-                # encode -> pinned slot -> H2D -> classifier kernel (+ outlier-forest kernel) -> D2H
-                scorer = getattr(model, "score", None)
-                proba, flags = scorer(frame) if scorer is not None else (model.predict_proba1(frame), None)
-                self.batches += 1
-                self.rows += len(frame)
-                off = 0
-                for it in items:
-                    part = (proba[off:off + it.n], None if flags is None else flags[off:off + it.n])
-                    off += it.n
+                parts = self._score_items(model, items)
+                for it, part in zip(items, parts):
                     it.loop.call_soon_threadsafe(_resolve, it.future, part, None)
             except BaseException as e:  # surfaces as HTTP 500, like any model exception in the reference
+                if len(items) == 1:
+                    items[0].loop.call_soon_threadsafe(_resolve, items[0].future, None, e)
+                    continue
+                # the reference scores requests independently (app/main.py:72): a request the model rejects (a value
+                # that overflows float32, NaN with the outlier forest attached ...) must fail ALONE -- re-score the
+                # batch one request at a time and route each outcome to its own caller
                 for it in items:
-                    it.loop.call_soon_threadsafe(_resolve, it.future, None, e)
+                    try:
+                        part = self._score_items(model, [it])[0]
+                        it.loop.call_soon_threadsafe(_resolve, it.future, part, None)
+                    except BaseException as e1:
+                        it.loop.call_soon_threadsafe(_resolve, it.future, None, e1)
 
 
 def _resolve(fut, value, err):
@@ -147,6 +163,31 @@ def _resolve(fut, value, err):
         fut.set_result(value)
 
 
+class _BoundedLogPool:
+    """One logging thread with a BOUNDED backlog: each queued record holds its request's DataFrame, so an unbounded
+    queue grows without limit when logging falls behind.  Above the backlog the record is written inline on the
+    caller's thread (back-pressure, nothing is dropped: the log schema is an API for the reference's KQL queries)."""
+
+    def __init__(self, backlog: int = 256):
+        self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="b200-log")
+        self._slots = threading.BoundedSemaphore(max(1, backlog))
+        self.inline = 0
+
+    def submit(self, fn, *args):
+        if not self._slots.acquire(blocking=False):
+            self.inline += 1
+            fn(*args)
+            return None
+
+        def run():
+            try:
+                fn(*args)
+            finally:
+                self._slots.release()
+
+        return self._pool.submit(run)
+
+
 def _log_record(kind: str, request_id: str, payload) -> None:
     logging.info(json.dumps({"service_name": _service_name(), "type": kind, "request_id": request_id, "data": payload}))
 
@@ -154,7 +195,7 @@ def _log_record(kind: str, request_id: str, payload) -> None:
 def create_app(model=None, loader=None) -> FastAPI:
     """Build the app.  ``model``: an already-built B200Model (tests); otherwise ``loader`` (default
     ``databricks_kubernetes_mlops_poc_b200.load_model``) is called in ``lifespan`` on ``MODEL_DIRECTORY``."""
-    log_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="b200-log")
+    log_pool = _BoundedLogPool(int(os.environ.get("B200_LOG_BACKLOG", "256")))
     parser = NativeRequestParser()
 
     @asynccontextmanager

@@ -50,7 +50,15 @@ extern "C" {
 #define B2F_ROWS_WORDS24 0  /* 24 x 32-bit words, 96 B (layout above) */
 #define B2F_ROWS_PACKED64 1 /* 16 x 32-bit words, 64 B: words 0..1 = nine 7-bit fields (category code + 1, 0 = unknown /
                                missing), little-endian bit order, field j at bit 7j; words 2..15 = the 14 float32 numerics.
-                               One third fewer bytes over PCIe; needs <= 9 categoricals of <= 126 categories, <= 14 numerics. */
+                               One third fewer bytes over PCIe; needs exactly 9 categoricals of <= 126 categories and <= 14 numerics (the credit-default shape). */
+
+#define B2F_ROWS_RANKED 2   /* per-model "ranked" rows (csrc/forest_rank.h): the categorical fields bit-packed in the first 4 or 8 bytes
+                               (code + 1, 0 = unknown / missing), then one uint16 per numeric feature = the RANK of the value among the
+                               forest's distinct split values of that feature (missing -> the rank of the imputation value), zero
+                               padded to a multiple of 8 bytes: 32 bytes per row for the credit-default schema.  Exact by construction
+                               (a forest only compares a value with its own split values) and scored by the integer-compare kernel
+                               k_forest_predict_rank.  Available when b2f_rank_info.ok; rows come from b2f_encoder_encode (after
+                               b2f_encoder_attach_ranker) or b2f_ranker_rank_rows. */
 
 /* error codes */
 #define B2F_OK 0
@@ -116,7 +124,10 @@ typedef struct b2f_info {
     int64_t launches_split; /* ... of which the small-batch (groups-across-warps) kernel */
     int64_t split_max_rows; /* launches of at most this many rows take it */
     int32_t outlier_trees;  /* trees of the attached outlier forest (0 = none attached) */
-    int32_t reserved;
+    int32_t rank_ok;        /* B2F_ROWS_RANKED is accepted (k_forest_predict_rank: forest resident in its rank layout) */
+    int64_t launches_rank;  /* ... of which the rank kernel */
+    int32_t rank_smem_bytes; /* dynamic shared memory per CTA of the rank kernel */
+    int32_t rank_row_bytes;  /* bytes per ranked row */
 } b2f_info;
 
 /* ---- library / device ------------------------------------------------------------------ */
@@ -132,6 +143,34 @@ int b2f_blob_validate(const void *forest_blob, size_t nbytes);
 b2f_model *b2f_model_create(const void *forest_blob, size_t nbytes, int device); /* NULL on error */
 void b2f_model_destroy(b2f_model *m);
 int b2f_model_info(const b2f_model *m, b2f_info *out);
+
+/* ---- ranked rows (no GPU involved): the forest's split-value tables and the row layout built from a forest blob -----------
+ * Replaces nothing in the reference by itself; it is the exact re-encoding that lets `x <= threshold` (sklearn's float32-vs-float64
+ * compare behind 02-register-model.ipynb:335-337) run as a 16-bit integer compare on the GPU. */
+typedef struct b2f_rank_info {
+    int32_t ok;            /* 1: the forest has a rank layout and B2F_ROWS_RANKED is accepted */
+    int32_t row_bytes;     /* bytes per ranked row (multiple of 8) */
+    int32_t cat_bytes;     /* 4 or 8: size of the categorical block at the start of a row */
+    int32_t n_cat, n_num;
+    int32_t depth;         /* depth every tree is padded to */
+    int32_t n_trees;
+    int32_t layout_bytes;  /* bytes of the rank layout of the forest (shared-memory resident in the kernel) */
+    int32_t cat_shift[16]; /* bit position of categorical field j inside the block */
+    int32_t cat_bits[16];  /* its width */
+    int32_t n_thresholds[24]; /* per numeric feature: number of distinct split values */
+    int32_t n_pairs;       /* (categorical feature, category) pairs some node tests: pseudo-features n_num .. n_num + n_pairs - 1 */
+    uint32_t pairs[128];   /* feature << 16 | category code, ascending */
+    char why[160];         /* when !ok: the reason */
+} b2f_rank_info;
+typedef struct b2f_ranker b2f_ranker;
+b2f_ranker *b2f_ranker_create(const void *forest_blob, size_t nbytes); /* NULL on a malformed blob; check b2f_rank_info.ok */
+void b2f_ranker_destroy(b2f_ranker *r);
+int b2f_ranker_info(const b2f_ranker *r, b2f_rank_info *out);
+const float *b2f_ranker_thresholds(const b2f_ranker *r, int k, int32_t *count); /* sorted distinct split values of numeric k */
+const void *b2f_ranker_layout(const b2f_ranker *r, int64_t *nbytes);            /* the rank layout (what the kernel walks) */
+/* encoded rows (B2F_ROWS_WORDS24 or B2F_ROWS_PACKED64) -> ranked rows, multi-threaded */
+int b2f_ranker_rank_rows(const b2f_ranker *r, const void *rows, int64_t n, int row_format, void *ranked_out, int threads);
+int b2f_model_rank_info(const b2f_model *m, b2f_rank_info *out);
 
 /* ---- native host-side row encoder (no GPU involved): columnar request data -> encoded rows -----------------
  * Replaces the pandas / sklearn lookup work in front of the arithmetic (reference app/main.py:54,
@@ -154,6 +193,8 @@ b2f_encoder *b2f_encoder_create(int n_cat, int n_num, const int32_t *vocab_count
 void b2f_encoder_destroy(b2f_encoder *e);
 /* num_cols[k] + i * num_strides[k] addresses row i of numeric column k (strides in elements).
  * Returns B2F_ERANGE if a value is infinite / overflows float32 (rows_out is then unspecified). */
+/* give the encoder the forest's split-value tables (copied): b2f_encoder_encode then accepts B2F_ROWS_RANKED */
+int b2f_encoder_attach_ranker(b2f_encoder *e, const b2f_ranker *r);
 int b2f_encoder_encode(const b2f_encoder *e, int64_t n, const b2f_str_column *cat_cols, const double *const *num_cols,
                        const int64_t *num_strides, int row_format, void *rows_out, int threads);
 
@@ -179,6 +220,36 @@ const uint8_t *b2f_json_parser_str_data(const b2f_json_parser *p, int j, int64_t
 /* ---- pinned host memory for request batches (the batching ring lives in these) ------------- */
 void *b2f_pinned_alloc(size_t nbytes); /* NULL on error */
 void b2f_pinned_free(void *p);
+
+/* page-locked memory whose pages sit on the NUMA node of GPU `device` (allocated and first touched from a thread bound to that
+ * node's CPUs; the node comes from /sys/bus/pci/devices/<bdf>/numa_node).  Host-to-device copies then leave from memory local to
+ * the GPU's PCIe root instead of crossing the socket interconnect.  Falls back to b2f_pinned_alloc's placement when the topology
+ * is not exposed.  Free with b2f_pinned_free. */
+void *b2f_pinned_alloc_near(int device, size_t nbytes);
+
+/* one page-locked buffer for a stream dealt round-robin over several GPUs (b2f_predict_stream): stripe s (bytes
+ * [s * stripe_bytes, (s + 1) * stripe_bytes)) is placed on the NUMA node of models[s mod n_models]'s GPU.  Free with
+ * b2f_pinned_free_striped. */
+void *b2f_pinned_alloc_striped(b2f_model **models, int n_models, size_t stripe_bytes, size_t total_bytes);
+void b2f_pinned_free_striped(void *p);
+
+/* ---- columnar request pipeline: replaces everything between `pd.DataFrame(data)` and `.tolist()` around the classifier call
+ *      (app/main.py:54-72, 02-register-model.ipynb:330-337) for one request: the columns of the DataFrame go in (same column
+ *      description as b2f_encoder_encode), the request is cut into chunks, and each chunk is encoded by a pool of host threads
+ *      (bound to the GPU's NUMA node) straight into pinned staging, copied, scored and copied back while the next chunk is being
+ *      encoded; results are collected chunk by chunk so the caller can build its output list while the tail is in flight. */
+typedef struct b2f_scorer b2f_scorer;
+b2f_scorer *b2f_scorer_create(b2f_model *m, const b2f_encoder *e, int threads /* 0 = half the CPUs of the GPU's NUMA node, <= 32 */);
+void b2f_scorer_destroy(b2f_scorer *s);
+/* out_mode: 0 = float proba1, 1 = double proba1, 3 = b2f_scored_full records (attached outlier forest; float32 row formats only).
+ * chunk_rows 0 = choose.  Returns the number of chunks (>= 0) or a negative error; one job at a time per scorer; the column
+ * buffers must stay valid until the last chunk has been waited for. */
+int b2f_scorer_start(b2f_scorer *s, int64_t n, const b2f_str_column *cat_cols, const double *const *num_cols, const int64_t *num_strides,
+                     int row_format, int out_mode, int64_t chunk_rows);
+int b2f_scorer_wait(b2f_scorer *s, int chunk);       /* chunk `chunk` (rows chunk*chunk_rows ...) is in the result buffer */
+const void *b2f_scorer_results(const b2f_scorer *s); /* pinned result buffer of the current job: n x {float | double | b2f_scored_full} */
+int64_t b2f_scorer_chunk_rows(const b2f_scorer *s);
+int b2f_scorer_threads(const b2f_scorer *s);
 
 /* ---- scoring: replaces classifier.predict_proba(df[all_features])[:, 1]
  *      (02-register-model.ipynb:335-337) and pipeline.predict (01-train-model.ipynb:290) --------
