@@ -494,10 +494,16 @@ static int rank_init(b2f_model *m, const uint8_t *blob) {
     rp.mul_64k = 65536u;
     rp.add_64k = 65535u;
     rp.n_pairs = (int)m->rk.pairs.size();
-    if (rp.n_pairs > (int)(sizeof(rp.pair) / sizeof(rp.pair[0]))) return B2F_OK; /* more tested categories than the kernel's table holds */
-    for (int i = 0; i < rp.n_pairs; ++i) {
+    for (int j = 0; j < 16; ++j) {
+        rp.cat_shift[j] = (uint8_t)m->rk.cat_shift[j];
+        rp.cat_bits[j] = (uint8_t)m->rk.cat_bits[j];
+        rp.cat_start[j] = 0;
+        rp.cat_mask[j] = 0ull;
+    }
+    for (int i = rp.n_pairs - 1; i >= 0; --i) { /* pairs are sorted by (feature, category): the last write per feature is its first pair */
         const uint32_t j = m->rk.pairs[i] >> 16, c = m->rk.pairs[i] & 0xFFFFu;
-        rp.pair[i] = (uint32_t)m->rk.cat_shift[j] | ((uint32_t)m->rk.cat_bits[j] << 8) | ((c + 1u) << 16);
+        rp.cat_start[j] = (uint8_t)i;
+        rp.cat_mask[j] |= 1ull << c;
     }
     m->rank_smem_bytes = (int)(B2F_RANK_XS_BYTES + (int64_t)max_tiles * B2F_RANK_XS_BYTES + (int64_t)B2F_RANK_PARTIALS * 32 * 8 + layout_bytes);
     CUDA_TRY(m->rank_u == 8 ? rank_set_attr_all<8>(rp.depth, m->rank_smem_bytes) : rank_set_attr_all<4>(rp.depth, m->rank_smem_bytes));

@@ -8,16 +8,19 @@
  *
  * Structure: a TMA-fed shared-memory ring per CTA.  A producer warp streams 256-row slabs (24 KB,
  * contiguous) with cp.async.bulk + mbarrier complete_tx into a 3-stage ring; 12 consumer warps read
- * their 16-byte vector of each row from shared memory (thread t owns vector t%6 of rows t/6 + 64 i, so
- * its four words -- and its accumulators -- never change).  Memory-level parallelism therefore comes
- * from the ring (3 CTAs x 3 stages x 24 KB = 216 KB in flight per SM), not from registers: a first
- * version that relied on unrolled LDG.128 got one or two loads in flight per warp from ptxas and
- * stalled on the long scoreboard at 2.7 TB/s.
+ * 16-byte vectors of the rows from shared memory.  WARP w owns vector q = w mod 6 of every row (its
+ * lanes take consecutive rows), so which of its four words are categorical (integer) and which numeric
+ * (float32, NaN = missing) is WARP-UNIFORM and compiled in (consume_slabs<NC>): no per-word type select,
+ * no NaN test on integer words, and the missing-value case is a predicate on the three accumulations
+ * instead of selects.  (Round 1 gave thread t vector t mod 6: every word went through both conversions
+ * and a select chain, 83 instructions per vector, issue-bound at 0.53 of the HBM roofline.)
+ * Memory-level parallelism comes from the ring (3 CTAs x 3 stages x 24 KB = 216 KB in flight per SM),
+ * not from registers: a first version that relied on unrolled LDG.128 got one or two loads in flight
+ * per warp from ptxas and stalled on the long scoreboard at 2.7 TB/s.
  * Arithmetic: shifted float64 sums sum(x-K), sum((x-K)^2) and an integer count per word (K = the word's
- * value in row 0; the shift removes the cancellation of the raw sum-of-squares form), branch-free (a
- * NaN contributes d = 0, count 0).  Block partials are reduced through shared memory in a fixed order,
- * written to global memory, and the last block to finish (atomic ticket) reduces the partials in a fixed
- * order, so the result is deterministic.
+ * value in row 0; the shift removes the cancellation of the raw sum-of-squares form).  Block partials are
+ * reduced through shared memory in a fixed order, written to global memory, and the last block to finish
+ * (atomic ticket) reduces the partials in a fixed order, so the result is deterministic.
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -42,6 +45,47 @@ __device__ __forceinline__ double mom_word_value(uint32_t w, int word, int n_cat
 
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+/* One consumer warp, its vector q of every row of its slabs; NC = how many of the vector's four words are categorical
+ * (integers, never missing): the words' types are compile-time, the accumulations of a missing numeric are predicated off. */
+template <int NC>
+__device__ __forceinline__ void consume_slabs(const uint8_t *ring, uint64_t *full_bar, uint64_t *empty_bar, long long my_slabs, long long n, int q,
+                                              int half, int lane, const double (&K)[4], unsigned int (&cnt)[4], double (&s)[4], double (&ss)[4]) {
+    for (long long k = 0; k < my_slabs; ++k) {
+        const int st = (int)(k % B2F_MOM_STAGES);
+        mbar_wait(&full_bar[st], (uint32_t)((k / B2F_MOM_STAGES) & 1));
+        const long long r0 = ((long long)blockIdx.x + k * gridDim.x) * B2F_MOM_SLAB_ROWS;
+        const int rows_here = (int)min((long long)B2F_MOM_SLAB_ROWS, n - r0);
+        const uint4 *slab = reinterpret_cast<const uint4 *>(ring + st * B2F_MOM_SLAB_BYTES);
+#pragma unroll
+        for (int i = 0; i < B2F_MOM_SLAB_ROWS / 64; ++i) {
+            const int row = i * 64 + half * 32 + lane;
+            if (row < rows_here) {
+                const uint4 v = slab[row * 6 + q];
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c < NC) {
+                        const double d = (double)(int32_t)w[c] - K[c];
+                        cnt[c] += 1u;
+                        s[c] += d;
+                        ss[c] = fma(d, d, ss[c]);
+                    } else {
+                        const float xf = __uint_as_float(w[c]);
+                        const double d = (double)xf - K[c];
+                        if (xf == xf) { /* a missing value contributes nothing */
+                            cnt[c] += 1u;
+                            s[c] += d;
+                            ss[c] = fma(d, d, ss[c]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cta(&empty_bar[st]);
+    }
 }
 
 __global__ void __launch_bounds__(B2F_MOM_THREADS, 3)
@@ -84,8 +128,8 @@ __global__ void __launch_bounds__(B2F_MOM_THREADS, 3)
             }
         }
     } else {
-        /* ===== consumer warps ===== */
-        const int q = threadIdx.x % 6; /* which 16-byte vector of the row: fixed per thread */
+        /* ===== consumer warps: warp w reads vector q = w mod 6 of rows half*32 + lane (+ 64 i) of every slab ===== */
+        const int q = warp % 6, half = warp / 6;
         double K[4];
         {
             const uint4 v0 = n > 0 ? __ldg(rows + q) : make_uint4(0, 0, 0, 0);
@@ -98,33 +142,13 @@ __global__ void __launch_bounds__(B2F_MOM_THREADS, 3)
         }
         unsigned int cnt[4] = {0, 0, 0, 0};
         double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
-        const bool is_cat[4] = {q * 4 + 0 < n_cat, q * 4 + 1 < n_cat, q * 4 + 2 < n_cat, q * 4 + 3 < n_cat};
-        for (long long k = 0; k < my_slabs; ++k) {
-            const int st = (int)(k % B2F_MOM_STAGES);
-            mbar_wait(&full_bar[st], (uint32_t)((k / B2F_MOM_STAGES) & 1));
-            const long long r0 = (blockIdx.x + k * gridDim.x) * B2F_MOM_SLAB_ROWS;
-            const int vecs = (int)(min((long long)B2F_MOM_SLAB_ROWS, n - r0) * 6);
-            const uint4 *slab = reinterpret_cast<const uint4 *>(ring + st * B2F_MOM_SLAB_BYTES);
-#pragma unroll
-            for (int i = 0; i < B2F_MOM_SLAB_ROWS * 6 / B2F_MOM_CONSUMERS; ++i) {
-                const int idx = i * B2F_MOM_CONSUMERS + threadIdx.x; /* idx % 6 == q */
-                if (idx < vecs) {
-                    const uint4 v = slab[idx];
-                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const float xf = __uint_as_float(w[c]);
-                        const bool ok = is_cat[c] || (xf == xf);
-                        const double x = is_cat[c] ? (double)(int32_t)w[c] : (double)xf;
-                        const double d = ok ? x - K[c] : 0.0;
-                        cnt[c] += ok ? 1u : 0u;
-                        s[c] += d;
-                        ss[c] = fma(d, d, ss[c]);
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cta(&empty_bar[st]);
+        const int nc = min(4, max(0, n_cat - q * 4)); /* categorical words of this warp's vector: warp-uniform */
+        switch (nc) {
+            case 0: consume_slabs<0>(ring, full_bar, empty_bar, my_slabs, n, q, half, lane, K, cnt, s, ss); break;
+            case 1: consume_slabs<1>(ring, full_bar, empty_bar, my_slabs, n, q, half, lane, K, cnt, s, ss); break;
+            case 2: consume_slabs<2>(ring, full_bar, empty_bar, my_slabs, n, q, half, lane, K, cnt, s, ss); break;
+            case 3: consume_slabs<3>(ring, full_bar, empty_bar, my_slabs, n, q, half, lane, K, cnt, s, ss); break;
+            default: consume_slabs<4>(ring, full_bar, empty_bar, my_slabs, n, q, half, lane, K, cnt, s, ss); break;
         }
         /* `red` aliases the ring: every consumer must be done reading slabs before anyone overwrites it */
         asm volatile("bar.sync 1, %0;" ::"n"(B2F_MOM_CONSUMERS) : "memory");
@@ -137,15 +161,17 @@ __global__ void __launch_bounds__(B2F_MOM_THREADS, 3)
     }
     __syncthreads();
 
-    /* (word, component) -> fixed-order sum over the 64 row lanes, in 4 segments of 16 so 288 threads
+    /* (word, component) -> fixed-order sum over the 64 threads of that vector, in 4 segments of 16 so 288 threads
      * share the latency-bound chain; the 4 segment sums are then added in order */
     if (threadIdx.x < 4 * B2F_MOM_VALUES) {
         const int v = threadIdx.x % B2F_MOM_VALUES, sg = threadIdx.x / B2F_MOM_VALUES;
         const int word = v / 3, comp = v % 3;
         const int wq = word / 4, wk = word % 4;
+        /* the 64 threads that hold vector wq: warps wq and wq + 6, lanes in order */
+        const int first = ((sg >> 1) * 6 + wq) * 32 + (sg & 1) * 16;
         double a = 0.0;
 #pragma unroll 4
-        for (int r = sg * 16; r < sg * 16 + 16; ++r) a += red[r * 6 + wq][wk * 3 + comp];
+        for (int r = first; r < first + 16; ++r) a += red[r][wk * 3 + comp];
         tot_seg[sg][v] = a;
     }
     __syncthreads();

@@ -41,7 +41,6 @@
 #define B2F_RANK_WARPS 32
 #define B2F_RANK_MAX_TILES 16                       /* 32-row tiles per CTA per round */
 #define B2F_RANK_XS_BYTES 8192                      /* per tile: 64 words x 32 lanes x 4 B (128 16-bit values per lane), 8 KB aligned */
-#define B2F_RANK_PAIR_CHUNK 24                      /* categorical pseudo-features staged per work item */
 #define B2F_RANK_PARTIALS (B2F_RANK_WARPS + B2F_RANK_MAX_TILES)
 
 struct RParams {
@@ -62,8 +61,11 @@ struct RParams {
     uint32_t mul_two;        /* = 2, mul_64k = 65536, add_64k = 65535: multiplier / addend operands handed over as run-time values so */
     uint32_t mul_64k;        /*   ptxas keeps the two multiply-adds of a node visit as IMAD (FMA pipe) instead of strength-reducing */
     uint32_t add_64k;        /*   them to LEA / IADD3 on the integer ALU pipe, which is the pipe that bounds the walk */
-    int32_t n_pairs;         /* tested (categorical feature, category) pairs = pseudo-features n_num .. n_num + n_pairs - 1 */
-    uint32_t pair[128 - 4];  /* per pair: bit position of the feature's field | field width << 8 | (code + 1) << 16 */
+    int32_t n_pairs;         /* tested (categorical feature, category) pairs = pseudo-features even(n_num) .. + n_pairs - 1 */
+    uint8_t cat_shift[16];   /* bit position / width of categorical field j inside the row's categorical block */
+    uint8_t cat_bits[16];
+    uint8_t cat_start[16];   /* pair index of feature j's first tested category (pairs are sorted by feature, then category) */
+    unsigned long long cat_mask[16]; /* bit c set: category c of feature j is tested by some node */
 };
 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -153,35 +155,38 @@ __global__ void __launch_bounds__(B2F_RANK_THREADS, 1)
         const int n_rows = (int)min((long long)T * 32, n - row0);
         if (round > 0) __syncthreads(); /* xs / partials of the previous round are free */
 
-        /* ---- phase 1: stage rows.  item = (part, row): consecutive lanes take consecutive rows, so every value store of a
-         *      warp goes to 32 different banks; part 0 writes the numeric ranks, parts 1.. a chunk of one-hot values each ---- */
+        /* ---- phase 1: stage rows.  item = (part, row): consecutive lanes take consecutive rows, so every store of a warp goes
+         *      to 32 different banks.  part 0 copies the numeric ranks (two uint16 per 32-bit word in the row and in the block
+         *      alike); part 1 clears the row's one-hot words and sets the <= n_cat values whose category some node tests ---- */
         {
-            const int n_parts = 1 + (p.n_pairs + B2F_RANK_PAIR_CHUNK - 1) / B2F_RANK_PAIR_CHUNK;
-            const int items = T * 32 * n_parts;
+            const int items = T * 32 * 2;
+            const int num_words = (p.n_num + 1) >> 1, hot_words = (p.n_pairs + 1) >> 1;
             for (int it = tid; it < items; it += B2F_RANK_THREADS) {
-                const int part = it / (T * 32), r = it - part * (T * 32);
+                const int part = it >= T * 32 ? 1 : 0, r = it - part * (T * 32);
                 const uint32_t col = xs_addr + (uint32_t)(r >> 5) * B2F_RANK_XS_BYTES + (uint32_t)(r & 31) * 4u;
                 const bool live = r < n_rows;
                 const uint8_t *row = rows + (size_t)(row0 + (live ? r : 0)) * p.row_bytes;
                 if (part == 0) {
-                    const uint16_t *q = reinterpret_cast<const uint16_t *>(row + p.cat_bytes);
-                    for (int k = 0; k < p.n_num; ++k) {
-                        const uint16_t v = live ? __ldg(q + k) : (uint16_t)0;
-                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(col + (uint32_t)(k >> 1) * 128u + (uint32_t)(k & 1) * 2u), "h"(v) : "memory");
+                    const uint32_t *q = reinterpret_cast<const uint32_t *>(row + p.cat_bytes);
+                    for (int w = 0; w < num_words; ++w) {
+                        uint32_t v = live ? __ldg(q + w) : 0u;
+                        if (2 * w + 1 >= p.n_num) v &= 0xFFFFu; /* odd feature count: the upper half is padding of the row */
+                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(col + (uint32_t)w * 128u), "r"(v) : "memory");
                     }
                 } else {
-                    unsigned long long cw = 0ull;
+                    const uint32_t hot = col + (uint32_t)num_words * 128u;
+                    for (int w = 0; w < hot_words; ++w) asm volatile("st.shared.u32 [%0], %1;" ::"r"(hot + (uint32_t)w * 128u), "r"(0u) : "memory");
                     if (live) {
-                        cw = __ldg(reinterpret_cast<const uint32_t *>(row));
+                        unsigned long long cw = __ldg(reinterpret_cast<const uint32_t *>(row));
                         if (p.cat_bytes == 8) cw |= (unsigned long long)__ldg(reinterpret_cast<const uint32_t *>(row) + 1) << 32;
-                    }
-                    const int i0 = (part - 1) * B2F_RANK_PAIR_CHUNK, i1 = min(p.n_pairs, i0 + B2F_RANK_PAIR_CHUNK);
-                    for (int i = i0; i < i1; ++i) {
-                        const uint32_t pr = p.pair[i];
-                        const uint32_t code1 = (uint32_t)(cw >> (pr & 0xFFu)) & ((1u << ((pr >> 8) & 0xFFu)) - 1u);
-                        const uint16_t v = (live && code1 == (pr >> 16)) ? (uint16_t)1 : (uint16_t)0;
-                        const uint32_t f = (uint32_t)(p.n_num + i);
-                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(col + (f >> 1) * 128u + (f & 1u) * 2u), "h"(v) : "memory");
+                        for (int j = 0; j < p.n_cat; ++j) {
+                            const uint32_t code1 = (uint32_t)(cw >> p.cat_shift[j]) & ((1u << p.cat_bits[j]) - 1u);
+                            const unsigned long long m = p.cat_mask[j];
+                            if (code1 != 0u && code1 <= 64u && ((m >> (code1 - 1u)) & 1ull)) {
+                                const uint32_t slot = (uint32_t)p.cat_start[j] + (uint32_t)__popcll(m & ((1ull << (code1 - 1u)) - 1ull));
+                                asm volatile("st.shared.u16 [%0], %1;" ::"r"(hot + (slot >> 1) * 128u + (slot & 1u) * 2u), "h"((uint16_t)1) : "memory");
+                            }
+                        }
                     }
                 }
             }

@@ -26,8 +26,8 @@
  * binary tree of the forest's depth D in breadth-first order, so the child of node i is 2i+1 (+1) and no child pointer
  * is stored; a tree is 2^D 4-byte node words (the last one unused) followed by 2^D float64 leaf payloads.
  * EVERY test is a rank test "value[f] >= t" over 16-bit values: pseudo-feature f is either numeric feature k (f = k, value
- * = its rank) or one (categorical feature j, category c) pair that some node of the forest tests (value = 1 if the row's
- * code is c, else 0; t = 1) -- the one-hot column sklearn's tree splits on (x_j <= 0.5), restated.
+ * = its rank) or one (categorical feature j, category c) pair that some node of the forest tests (f = even(n_num) + pair
+ * index; value = 1 if the row's code is c, else 0; t = 1) -- the one-hot column sklearn's tree splits on (x_j <= 0.5), restated.
  *     node word   bits 16..31  t     (second child iff value[f] >= t)
  *                 bits 0..15   byte offset of value[f] inside the kernel's per-tile value block: (f >> 1) * 128 + (f & 1) * 2
  *                              (two 16-bit values per 32-bit word of a lane's column, so a lane's fetch always hits its own bank)
@@ -80,6 +80,10 @@ struct b2f_ranker {
     std::vector<uint8_t> layout;         /* n_trees_padded * tree_stride */
     int n_trees_padded = 0;              /* multiple of 8 (stub trees: all-zero nodes and payloads) */
 };
+
+/* pseudo-feature index of the first one-hot value: numerics occupy 0 .. n_num-1, one-hot values start at the next EVEN index so
+ * that no 32-bit word of the kernel's value block mixes a rank with a one-hot value */
+static inline int rank_onehot_base(int n_num) { return (n_num + 1) & ~1; }
 
 namespace rankdetail {
 
@@ -228,7 +232,9 @@ static bool ranker_build(b2f_ranker *r, const uint8_t *blob, const b2f_blob_head
         }
     std::sort(r->pairs.begin(), r->pairs.end());
     r->pairs.erase(std::unique(r->pairs.begin(), r->pairs.end()), r->pairs.end());
-    if (r->n_num + (int)r->pairs.size() > B2F_RANK_MAX_FEATS) return fail("more than 128 numeric features + tested categories");
+    if (rank_onehot_base(r->n_num) + (int)r->pairs.size() > B2F_RANK_MAX_FEATS) return fail("more than 128 numeric features + tested categories");
+    for (uint32_t pr : r->pairs)
+        if ((pr & 0xFFFFu) >= 64u) return fail("a tested category code does not fit the kernel's 64-bit per-feature mask");
     r->nan_rank.assign(r->n_num, 0);
     for (int k = 0; k < r->n_num; ++k) {
         auto &v = r->thr[k];
@@ -282,7 +288,7 @@ static bool ranker_build(b2f_ranker *r, const uint8_t *blob, const b2f_blob_head
                     const uint32_t key = (w << 16) | t.T[it.s];
                     const uint32_t pi = (uint32_t)(std::lower_bound(r->pairs.begin(), r->pairs.end(), key) - r->pairs.begin());
                     if (pi >= r->pairs.size() || r->pairs[pi] != key) bad = true;
-                    word = (1u << 16) | feat_off((uint32_t)r->n_num + pi); /* one-hot value >= 1 */
+                    word = (1u << 16) | feat_off((uint32_t)rank_onehot_base(r->n_num) + pi); /* one-hot value >= 1 */
                 }
             } else if (w == B2F_SENTINEL_WORD) {
                 word = 0u; /* always second child */

@@ -28,14 +28,26 @@
 
 struct EncEntry {
     uint64_t prefix; /* first min(len, 8) bytes, zero padded */
-    uint32_t len;
+    uint64_t suffix; /* last 8 bytes (len >= 8), else the prefix again */
+    uint32_t len;    /* 0xFFFFFFFF = empty slot */
     int32_t code;
+};
+
+/* Per categorical feature a PERFECT hash of its vocabulary: slot = ((prefix * m1) ^ (suffix * m2) ^ (len * m3)) >> shift,
+ * multipliers searched at construction until no two vocabulary strings share a slot.  A lookup is two unaligned 8-byte loads,
+ * three multiplies, ONE table probe and three integer compares -- no scan over the vocabulary, no data-dependent branch
+ * except hit / miss (the linear (length, prefix) scan of round 1 mispredicted on nearly every row: ~35 ns per string,
+ * 300 ns per row, 15 ms of one core for a 65 536-row request). */
+struct EncHash {
+    uint64_t m1 = 0, m2 = 0, m3 = 0;
+    int shift = 58;
+    std::vector<EncEntry> slots;
 };
 
 struct b2f_encoder {
     int n_cat = 0, n_num = 0;
     std::vector<std::vector<std::string>> vocab; /* per categorical feature, in code order */
-    std::vector<std::vector<EncEntry>> index;    /* same, as (length, 8-byte prefix) keys */
+    std::vector<EncHash> hash;                   /* per categorical feature */
     std::vector<int32_t> null_code;              /* per categorical feature: code of a null entry, or -1 */
     bool packed_ok = false;
     b2f_ranker *ranker = nullptr; /* copy of the forest's split-value tables (b2f_encoder_attach_ranker): B2F_ROWS_RANKED output */
@@ -46,11 +58,47 @@ static inline uint64_t enc_prefix(const uint8_t *s, int64_t len) {
     memcpy(&p, s, (size_t)(len < 8 ? len : 8));
     return p;
 }
+static inline uint64_t enc_suffix(const uint8_t *s, int64_t len, uint64_t prefix) {
+    if (len < 8) return prefix;
+    uint64_t q;
+    memcpy(&q, s + len - 8, 8);
+    return q;
+}
+static inline size_t enc_slot(const EncHash &h, uint64_t p, uint64_t q, uint64_t len) { return (size_t)(((p * h.m1) ^ (q * h.m2) ^ (len * h.m3)) >> h.shift); }
+
+static bool enc_build_hash(const std::vector<std::string> &vocab, EncHash &h) {
+    int bits = 4;
+    while ((size_t)1 << bits < 2 * vocab.size() + 2) ++bits;
+    uint64_t seed = 0x9E3779B97F4A7C15ull;
+    auto next = [&seed] { /* splitmix64 */
+        uint64_t z = (seed += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    };
+    for (; bits <= 16; ++bits) {
+        for (int attempt = 0; attempt < 2000; ++attempt) {
+            h.m1 = next() | 1ull, h.m2 = next() | 1ull, h.m3 = next() | 1ull;
+            h.shift = 64 - bits;
+            h.slots.assign((size_t)1 << bits, EncEntry{0, 0, 0xFFFFFFFFu, -1});
+            bool ok = true;
+            for (size_t k = 0; k < vocab.size() && ok; ++k) {
+                const uint8_t *w = reinterpret_cast<const uint8_t *>(vocab[k].data());
+                const int64_t len = (int64_t)vocab[k].size();
+                const uint64_t p = enc_prefix(w, len), q = enc_suffix(w, len, p);
+                EncEntry &e = h.slots[enc_slot(h, p, q, (uint64_t)len)];
+                if (e.len != 0xFFFFFFFFu) ok = false; /* duplicate vocabulary strings cannot happen (OneHotEncoder categories are unique) */
+                e = EncEntry{p, q, (uint32_t)len, (int32_t)k};
+            }
+            if (ok) return true;
+        }
+    }
+    return false;
+}
 
 static inline int32_t enc_lookup(const b2f_encoder *e, int j, const uint8_t *s, int64_t len, bool can_read8) {
-    /* vocabularies here have <= a few dozen short entries: compare (length, first 8 bytes) as two integers and
-     * fall back to memcmp only for longer strings -- cheaper than hashing.  The prefix is one unaligned 8-byte load
-     * masked to the string's length whenever 8 bytes are readable (always, except at the very end of the buffer). */
+    /* prefix: one unaligned 8-byte load masked to the string's length whenever 8 bytes are readable (always, except at the
+     * very end of the buffer) */
     uint64_t p;
     if (can_read8) {
         memcpy(&p, s, 8);
@@ -58,10 +106,13 @@ static inline int32_t enc_lookup(const b2f_encoder *e, int j, const uint8_t *s, 
     } else {
         p = enc_prefix(s, len);
     }
-    for (const EncEntry &en : e->index[j])
-        if (en.len == (uint32_t)len && en.prefix == p && (len <= 8 || memcmp(e->vocab[j][en.code].data() + 8, s + 8, (size_t)len - 8) == 0))
-            return en.code;
-    return -1;
+    const uint64_t q = enc_suffix(s, len, p);
+    const EncHash &h = e->hash[j];
+    const EncEntry &en = h.slots[enc_slot(h, p, q, (uint64_t)len)];
+    if (en.len != (uint32_t)len || en.prefix != p || en.suffix != q) return -1;
+    /* up to 16 bytes the two words cover the whole string; longer ones are compared in full */
+    if (len > 16 && memcmp(e->vocab[j][en.code].data() + 8, s + 8, (size_t)len - 16) != 0) return -1;
+    return en.code;
 }
 
 static inline int32_t enc_code(const b2f_encoder *e, int j, const b2f_str_column &c, int64_t i) {
@@ -160,10 +211,10 @@ extern "C" b2f_encoder *b2f_encoder_create(int n_cat, int n_num, const int32_t *
             e->vocab[j].emplace_back(vocab_bytes + vocab_offsets[s], (size_t)(vocab_offsets[s + 1] - vocab_offsets[s]));
         if (null_codes) e->null_code[j] = null_codes[j];
         if (vocab_counts[j] > 126) e->packed_ok = false;
-        e->index.emplace_back();
-        for (int k = 0; k < vocab_counts[j]; ++k) {
-            const std::string &w = e->vocab[j][k];
-            e->index[j].push_back(EncEntry{enc_prefix(reinterpret_cast<const uint8_t *>(w.data()), (int64_t)w.size()), (uint32_t)w.size(), k});
+        e->hash.emplace_back();
+        if (!enc_build_hash(e->vocab[j], e->hash[j])) {
+            delete e;
+            return nullptr;
         }
     }
     return e;

@@ -225,18 +225,21 @@ static void scorer_submit_chunk(b2f_scorer *s, int c) {
     s->chunk_state[c].store(rc == B2F_OK ? 1 : rc, std::memory_order_release);
 }
 
-static void scorer_work(b2f_scorer *s) {
-    /* items = (chunk, part), handed out in order so chunk 0 completes first */
+/* take one (chunk, part) item, encode it, submit the chunk if it was its last part; false when every item is handed out */
+static bool scorer_work_one(b2f_scorer *s) {
     const int n_items = s->n_chunks * s->parts_per_chunk;
-    for (;;) {
-        const int it = s->next_item.fetch_add(1, std::memory_order_relaxed);
-        if (it >= n_items) break;
-        const int c = it / s->parts_per_chunk, part = it % s->parts_per_chunk;
-        const int64_t c_lo = (int64_t)c * s->chunk_rows, c_cnt = std::min(s->chunk_rows, s->n - c_lo);
-        const int64_t lo = c_lo + c_cnt * part / s->parts_per_chunk, hi = c_lo + c_cnt * (part + 1) / s->parts_per_chunk;
-        if (hi > lo && enc_range(s->e, lo, hi, s->cats, s->nums, s->strides, s->row_format, reinterpret_cast<uint32_t *>(s->h_rows))) s->bad_range.store(1);
-        if (s->parts_left[c].fetch_sub(1, std::memory_order_acq_rel) == 1) scorer_submit_chunk(s, c);
-        s->items_done.fetch_add(1, std::memory_order_release);
+    const int it = s->next_item.fetch_add(1, std::memory_order_relaxed);
+    if (it >= n_items) return false;
+    const int c = it / s->parts_per_chunk, part = it % s->parts_per_chunk; /* items go out in order: chunk 0 completes first */
+    const int64_t c_lo = (int64_t)c * s->chunk_rows, c_cnt = std::min(s->chunk_rows, s->n - c_lo);
+    const int64_t lo = c_lo + c_cnt * part / s->parts_per_chunk, hi = c_lo + c_cnt * (part + 1) / s->parts_per_chunk;
+    if (hi > lo && enc_range(s->e, lo, hi, s->cats, s->nums, s->strides, s->row_format, reinterpret_cast<uint32_t *>(s->h_rows))) s->bad_range.store(1);
+    if (s->parts_left[c].fetch_sub(1, std::memory_order_acq_rel) == 1) scorer_submit_chunk(s, c);
+    s->items_done.fetch_add(1, std::memory_order_release);
+    return true;
+}
+static void scorer_work(b2f_scorer *s) {
+    while (scorer_work_one(s)) {
     }
 }
 
@@ -384,9 +387,11 @@ extern "C" int b2f_scorer_start(b2f_scorer *s, int64_t n, const b2f_str_column *
  * waits (it is the pool's last worker), so a scorer with one thread is simply synchronous. */
 extern "C" int b2f_scorer_wait(b2f_scorer *s, int chunk) {
     if (!s || chunk < 0 || chunk >= s->n_chunks) return set_err(B2F_EINVAL, "bad chunk index");
-    scorer_work(s); /* returns at once when every item has been handed out */
+    /* the caller's thread helps with the encoding only while ITS chunk is not on the GPU yet -- then it goes back to the caller,
+     * who has the previous chunk's Python objects to build while the workers carry on */
     int st;
-    while ((st = s->chunk_state[chunk].load(std::memory_order_acquire)) == 0) __builtin_ia32_pause();
+    while ((st = s->chunk_state[chunk].load(std::memory_order_acquire)) == 0)
+        if (!scorer_work_one(s)) __builtin_ia32_pause();
     if (st < 0) return set_err(st, "%s", s->err);
     CUDA_TRY(cudaSetDevice(s->m->device));
     CUDA_TRY(cudaEventSynchronize(s->ev[chunk]));

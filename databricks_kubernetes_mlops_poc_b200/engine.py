@@ -40,6 +40,11 @@ class ForestEngine:
         if not self._h:
             raise B2FError(f"b2f_model_create(device={device}) failed: {_cabi.last_error()}")
         self._pinned: dict[str, PinnedBuffer] = {}
+        inf = self.info()
+        self.rank_words = inf["rank_row_bytes"] // 4 if inf["rank_ok"] else 0  # width of a ranked row, 0 = not available
+
+    def _fmt(self, rows: np.ndarray) -> int:
+        return _row_format(rows, self.rank_words)
 
     # ------------------------------------------------------------------ lifetime
     def close(self) -> None:
@@ -100,7 +105,7 @@ class ForestEngine:
     def predict_rows(self, rows: np.ndarray, proba_dtype=np.float64, want_label: bool = True, out_proba=None, out_label=None):
         """Encoded rows (N, 24) uint32 in host memory -> (proba1, label)."""
         rows = np.ascontiguousarray(rows)
-        fmt = _row_format(rows)
+        fmt = self._fmt(rows)
         n = rows.shape[0]
         f64 = np.dtype(proba_dtype) == np.float64
         proba = out_proba if out_proba is not None else np.empty(n, dtype=np.float64 if f64 else np.float32)
@@ -114,7 +119,7 @@ class ForestEngine:
         n = rows.shape[0]
         if out is None:
             out = np.empty(n, dtype=_cabi.SCORED_DTYPE)
-        check(self._lib.b2f_predict_pairs(self._h, ptr(rows), n, _row_format(rows), ptr(out)), "b2f_predict_pairs")
+        check(self._lib.b2f_predict_pairs(self._h, ptr(rows), n, self._fmt(rows), ptr(out)), "b2f_predict_pairs")
         return out
 
     # ------------------------------------------------------------------ columnar request pipeline (csrc/scorer.h)
@@ -135,7 +140,7 @@ class ForestEngine:
         n = rows.shape[0]
         if out is None:
             out = np.empty(n, dtype=_cabi.SCORED_FULL_DTYPE)
-        check(self._lib.b2f_predict_full(self._h, ptr(rows), n, _row_format(rows), ptr(out)), "b2f_predict_full")
+        check(self._lib.b2f_predict_full(self._h, ptr(rows), n, self._fmt(rows), ptr(out)), "b2f_predict_full")
         return out
 
     def predict_rows_async(self, rows: np.ndarray, proba: np.ndarray, label: np.ndarray | None) -> int:
@@ -143,7 +148,7 @@ class ForestEngine:
         t = C.c_uint64(0)
         check(
             self._lib.b2f_predict_async_ex(
-                self._h, ptr(rows), rows.shape[0], _row_format(rows), ptr(proba), int(proba.dtype == np.float64), ptr(label), C.byref(t)
+                self._h, ptr(rows), rows.shape[0], self._fmt(rows), ptr(proba), int(proba.dtype == np.float64), ptr(label), C.byref(t)
             ),
             "b2f_predict_async_ex",
         )
@@ -153,7 +158,7 @@ class ForestEngine:
         """Asynchronous ``predict_pairs`` on pinned buffers (``out``: SCORED_DTYPE); pair with wait()."""
         t = C.c_uint64(0)
         check(
-            self._lib.b2f_predict_async_ex(self._h, ptr(rows), rows.shape[0], _row_format(rows), ptr(out), 2, None, C.byref(t)),
+            self._lib.b2f_predict_async_ex(self._h, ptr(rows), rows.shape[0], self._fmt(rows), ptr(out), 2, None, C.byref(t)),
             "b2f_predict_async_ex",
         )
         return t.value
@@ -310,14 +315,17 @@ class Scorer:
         return self._chunk
 
 
-def _row_format(rows: np.ndarray) -> int:
-    """Row layout from the array shape: (N, 24) words, (N, 16) packed, any other width = ranked rows (2 .. 14 words:
-    4 or 8 bytes of categorical fields + one uint16 per numeric, never 16 or 24 words)."""
-    if rows.dtype != np.uint32 or rows.ndim != 2 or not (2 <= rows.shape[1] <= ROW_WORDS):
-        raise ValueError(f"rows must be uint32 (N, {ROW_WORDS}), packed (N, {PACKED_ROW_WORDS}) or ranked (N, row_bytes / 4)")
-    if rows.shape[1] == ROW_WORDS:
-        return ROWS_WORDS24
-    return ROWS_PACKED64 if rows.shape[1] == PACKED_ROW_WORDS else ROWS_RANKED
+def _row_format(rows: np.ndarray, rank_words: int = 0) -> int:
+    """Row layout from the array shape: (N, 24) words, (N, 16) packed, (N, rank_words) ranked rows (the model's own
+    ``rank_row_bytes / 4``: 8 words for the credit-default schema; never 16 or 24)."""
+    if rows.dtype == np.uint32 and rows.ndim == 2:
+        if rows.shape[1] == ROW_WORDS:
+            return ROWS_WORDS24
+        if rows.shape[1] == PACKED_ROW_WORDS:
+            return ROWS_PACKED64
+        if rank_words and rows.shape[1] == rank_words:
+            return ROWS_RANKED
+    raise ValueError(f"rows must be uint32 (N, {ROW_WORDS}), packed (N, {PACKED_ROW_WORDS})" + (f" or ranked (N, {rank_words})" if rank_words else ""))
 
 
 def moments_merge(parts: np.ndarray) -> np.ndarray:
@@ -356,7 +364,7 @@ class EngineGroup:
         proba = out_proba if out_proba is not None else np.empty(n, dtype=np.float64 if f64 else np.float32)
         label = out_label if out_label is not None else np.empty(n, dtype=np.int32)
         check(
-            self._lib.b2f_predict_multi_ex(self._handles, len(self.engines), ptr(rows), n, _row_format(rows), ptr(proba), int(f64), ptr(label)),
+            self._lib.b2f_predict_multi_ex(self._handles, len(self.engines), ptr(rows), n, self.engines[0]._fmt(rows), ptr(proba), int(f64), ptr(label)),
             "b2f_predict_multi_ex",
         )
         return proba, label
@@ -371,7 +379,7 @@ class EngineGroup:
         if out is None:
             out = np.empty(n, dtype=_cabi.SCORED_FULL_DTYPE)
         check(
-            self._lib.b2f_predict_multi_ex(self._handles, len(self.engines), ptr(rows), n, _row_format(rows), ptr(out), 3, None),
+            self._lib.b2f_predict_multi_ex(self._handles, len(self.engines), ptr(rows), n, self.engines[0]._fmt(rows), ptr(out), 3, None),
             "b2f_predict_multi_ex",
         )
         return out
@@ -393,7 +401,7 @@ class EngineGroup:
         the C call, ``inflight`` batches in flight per GPU).  Buffers should be pinned."""
         check(
             self._lib.b2f_predict_stream(
-                self._handles, len(self.engines), ptr(rows), rows.shape[0], int(batch), _row_format(rows), ptr(out_proba),
+                self._handles, len(self.engines), ptr(rows), rows.shape[0], int(batch), self.engines[0]._fmt(rows), ptr(out_proba),
                 int(out_proba.dtype == np.float64), ptr(out_label), int(inflight)
             ),
             "b2f_predict_stream",

@@ -25,6 +25,7 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 import pandas as pd
 
+from ._pylists import ListBuilder
 from .encode import RowEncoder
 from .engine import EngineGroup, ForestEngine
 from .flatten import FlatForest, flatten_isolation_forest, flatten_pipeline
@@ -130,7 +131,7 @@ class B200Model:
         """``pipeline.predict(df)`` (hard labels, 01-train-model.ipynb:290)."""
         return self.classes[np.array(self._score(df)[1])]
 
-    PIPELINE_MIN_ROWS = 2048  # from here up a request goes through the chunked columnar pipeline
+    PIPELINE_MIN_ROWS = int(os.environ.get("B200_PIPELINE_MIN_ROWS", "129"))  # from here up a request goes through the columnar pipeline
 
     def _pipeline(self, df: pd.DataFrame):
         """Large requests on one GPU: the DataFrame's column buffers go to the native scorer in ONE call; chunks come back while
@@ -160,7 +161,9 @@ class B200Model:
         n_chunks = sc.start(n, cols, out_mode=3 if full else 1, fmt=(1 if self.encoder.packed_ok else 0) if full else None)
         out = sc.results()
         step = sc.chunk_rows
-        preds, flags = [], ([] if full else None)
+        # Python lists are built chunk by chunk while later chunks are in flight (float objects recycled: _pylists.py)
+        preds = ListBuilder(n)
+        flags = ListBuilder(n) if full else None
         t_first = None
         for c in range(n_chunks):
             sc.wait(c)
@@ -168,10 +171,11 @@ class B200Model:
                 t_first = time.perf_counter()
             part = out[c * step:(c + 1) * step]
             if full:
-                preds += part["proba1"].tolist()
-                flags += part["is_outlier"].tolist()
+                preds.fill(c * step, part["proba1"])
+                flags.fill(c * step, part["is_outlier"])
             else:
-                preds += part.tolist()
+                preds.fill(c * step, part)
+        preds, flags = preds.items, (flags.items if full else None)
         t2 = time.perf_counter()
         self.last_timing = {"columns_s": t1 - t0, "first_chunk_s": (t_first or t2) - t1, "chunks_and_lists_s": t2 - t1, "chunks": n_chunks,
                             "threads": sc.threads, "row_format": sc.fmt if not full else 1}

@@ -14,19 +14,20 @@ from databricks_kubernetes_mlops_poc_b200.flatten import parse_header
 
 def unpack_ranked(rows: np.ndarray, info) -> np.ndarray:
     """ranked rows (N, row_bytes/4) uint32 -> the kernel's per-row 16-bit values (N, n_num + n_pairs) as phase 1 builds them:
-    pseudo-feature k < n_num = rank of numeric k; n_num + i = 1 iff the row's code of pair i's feature is pair i's category."""
+    pseudo-feature k < n_num = rank of numeric k; even(n_num) + i = 1 iff the row's code of pair i's feature is pair i's category."""
     raw = np.ascontiguousarray(rows).view(np.uint8).reshape(rows.shape[0], -1)
     n = raw.shape[0]
     cw = np.zeros(n, dtype=np.uint64)
     for b in range(info.cat_bytes):
         cw |= raw[:, b].astype(np.uint64) << np.uint64(8 * b)
-    out = np.zeros((n, info.n_num + info.n_pairs), dtype=np.uint32)
+    base = (info.n_num + 1) & ~1  # one-hot values start at an even pseudo-feature index
+    out = np.zeros((n, base + info.n_pairs), dtype=np.uint32)
     ranks = raw[:, info.cat_bytes : info.cat_bytes + 2 * info.n_num].copy().view(np.uint16).reshape(n, info.n_num)
     out[:, : info.n_num] = ranks
     for i in range(info.n_pairs):
         j, c = info.pairs[i] >> 16, info.pairs[i] & 0xFFFF
         code1 = (cw >> np.uint64(info.cat_shift[j])) & np.uint64((1 << info.cat_bits[j]) - 1)
-        out[:, info.n_num + i] = code1 == np.uint64(c + 1)
+        out[:, base + i] = code1 == np.uint64(c + 1)
     return out
 
 

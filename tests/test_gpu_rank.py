@@ -71,15 +71,19 @@ def test_rank_kernel_batch_size_edges_and_determinism(curated, rf100d6):
 
 def test_rank_unavailable_is_refused(curated):
     """A forest without a rank layout (depth > 8) refuses ranked rows loudly and keeps scoring float32 rows."""
-    from databricks_kubernetes_mlops_poc_b200._cabi import B2FError
     from oracle import reference_pipeline as rp
 
     pipe = rp.fit_reference_pipeline(curated.iloc[:3000], dict(n_estimators=9, max_depth=12, random_state=0))
     eng, enc = _engine(pipe)
     try:
         assert not eng.info()["rank_ok"]
-        with pytest.raises(B2FError):
+        with pytest.raises(ValueError):  # the Python layer does not even know a ranked width for this model
             eng.predict_rows(np.zeros((4, 8), dtype=np.uint32), np.float64)
+        from databricks_kubernetes_mlops_poc_b200 import _cabi
+
+        rows, out = np.zeros((4, 8), dtype=np.uint32), np.zeros(4, dtype=np.float64)
+        rc = _cabi.load_library().b2f_predict_ex(eng.handle, _cabi.ptr(rows), 4, _cabi.ROWS_RANKED, _cabi.ptr(out), 1, None)
+        assert rc == -1 and "not available" in _cabi.last_error()  # the C ABI refuses the format with B2F_EINVAL
         want_p, want_l = rp.oracle_predict(pipe, curated.iloc[3000:3500])
         p, l = eng.predict_rows(enc.encode_frame(curated.iloc[3000:3500]), np.float64)
         assert np.abs(p - want_p).max() <= TOL64 and (l == want_l).all()
