@@ -213,6 +213,7 @@ SIGNATURES = {
         [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)],
     ),
     "b2f_drift_launches": (C.c_int64, [C.c_void_p]),
+    "b2f_kstwo_sf": (C.c_double, [C.c_double, C.c_double]),
 }
 
 _lib = None

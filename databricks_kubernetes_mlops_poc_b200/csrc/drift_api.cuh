@@ -29,6 +29,8 @@ struct b2f_drift {
     int32_t *d_new_off = nullptr;
     int64_t *d_new_counts = nullptr;
     int64_t new_cap = 0;
+    double *d_rows = nullptr; /* row-scan scratch: [n_num][2][B2F_DRIFT_ROW_STRIDE(n_ref)] */
+    int rowscan_max_n = 0;
     void *d_out = nullptr; /* p_val[F] | stat[F] | flags[F] */
     void *h_out = nullptr; /* pinned mirror */
     int64_t launches = 0;
@@ -46,6 +48,7 @@ extern "C" void b2f_drift_destroy(b2f_drift *d) {
     if (d->d_codes) cudaFree(d->d_codes);
     if (d->d_new_off) cudaFree(d->d_new_off);
     if (d->d_new_counts) cudaFree(d->d_new_counts);
+    if (d->d_rows) cudaFree(d->d_rows);
     if (d->d_out) cudaFree(d->d_out);
     if (d->h_out) cudaFreeHost(d->h_out);
     if (d->ev0) cudaEventDestroy(d->ev0);
@@ -87,6 +90,11 @@ static int drift_init(b2f_drift *d, const double *ref_sorted, const int32_t *cat
     CUDA_TRY(cudaMalloc(&d->d_out, out_bytes));
     CUDA_TRY(cudaHostAlloc(&d->h_out, out_bytes, cudaHostAllocPortable));
     CUDA_TRY(cudaMalloc((void **)&d->d_new_off, (d->n_cat + 1) * sizeof(int32_t)));
+    /* row-scan form of the exact p-value for request-sized batches (B2F_DRIFT_ROWSCAN=0 keeps the anti-diagonal sweep) */
+    d->rowscan_max_n = B2F_DRIFT_ROWSCAN_MAX;
+    if (const char *rs = getenv("B2F_DRIFT_ROWSCAN")) d->rowscan_max_n = std::max(0, std::min(B2F_DRIFT_ROWSCAN_MAX, atoi(rs)));
+    if (d->rowscan_max_n > 0 && d->n_num > 0 && d->n_ref >= 1024)
+        CUDA_TRY(cudaMalloc((void **)&d->d_rows, (size_t)d->n_num * 2 * (size_t)B2F_DRIFT_ROW_STRIDE(d->n_ref) * sizeof(double)));
     CUDA_TRY(cudaFuncSetAttribute(k_drift_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * B2F_DRIFT_RING_MAX * (int)sizeof(double)));
     return B2F_OK;
 }
@@ -121,6 +129,91 @@ extern "C" b2f_drift *b2f_drift_create(int device, int64_t n_ref, int n_num, con
         return nullptr;
     }
     return d;
+}
+
+/* ---- the asymptotic branch of scipy's ks_2samp, natively (host; a handful of scalar formulas) ---------------------------------
+ * Where lcm(m, n) >= 2^31 scipy itself leaves the exact lattice-path method and returns kstwo.sf(D, round(m n / (m + n)))
+ * (scipy/stats/_stats_py.py `_attempt_exact_2kssamp` / `ks_2samp`), i.e. the ONE-sample two-sided K-S survival function
+ * `scipy.stats._ksstats._kolmogn(n, x, cdf=False)` (Simard & L'Ecuyer 2011).  Its decision tree is restated here for the
+ * sample sizes that can reach this branch (n_eff in the thousands):
+ *   n x <= 1 and n x >= n - 1        Ruben-Gambino closed forms
+ *   x >= 0.5, or n x^2 >= 2.2        2 * Smirnov's one-sided exact formula  P(D+ >= x) = x sum_j C(n,j) (x + j/n)^(j-1) (1 - x - j/n)^(n-j)
+ *                                    (all terms positive: summed in log space, lgamma-limited to ~1e-10 relative)
+ *   n x^2 >= 370                     0
+ *   otherwise                        1 - Pelz-Good (1976) four-term expansion of the CDF  (scipy runs Durbin's matrix algorithm
+ *                                    for n x^1.5 <= 1.4; there the CDF is below 1e-8 and both agree to ~1e-13 in the survival value)
+ * Checked against scipy itself in tests/test_drift_cpu.py.  The response carries float32 p-values. */
+static double smirnov_sf(double n, double x) {
+    if (x <= 0.0) return 1.0;
+    if (x >= 1.0) return 0.0;
+    const double lgn = lgamma(n + 1.0);
+    double sum = 0.0;
+    const double jmax = floor(n * (1.0 - x));
+    for (double j = 0.0; j <= jmax; j += 1.0) {
+        const double a = x + j / n, b = 1.0 - x - j / n;
+        if (b < 0.0) break;
+        double lt = lgn - lgamma(j + 1.0) - lgamma(n - j + 1.0) + (j - 1.0) * log(a);
+        if (n - j > 0.0) {
+            if (b <= 0.0) continue;
+            lt += (n - j) * log(b);
+        }
+        sum += exp(lt);
+    }
+    return std::min(1.0, std::max(0.0, x * sum));
+}
+
+static double pelz_good_cdf(double n, double x) {
+    const double PI = 3.14159265358979323846, PI2 = PI * PI, PI4 = PI2 * PI2, PI6 = PI4 * PI2;
+    const double z = sqrt(n) * x, z2 = z * z, z3 = z2 * z, z4 = z2 * z2, z6 = z4 * z2, z8 = z4 * z4;
+    const double qlog = -PI2 / 8.0 / z2;
+    if (qlog < -745.0) return 0.0;
+    double q = exp(qlog);
+    const double k1a = -z2, k1b = PI2 / 4.0;
+    const double k2a = 6.0 * z6 + 2.0 * z4, k2b = (2.0 * z4 - 5.0 * z2) * PI2 / 4.0, k2c = PI4 * (1.0 - 2.0 * z2) / 16.0;
+    const double k3d = PI6 * (5.0 - 30.0 * z2) / 64.0, k3c = PI4 * (-60.0 * z2 + 212.0 * z4) / 16.0, k3b = PI2 * (135.0 * z4 - 96.0 * z6) / 4.0,
+                 k3a = -30.0 * z6 - 90.0 * z8;
+    double K[4] = {0.0, 0.0, 0.0, 0.0};
+    const int maxk = (int)ceil(16.0 * z / PI);
+    for (int k = maxk; k > 0; --k) {
+        const double m = 2.0 * k - 1.0, m2 = m * m, m4 = m2 * m2, m6 = m4 * m2;
+        const double qp = pow(q, 8.0 * k);
+        const double c[4] = {1.0, k1a + k1b * m2, k2a + k2b * m2 + k2c * m4, k3a + k3b * m2 + k3c * m4 + k3d * m6};
+        for (int i = 0; i < 4; ++i) K[i] = K[i] * qp + c[i];
+    }
+    const double SQRT2PI = sqrt(2.0 * PI);
+    const double div[4] = {z, 6.0 * z4, 72.0 * z4 * z3, 6480.0 * z8 * z2};
+    for (int i = 0; i < 4; ++i) K[i] = K[i] * q * SQRT2PI / div[i];
+    q = exp(-PI2 / 2.0 / z2);
+    double k2e = 0.0, k3e = 0.0;
+    const double s3z = sqrt(3.0) * z;
+    for (int k = maxk; k > 0; --k) {
+        const double k2 = (double)k * k, qp = pow(q, k2), kp = PI * k;
+        k2e += k2 * qp;
+        k3e += (s3z + kp) * (s3z - kp) * k2 * qp;
+    }
+    K[2] += k2e * PI2 * SQRT2PI / (-36.0 * z3);
+    K[3] += k3e * PI2 * SQRT2PI / (216.0 * z6);
+    return K[0] + K[1] / sqrt(n) + K[2] / n + K[3] / (n * sqrt(n));
+}
+
+/* scipy.stats.kstwo.sf(x, n): survival function of the one-sample two-sided K-S statistic (large n) */
+extern "C" double b2f_kstwo_sf(double x, double n) {
+    if (!(n >= 1.0) || x != x) return nan("");
+    auto clip = [](double p) { return std::min(1.0, std::max(0.0, p)); };
+    if (x >= 1.0) return 0.0;
+    if (x <= 0.0) return 1.0;
+    const double t = n * x;
+    if (t <= 1.0) {
+        if (t <= 0.5) return 1.0;
+        const double cdf = exp(lgamma(n + 1.0) - n * log(n) + n * log(2.0 * t - 1.0));
+        return clip(1.0 - cdf);
+    }
+    if (t >= n - 1.0) return clip(2.0 * pow(1.0 - x, n));
+    if (x >= 0.5) return clip(2.0 * smirnov_sf(n, x));
+    const double nx2 = t * x;
+    if (nx2 >= 370.0) return 0.0;
+    if (nx2 >= 2.2) return clip(2.0 * smirnov_sf(n, x));
+    return clip(1.0 - pelz_good_cdf(n, x));
 }
 
 extern "C" int b2f_drift_score(b2f_drift *d, int64_t n, const double *num_cols, const int32_t *cat_codes, const int32_t *new_offsets,
@@ -187,6 +280,8 @@ extern "C" int b2f_drift_score(b2f_drift *d, int64_t n, const double *num_cols, 
     p.p_val = static_cast<double *>(d->d_out);
     p.stat = p.p_val + F;
     p.flags = reinterpret_cast<int32_t *>(p.stat + F);
+    p.row_scratch = d->d_rows;
+    p.rowscan_max_n = d->rowscan_max_n;
     const int64_t total = n * F;
     const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)d->sm_count * 8));
     k_drift_count<<<blocks, 256, 0, d->stream>>>(p);
@@ -198,7 +293,14 @@ extern "C" int b2f_drift_score(b2f_drift *d, int64_t n, const double *num_cols, 
     CUDA_TRY(cudaMemcpyAsync(d->h_out, d->d_out, out_bytes, cudaMemcpyDeviceToHost, d->stream));
     CUDA_TRY(cudaEventRecord(d->ev1, d->stream));
     CUDA_TRY(cudaStreamSynchronize(d->stream));
-    const double *hp_p = static_cast<const double *>(d->h_out);
+    double *hp_p = static_cast<double *>(d->h_out);
+    {
+        /* flag 1 (lcm of the sample sizes >= 2^31): scipy's own asymptotic branch, kstwo.sf(D, round(m n / (m + n))) */
+        const int32_t *hf = reinterpret_cast<const int32_t *>(hp_p + 2 * F);
+        const double en = nearbyint((double)d->n_ref * (double)n / ((double)d->n_ref + (double)n));
+        for (int f = 0; f < F; ++f)
+            if (hf[f] == 1) hp_p[f] = b2f_kstwo_sf(hp_p[F + f], en);
+    }
     memcpy(p_val, hp_p, (size_t)F * sizeof(double));
     if (stat) memcpy(stat, hp_p + F, (size_t)F * sizeof(double));
     if (flags) memcpy(flags, hp_p + 2 * F, (size_t)F * sizeof(int32_t));

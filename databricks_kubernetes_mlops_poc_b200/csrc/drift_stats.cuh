@@ -55,6 +55,8 @@ struct DriftParams {
     double *p_val;            /* [n_cat + n_num]  categorical features first */
     double *stat;             /* chi-squared statistic / K-S D */
     int32_t *flags;           /* 0 ok; 1 = exact K-S not applicable (scipy switches to the asymptotic formula); 2 = NaN input */
+    double *row_scratch;      /* [n_num][2][B2F_DRIFT_ROW_STRIDE(n_ref)]: the two rows of the row-scan form of the exact p-value (NULL: sweep only) */
+    int32_t rowscan_max_n;    /* batches of 2 .. this many rows take the row scan (0 = never) */
 };
 
 /* ------------------------------------------------------------------ k_drift_count */
@@ -311,6 +313,149 @@ __device__ __forceinline__ double sweep_block(const SweepConst &c, int tid, int 
     return prev[(int)(c.n & mask)]; /* written before the last barrier */
 }
 
+/* ---- the row-scan form (request-sized batches) ---------------------------------------------------------------------
+ * W(i,j) = number of lattice paths (0,0)->(i,j) that have left the band.  Multiplying the recursion above through by
+ * C(i+j, j) removes the divisions:  inside the band  W(i,j) = W(i-1,j) + W(i,j-1),  outside  W(i,j) = C(i+j, j).
+ * The in-band cells of row j are the interval lo_j <= i <= hi_j (it moves right with j), so row j is ONE prefix sum over i
+ * of row j-1 -- extended on its right by the binomials of the cells that row j-1 had outside the band -- seeded with the
+ * binomial of the cell left of the band:  n block-wide prefix sums of <= m elements instead of m + n dependent steps
+ * (n = the batch size: 16 rows against 30 000 reference points is 16 scans, not 30 016 steps).
+ * Rows live in a global scratch (L2), element i at (i mod CH) * NT + i / CH so that thread t owns the CH consecutive
+ * columns [t CH, (t+1) CH) and every load / store of a pass is coalesced; row j is scaled by 2^-E_j, E_j the exponent of
+ * its largest binomial, so nothing overflows.  Sums run in a fixed order (deterministic).  p = W(m,n) / C(m+n, n). */
+#define B2F_DRIFT_ROWSCAN_MAX 128
+/* doubles per scratch row: the transposed layout (i mod CH) * NT + i / CH spans CH * NT >= m + 1 slots */
+#define B2F_DRIFT_ROW_STRIDE(m) ((((int64_t)(m) + 1 + B2F_DRIFT_THREADS - 1) / B2F_DRIFT_THREADS) * B2F_DRIFT_THREADS)
+
+struct BinomME {
+    double mant; /* in [1, 2^400) */
+    int ex;      /* value = mant * 2^ex */
+};
+/* C(t, k) = prod_{r=1..k} (t - k + r) / r as numerator / denominator products with exponent tracking (no division in the loop) */
+__device__ inline BinomME binom_me(int64_t t, int k) {
+    double num = 1.0, den = 1.0;
+    int ex = 0;
+    for (int r = 1; r <= k; ++r) {
+        num *= (double)(t - k + r);
+        den *= (double)r;
+        if (num > 0x1p400) {
+            num *= 0x1p-400;
+            ex += 400;
+        }
+        if (den > 0x1p400) {
+            den *= 0x1p-400;
+            ex -= 400;
+        }
+    }
+    BinomME b;
+    b.mant = num / den;
+    b.ex = ex;
+    return b;
+}
+__device__ inline double binom_scaled(int64_t t, int k, int e) {
+    const BinomME b = binom_me(t, k);
+    return ldexp(b.mant, b.ex - e);
+}
+__device__ inline int binom_exponent(int64_t t, int k) {
+    const BinomME b = binom_me(t, k);
+    int fe;
+    frexp(b.mant, &fe);
+    return b.ex + fe;
+}
+__device__ inline int64_t floor_div(int64_t a, int64_t b) { /* b > 0 */
+    int64_t q = a / b;
+    if ((a % b != 0) && (a < 0)) --q;
+    return q;
+}
+
+/* all B2F_DRIFT_THREADS threads of the CTA; buf0 / buf1: B2F_DRIFT_ROW_STRIDE(m) doubles each.  Returns the p-value on thread 0. */
+__device__ double rows_scan(const SweepConst &c, double *buf0, double *buf1, int tid, int nt) {
+    __shared__ double s_warp[32];
+    __shared__ double s_seed;
+    __shared__ int s_e;
+    const int64_t m = c.m, mg = c.mg, ng = c.ng, h = c.h;
+    const int n = (int)c.n;
+    const int64_t CH = (m + 1 + nt - 1) / nt;
+    const int64_t i0 = (int64_t)tid * CH, i1 = min(i0 + CH, m + 1);
+    auto pos = [&](int64_t i) { return (i % CH) * nt + i / CH; };
+    const int lane = tid & 31, warp = tid >> 5;
+
+    /* row 0: inside the band no path has left it */
+    for (int64_t i = i0; i < i1; ++i) __stcg(buf0 + pos(i), 0.0);
+    int64_t hi_p = min(-floor_div(-(h), ng) - 1, m); /* last i with ng*i < h */
+    int e_p = 1;                                      /* exponent of C(hi_0, 0) = 1 */
+    double *prev = buf0, *cur = buf1;
+    __syncthreads();
+    for (int j = 1; j <= n; ++j) {
+        const int64_t lo = max(floor_div(mg * j - h, ng) + 1, (int64_t)0);
+        const int64_t hi = min(-floor_div(-(mg * j + h), ng) - 1, m);
+        /* the row's scale and seed (two threads in different warps), and the cells the previous row had outside the band */
+        if (tid == 0) s_e = binom_exponent(hi + j, j);
+        if (tid == 32) {
+            const BinomME b = lo >= 1 ? binom_me(lo - 1 + j, j) : BinomME{0.0, 0};
+            s_seed = b.mant;
+            s_warp[0] = (double)b.ex; /* applied after the barrier, when the row's exponent is known */
+        }
+        for (int64_t i = hi_p + 1 + tid; i <= hi; i += nt) __stcg(prev + pos(i), binom_scaled(i + j - 1, j - 1, e_p));
+        __syncthreads();
+        const int e = s_e;
+        const double seed = ldexp(s_seed, (int)s_warp[0] - e);
+        const double scale = ldexp(1.0, e_p - e);
+        __syncthreads(); /* s_warp is reused by the scan */
+        /* pass A: this thread's partial sum.  The row lives in L2: loads go out eight at a time (independent, so their
+         * latencies overlap) before the dependent adds consume them */
+        const int64_t a0 = max(i0, lo), a1 = min(i1, hi + 1);
+        double local = 0.0;
+        for (int64_t b = a0; b < a1; b += 8) {
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = (b + q < a1) ? __ldcg(prev + pos(b + q)) : 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) local += v[q] * scale;
+        }
+        /* exclusive block scan of the partials, fixed order */
+        double incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            double w = lane < (nt >> 5) ? s_warp[lane] : 0.0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double v = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += v;
+            }
+            s_warp[lane] = w; /* inclusive over warps */
+        }
+        __syncthreads();
+        double run = seed + (warp > 0 ? s_warp[warp - 1] : 0.0) + (incl - local);
+        /* pass B: the row's values */
+        for (int64_t b = a0; b < a1; b += 8) {
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = (b + q < a1) ? __ldcg(prev + pos(b + q)) : 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (b + q < a1) {
+                    run += v[q] * scale;
+                    __stcg(cur + pos(b + q), run);
+                }
+        }
+        double *t = prev;
+        prev = cur;
+        cur = t;
+        hi_p = hi;
+        e_p = e;
+        __syncthreads();
+    }
+    if (tid == 0) return __ldcg(prev + pos(m)) / binom_scaled(m + n, n, e_p);
+    return 0.0;
+}
+
 extern __shared__ unsigned char drift_smem[];
 
 __global__ void __launch_bounds__(B2F_DRIFT_THREADS) k_drift_finish(DriftParams p) {
@@ -427,6 +572,13 @@ __global__ void __launch_bounds__(B2F_DRIFT_THREADS) k_drift_finish(DriftParams 
     c.T = m + n;
     c.ring = ring;
     double res;
+    if (p.row_scratch && n >= 2 && n <= (int64_t)p.rowscan_max_n && m == m0 && m >= 1024) {
+        /* request-sized batch against the big reference table: n prefix sums instead of m + n dependent steps */
+        double *rows2 = p.row_scratch + (int64_t)f * 2 * B2F_DRIFT_ROW_STRIDE(m0);
+        res = rows_scan(c, rows2, rows2 + B2F_DRIFT_ROW_STRIDE(m0), tid, nt);
+        if (tid == 0) p.p_val[out] = fmin(fmax(res, 0.0), 1.0);
+        return;
+    }
     if (ring == 32) {
         if (tid >= 32) return;
         res = sweep_warp(c, tid);

@@ -20,6 +20,7 @@
 #include <sched.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 
@@ -169,6 +170,7 @@ struct b2f_scorer {
     std::condition_variable cv; /* workers sleep here between jobs */
     std::atomic<uint64_t> generation{0};
     bool stop = false;
+    int spin_us = 1500; /* how long an idle worker polls for the next job before it sleeps (B200_SPIN_US) */
     /* pinned staging, grown on demand */
     uint8_t *h_rows = nullptr;
     uint8_t *h_out = nullptr;
@@ -250,11 +252,16 @@ static void scorer_worker(b2f_scorer *s, int idx) {
     cudaSetDevice(s->m->device);
     uint64_t seen = 0;
     for (;;) {
-        /* spin briefly for the next job (a request right behind the last one), then sleep */
+        /* spin for the next job for a while (a service under load gets the next request within a millisecond; waking 30
+         * sleeping threads through a condition variable costs ~100 us of the request that does it), then sleep */
         uint64_t g = s->generation.load(std::memory_order_acquire);
-        for (int spin = 0; g == seen && spin < 4000; ++spin) {
-            __builtin_ia32_pause();
-            g = s->generation.load(std::memory_order_acquire);
+        if (g == seen) {
+            const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(s->spin_us);
+            for (int spin = 0; g == seen; ++spin) {
+                __builtin_ia32_pause();
+                g = s->generation.load(std::memory_order_acquire);
+                if ((spin & 255) == 255 && std::chrono::steady_clock::now() > until) break;
+            }
         }
         if (g == seen) {
             std::unique_lock<std::mutex> lk(s->mu);
@@ -284,9 +291,10 @@ extern "C" b2f_scorer *b2f_scorer_create(b2f_model *m, const b2f_encoder *e, int
     if (threads <= 0) {
         cpu_set_t set;
         int local = numa_cpus_of_device(m->device, &set) ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
-        threads = std::max(1, std::min(32, local / 2)); /* physical cores of the node, not hyper-threads */
+        threads = std::max(1, std::min(48, local * 3 / 4)); /* the node's cores and half of their hyper-threads */
     }
     s->n_threads = std::min(threads, 64);
+    if (const char *sp = getenv("B200_SPIN_US")) s->spin_us = std::max(0, atoi(sp));
     cudaSetDevice(m->device);
     for (auto &e2 : s->ev)
         if (cudaEventCreateWithFlags(&e2, cudaEventDisableTiming) != cudaSuccess) {

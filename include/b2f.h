@@ -239,7 +239,7 @@ void b2f_pinned_free_striped(void *p);
  *      (bound to the GPU's NUMA node) straight into pinned staging, copied, scored and copied back while the next chunk is being
  *      encoded; results are collected chunk by chunk so the caller can build its output list while the tail is in flight. */
 typedef struct b2f_scorer b2f_scorer;
-b2f_scorer *b2f_scorer_create(b2f_model *m, const b2f_encoder *e, int threads /* 0 = half the CPUs of the GPU's NUMA node, <= 32 */);
+b2f_scorer *b2f_scorer_create(b2f_model *m, const b2f_encoder *e, int threads /* 0 = three quarters of the CPUs of the GPU's NUMA node, <= 48 */);
 void b2f_scorer_destroy(b2f_scorer *s);
 /* out_mode: 0 = float proba1, 1 = double proba1, 3 = b2f_scored_full records (attached outlier forest; float32 row formats only).
  * chunk_rows 0 = choose.  Returns the number of chunks (>= 0) or a negative error; one job at a time per scorer; the column
@@ -323,13 +323,16 @@ void b2f_drift_destroy(b2f_drift *d);
  * union of reference and batch categories): new_offsets[n_cat + 1] / new_counts list their counts per feature
  * (both NULL when every batch value is a reference category).
  * Outputs, categorical features first then numeric ones: p_val (required), stat (chi-squared statistic / K-S D) and
- * flags (0 = ok; 1 = scipy would switch to the asymptotic K-S formula (lcm of the sample sizes >= 2^31): p_val is -1 and
- * the caller applies kstwo.sf(D, round(m*n/(m+n))); 2 = NaN in the batch column: p_val is NaN) may be NULL.
+ * flags (0 = ok; 1 = scipy itself switches to the asymptotic K-S formula there (lcm of the sample sizes >= 2^31): p_val is
+ * kstwo.sf(D, round(m*n/(m+n))), computed by the library (b2f_kstwo_sf); 2 = NaN in the batch column: p_val is NaN) may be NULL.
  * device_ms (may be NULL): device time of the call (copies + kernels), from CUDA events. */
 int b2f_drift_score(b2f_drift *d, int64_t n, const double *num_cols, const int32_t *cat_codes,
                     const int32_t *new_offsets, const int64_t *new_counts, double *p_val, double *stat,
                     int32_t *flags, float *device_ms);
 int64_t b2f_drift_launches(const b2f_drift *d); /* kernels launched by this handle so far */
+/* scipy.stats.kstwo.sf(x, n) for the sample sizes where ks_2samp leaves the exact method (host, scalar; b2f_drift_score applies
+ * it itself to features it flags 1, so the p-values it returns are final) */
+double b2f_kstwo_sf(double x, double n);
 
 /* ---- device-resident interface (measurement and callers that already hold rows in HBM) ----- */
 void *b2f_device_alloc(b2f_model *m, size_t nbytes);

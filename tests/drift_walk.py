@@ -144,3 +144,64 @@ def chi2(ref_counts, batch_counts, new_counts=()):
         d1 = np.where(d1 > 0, d1 - np.minimum(0.5, d1), d1 + np.minimum(0.5, -d1))
     s = float((d0 * d0 / e0 + d1 * d1 / e1).sum())
     return s, gamma_q(0.5 * (K - 1), 0.5 * s)
+
+
+# ----------------------------------------------------------------------------- row-scan form of the exact p-value
+def _binom_scaled(t: int, k: int, e: int) -> float:
+    """C(t, k) * 2**(-e) by the running product prod (t - k + r) / r with exponent tracking (as the kernel does it)."""
+    v, ex = 1.0, 0
+    for r in range(1, k + 1):
+        v = v * float(t - k + r) / float(r)
+        if v > 2.0 ** 400:
+            v *= 2.0 ** -400
+            ex += 400
+    return math.ldexp(v, ex - e)
+
+
+def _binom_exponent(t: int, k: int) -> int:
+    v, ex = 1.0, 0
+    for r in range(1, k + 1):
+        v = v * float(t - k + r) / float(r)
+        if v > 2.0 ** 400:
+            v *= 2.0 ** -400
+            ex += 400
+    return ex + math.frexp(v)[1]
+
+
+def exact_p_rows(m0: int, n0: int, num: int):
+    """The ROW-SCAN form of the exact two-sided p-value (k_drift_finish for request-sized batches):
+    W(i, j) = number of lattice paths (0,0)->(i,j) that left the band |ng*i - mg*j| < h obeys, inside the band,
+    W(i, j) = W(i-1, j) + W(i, j-1) -- the (i+j)-normalised recursion of scipy multiplied through by C(i+j, j) -- and is
+    C(i+j, j) outside.  Inside the band a row is therefore ONE prefix sum over i of the previous row (extended by the
+    binomials of the cells that were outside one row earlier), seeded with the binomial of the cell left of the band:
+    n prefix sums of length <= m instead of m + n dependent anti-diagonal steps.  Every row is scaled by 2**-E_j
+    (E_j = exponent of the largest binomial of the row) so nothing overflows.  -> (p, flag)."""
+    g = math.gcd(m0, n0)
+    m, n = max(m0, n0), min(m0, n0)
+    mg, ng = m // g, n // g
+    h = num // g
+    if (m0 // g) >= 2147483647.0 / (n0 // g):
+        return -1.0, 1
+    if h == 0:
+        return 1.0, 0
+
+    def lo_hi(j):
+        lo = (mg * j - h) // ng + 1  # first i with ng*i - mg*j > -h
+        hi = -((-(mg * j + h)) // ng) - 1  # last i with ng*i - mg*j < h
+        return max(lo, 0), min(hi, m)
+
+    lo_p, hi_p = lo_hi(0)
+    prev = np.zeros(m + 1, dtype=np.float64)  # row 0 inside the band: no path has left it yet
+    e_prev = _binom_exponent(hi_p + 0, 0)
+    for j in range(1, n + 1):
+        lo, hi = lo_hi(j)
+        e = _binom_exponent(hi + j, j)
+        # cells (i, j-1) right of the previous row's band are outside it: every path to them has left the band
+        for i in range(hi_p + 1, hi + 1):
+            prev[i] = _binom_scaled(i + j - 1, j - 1, e_prev)
+        seed = _binom_scaled(lo - 1 + j, j, e) if lo >= 1 else 0.0
+        cur = np.zeros(m + 1, dtype=np.float64)
+        cur[lo : hi + 1] = seed + np.cumsum(prev[lo : hi + 1] * math.ldexp(1.0, e_prev - e))
+        prev, lo_p, hi_p, e_prev = cur, lo, hi, e
+    total = _binom_scaled(m + n, n, e_prev)
+    return float(min(max(prev[m] / total, 0.0), 1.0)), 0

@@ -161,3 +161,55 @@ def test_frozen_detector_outputs_are_reproduced(curated, inference, iforest):
         got = -iforest.decision_function(curated[rp.NUMERIC_FEATURES].iloc[:3000].to_numpy())
         assert np.abs(got - exp["iforest_score_head3000"]).max() <= 1e-12
     assert str(exp["scipy_version"]) and scipy.__version__
+
+
+def test_row_scan_form_matches_scipy():
+    """The row-scan form of the exact p-value (what k_drift_finish runs for request-sized batches: n prefix sums over the
+    unnormalised path counts, binomials outside the band, rows scaled by powers of two) against scipy's compiled
+    recursion, small lattices exhaustively in h and the reference-table size for a few batch sizes."""
+    import math
+
+    import drift_walk as dw
+    from scipy.stats import _stats_pythran as sp
+
+    worst = 0.0
+    for m, n in [(50, 7), (64, 48), (300, 2), (300, 16), (1000, 37), (500, 125), (97, 100), (31, 31)]:
+        g = math.gcd(m, n)
+        lcm = m // g * n
+        for h in sorted({1, 2, 3, lcm // 50 + 1, lcm // 10 + 1, lcm // 3 + 1, lcm - 1, lcm}):
+            if 1 <= h <= lcm:
+                want = min(max(sp._compute_outer_prob_inside_method(max(m, n), min(m, n), g, h), 0.0), 1.0)
+                got, flag = dw.exact_p_rows(m, n, h * g)
+                assert flag == 0
+                worst = max(worst, abs(got - want) / max(want, 1e-300))
+    for n, d in ((2, 0.7), (16, 0.33), (100, 0.12), (128, 0.09)):
+        m = 30000
+        g = math.gcd(m, n)
+        h = max(1, int(d * (m // g) * n))
+        want = min(max(sp._compute_outer_prob_inside_method(m, n, g, h), 0.0), 1.0)
+        got, flag = dw.exact_p_rows(m, n, h * g)
+        worst = max(worst, abs(got - want) / max(want, 1e-300))
+    assert worst <= 1e-12, worst
+    # and equal to the anti-diagonal sweep of the same kernel
+    for m, n, num in ((30000, 16, 30000 * 16 // 3), (30000, 128, 30000 * 128 // 9), (4096, 5, 4096 * 5 // 2)):
+        a, _ = dw.exact_p(m, n, num)
+        b, _ = dw.exact_p_rows(m, n, num)
+        assert abs(a - b) <= 1e-12 * max(a, 1e-300)
+
+
+def test_native_kstwo_sf_matches_scipy():
+    """b2f_kstwo_sf (host, csrc/drift_api.cuh) restates the branch scipy's ks_2samp takes when the exact method is not
+    applicable (lcm of the sample sizes >= 2^31): kstwo.sf(D, round(m n / (m + n))).  Checked against scipy over the
+    whole range of D for the effective sample sizes that reach that branch with a 30 000-row reference table."""
+    from scipy.stats import distributions
+
+    from databricks_kubernetes_mlops_poc_b200 import _cabi
+
+    lib = _cabi.load_library()
+    for n in (5000, 21145, 25000, 29999):
+        xs = list(np.geomspace(1e-5, 0.9, 60)) + [1 / n, 0.6 / n, 0.4 / n, 1 - 0.5 / n, 0.5, 0.51, 0.0, 1.0, 1.5, -0.1]
+        for x in xs:
+            want = float(distributions.kstwo.sf(x, n))
+            got = lib.b2f_kstwo_sf(float(x), float(n))
+            assert abs(got - want) <= 1e-10 * max(want, 1e-300) + 1e-300, (n, x, got, want)
+    assert np.isnan(lib.b2f_kstwo_sf(float("nan"), 100.0))

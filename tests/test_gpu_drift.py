@@ -199,3 +199,40 @@ def test_drift_against_frozen_library_outputs(curated, inference):
             assert (np.abs(p - want_p) <= RTOL * want_p + 1e-300).all(), key
     finally:
         det.close()
+
+
+def test_row_scan_and_sweep_agree(curated):
+    """Request-sized batches take the row-scan form of the exact p-value (B2F_DRIFT_ROWSCAN: batches of 2 .. 128 rows), larger
+    ones the anti-diagonal sweep; the same batches through both forms give the same p-values (and both equal scipy's, above)."""
+    import os
+
+    from oracle import reference_pipeline as rp
+
+    from databricks_kubernetes_mlops_poc_b200.drift import TabularDrift
+
+    ref = curated[rp.FEATURES]
+    rng = np.random.default_rng(11)
+    batches = [ref.iloc[rng.integers(0, len(ref), n)].reset_index(drop=True) for n in (2, 3, 16, 17, 64, 127, 128)]
+    shifted = ref.iloc[:40].copy()
+    for c in rp.NUMERIC_FEATURES:
+        shifted[c] = shifted[c] * 1.7 + 3.0
+    batches.append(shifted)
+    det = TabularDrift(ref, rp.CATEGORICAL_FEATURES, device=0)
+    try:
+        a = [det.statistics(b) for b in batches]
+        for b in batches:
+            _check(det, ref, b)
+    finally:
+        det.close()
+    os.environ["B2F_DRIFT_ROWSCAN"] = "0"
+    try:
+        det = TabularDrift(ref, rp.CATEGORICAL_FEATURES, device=0)
+    finally:
+        os.environ.pop("B2F_DRIFT_ROWSCAN")
+    try:
+        for b, (p, stat, flags) in zip(batches, a):
+            p2, stat2, flags2 = det.statistics(b)
+            assert (flags == flags2).all() and (stat == stat2).all()
+            assert np.abs(p - p2).max() <= 1e-11 * np.maximum(np.abs(p2), 1e-300).max()
+    finally:
+        det.close()

@@ -112,8 +112,9 @@ def test_pipeline_predict_large_frames(curated, inference, adversarial, rf100d6,
         # the same frame again (staging reuse), reversed column order, a slice with an offset
         assert model.predict(df)["predictions"] == out["predictions"]
         assert model.predict(df[ALL_FEATURES[::-1]])["predictions"] == out["predictions"]
+        # another batch size groups the per-warp partial sums differently: equal to the last bit or two, not bitwise
         part = model.predict(df.iloc[1234:9999])
-        assert part["predictions"] == out["predictions"][1234:9999]
+        assert np.abs(np.asarray(part["predictions"]) - np.asarray(out["predictions"][1234:9999])).max() <= 1e-15
         # object-dtype string columns with None / NaN / unknown categories: the general path, same answers
         big_adv = pd.concat([adversarial] * 5, ignore_index=True)
         wa, _ = rp.oracle_predict(rf100d6, big_adv)
@@ -130,7 +131,8 @@ def test_pipeline_predict_large_frames(curated, inference, adversarial, rf100d6,
         bad.iloc[4321, bad.columns.get_loc("credit_limit")] = 1e39
         with pytest.raises(ValueError):
             model.predict(bad)
-        assert model.predict(df.iloc[:5000])["predictions"] == out["predictions"][:5000]  # the scorer survives a refused request
+        again = model.predict(df.iloc[:5000])["predictions"]  # the scorer survives a refused request
+        assert np.abs(np.asarray(again) - np.asarray(out["predictions"][:5000])).max() <= 1e-15
     finally:
         model.close()
 

@@ -1,35 +1,28 @@
-"""Device time of one drift-scoring request (K3) by batch size, with scipy's own time beside it (gpurun helper)."""
-import json
-import os
-import sys
-import time
-
+"""gpurun helper: K3 device / call time by batch size (row-scan form vs anti-diagonal sweep), scipy beside it."""
+import json, os, sys, time
 import numpy as np
-
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from databricks_kubernetes_mlops_poc_b200.drift import TabularDrift  # noqa: E402
-from oracle import datasets, drift as od, reference_pipeline as rp  # noqa: E402
+from databricks_kubernetes_mlops_poc_b200 import training
+from databricks_kubernetes_mlops_poc_b200.drift import TabularDrift
+from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES, CATEGORICAL_FEATURES
 
-cur = datasets.load_curated()
-ref = cur[rp.FEATURES]
-det = TabularDrift(ref, rp.CATEGORICAL_FEATURES, device=0)
-rng = np.random.default_rng(0)
-out = []
-for n in (1, 16, 256, 1000, 4096, 65536):
-    batch = ref.iloc[rng.integers(0, len(ref), n)].reset_index(drop=True)
-    det.statistics(batch)
-    dev, wall = [], []
-    for _ in range(10 if n < 65536 else 3):
-        t = time.perf_counter()
+base = training.load_base_frame()
+ref = base[ALL_FEATURES]
+rng = np.random.default_rng(7)
+out = {}
+for mode in ("rowscan", "sweep"):
+    if mode == "sweep":
+        os.environ["B2F_DRIFT_ROWSCAN"] = "0"
+    det = TabularDrift(ref, CATEGORICAL_FEATURES, device=0)
+    rows = {}
+    for n in (1, 2, 16, 64, 128, 129, 1000):
+        batch = ref.iloc[rng.integers(0, len(ref), n)].reset_index(drop=True)
         det.statistics(batch)
-        wall.append(time.perf_counter() - t)
-        dev.append(det.last_device_ms)
-    cpu = None
-    if n <= 4096:
-        t = time.perf_counter()
-        od.tabular_drift_p_values(ref, batch, rp.CATEGORICAL_FEATURES)
-        cpu = time.perf_counter() - t
-    out.append(dict(n=n, device_ms=float(np.median(dev)), wall_ms=1e3 * float(np.median(wall)), scipy_ms=None if cpu is None else 1e3 * cpu))
-    print(out[-1], flush=True)
-os.makedirs("gpurun_out", exist_ok=True)
+        dev, wall = [], []
+        for _ in range(10):
+            t0 = time.perf_counter(); det.statistics(batch); wall.append(time.perf_counter() - t0); dev.append(det.last_device_ms)
+        rows[str(n)] = {"device_ms": float(np.median(dev)), "call_ms": 1e3 * float(np.median(wall))}
+    det.close()
+    out[mode] = rows
+print(json.dumps(out, indent=1))
 json.dump(out, open("gpurun_out/drift_time.json", "w"), indent=1)
