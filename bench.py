@@ -529,7 +529,7 @@ def run_b200(args, dist: Dist):
             "kernel_frac_of_hbm_peak_201MB": MOM_BYTES_PER_ROW * n_pool / (float(np.median(ms_big)) * 1e-3) / 1e9 / peak,
             "count0": float(merged[9, 0]),
         }
-        if dist.rank == 0 and not args.no_gib:
+        if dist.rank == 0 and dist.world == 1 and not args.no_gib:
             n_gib = 11_200_000  # x 96 B = 1.075 GB of 96-byte rows (1.03 GB algorithmic at 92 B/row)
             d_gib = eng.device_alloc(n_gib * 96)
             reps = (n_gib + rows24.shape[0] - 1) // rows24.shape[0]
@@ -614,7 +614,7 @@ def run_b200(args, dist: Dist):
         "sustained_rows_per_s": sustained,
         "parity_max_abs_dp_vs_sklearn_2048rows_all_ranks": parity, "parity_labels_equal_all_ranks": labels_equal,
     }
-    if dist.rank == 0 and not args.no_sweep:
+    if dist.rank == 0 and dist.world == 1 and not args.no_sweep:  # single-process runs only (the sweep fits / loads its own models)
         line["latency_sweep"] = {m: latency_sweep(args, dist, m, full=args.sweep) for m in (["rf500d8", "gbdt500d8"] if not args.sweep_model else [args.sweep_model])}
     if cpu is not None:
         line["cpu_baseline"] = cpu

@@ -126,6 +126,7 @@ SIGNATURES = {
     "b2f_encoder_attach_ranker": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b2f_encoder_create": (C.c_void_p, [C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]),
     "b2f_encoder_destroy": (None, [C.c_void_p]),
+    "b2f_encoder_codes": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(StrColumn), C.c_void_p, C.c_int]),
     "b2f_encoder_encode": (
         C.c_int,
         [C.c_void_p, C.c_int64, C.POINTER(StrColumn), C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_void_p, C.c_int],

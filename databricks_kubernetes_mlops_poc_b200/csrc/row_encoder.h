@@ -235,6 +235,28 @@ extern "C" int b2f_encoder_attach_ranker(b2f_encoder *e, const b2f_ranker *r) {
     return B2F_OK;
 }
 
+/* category codes only, column-major (codes_out[j * n + i]): the drift detector's view of a request (its reference categories are
+ * this encoder's vocabulary); -1 = not a reference category, nulls take the feature's null code */
+extern "C" int b2f_encoder_codes(const b2f_encoder *e, int64_t n, const b2f_str_column *cat_cols, int32_t *codes_out, int threads) {
+    if (!e || n < 0 || !codes_out || (e->n_cat > 0 && !cat_cols)) return B2F_EINVAL;
+    threads = (int)std::min<int64_t>(std::max(threads, 1), std::max<int64_t>(1, n / 8192));
+    auto work = [&](int64_t lo, int64_t hi) {
+        for (int j = 0; j < e->n_cat; ++j) {
+            int32_t *out = codes_out + (size_t)j * n;
+            for (int64_t i = lo; i < hi; ++i) out[i] = enc_code(e, j, cat_cols[j], i);
+        }
+    };
+    if (threads == 1) {
+        work(0, n);
+        return B2F_OK;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work, n * t / threads, n * (t + 1) / threads);
+    work(0, n / threads);
+    for (auto &th : pool) th.join();
+    return B2F_OK;
+}
+
 extern "C" int b2f_encoder_encode(const b2f_encoder *e, int64_t n, const b2f_str_column *cat_cols, const double *const *num_cols,
                                   const int64_t *num_strides, int row_format, void *rows_out, int threads) {
     if (!e || n < 0 || !rows_out || (e->n_cat > 0 && !cat_cols) || (e->n_num > 0 && (!num_cols || !num_strides))) return B2F_EINVAL;

@@ -61,6 +61,7 @@ class TabularDrift:
         order = self.cat_features + self.num_features
         self._perm = np.array([order.index(f) for f in self.features], dtype=np.int64)
         self.last_device_ms = 0.0
+        self._num_pos, self._cat_pos = {}, {}  # column positions per columns Index (encode.column_positions)
 
     def _open(self, device: int, handles: int | None = None) -> None:
         """Upload the reference table.  ``handles`` (default ``B200_DRIFT_HANDLES`` or 4) independent device states,
@@ -91,6 +92,9 @@ class TabularDrift:
             self._lib.b2f_drift_destroy(h)
         self._handles = []
         self._h = None
+        if getattr(self, "_enc", None) is not None:
+            self._enc_lib.b2f_encoder_destroy(self._enc)
+            self._enc = None
 
     def __del__(self):
         try:
@@ -110,13 +114,31 @@ class TabularDrift:
         n = len(batch)
         nn, nc = len(self.num_features), len(self.cat_features)
         x = np.empty((nn, n), dtype=np.float64)
-        for k, name in enumerate(self.num_features):
-            x[k] = batch[name].to_numpy(dtype=np.float64)
+        try:  # block-manager access: a Series per column costs more than everything else at request size
+            from .encode import column_positions
+
+            pos = column_positions(batch, self.num_features, self._num_pos)
+            fetch = batch._mgr.iget_values
+            for k, i in enumerate(pos):
+                if i < 0:
+                    raise KeyError(self.num_features[k])
+                x[k] = fetch(int(i))
+        except (AttributeError, TypeError, ValueError):
+            for k, name in enumerate(self.num_features):
+                x[k] = batch[name].to_numpy(dtype=np.float64)
         codes = np.empty((nc, n), dtype=np.int32)
         new_off = np.zeros(nc + 1, dtype=np.int32)
         new_counts = []
+        # Arrow-backed string columns: the native encoder's perfect-hash lookup over the buffers (no per-column pandas hashing, no
+        # per-row Python); only a column that holds values outside the reference categories still goes through the general path
+        native_ok = np.zeros(nc, dtype=bool)
+        if nc and self._native_codes(batch, codes):
+            native_ok = (codes >= 0).all(axis=1)
         for c, name in enumerate(self.cat_features):
             idx = self._index[name]
+            if native_ok[c]:
+                new_off[c + 1] = len(new_counts)
+                continue
             if n <= 128:  # request-sized batches: a Python loop beats the vectorised machinery
                 # missing values (None / NaN) are outside the reference's contract (alibi-detect's np.unique raises on
                 # them); both paths here count them as one category "nan"
@@ -142,6 +164,28 @@ class TabularDrift:
             new_counts.extend(unseen[v] for v in sorted(unseen))
             new_off[c + 1] = len(new_counts)
         return x, codes, new_off, np.asarray(new_counts, dtype=np.int64)
+
+    def _native_codes(self, batch: pd.DataFrame, codes: np.ndarray) -> bool:
+        """codes[c, i] = index of batch[cat c][i] among the reference categories (-1: not one of them) through
+        b2f_encoder_codes; False when the columns are not Arrow-backed strings (the caller takes the general path)."""
+        from .encode import NATIVE_THREADS, arrow_string_columns, column_positions
+
+        got = arrow_string_columns(batch, self.cat_features, column_positions(batch, self.cat_features, self._cat_pos))
+        if got is None:
+            return False
+        if getattr(self, "_enc", None) is None:
+            lib = _cabi.load_library()
+            blobs = [str(v).encode("utf-8") for name in self.cat_features for v in self.ref_cats[name].tolist()]
+            offsets = np.zeros(len(blobs) + 1, dtype=np.int64)
+            np.cumsum([len(b) for b in blobs], out=offsets[1:])
+            counts = np.array([len(self.ref_cats[name]) for name in self.cat_features], dtype=np.int32)
+            nulls = np.array([self._index[name].get("nan", -1) for name in self.cat_features], dtype=np.int32)  # missing counts as "nan"
+            h = lib.b2f_encoder_create(len(self.cat_features), 0, ptr(counts), b"".join(blobs), ptr(offsets), ptr(nulls))
+            if not h:
+                return False
+            self._enc, self._enc_lib = h, lib
+        scol, _keep = got
+        return self._enc_lib.b2f_encoder_codes(self._enc, len(batch), scol, ptr(codes), NATIVE_THREADS) == 0
 
     def statistics(self, batch: pd.DataFrame):
         """-> (p float64, stat float64, flags int32), each in ``self.features`` order."""

@@ -20,6 +20,7 @@ when a reference table is supplied; without one every score is 0.0.
 from __future__ import annotations
 
 import os
+import threading
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -64,6 +65,7 @@ class B200Model:
         self.replicas = [_Replica(self.encoder, e, outlier_blob is not None, self.numeric_features) for e in engines]
         # the columnar request pipeline of the first GPU (csrc/scorer.h): created on first use
         self._scorer = None
+        self._scorer_lock = threading.Lock()
         self.host_threads = int(os.environ.get("B200_HOST_THREADS", host_threads or 0))  # 0: half the CPUs of the GPU's NUMA node
         self._scorer_failed = os.environ.get("B200_SCORER", "1") == "0"
         self.last_timing = None  # seconds spent in the stages of the last large predict(): columns / first chunk / lists
@@ -90,6 +92,10 @@ class B200Model:
         return cls(flat, drift=drift, outlier_blob=blob, **kw)
 
     def close(self) -> None:
+        for r in self.replicas:
+            if r._scorer is not None:
+                r._scorer.close()
+                r._scorer = None
         if self._scorer is not None:
             self._scorer.close()
             self._scorer = None
@@ -131,7 +137,7 @@ class B200Model:
         """``pipeline.predict(df)`` (hard labels, 01-train-model.ipynb:290)."""
         return self.classes[np.array(self._score(df)[1])]
 
-    PIPELINE_MIN_ROWS = int(os.environ.get("B200_PIPELINE_MIN_ROWS", "129"))  # from here up a request goes through the columnar pipeline
+    PIPELINE_MIN_ROWS = int(os.environ.get("B200_PIPELINE_MIN_ROWS", "1"))  # from here up a request goes through the columnar pipeline
 
     def _pipeline(self, df: pd.DataFrame):
         """Large requests on one GPU: the DataFrame's column buffers go to the native scorer in ONE call; chunks come back while
@@ -154,6 +160,12 @@ class B200Model:
         sc = self._scorer
         n = len(df)
         full = self.outlier_blob is not None
+        with self._scorer_lock:  # one job at a time per scorer: concurrent predict() calls on one model take turns
+            return self._pipeline_locked(sc, df, n, full, cols, t0)
+
+    def _pipeline_locked(self, sc, df, n, full, cols, t0):
+        import time
+
         if full:
             _reject_nan(df, self.numeric_features)
         t1 = time.perf_counter()
@@ -221,10 +233,33 @@ class _Replica:
 
     def __init__(self, encoder: RowEncoder, engine: ForestEngine, has_outlier: bool = False, numeric_features=()):
         self.encoder, self.engine, self.has_outlier, self.numeric_features = encoder, engine, has_outlier, list(numeric_features)
+        self._scorer, self._scorer_failed = None, os.environ.get("B200_SCORER", "1") == "0"
+
+    def _scorer_for(self):
+        if self._scorer is None and not self._scorer_failed:
+            try:
+                self._scorer = self.engine.scorer(self.encoder, int(os.environ.get("B200_HOST_THREADS", "0")))
+            except Exception:
+                self._scorer_failed = True
+        return self._scorer
 
     def score(self, df: pd.DataFrame):
         """-> (proba1 float64 (n,), is_outlier int32 (n,) or None)."""
         n = len(df)
+        sc = self._scorer_for() if n else None
+        cols = self.encoder.frame_columns(df) if sc is not None else None
+        if cols is not None:
+            # the columnar request pipeline (csrc/scorer.h): column buffers -> encode threads -> H2D -> kernel(s) -> D2H
+            if self.has_outlier:
+                _reject_nan(df, self.numeric_features)
+            n_chunks = sc.start(n, cols, out_mode=3 if self.has_outlier else 1,
+                                fmt=(1 if self.encoder.packed_ok else 0) if self.has_outlier else None)
+            for c in range(n_chunks):  # chunks ride different streams: each has its own completion event
+                sc.wait(c)
+            out = sc.results()
+            if self.has_outlier:
+                return np.array(out["proba1"], dtype=np.float64), np.array(out["is_outlier"])
+            return np.array(out, dtype=np.float64), None
         packed = self.encoder.packed_ok and n > self.encoder.SMALL_BATCH
         rows, proba, _ = self.engine.staging(n, packed=packed)
         if packed:

@@ -188,6 +188,17 @@ class _BoundedLogPool:
         return self._pool.submit(run)
 
 
+def _as_list(a: np.ndarray) -> list:
+    """ndarray -> list; large float64 / int32 results go through the recycling list builder (``_pylists.py``)."""
+    if len(a) >= 256 and a.ndim == 1 and a.dtype in (np.float64, np.int32):
+        from ._pylists import ListBuilder
+
+        b = ListBuilder(len(a))
+        b.fill(0, a)
+        return b.items
+    return a.tolist()
+
+
 def _log_record(kind: str, request_id: str, payload) -> None:
     logging.info(json.dumps({"service_name": _service_name(), "type": kind, "request_id": request_id, "data": payload}))
 
@@ -243,8 +254,8 @@ def create_app(model=None, loader=None) -> FastAPI:
         finally:
             drift_scores = (await pending) if pending is not None else [0.0] * len(ALL_FEATURES)
         model_output = {
-            "predictions": proba.tolist(),
-            "outliers": flags.tolist() if flags is not None else [0] * len(input_df),
+            "predictions": _as_list(proba),
+            "outliers": _as_list(flags) if flags is not None else [0] * len(input_df),
             "feature_drift_batch": dict(zip(ALL_FEATURES, drift_scores)),
         }
         log_pool.submit(_log_record, "ModelOutput", request_id, model_output)

@@ -195,6 +195,9 @@ void b2f_encoder_destroy(b2f_encoder *e);
  * Returns B2F_ERANGE if a value is infinite / overflows float32 (rows_out is then unspecified). */
 /* give the encoder the forest's split-value tables (copied): b2f_encoder_encode then accepts B2F_ROWS_RANKED */
 int b2f_encoder_attach_ranker(b2f_encoder *e, const b2f_ranker *r);
+/* category codes only, column-major (codes_out[j * n + i]): -1 = not in the vocabulary, nulls take the feature's null code.
+ * The drift detector (b2f_drift_score) takes its categorical columns in this form. */
+int b2f_encoder_codes(const b2f_encoder *e, int64_t n, const b2f_str_column *cat_cols, int32_t *codes_out, int threads);
 int b2f_encoder_encode(const b2f_encoder *e, int64_t n, const b2f_str_column *cat_cols, const double *const *num_cols,
                        const int64_t *num_strides, int row_format, void *rows_out, int threads);
 

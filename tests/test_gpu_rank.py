@@ -173,3 +173,46 @@ def test_scorer_c_abi_directly(curated, rf100d6):
             sc.close()
     finally:
         eng.close()
+
+
+def test_schema_with_fewer_categoricals(curated):
+    """A model with 7 categorical and 11 numeric features (round-1 advisor finding: the packed 64-byte row is decoded for
+    exactly nine categoricals).  Such a model is never offered packed rows; 96-byte rows, ranked rows and the plugin call on
+    more than 128 rows all agree with the library."""
+    from sklearn.compose import ColumnTransformer
+    from sklearn.ensemble import RandomForestClassifier
+    from sklearn.impute import SimpleImputer
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import OneHotEncoder
+
+    from databricks_kubernetes_mlops_poc_b200 import _cabi
+    from databricks_kubernetes_mlops_poc_b200.model import B200Model
+    from oracle import reference_pipeline as rp
+
+    cat, num = rp.CATEGORICAL_FEATURES[:7], rp.NUMERIC_FEATURES[:11]
+    catp = Pipeline([("imputer", SimpleImputer(strategy="constant", fill_value="missing")), ("ohe", OneHotEncoder(handle_unknown="ignore"))])
+    nump = Pipeline([("imputer", SimpleImputer(strategy="median"))])
+    pipe = Pipeline([("preprocessor", ColumnTransformer([("categorical", catp, cat), ("numeric", nump, num)])),
+                     ("classifier", RandomForestClassifier(n_estimators=30, max_depth=6, random_state=0, n_jobs=-1))])
+    tr = curated.iloc[:4000]
+    pipe.fit(tr[cat + num], tr[rp.TARGET].to_numpy())
+    df = curated[cat + num].iloc[4000:4700]
+    want = pipe.predict_proba(df)[:, 1]
+    model = B200Model.from_pipeline(pipe, devices=[0])
+    try:
+        eng, enc = model.engine, model.encoder
+        assert not enc.packed_ok and not eng.info()["packed_ok"] and eng.info()["rank_ok"]
+        rows = enc.encode_frame(df)
+        p, _ = eng.predict_rows(rows, np.float64)
+        assert np.abs(p - want).max() <= TOL64
+        p, _ = eng.predict_rows(enc.rank_rows(rows), np.float64)
+        assert np.abs(p - want).max() <= TOL64
+        bad = np.zeros((4, 16), dtype=np.uint32)
+        out = np.zeros(4, dtype=np.float64)
+        assert _cabi.load_library().b2f_predict_ex(eng.handle, _cabi.ptr(bad), 4, _cabi.ROWS_PACKED64, _cabi.ptr(out), 1, None) == -1
+        got = model.predict(df)["predictions"]  # 700 rows: the columnar pipeline, ranked rows
+        assert model.last_timing is not None and np.abs(np.asarray(got) - want).max() <= TOL64
+        small = model.predict(df.iloc[:5])["predictions"]
+        assert np.abs(np.asarray(small) - want[:5]).max() <= TOL64
+    finally:
+        model.close()
