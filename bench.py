@@ -742,8 +742,17 @@ def latency_sweep(args, dist: Dist, name: str, full: bool = False):
     eng, enc = model.engine, model.encoder
     n_max = 65536
     vocabs, codes, nums = training.synth_arrays(base, n_max, DATA_SEED + 1)
-    pk = eng.pinned("sweep_rows", n_max * 64).view(np.uint32, (n_max, 16))
-    enc.encode_arrays_packed(codes, nums, out=pk)
+    from databricks_kubernetes_mlops_poc_b200.engine import STREAMED_RANK_MIN_ROWS
+
+    pk64 = eng.pinned("sweep_rows", n_max * 64).view(np.uint32, (n_max, 16))
+    enc.encode_arrays_packed(codes, nums, out=pk64)
+    inf0 = eng.info()
+    rk = None
+    if inf0["rank_ok"]:  # ranked 32-byte rows: every size when the rank layout is resident, the large sizes when it streams
+        words = enc.ranked_row_words
+        rk = eng.pinned("sweep_rows_rk", n_max * words * 4).view(np.uint32, (n_max, words))
+        enc.rank_rows(enc.encode_arrays(codes, nums), out=rk)
+    rank_from = (STREAMED_RANK_MIN_ROWS if inf0["rank_stream"] else 0) if rk is not None else n_max + 1
     out = eng.pinned("sweep_out", n_max * 8).view(SCORED_DTYPE, (n_max,))
     df_all = training.arrays_to_frame(vocabs, codes, nums)[ALL_FEATURES]
     # parity of the plugin call at every sweep size against the library (float64 outputs)
@@ -752,6 +761,7 @@ def latency_sweep(args, dist: Dist, name: str, full: bool = False):
     parity = 0.0
     for n in (1, 16, 256, 4096, 65536):
         calls = (1000 if n <= 4096 else 200) if full else (200 if n <= 4096 else 50)
+        pk = rk if n >= rank_from else pk64
         for _ in range(20):
             eng.predict_pairs(pk[:n], out=out[:n])
         ts = np.empty(calls)
@@ -797,9 +807,11 @@ def latency_sweep(args, dist: Dist, name: str, full: bool = False):
             res[str(n)]["predict_full_p50_us"] = 1e6 * float(np.percentile(tp, 50))
             res[str(n)]["predict_full_p99_us"] = 1e6 * float(np.percentile(tp, 99))
         fullm.close()
-    return {"model": name, "walk": info["walk"], "tile_resident": info["tile_resident"], "rank_ok": info["rank_ok"], "split_max_rows": info["split_max_rows"],
+    return {"model": name, "walk": info["walk"], "tile_resident": info["tile_resident"], "rank_ok": info["rank_ok"], "rank_stream": info["rank_stream"],
+            "row_bytes_by_batch": {str(n): int((rk if n >= rank_from else pk64).shape[1] * 4) for n in (1, 16, 256, 4096, 65536)},
+            "split_max_rows": info["split_max_rows"],
             "parity_max_abs_dp_vs_sklearn": parity,
-            "api": "C ABI: b2f_predict_pairs on pinned 64-byte rows; plugin: B200Model.predict(DataFrame) -> dict, classifier only "
+            "api": "C ABI: b2f_predict_pairs on pinned pre-encoded rows; plugin: B200Model.predict(DataFrame) -> dict, classifier only "
                    "(predict_*)" + ("; predict_full_*: with the outlier forest + drift detector attached (the whole CustomModel.predict)" if full else ""),
             "batches": res}
 

@@ -69,6 +69,8 @@ class Info(C.Structure):
         ("launches_rank", C.c_int64),
         ("rank_smem_bytes", C.c_int32),
         ("rank_row_bytes", C.c_int32),
+        ("rank_stream", C.c_int32),
+        ("reserved2", C.c_int32),
     ]
 
 

@@ -158,6 +158,7 @@ struct b2f_model {
     void *d_rank_layout = nullptr;
     int rank_smem_bytes = 0;
     int rank_u = 4;
+    bool rank_stream = false; /* the rank layout streams through shared memory in pieces (too large to stay resident) */
     int64_t launches_rank = 0;
     void *d_blob = nullptr;
     int64_t forest_bytes = 0;
@@ -439,17 +440,17 @@ static bool build_tile_layout(const uint8_t *blob, const b2f_blob_header &h, uin
     return true;
 }
 
-template <int D, int U, typename OutT>
+template <int D, int U, bool ST, typename OutT>
 static cudaError_t rank_set_attr(int bytes) {
-    return cudaFuncSetAttribute(k_forest_predict_rank<D, U, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return cudaFuncSetAttribute(k_forest_predict_rank<D, U, ST, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
-template <int U>
+template <int U, bool ST>
 static cudaError_t rank_set_attr_all(int depth, int bytes) {
     cudaError_t e = cudaSuccess;
-#define RK_ATTR(DD)                                                    \
-    case DD:                                                           \
-        e = rank_set_attr<DD, U, float>(bytes);                        \
-        if (e == cudaSuccess) e = rank_set_attr<DD, U, double>(bytes); \
+#define RK_ATTR(DD)                                                        \
+    case DD:                                                               \
+        e = rank_set_attr<DD, U, ST, float>(bytes);                        \
+        if (e == cudaSuccess) e = rank_set_attr<DD, U, ST, double>(bytes); \
         break;
     switch (depth) {
         RK_ATTR(1) RK_ATTR(2) RK_ATTR(3) RK_ATTR(4) RK_ATTR(5) RK_ATTR(6) RK_ATTR(7) RK_ATTR(8)
@@ -466,12 +467,23 @@ static int rank_init(b2f_model *m, const uint8_t *blob) {
     const char *off = getenv("B2F_RANK");
     if (off && !strcmp(off, "0")) return B2F_OK;
     const int64_t layout_bytes = (int64_t)m->rk.layout.size();
-    const int64_t fixed = B2F_RANK_XS_BYTES /* alignment slack */ + (int64_t)B2F_RANK_PARTIALS * 32 * 8 + layout_bytes + 256;
-    int max_tiles = (int)std::min<int64_t>(B2F_RANK_MAX_TILES, ((int64_t)m->max_smem_optin - fixed) / B2F_RANK_XS_BYTES);
+    const int64_t base = B2F_RANK_XS_BYTES /* alignment slack */ + (int64_t)B2F_RANK_PARTIALS * 32 * 8 + 256;
+    int max_tiles = (int)std::min<int64_t>(B2F_RANK_MAX_TILES, ((int64_t)m->max_smem_optin - base - layout_bytes) / B2F_RANK_XS_BYTES);
     if (const char *mt = getenv("B2F_RANK_MAX_TILES")) max_tiles = std::min(max_tiles, std::max(1, atoi(mt)));
-    if (max_tiles < 4) return B2F_OK; /* forest too large to stay resident next to a useful number of row tiles */
+    /* resident while the whole layout fits next to a useful number of row tiles; otherwise it streams through a two-slot ring
+     * in pieces of 8 trees (2 groups of 4: warp w owns (tile w / 2, group w mod 2), so <= 16 tiles per round) */
+    m->rank_stream = max_tiles < 8;
+    if (const char *fs = getenv("B2F_RANK_STREAM")) m->rank_stream = atoi(fs) != 0;
+    int64_t forest_smem = layout_bytes;
     m->rank_u = 4;
     if (const char *ru = getenv("B2F_RANK_U")) m->rank_u = atoi(ru) == 8 ? 8 : 4;
+    if (m->rank_stream) {
+        m->rank_u = 4;
+        const int64_t piece = 8 * (int64_t)m->rk.tree_stride; /* n_trees_padded is a multiple of 8 */
+        forest_smem = 2 * piece;
+        max_tiles = (int)std::min<int64_t>(B2F_RANK_MAX_TILES, ((int64_t)m->max_smem_optin - base - forest_smem) / B2F_RANK_XS_BYTES);
+        if (max_tiles < 4 || piece % 16) return B2F_OK;
+    }
     CUDA_TRY(cudaMalloc(&m->d_rank_layout, (size_t)layout_bytes));
     CUDA_TRY(cudaMemcpy(m->d_rank_layout, m->rk.layout.data(), (size_t)layout_bytes, cudaMemcpyHostToDevice));
     RParams &rp = m->rp;
@@ -487,6 +499,9 @@ static int rank_init(b2f_model *m, const uint8_t *blob) {
     rp.row_bytes = m->rk.row_bytes;
     rp.cat_bytes = m->rk.cat_bytes;
     rp.max_tiles = max_tiles;
+    rp.groups_per_piece = 2;
+    rp.piece_bytes = 8u * m->rk.tree_stride;
+    rp.n_pieces = m->rk.n_trees_padded / 8;
     rp.init_raw = m->hdr.init_raw;
     rp.denom = m->hdr.denom;
     rp.threshold = m->hdr.threshold;
@@ -505,8 +520,11 @@ static int rank_init(b2f_model *m, const uint8_t *blob) {
         rp.cat_start[j] = (uint8_t)i;
         rp.cat_mask[j] |= 1ull << c;
     }
-    m->rank_smem_bytes = (int)(B2F_RANK_XS_BYTES + (int64_t)max_tiles * B2F_RANK_XS_BYTES + (int64_t)B2F_RANK_PARTIALS * 32 * 8 + layout_bytes);
-    CUDA_TRY(m->rank_u == 8 ? rank_set_attr_all<8>(rp.depth, m->rank_smem_bytes) : rank_set_attr_all<4>(rp.depth, m->rank_smem_bytes));
+    m->rank_smem_bytes = (int)(B2F_RANK_XS_BYTES + (int64_t)max_tiles * B2F_RANK_XS_BYTES + (int64_t)B2F_RANK_PARTIALS * 32 * 8 + forest_smem);
+    if (m->rank_stream)
+        CUDA_TRY((rank_set_attr_all<4, true>(rp.depth, m->rank_smem_bytes)));
+    else
+        CUDA_TRY(m->rank_u == 8 ? (rank_set_attr_all<8, false>(rp.depth, m->rank_smem_bytes)) : (rank_set_attr_all<4, false>(rp.depth, m->rank_smem_bytes)));
     m->rank_ok = true;
     return B2F_OK;
 }
@@ -767,6 +785,7 @@ extern "C" int b2f_model_info(const b2f_model *m, b2f_info *out) {
     out->launches_rank = m->launches_rank;
     out->rank_smem_bytes = m->rank_ok ? m->rank_smem_bytes : 0;
     out->rank_row_bytes = m->rk.row_bytes;
+    out->rank_stream = (m->rank_ok && m->rank_stream) ? 1 : 0;
     return B2F_OK;
 }
 
@@ -822,7 +841,7 @@ static cudaError_t launch_split(const b2f_model *m, cudaStream_t st, const void 
 
 /* the rank kernel goes out with programmatic stream serialization: back-to-back launches on one stream overlap the
  * next launch's prologue (forest fill) with this launch's tail; the kernel orders its own global accesses with griddepcontrol.wait */
-template <int D, int U, typename OutT>
+template <int D, int U, bool ST, typename OutT>
 static cudaError_t launch_rank_du(const b2f_model *m, cudaStream_t st, const void *rows, int64_t n, void *proba, int32_t *label, int ostride) {
     const int64_t n_tiles = (n + 31) / 32;
     cudaLaunchConfig_t cfg = {};
@@ -836,15 +855,16 @@ static cudaError_t launch_rank_du(const b2f_model *m, cudaStream_t st, const voi
     static const bool no_pdl = getenv("B2F_NO_PDL") != nullptr;
     cfg.attrs = attr;
     cfg.numAttrs = no_pdl ? 0 : 1;
-    return cudaLaunchKernelEx(&cfg, k_forest_predict_rank<D, U, OutT>, m->rp, static_cast<const uint8_t *>(rows), (long long)n,
+    return cudaLaunchKernelEx(&cfg, k_forest_predict_rank<D, U, ST, OutT>, m->rp, static_cast<const uint8_t *>(rows), (long long)n,
                               static_cast<OutT *>(proba), label, ostride);
 }
 template <typename OutT>
 static cudaError_t launch_rank(const b2f_model *m, cudaStream_t st, const void *rows, int64_t n, void *proba, int32_t *label, int ostride) {
-#define RK_CASE(DD)                                                                                         \
-    case DD:                                                                                                \
-        return m->rank_u == 8 ? launch_rank_du<DD, 8, OutT>(m, st, rows, n, proba, label, ostride)           \
-                              : launch_rank_du<DD, 4, OutT>(m, st, rows, n, proba, label, ostride);
+#define RK_CASE(DD)                                                                                                  \
+    case DD:                                                                                                         \
+        if (m->rank_stream) return launch_rank_du<DD, 4, true, OutT>(m, st, rows, n, proba, label, ostride);          \
+        return m->rank_u == 8 ? launch_rank_du<DD, 8, false, OutT>(m, st, rows, n, proba, label, ostride)             \
+                              : launch_rank_du<DD, 4, false, OutT>(m, st, rows, n, proba, label, ostride);
     switch (m->rp.depth) {
         RK_CASE(1) RK_CASE(2) RK_CASE(3) RK_CASE(4) RK_CASE(5) RK_CASE(6) RK_CASE(7) RK_CASE(8)
     }
@@ -861,7 +881,7 @@ static int check_row_format(const b2f_model *m, int fmt) {
     if (fmt == B2F_ROWS_RANKED) {
         if (!m->rank_ok)
             return set_err(B2F_EINVAL, "B2F_ROWS_RANKED is not available for this model (%s)",
-                           m->rk.ok ? "its rank layout does not stay resident in shared memory" : m->rk.why);
+                           m->rk.ok ? "its rank layout fits neither shared memory nor the streaming ring" : m->rk.why);
         return B2F_OK;
     }
     if (fmt != B2F_ROWS_PACKED64) return set_err(B2F_EINVAL, "unknown row format %d", fmt);

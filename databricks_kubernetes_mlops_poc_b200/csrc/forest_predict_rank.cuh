@@ -26,6 +26,10 @@
  *              size -- and leaves one float64 partial per (warp, tile) it touched;
  *   - phase 3  one thread per row adds that row's partials in warp order (fixed order: deterministic), aggregates
  *              (RF mean | GBDT expit | isolation-forest score) and stores probability + label, coalesced.
+ *   - STREAM = true (rank layouts larger than shared memory, e.g. 500 trees x depth 8 = 1.5 MB): the layout is cut into pieces of
+ *     8 trees (2 tree groups) that travel through a two-slot ring -- thread 0 issues the TMA copy of piece k + 2 right after the
+ *     barrier that ends piece k, so the copy overlaps the walk of piece k + 1 -- and warp w owns (tile w / 2, group w mod 2) of
+ *     EVERY piece: its float64 sum stays in a register across the whole forest (<= 16 tiles per round).
  *   - launched with programmatic stream serialization (PDL): `griddepcontrol.launch_dependents` is issued at entry so the next
  *     launch's CTAs take over SMs as this launch's CTAs retire (its forest fill and row staging overlap this launch's tail);
  *     `griddepcontrol.wait` sits before the first global access that could depend on the previous kernel.
@@ -55,6 +59,9 @@ struct RParams {
     int32_t row_bytes;       /* multiple of 8 */
     int32_t cat_bytes;       /* 4 or 8 */
     int32_t max_tiles;       /* tiles per round (<= B2F_RANK_MAX_TILES, what shared memory allows) */
+    int32_t n_pieces;        /* STREAM: pieces per pass over the forest; piece = groups_per_piece tree groups, piece_bytes bytes */
+    int32_t groups_per_piece;
+    uint32_t piece_bytes;
     double init_raw;
     double denom;
     double threshold;
@@ -105,12 +112,12 @@ __device__ __forceinline__ void rank_walk_group(uint32_t t0, uint32_t tree_strid
     for (int u = 0; u < U; ++u) acc += lds_f64(at[u] + at[u] + k4[u] + 4u - (4u << D));
 }
 
-template <int D, int U, typename OutT>
+template <int D, int U, bool STREAM, typename OutT>
 __global__ void __launch_bounds__(B2F_RANK_THREADS, 1)
     k_forest_predict_rank(const __grid_constant__ RParams p, const uint8_t *__restrict__ rows, long long n, OutT *__restrict__ proba,
                           int32_t *__restrict__ label, int ostride) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t forest_bar;
+    __shared__ __align__(8) uint64_t forest_bar[2]; /* resident: [0] = the whole layout; STREAM: one per ring slot */
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -118,23 +125,32 @@ __global__ void __launch_bounds__(B2F_RANK_THREADS, 1)
 
     pdl_launch_dependents(); /* the next launch may start filling SMs as this one's CTAs retire */
 
-    /* shared-memory plan: [xs: max_tiles x 8 KB value blocks, 8 KB aligned][partials][forest] */
+    /* shared-memory plan: [xs: max_tiles x 8 KB value blocks, 8 KB aligned][partials][forest | two-slot piece ring] */
     const uint32_t pad = (B2F_RANK_XS_BYTES - (smem_addr(smem) & (B2F_RANK_XS_BYTES - 1u))) & (B2F_RANK_XS_BYTES - 1u);
     uint8_t *xs_all = smem + pad;
     double *partial = reinterpret_cast<double *>(xs_all + (size_t)p.max_tiles * B2F_RANK_XS_BYTES);
     uint8_t *forest = reinterpret_cast<uint8_t *>(partial + B2F_RANK_PARTIALS * 32);
 
     if (tid == 0) {
-        mbar_init(&forest_bar, 1);
+        mbar_init(&forest_bar[0], 1);
+        mbar_init(&forest_bar[1], 1);
         fence_mbar_init();
         fence_proxy_async();
-        /* the forest is launch-invariant (never written by a kernel): safe to fetch before griddepcontrol.wait */
-        mbar_arrive_expect_tx(&forest_bar, p.layout_bytes);
-        for (uint32_t o = 0; o < p.layout_bytes; o += B2F_BULK_PIECE) {
-            const uint32_t part = min(B2F_BULK_PIECE, p.layout_bytes - o);
-            tma_bulk_g2s(forest + o, p.layout + o, part, &forest_bar);
+        if constexpr (!STREAM) {
+            /* the forest is launch-invariant (never written by a kernel): safe to fetch before griddepcontrol.wait */
+            mbar_arrive_expect_tx(&forest_bar[0], p.layout_bytes);
+            for (uint32_t o = 0; o < p.layout_bytes; o += B2F_BULK_PIECE) {
+                const uint32_t part = min(B2F_BULK_PIECE, p.layout_bytes - o);
+                tma_bulk_g2s(forest + o, p.layout + o, part, &forest_bar[0]);
+            }
         }
     }
+    /* STREAM: piece k (counted over all rounds) lands in slot k mod 2; issued by thread 0 only */
+    auto issue_piece = [&](uint32_t k) {
+        const uint32_t slot = k & 1u, piece = k % (uint32_t)p.n_pieces;
+        mbar_arrive_expect_tx(&forest_bar[slot], p.piece_bytes);
+        tma_bulk_g2s(forest + slot * p.piece_bytes, p.layout + (size_t)piece * p.piece_bytes, p.piece_bytes, &forest_bar[slot]);
+    };
 
     /* this CTA's run of tiles (32-bit arithmetic: n < 2^31 rows) */
     const uint32_t n_tiles = (uint32_t)((n + 31) >> 5);
@@ -191,10 +207,49 @@ __global__ void __launch_bounds__(B2F_RANK_THREADS, 1)
                 }
             }
         }
+        if constexpr (STREAM) {
+            /* the first two pieces of this pass: both ring slots are free (every warp is past the previous pass's last barrier) */
+            if (tid == 0) {
+                issue_piece(round * (uint32_t)p.n_pieces);
+                if (p.n_pieces > 1) issue_piece(round * (uint32_t)p.n_pieces + 1u);
+            }
+        }
         __syncthreads();
-        if (!forest_ready) {
-            mbar_wait(&forest_bar, 0);
-            forest_ready = true;
+        if constexpr (!STREAM) {
+            if (!forest_ready) {
+                mbar_wait(&forest_bar[0], 0);
+                forest_ready = true;
+            }
+        }
+
+        if constexpr (STREAM) {
+            /* ---- phase 2 (streamed): warp w owns (tile w / GP, group w mod GP) of every piece; the sum stays in a register ---- */
+            const int GP = p.groups_per_piece;
+            const bool mine = warp < T * GP;
+            const uint32_t xs_lane = xs_addr + (uint32_t)(warp / GP) * B2F_RANK_XS_BYTES + (uint32_t)lane * 4u;
+            const uint32_t g_off = (uint32_t)(warp % GP) * U * p.tree_stride;
+            double acc = 0.0;
+            for (int piece = 0; piece < p.n_pieces; ++piece) {
+                const uint32_t k = round * (uint32_t)p.n_pieces + (uint32_t)piece;
+                mbar_wait(&forest_bar[k & 1u], (k >> 1) & 1u);
+                if (mine) rank_walk_group<D, U>(forest_addr + (k & 1u) * p.piece_bytes + g_off, p.tree_stride, xs_lane, p.mul_two, p.mul_64k, p.add_64k, acc);
+                __syncthreads(); /* every warp is done with this slot: refill it while the other slot is walked */
+                if (tid == 0 && piece + 2 < p.n_pieces) issue_piece(k + 2u);
+            }
+            if (mine) partial[warp * 32 + lane] = acc;
+            __syncthreads();
+            for (int r = tid; r < n_rows; r += B2F_RANK_THREADS) {
+                const int t = r >> 5, ln = r & 31;
+                double s = p.agg_mode == B2F_AGG_GBDT_LOGISTIC ? p.init_raw : 0.0;
+                for (int g = 0; g < GP; ++g) s += partial[(t * GP + g) * 32 + ln];
+                double p1;
+                int lab;
+                aggregate(p.agg_mode, p.agg_mode == B2F_AGG_GBDT_LOGISTIC ? 0.0 : p.init_raw, p.denom, p.threshold, s, p1, lab);
+                const long long row = row0 + r;
+                if (proba) proba[row * ostride_p(ostride)] = (OutT)p1;
+                if (label) label[row * ostride_l(ostride)] = lab;
+            }
+            continue;
         }
 
         /* ---- phase 2: walk.  units = T x groups, warp w takes [w * units / 32, (w + 1) * units / 32) ---- */
@@ -233,5 +288,7 @@ __global__ void __launch_bounds__(B2F_RANK_THREADS, 1)
             if (label) label[row * ostride_l(ostride)] = lab;
         }
     }
-    if (!forest_ready) mbar_wait(&forest_bar, 0); /* never retire a CTA while a bulk copy into its shared memory is in flight */
+    if constexpr (!STREAM) {
+        if (!forest_ready) mbar_wait(&forest_bar[0], 0); /* never retire a CTA while a bulk copy into its shared memory is in flight */
+    }
 }

@@ -253,6 +253,9 @@ class ForestEngine:
         return out.reshape(ROW_WORDS, 3)
 
 
+STREAMED_RANK_MIN_ROWS = 16384  # below this a streamed rank layout loses to the float32-row latency kernels
+
+
 class Scorer:
     """Owner of a ``b2f_scorer*``: DataFrame columns -> encode (worker threads, pinned staging) -> H2D -> kernel -> D2H,
     chunk by chunk (``csrc/scorer.h``).  One job at a time."""
@@ -263,12 +266,15 @@ class Scorer:
         h_enc = encoder._native_handle()
         if h_enc is None:
             raise B2FError("the native row encoder is not available")
-        self.fmt = ROWS_WORDS24
-        if encoder.ranked_ok and engine.info()["rank_ok"] and self._lib.b2f_encoder_attach_ranker(h_enc, encoder._ranker) == 0:
+        self.fmt = self.fmt_small = ROWS_PACKED64 if encoder.packed_ok else ROWS_WORDS24
+        self.rank_min_rows = 0
+        info = engine.info()
+        if encoder.ranked_ok and info["rank_ok"] and self._lib.b2f_encoder_attach_ranker(h_enc, encoder._ranker) == 0:
             encoder._ranker_attached = True
             self.fmt = ROWS_RANKED  # 32-byte ranked rows: half the PCIe bytes, integer-compare kernel
-        elif encoder.packed_ok:
-            self.fmt = ROWS_PACKED64
+            # a forest whose rank layout STREAMS through shared memory pays a full pass over it per launch: small requests keep
+            # the float32 rows and the latency kernels (split / warp-per-row), large ones take the ranked rows
+            self.rank_min_rows = STREAMED_RANK_MIN_ROWS if info["rank_stream"] else 0
         self._h = self._lib.b2f_scorer_create(engine.handle, h_enc, int(threads))
         if not self._h:
             raise B2FError(f"b2f_scorer_create failed: {_cabi.last_error()}")
@@ -288,7 +294,10 @@ class Scorer:
     def start(self, n: int, columns, out_mode: int = 1, chunk_rows: int = 0, fmt: int | None = None) -> int:
         """``columns``: what ``RowEncoder.frame_columns`` returned.  -> number of chunks."""
         scol, ptrs, strides, _keep = columns
-        rc = self._lib.b2f_scorer_start(self._h, n, scol, ptrs, ptr(strides), self.fmt if fmt is None else fmt, out_mode, chunk_rows)
+        if fmt is None:
+            fmt = self.fmt if n >= self.rank_min_rows else self.fmt_small
+        self.last_fmt = fmt
+        rc = self._lib.b2f_scorer_start(self._h, n, scol, ptrs, ptr(strides), fmt, out_mode, chunk_rows)
         if rc == -7:
             raise ValueError("Input X contains infinity or a value too large for dtype('float32').")
         if rc < 0:

@@ -190,7 +190,7 @@ class B200Model:
         preds, flags = preds.items, (flags.items if full else None)
         t2 = time.perf_counter()
         self.last_timing = {"columns_s": t1 - t0, "first_chunk_s": (t_first or t2) - t1, "chunks_and_lists_s": t2 - t1, "chunks": n_chunks,
-                            "threads": sc.threads, "row_format": sc.fmt if not full else 1}
+                            "threads": sc.threads, "row_format": sc.last_fmt}
         return preds, flags
 
     def predict(self, model_input) -> dict:

@@ -128,6 +128,8 @@ typedef struct b2f_info {
     int64_t launches_rank;  /* ... of which the rank kernel */
     int32_t rank_smem_bytes; /* dynamic shared memory per CTA of the rank kernel */
     int32_t rank_row_bytes;  /* bytes per ranked row */
+    int32_t rank_stream;     /* the rank layout streams through shared memory piece by piece (too large to stay resident) */
+    int32_t reserved2;
 } b2f_info;
 
 /* ---- library / device ------------------------------------------------------------------ */

@@ -107,8 +107,11 @@ def test_cfg3_500d8_at_the_sweep_sizes(bench_mod, name):
     pk = enc.pack_rows(rows24)
     eng = ForestEngine(flat, 0)
     try:
+        info = eng.info()
+        assert info["rank_ok"] and info["rank_stream"], "500 x depth-8: the rank layout (1.5 MB) streams through shared memory"
+        rk = enc.rank_rows(rows24)
         for n in (1, 16, 256, 4096, 65536):
-            for rows in (rows24, pk):
+            for rows in (rows24, pk, rk):
                 p, l = eng.predict_rows(rows[:n], np.float64)
                 assert np.abs(p - want_p[:n]).max() <= TOL64 and (l == want_l[:n]).all(), (name, n, rows.shape[1])
     finally:
