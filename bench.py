@@ -283,6 +283,32 @@ def cpu_port_rate(pipe, codes, nums, repeats: int):
     return len(codes) / min(times)
 
 
+def cpu_bandwidth() -> float:
+    """CPUs the container may burn (cgroup CFS quota / period), 0.0 when unlimited.  The B200 boxes give a 128-CPU host a quota
+    of 16: more busy workers than that (forked sklearn processes, polling encoder threads) get the whole cgroup throttled."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        return 0.0 if q == "max" else float(q) / float(per)
+    except (OSError, ValueError):
+        pass
+    try:
+        q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        return q / per if q > 0 and per > 0 else 0.0
+    except (OSError, ValueError):
+        return 0.0
+
+
+def reference_procs(kind: str) -> int:
+    """Worker processes of the reference arm: RF threads itself (n_jobs=-1, as the reference sets it); a GBDT is single-threaded
+    in sklearn, so the batch is split over forked processes -- as many as the host has CPUs, at most 64, at most the quota."""
+    if kind == "rf":
+        return 1
+    cores = os.cpu_count() or 1
+    bw = cpu_bandwidth()
+    return max(1, min(cores, 64, int(bw) if bw >= 1.0 else cores))
+
+
 # ----------------------------------------------------------------------------- arms
 def run_reference(args, dist: Dist):
     """--impl reference: the reference-style CPU path (sklearn Pipeline.predict_proba, the library the
@@ -298,7 +324,7 @@ def run_reference(args, dist: Dist):
     cores = os.cpu_count() or 1
     vocabs, codes, nums = training.synth_arrays(base, BATCH, DATA_SEED)
     df = training.arrays_to_frame(vocabs, codes, nums)[ALL_FEATURES]
-    procs = 1 if kind == "rf" else min(cores, 64)  # RF threads itself (n_jobs=-1, as the reference sets it)
+    procs = reference_procs(kind)
     K = max(args.steps, 1)
     _, _, t_probe = cpu_reference_rate(pipe, df, 1, procs)
     rows = BATCH
@@ -316,7 +342,7 @@ def run_reference(args, dist: Dist):
         "dtype": "f32cmp+f64acc", "data": "synthetic",
         "config": {"workload": workload_label(args.model), "batch": BATCH, "forest": args.model, "rows_per_step": rows},
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores if procs == 1 else procs, "kind": "reference", "sample": sample,
-                         "host_cores": cores, "best": best, "mean": rows / statistics.mean(times)},
+                         "host_cores": cores, "cpu_quota": cpu_bandwidth(), "best": best, "mean": rows / statistics.mean(times)},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "api": "sklearn Pipeline.predict_proba(DataFrame) -> ndarray (what the reference's CustomModel.predict calls, 02-register-model.ipynb:335-337)"},
         "gpu_launches": 0,
@@ -325,12 +351,25 @@ def run_reference(args, dist: Dist):
 
 
 def host_thread_share(dist: Dist) -> int:
-    """Encoder threads for this rank: the physical cores of one socket shared by the ranks that sit on it."""
+    """Encoder threads for this rank: the library's default for one GPU (the GPU's NUMA node, capped by the container's CPU
+    bandwidth -- `b2f_host_threads_default`), and under torchrun this rank's share of the node's cores / of that bandwidth."""
+    env = os.environ.get("B200_HOST_THREADS")
+    if env:
+        return int(env)
+    if dist.world == 1:
+        return 0  # the library's default
+    from databricks_kubernetes_mlops_poc_b200 import _cabi
+
+    lib = _cabi.load_library()
     cores = os.cpu_count() or 2
     per_node = max(1, cores // 2 // 2)  # two sockets, two hyper-threads per core on the B200 hosts
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(dist.world)))
     ranks_per_node = max(1, (local_world + 1) // 2)
-    return int(os.environ.get("B200_HOST_THREADS", str(max(2, min(32, per_node // ranks_per_node)))))
+    share = per_node // ranks_per_node
+    limit = float(lib.b2f_host_cpu_limit())
+    if limit > 0:
+        share = min(share, int(limit) // local_world - 1)
+    return max(1, min(32, share))
 
 
 def run_b200(args, dist: Dist):
@@ -563,7 +602,7 @@ def run_b200(args, dist: Dist):
 
         kind = MODELS[args.model][0]
         cores = os.cpu_count() or 1
-        procs = 1 if kind == "rf" else min(cores, 64)
+        procs = reference_procs(kind)
         best, med, times = cpu_reference_rate(pipe, df0, 5, procs)
         one_best, _, _ = cpu_reference_rate(pipe, df0.iloc[:16384], 2, 1) if procs > 1 else (best, None, None)
         port = cpu_port_rate(pipe, pc, pn, 5)
@@ -572,7 +611,7 @@ def run_b200(args, dist: Dist):
             "sample": (f"5 x the {BATCH}-row cfg2 DataFrame through sklearn {sklearn.__version__} Pipeline.predict_proba, "
                        f"{'n_jobs=-1 threads' if procs == 1 else str(procs) + ' forked processes'}; median"),
             "best": best, "single_process": one_best,
-            "port_openmp_rows_per_s": port, "host_cores": cores,
+            "port_openmp_rows_per_s": port, "host_cores": cores, "cpu_quota": cpu_bandwidth(),
         }
 
     avg_launch_ms = ms_total_max / K  # the kernel is the only work of the timed region: region time / launches

@@ -74,6 +74,47 @@ static void bind_thread_near(int device) {
     if (!off && numa_cpus_of_device(device, &set)) pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
 }
 
+/* CPUs this process may actually burn: the cgroup's CFS bandwidth (v2 cpu.max "quota period", v1 cpu.cfs_quota_us /
+ * cpu.cfs_period_us) next to its affinity mask.  A pool of polling workers larger than the quota gets the WHOLE cgroup
+ * throttled for the rest of the 100 ms period -- measured on the GPU boxes (cpu.max = 1600000 100000 on a 128-CPU host): with 48
+ * workers 2 % of the 65 536-row requests took 55-75 ms instead of 0.6 (profiles/r02_e2e_stalls.json).  0 = no limit found. */
+static double cgroup_cpu_limit() {
+    double best = 0.0;
+    if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        char q[32] = "";
+        long long period = 0;
+        if (fscanf(f, "%31s %lld", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0) best = (double)atoll(q) / (double)period;
+        fclose(f);
+    }
+    if (best <= 0.0) {
+        long long quota = -1, period = 0;
+        if (FILE *f = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) {
+            if (fscanf(f, "%lld", &quota) != 1) quota = -1;
+            fclose(f);
+        }
+        if (FILE *f = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) {
+            if (fscanf(f, "%lld", &period) != 1) period = 0;
+            fclose(f);
+        }
+        if (quota > 0 && period > 0) best = (double)quota / (double)period;
+    }
+    return best;
+}
+
+/* worker threads a scorer may start by default: the GPU's NUMA node (its cores and half of their hyper-threads), capped at 48
+ * and at the cgroup's CPU bandwidth minus two (the caller's thread builds the response while the workers encode) */
+static int default_host_threads(int device) {
+    cpu_set_t set;
+    int local = numa_cpus_of_device(device, &set) ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+    int threads = std::max(1, std::min(48, local * 3 / 4));
+    const double lim = cgroup_cpu_limit();
+    if (lim > 0.0) threads = std::max(1, std::min(threads, (int)lim - 2));
+    return threads;
+}
+
+extern "C" double b2f_host_cpu_limit(void) { return cgroup_cpu_limit(); }
+extern "C" int b2f_host_threads_default(int device) { return default_host_threads(device); }
+
 /* page-locked host memory whose pages sit on the GPU's NUMA node: allocated from a thread bound to that node's CPUs */
 static void *pinned_alloc_near(int device, size_t nbytes) {
     void *p = nullptr;
@@ -289,9 +330,7 @@ extern "C" b2f_scorer *b2f_scorer_create(b2f_model *m, const b2f_encoder *e, int
     s->m = m;
     s->e = e;
     if (threads <= 0) {
-        cpu_set_t set;
-        int local = numa_cpus_of_device(m->device, &set) ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
-        threads = std::max(1, std::min(48, local * 3 / 4)); /* the node's cores and half of their hyper-threads */
+        threads = default_host_threads(m->device);
     }
     s->n_threads = std::min(threads, 64);
     if (const char *sp = getenv("B200_SPIN_US")) s->spin_us = std::max(0, atoi(sp));

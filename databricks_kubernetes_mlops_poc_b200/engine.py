@@ -8,6 +8,7 @@ purposes of ``predict_proba(...)[:, 1]`` / ``predict`` (``:335-337``).  No CPU f
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -253,6 +254,7 @@ class ForestEngine:
         return out.reshape(ROW_WORDS, 3)
 
 
+_FMT_OVERRIDE = {"ranked": ROWS_RANKED, "packed64": ROWS_PACKED64}.get(os.environ.get("B200_SCORER_ROWS", ""))  # experiments
 STREAMED_RANK_MIN_ROWS = 16384  # below this a streamed rank layout loses to the float32-row latency kernels
 
 
@@ -296,6 +298,8 @@ class Scorer:
         scol, ptrs, strides, _keep = columns
         if fmt is None:
             fmt = self.fmt if n >= self.rank_min_rows else self.fmt_small
+            if _FMT_OVERRIDE is not None and fmt != ROWS_WORDS24:
+                fmt = _FMT_OVERRIDE if (_FMT_OVERRIDE != ROWS_RANKED or self.fmt == ROWS_RANKED) else fmt
         self.last_fmt = fmt
         rc = self._lib.b2f_scorer_start(self._h, n, scol, ptrs, ptr(strides), fmt, out_mode, chunk_rows)
         if rc == -7:

@@ -244,7 +244,12 @@ void b2f_pinned_free_striped(void *p);
  *      (bound to the GPU's NUMA node) straight into pinned staging, copied, scored and copied back while the next chunk is being
  *      encoded; results are collected chunk by chunk so the caller can build its output list while the tail is in flight. */
 typedef struct b2f_scorer b2f_scorer;
-b2f_scorer *b2f_scorer_create(b2f_model *m, const b2f_encoder *e, int threads /* 0 = three quarters of the CPUs of the GPU's NUMA node, <= 48 */);
+b2f_scorer *b2f_scorer_create(b2f_model *m, const b2f_encoder *e, int threads /* 0 = b2f_host_threads_default(the model's device) */);
+/* the default size of a scorer's thread pool: three quarters of the CPUs of the GPU's NUMA node, at most 48, and at most the
+ * cgroup's CPU bandwidth minus two (b2f_host_cpu_limit: cpu.max quota / period, 0.0 when unlimited) -- polling workers beyond
+ * the quota get the whole container throttled */
+int b2f_host_threads_default(int device);
+double b2f_host_cpu_limit(void);
 void b2f_scorer_destroy(b2f_scorer *s);
 /* out_mode: 0 = float proba1, 1 = double proba1, 3 = b2f_scored_full records (attached outlier forest; float32 row formats only).
  * chunk_rows 0 = choose.  Returns the number of chunks (>= 0) or a negative error; one job at a time per scorer; the column
