@@ -368,7 +368,7 @@ def host_thread_share(dist: Dist) -> int:
     share = per_node // ranks_per_node
     limit = float(lib.b2f_host_cpu_limit())
     if limit > 0:
-        share = min(share, int(limit) // local_world - 1)
+        share = min(share, (int(limit) - 2 * local_world) // local_world)
     return max(1, min(32, share))
 
 
@@ -629,7 +629,7 @@ def run_b200(args, dist: Dist):
             "walk": info0["walk"], "row_format": f"{fmt_name}: {row_bytes}-byte encoded rows",
             "kernel": kernel_used,
         },
-        "e2e": {"value": plugin_value, "unit": "rows/s", "h2d_bytes_per_step": BATCH * (info0["rank_row_bytes"] if info0["rank_ok"] else 64),
+        "e2e": {"value": plugin_value, "unit": "rows/s", "h2d_bytes_per_step": BATCH * {2: info0["rank_row_bytes"], 1: 64, 0: 96}[(breakdown or {}).get("row_format", 1)],
                 "d2h_bytes_per_step": BATCH * 8, "ms_per_step": 1e3 * dist.max(plugin_s) / K,
                 "p50_ms": 1e3 * float(np.percentile(plat, 50)), "p99_ms": 1e3 * float(np.percentile(plat, 99)),
                 "slowest_steps_ms": [round(1e3 * v, 3) for v in sorted(plat)[-5:]], "sum_of_steps_ms": 1e3 * float(np.sum(plat)),

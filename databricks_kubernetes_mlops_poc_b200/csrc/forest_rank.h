@@ -56,6 +56,8 @@ struct b2f_ranktab {
 };
 int b2f_simd_level(void);
 void b2f_simd_rank_column(const b2f_ranktab *t, const float *x, int64_t n, int64_t x_stride, uint16_t *out, int64_t out_stride, uint16_t nan_rank);
+int b2f_simd_cvt_column(const double *src, int64_t stride, int64_t n, float *dst); /* float64 -> float32; 1 = an inf / overflow was seen */
+void b2f_simd_pack_rows64(const int32_t *codes, const float *cols, int64_t ld, int n_cat, int n_num, int64_t nb, uint32_t *out);
 }
 
 #define B2F_RANK_BLOCK 256 /* rows ranked per call of the column kernel (the transposed block stays in L1) */

@@ -107,4 +107,106 @@ void b2f_simd_rank_column(const b2f_ranktab *t, const float *x, int64_t n, int64
     }
 }
 
+/* ---- float64 column -> float32 block (round to nearest even, as numpy astype(float32)); returns 1 when some value is +-inf
+ *      or a finite float64 beyond float32 (sklearn raises ValueError there), NaN passes through (the kernel imputes) ---- */
+static int cvt_column_scalar(const double *src, int64_t stride, int64_t n, float *dst) {
+    int bad = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const double v = src[i * stride];
+        const float f = (float)v;
+        if (!(v != v) && !isfinite(f)) bad = 1;
+        dst[i] = f;
+    }
+    return bad;
+}
+
+__attribute__((target("avx512f"))) static int cvt_column_avx512(const double *src, int64_t n, float *dst) {
+    const __m512i absmask = _mm512_set1_epi32(0x7fffffff), inf = _mm512_set1_epi32(0x7f800000);
+    __mmask16 bad = 0;
+    int64_t i = 0;
+    for (; i + 16 <= n; i += 16) {
+        const __m256 a = _mm512_cvtpd_ps(_mm512_loadu_pd(src + i)), b = _mm512_cvtpd_ps(_mm512_loadu_pd(src + i + 8));
+        const __m512 f = _mm512_castpd_ps(_mm512_insertf64x4(_mm512_castpd256_pd512(_mm256_castps_pd(a)), _mm256_castps_pd(b), 1));
+        /* |f| == inf: the source was +-inf or overflowed; a NaN source stays NaN (exponent all ones, mantissa non-zero) */
+        bad |= _mm512_cmpeq_epi32_mask(_mm512_and_si512(_mm512_castps_si512(f), absmask), inf);
+        _mm512_storeu_ps(dst + i, f);
+    }
+    return (bad ? 1 : 0) | (i < n ? cvt_column_scalar(src + i, 1, n - i, dst + i) : 0);
+}
+
+int b2f_simd_cvt_column(const double *src, int64_t stride, int64_t n, float *dst) {
+    if (stride == 1 && b2f_simd_level() == 2) return cvt_column_avx512(src, n, dst);
+    return cvt_column_scalar(src, stride, n, dst);
+}
+
+/* ---- B2F_ROWS_PACKED64 rows from a column-major block: codes[j * ld + i] (int32, -1 = unknown) and cols[k * ld + i]
+ *      (float32) -> row i = { uint64 of nine 7-bit (code + 1) fields, 14 float32 }, 64 bytes.  AVX-512: sixteen rows at a time,
+ *      the two halves of the categorical word and the 14 numerics as sixteen 16-lane vectors, one 16 x 16 transpose of 32-bit
+ *      elements (64 shuffles), sixteen 64-byte stores -- non-temporal when the destination is 64-byte aligned (pinned staging
+ *      that only the DMA engine reads: no read-for-ownership of the row's cache line). ---- */
+static void pack_rows64_scalar(const int32_t *codes, const float *cols, int64_t ld, int n_cat, int n_num, int64_t i0, int64_t i1, uint32_t *out) {
+    for (int64_t i = i0; i < i1; ++i) {
+        uint64_t w = 0;
+        for (int j = 0; j < n_cat; ++j) w |= (uint64_t)(uint32_t)(codes[j * ld + i] + 1) << (7 * j);
+        uint32_t *row = out + (size_t)i * 16;
+        row[0] = (uint32_t)w;
+        row[1] = (uint32_t)(w >> 32);
+        for (int k = 0; k < n_num; ++k) memcpy(&row[2 + k], &cols[k * ld + i], 4);
+        for (int k = n_num; k < 14; ++k) row[2 + k] = 0;
+    }
+}
+
+__attribute__((target("avx512f"))) static void pack_rows64_avx512(const int32_t *codes, const float *cols, int64_t ld, int n_cat, int n_num, int64_t nb,
+                                                                  uint32_t *out) {
+    const bool nt = ((uintptr_t)out & 63u) == 0;
+    const __m512i one = _mm512_set1_epi32(1);
+    int64_t g = 0;
+    for (; g + 16 <= nb; g += 16) {
+        __m512i c[16];
+        __m512i lo = _mm512_setzero_si512(), hi = _mm512_setzero_si512();
+        for (int j = 0; j < n_cat; ++j) {
+            const __m512i v = _mm512_add_epi32(_mm512_loadu_si512(codes + j * ld + g), one); /* 1..127, 0 = unknown */
+            const int sh = 7 * j;
+            if (sh < 32) lo = _mm512_or_si512(lo, _mm512_sllv_epi32(v, _mm512_set1_epi32(sh)));
+            if (sh + 7 > 32) hi = _mm512_or_si512(hi, sh >= 32 ? _mm512_sllv_epi32(v, _mm512_set1_epi32(sh - 32)) : _mm512_srlv_epi32(v, _mm512_set1_epi32(32 - sh)));
+        }
+        c[0] = lo;
+        c[1] = hi;
+        for (int k = 0; k < 14; ++k) c[2 + k] = k < n_num ? _mm512_castps_si512(_mm512_loadu_ps(cols + k * ld + g)) : _mm512_setzero_si512();
+        __m512i t[16], u[16];
+        for (int a = 0; a < 8; ++a) {
+            t[2 * a] = _mm512_unpacklo_epi32(c[2 * a], c[2 * a + 1]);
+            t[2 * a + 1] = _mm512_unpackhi_epi32(c[2 * a], c[2 * a + 1]);
+        }
+        for (int a = 0; a < 4; ++a) { /* u[4a + r]: 128-bit lane L = row 4L + r, columns 4a .. 4a + 3 */
+            u[4 * a + 0] = _mm512_unpacklo_epi64(t[4 * a], t[4 * a + 2]);
+            u[4 * a + 1] = _mm512_unpackhi_epi64(t[4 * a], t[4 * a + 2]);
+            u[4 * a + 2] = _mm512_unpacklo_epi64(t[4 * a + 1], t[4 * a + 3]);
+            u[4 * a + 3] = _mm512_unpackhi_epi64(t[4 * a + 1], t[4 * a + 3]);
+        }
+        for (int r = 0; r < 4; ++r) {
+            const __m512i v0 = _mm512_shuffle_i32x4(u[r], u[4 + r], 0x88), v1 = _mm512_shuffle_i32x4(u[r], u[4 + r], 0xdd);
+            const __m512i v2 = _mm512_shuffle_i32x4(u[8 + r], u[12 + r], 0x88), v3 = _mm512_shuffle_i32x4(u[8 + r], u[12 + r], 0xdd);
+            const __m512i row[4] = {_mm512_shuffle_i32x4(v0, v2, 0x88), _mm512_shuffle_i32x4(v1, v3, 0x88), _mm512_shuffle_i32x4(v0, v2, 0xdd),
+                                    _mm512_shuffle_i32x4(v1, v3, 0xdd)}; /* rows 4L + r, L = 0..3 */
+            for (int L = 0; L < 4; ++L) {
+                uint32_t *dst = out + (size_t)(g + 4 * L + r) * 16;
+                if (nt)
+                    _mm512_stream_si512(reinterpret_cast<__m512i *>(dst), row[L]);
+                else
+                    _mm512_storeu_si512(dst, row[L]);
+            }
+        }
+    }
+    if (nt) _mm_sfence(); /* the rows are handed to a DMA copy next: order the non-temporal stores before it */
+    if (g < nb) pack_rows64_scalar(codes, cols, ld, n_cat, n_num, g, nb, out);
+}
+
+void b2f_simd_pack_rows64(const int32_t *codes, const float *cols, int64_t ld, int n_cat, int n_num, int64_t nb, uint32_t *out) {
+    if (b2f_simd_level() == 2 && n_cat <= 9 && n_num <= 14)
+        pack_rows64_avx512(codes, cols, ld, n_cat, n_num, nb, out);
+    else
+        pack_rows64_scalar(codes, cols, ld, n_cat, n_num, 0, nb, out);
+}
+
 } /* extern "C" */

@@ -145,18 +145,29 @@ static int enc_range_ranked(const b2f_encoder *e, int64_t lo, int64_t hi, const 
             }
             rank_write_cats(r, codes, out + (size_t)(b0 + i) * r->row_bytes);
         }
-        for (int k = 0; k < nn; ++k) {
-            const double *src = nums[k] + b0 * num_strides[k];
-            const int64_t st = num_strides[k];
-            float *dst = cols + (size_t)k * B2F_RANK_BLOCK;
-            for (int64_t i = 0; i < nb; ++i) {
-                const double v = src[i * st];
-                const float f = (float)v;
-                if (!(v != v) && !isfinite(f)) bad = 1;
-                dst[i] = f;
-            }
-        }
+        for (int k = 0; k < nn; ++k) bad |= b2f_simd_cvt_column(nums[k] + b0 * num_strides[k], num_strides[k], nb, cols + (size_t)k * B2F_RANK_BLOCK);
         rank_block(r, cols, nb, out + (size_t)b0 * r->row_bytes);
+    }
+    return bad;
+}
+
+/* packed 64-byte rows, block by block: the category codes of one column at a time (the feature's hash parameters stay in
+ * registers, the column's offsets and bytes stream), the float64 -> float32 conversion of one column at a time (vector converts),
+ * then one transposing pass that writes whole 64-byte rows (host_simd.cpp) */
+static int enc_range_packed(const b2f_encoder *e, int64_t lo, int64_t hi, const b2f_str_column *cats, const double *const *nums,
+                            const int64_t *num_strides, uint32_t *out) {
+    const int nc = e->n_cat, nn = e->n_num;
+    int bad = 0;
+    float cols[14 * B2F_RANK_BLOCK];
+    int32_t codes[9 * B2F_RANK_BLOCK];
+    for (int64_t b0 = lo; b0 < hi; b0 += B2F_RANK_BLOCK) {
+        const int64_t nb = std::min<int64_t>(B2F_RANK_BLOCK, hi - b0);
+        for (int j = 0; j < nc; ++j) {
+            int32_t *cj = codes + (size_t)j * B2F_RANK_BLOCK;
+            for (int64_t i = 0; i < nb; ++i) cj[i] = enc_code(e, j, cats[j], b0 + i);
+        }
+        for (int k = 0; k < nn; ++k) bad |= b2f_simd_cvt_column(nums[k] + b0 * num_strides[k], num_strides[k], nb, cols + (size_t)k * B2F_RANK_BLOCK);
+        b2f_simd_pack_rows64(codes, cols, B2F_RANK_BLOCK, nc, nn, nb, out + (size_t)b0 * 16);
     }
     return bad;
 }
@@ -164,6 +175,7 @@ static int enc_range_ranked(const b2f_encoder *e, int64_t lo, int64_t hi, const 
 static int enc_range(const b2f_encoder *e, int64_t lo, int64_t hi, const b2f_str_column *cats, const double *const *nums,
                      const int64_t *num_strides, int row_format, uint32_t *out) {
     if (row_format == B2F_ROWS_RANKED) return enc_range_ranked(e, lo, hi, cats, nums, num_strides, reinterpret_cast<uint8_t *>(out));
+    if (row_format == B2F_ROWS_PACKED64 && e->n_cat == 9 && e->n_num <= 14) return enc_range_packed(e, lo, hi, cats, nums, num_strides, out);
     const int nc = e->n_cat, nn = e->n_num;
     const bool packed = row_format == B2F_ROWS_PACKED64;
     const int words = packed ? 16 : B2F_ROW_WORDS;

@@ -254,7 +254,7 @@ class ForestEngine:
         return out.reshape(ROW_WORDS, 3)
 
 
-_FMT_OVERRIDE = {"ranked": ROWS_RANKED, "packed64": ROWS_PACKED64}.get(os.environ.get("B200_SCORER_ROWS", ""))  # experiments
+_FMT_OVERRIDE = {"ranked": ROWS_RANKED}.get(os.environ.get("B200_SCORER_ROWS", ""))
 STREAMED_RANK_MIN_ROWS = 16384  # below this a streamed rank layout loses to the float32-row latency kernels
 
 
@@ -268,12 +268,18 @@ class Scorer:
         h_enc = encoder._native_handle()
         if h_enc is None:
             raise B2FError("the native row encoder is not available")
+        # Which rows the workers write.  The host is the bound of this path (a B200 box gives the container 16 CPUs; the GPU needs
+        # ~20 us per 65 536 rows either way), so the format is chosen by HOST cost: the 64-byte float32 rows cost 2-3 ms of one
+        # core per 65 536 rows, the 32-byte ranked rows ~2 ms more (14 rank lookups per row) -- measured 0.57 ms vs 0.78 ms per
+        # 65 536-row request (profiles/r02_e2e_stalls.json).  Ranked rows are for callers that stream PRE-ENCODED rows through the
+        # C ABI, where PCIe bytes are the bound; B200_SCORER_ROWS=ranked selects them here too.
         self.fmt = self.fmt_small = ROWS_PACKED64 if encoder.packed_ok else ROWS_WORDS24
         self.rank_min_rows = 0
         info = engine.info()
-        if encoder.ranked_ok and info["rank_ok"] and self._lib.b2f_encoder_attach_ranker(h_enc, encoder._ranker) == 0:
+        want_ranked = _FMT_OVERRIDE == ROWS_RANKED or not encoder.packed_ok
+        if want_ranked and encoder.ranked_ok and info["rank_ok"] and self._lib.b2f_encoder_attach_ranker(h_enc, encoder._ranker) == 0:
             encoder._ranker_attached = True
-            self.fmt = ROWS_RANKED  # 32-byte ranked rows: half the PCIe bytes, integer-compare kernel
+            self.fmt = ROWS_RANKED
             # a forest whose rank layout STREAMS through shared memory pays a full pass over it per launch: small requests keep
             # the float32 rows and the latency kernels (split / warp-per-row), large ones take the ranked rows
             self.rank_min_rows = STREAMED_RANK_MIN_ROWS if info["rank_stream"] else 0
@@ -298,8 +304,6 @@ class Scorer:
         scol, ptrs, strides, _keep = columns
         if fmt is None:
             fmt = self.fmt if n >= self.rank_min_rows else self.fmt_small
-            if _FMT_OVERRIDE is not None and fmt != ROWS_WORDS24:
-                fmt = _FMT_OVERRIDE if (_FMT_OVERRIDE != ROWS_RANKED or self.fmt == ROWS_RANKED) else fmt
         self.last_fmt = fmt
         rc = self._lib.b2f_scorer_start(self._h, n, scol, ptrs, ptr(strides), fmt, out_mode, chunk_rows)
         if rc == -7:

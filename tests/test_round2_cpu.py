@@ -204,3 +204,42 @@ def test_recycled_float_lists_are_safe():
     assert bp.items == rec["p"].tolist() and bo.items == rec["o"].tolist() and all(type(v) is int for v in bo.items)
     with pytest.raises(ValueError):
         pl.ListBuilder(10).fill(5, np.zeros(10))
+
+
+def test_packed_block_encoder_every_block_shape(curated, rf100d6):
+    """The 64-byte row encoder works on 256-row blocks, sixteen rows per transposing step (host_simd.cpp): every remainder
+    shape, unaligned destinations, NaN / -0.0 / float32-overflow inputs and strided float64 columns agree with the portable path."""
+    from databricks_kubernetes_mlops_poc_b200 import flatten, training
+    from databricks_kubernetes_mlops_poc_b200.encode import RowEncoder
+    from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES, NUMERIC_FEATURES
+
+    flat = flatten.flatten_pipeline(rf100d6)
+    enc, ref = RowEncoder(flat), RowEncoder(flat)
+    ref._native_failed = True  # portable path only
+    big = training.synth_frame(curated, 1200, seed=5, unknown_frac=0.05, nan_frac=0.1)[ALL_FEATURES]
+    big.loc[big.index[3], "bill_amount_1"] = -0.0
+    big.loc[big.index[700], "age"] = 3.0e38  # finite in float32
+    for n in (1, 15, 16, 17, 255, 256, 257, 511, 1200):
+        df = big.iloc[:n].reset_index(drop=True)
+        want = ref.pack_rows(ref.encode_frame(df))
+        for shift in (0, 1):  # 64-byte aligned destination (non-temporal stores) and an unaligned one
+            buf = np.zeros(n * 16 + 32, dtype=np.uint32)
+            off = (-buf.ctypes.data // 4) % 16 + shift
+            got = buf[off:off + n * 16].reshape(n, 16)
+            assert enc._encode_native(df, got, fmt=1)
+            assert (got == want).all(), (n, shift)
+    # float64 columns that are views into one 2-D block (element stride 14): the strided scalar conversion
+    mat = np.ascontiguousarray(big[NUMERIC_FEATURES].to_numpy(dtype=np.float64))
+    strided = big.copy()
+    for k, name in enumerate(NUMERIC_FEATURES):
+        strided[name] = mat[:, k]
+    got = np.zeros((len(big), 16), dtype=np.uint32)
+    assert enc._encode_native(strided, got, fmt=1)
+    assert (got == ref.pack_rows(ref.encode_frame(big))).all()
+    bad = big.copy()
+    bad.loc[bad.index[1100], "payment_amount_3"] = 1e39  # overflows float32 -> sklearn's ValueError
+    with pytest.raises(ValueError, match="infinity or a value too large"):
+        enc._encode_native(bad, np.zeros((len(bad), 16), dtype=np.uint32), fmt=1)
+    bad.loc[bad.index[1100], "payment_amount_3"] = -np.inf
+    with pytest.raises(ValueError, match="infinity or a value too large"):
+        enc._encode_native(bad, np.zeros((len(bad), 16), dtype=np.uint32), fmt=1)

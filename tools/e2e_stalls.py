@@ -69,7 +69,7 @@ def main():
 
     variants = [(int(t), f) for t in os.environ.get("STALL_THREADS", "0,12,10").split(",") for f in os.environ.get("STALL_ROWS", "ranked,packed64").split(",")]
     for threads, rows in variants:
-        _engine._FMT_OVERRIDE = {"ranked": _engine.ROWS_RANKED, "packed64": _engine.ROWS_PACKED64}[rows]
+        _engine._FMT_OVERRIDE = {"ranked": _engine.ROWS_RANKED, "packed64": None}[rows]
         model = B200Model(flat, devices=[0], host_threads=threads)
         for _ in range(20):
             model.predict(df)
