@@ -102,14 +102,14 @@ static double cgroup_cpu_limit() {
 }
 
 /* worker threads a scorer may start by default: the GPU's NUMA node (its cores and half of their hyper-threads), capped at 48
- * and at the cgroup's CPU bandwidth minus four (the caller's thread builds the response while the workers encode, the CUDA
- * driver has threads of its own; with a quota of 16, 12 workers measured faster than 14 and than 10) */
+ * and at the cgroup's CPU bandwidth minus two (the caller's thread builds the response while the workers encode; with a quota of 16:
+ * 0.45 ms per 65 536-row request with 14 workers, 0.51 with 12 or 10, and 55-75 ms stalls from 17 up) */
 static int default_host_threads(int device) {
     cpu_set_t set;
     int local = numa_cpus_of_device(device, &set) ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
     int threads = std::max(1, std::min(48, local * 3 / 4));
     const double lim = cgroup_cpu_limit();
-    if (lim > 0.0) threads = std::max(1, std::min(threads, (int)lim - 4));
+    if (lim > 0.0) threads = std::max(1, std::min(threads, (int)lim - 2));
     return threads;
 }
 

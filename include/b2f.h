@@ -246,7 +246,7 @@ void b2f_pinned_free_striped(void *p);
 typedef struct b2f_scorer b2f_scorer;
 b2f_scorer *b2f_scorer_create(b2f_model *m, const b2f_encoder *e, int threads /* 0 = b2f_host_threads_default(the model's device) */);
 /* the default size of a scorer's thread pool: three quarters of the CPUs of the GPU's NUMA node, at most 48, and at most the
- * cgroup's CPU bandwidth minus four (b2f_host_cpu_limit: cpu.max quota / period, 0.0 when unlimited) -- polling workers beyond
+ * cgroup's CPU bandwidth minus two (b2f_host_cpu_limit: cpu.max quota / period, 0.0 when unlimited) -- polling workers beyond
  * the quota get the whole container throttled */
 int b2f_host_threads_default(int device);
 double b2f_host_cpu_limit(void);

@@ -91,22 +91,27 @@ def test_rank_unavailable_is_refused(curated):
         eng.close()
 
 
-def test_pipeline_predict_large_frames(curated, inference, adversarial, rf100d6, iforest):
+@pytest.mark.parametrize("rows", ["packed64", "ranked"])
+def test_pipeline_predict_large_frames(curated, inference, adversarial, rf100d6, iforest, rows, monkeypatch):
     """B200Model.predict on frames large enough for the chunked columnar pipeline (b2f_scorer): every row of the reference
-    table, other column orders, object-dtype columns (portable path), float32 overflow, and the outlier forest riding along."""
+    table, other column orders, object-dtype columns (portable path), float32 overflow, and the outlier forest riding along.
+    Both row formats the scorer's workers can write: the 64-byte float32 rows (default: cheapest on the host) and the
+    32-byte ranked rows (B200_SCORER_ROWS=ranked)."""
     import pandas as pd
 
+    from databricks_kubernetes_mlops_poc_b200 import engine as engine_mod
     from databricks_kubernetes_mlops_poc_b200.model import B200Model
     from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES
     from oracle import reference_pipeline as rp
 
+    monkeypatch.setattr(engine_mod, "_FMT_OVERRIDE", engine_mod.ROWS_RANKED if rows == "ranked" else None)
     model = B200Model.from_pipeline(rf100d6, devices=[0])
     try:
         want_p, _ = rp.oracle_predict(rf100d6, curated)
         df = curated[ALL_FEATURES]
         out = model.predict(df)
         assert model.last_timing is not None and model.last_timing["chunks"] >= 2, "30 000 rows must take the chunked pipeline"
-        assert model.last_timing["row_format"] == 2, "classifier-only requests travel as ranked rows"
+        assert model.last_timing["row_format"] == (2 if rows == "ranked" else 1)
         assert np.abs(np.asarray(out["predictions"]) - want_p).max() <= TOL64
         assert out["outliers"] == [0] * len(df) and len(out["predictions"]) == len(df)
         # the same frame again (staging reuse), reversed column order, a slice with an offset
