@@ -30,7 +30,8 @@ struct b2f_drift {
     int64_t *d_new_counts = nullptr;
     int64_t new_cap = 0;
     double *d_rows = nullptr; /* row-scan scratch: [n_num][2][B2F_DRIFT_ROW_STRIDE(n_ref)] */
-    int rowscan_max_n = 0;
+    int rowscan_max_n = 0, rowscan_smem_max_n = 0;
+    size_t finish_smem = 0;
     void *d_out = nullptr; /* p_val[F] | stat[F] | flags[F] */
     void *h_out = nullptr; /* pinned mirror */
     int64_t launches = 0;
@@ -95,7 +96,12 @@ static int drift_init(b2f_drift *d, const double *ref_sorted, const int32_t *cat
     if (const char *rs = getenv("B2F_DRIFT_ROWSCAN")) d->rowscan_max_n = std::max(0, std::min(B2F_DRIFT_ROWSCAN_MAX, atoi(rs)));
     if (d->rowscan_max_n > 0 && d->n_num > 0 && d->n_ref >= 1024)
         CUDA_TRY(cudaMalloc((void **)&d->d_rows, (size_t)d->n_num * 2 * (size_t)B2F_DRIFT_ROW_STRIDE(d->n_ref) * sizeof(double)));
-    CUDA_TRY(cudaFuncSetAttribute(k_drift_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * B2F_DRIFT_RING_MAX * (int)sizeof(double)));
+    /* B2F_DRIFT_ROWSCAN=0 switches both row-scan forms off; B2F_DRIFT_ROWSCAN_SMEM=<n> caps the shared-memory form alone */
+    d->rowscan_smem_max_n = getenv("B2F_DRIFT_ROWSCAN") && d->rowscan_max_n == 0 ? 0 : B2F_DRIFT_ROWSCAN_SMEM_MAX;
+    if (const char *rs = getenv("B2F_DRIFT_ROWSCAN_SMEM")) d->rowscan_smem_max_n = std::max(0, std::min(B2F_DRIFT_ROWSCAN_SMEM_MAX, atoi(rs)));
+    d->finish_smem = 2 * B2F_DRIFT_RING_MAX * sizeof(double);
+    if (d->rowscan_smem_max_n > 0) d->finish_smem = std::max(d->finish_smem, (size_t)B2F_DRIFT_ROWSCAN_CAP * sizeof(double));
+    CUDA_TRY(cudaFuncSetAttribute(k_drift_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(d->finish_smem, (size_t)B2F_DRIFT_ROWSCAN_CAP * sizeof(double))));
     return B2F_OK;
 }
 
@@ -282,10 +288,12 @@ extern "C" int b2f_drift_score(b2f_drift *d, int64_t n, const double *num_cols, 
     p.flags = reinterpret_cast<int32_t *>(p.stat + F);
     p.row_scratch = d->d_rows;
     p.rowscan_max_n = d->rowscan_max_n;
+    p.rowscan_smem_max_n = d->rowscan_smem_max_n;
+    p.rowscan_cap = B2F_DRIFT_ROWSCAN_CAP;
     const int64_t total = n * F;
     const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)d->sm_count * 8));
     k_drift_count<<<blocks, 256, 0, d->stream>>>(p);
-    k_drift_finish<<<(unsigned)F, B2F_DRIFT_THREADS, 2 * B2F_DRIFT_RING_MAX * sizeof(double), d->stream>>>(p);
+    k_drift_finish<<<(unsigned)F, B2F_DRIFT_THREADS, d->finish_smem, d->stream>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_err(B2F_ECUDA, "drift kernel launch failed: %s", cudaGetErrorString(e));
     d->launches += 2;

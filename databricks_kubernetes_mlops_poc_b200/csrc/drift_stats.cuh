@@ -56,7 +56,9 @@ struct DriftParams {
     double *stat;             /* chi-squared statistic / K-S D */
     int32_t *flags;           /* 0 ok; 1 = exact K-S not applicable (scipy switches to the asymptotic formula); 2 = NaN input */
     double *row_scratch;      /* [n_num][2][B2F_DRIFT_ROW_STRIDE(n_ref)]: the two rows of the row-scan form of the exact p-value (NULL: sweep only) */
-    int32_t rowscan_max_n;    /* batches of 2 .. this many rows take the row scan (0 = never) */
+    int32_t rowscan_max_n;    /* batches of 2 .. this many rows take the row scan through the global scratch (0 = never) */
+    int32_t rowscan_smem_max_n; /* batches of 2 .. this many rows take the shared-memory row scan when their band fits (0 = never) */
+    int32_t rowscan_cap;      /* doubles of dynamic shared memory available to it */
 };
 
 /* ------------------------------------------------------------------ k_drift_count */
@@ -323,7 +325,9 @@ __device__ __forceinline__ double sweep_block(const SweepConst &c, int tid, int 
  * Rows live in a global scratch (L2), element i at (i mod CH) * NT + i / CH so that thread t owns the CH consecutive
  * columns [t CH, (t+1) CH) and every load / store of a pass is coalesced; row j is scaled by 2^-E_j, E_j the exponent of
  * its largest binomial, so nothing overflows.  Sums run in a fixed order (deterministic).  p = W(m,n) / C(m+n, n). */
-#define B2F_DRIFT_ROWSCAN_MAX 128
+#define B2F_DRIFT_ROWSCAN_MAX 48       /* global-scratch form: ~20 us per row, the sweep is faster beyond */
+#define B2F_DRIFT_ROWSCAN_SMEM_MAX 1024 /* shared-memory form: ~1-2 us per row */
+#define B2F_DRIFT_ROWSCAN_CAP 26624     /* doubles of the shared-memory row ring (208 KB; the kernel has 16 KB of static arrays) */
 /* doubles per scratch row: the transposed layout (i mod CH) * NT + i / CH spans CH * NT >= m + 1 slots */
 #define B2F_DRIFT_ROW_STRIDE(m) ((((int64_t)(m) + 1 + B2F_DRIFT_THREADS - 1) / B2F_DRIFT_THREADS) * B2F_DRIFT_THREADS)
 
@@ -456,6 +460,139 @@ __device__ double rows_scan(const SweepConst &c, double *buf0, double *buf1, int
     return 0.0;
 }
 
+/* ---- the row-scan with the row RESIDENT IN SHARED MEMORY ---------------------------------------------------------------
+ * The global-scratch form above pays two dependent trips to L2 per row (~20 us per row measured: it loses to the sweep beyond
+ * ~48 rows).  A row only ever needs its in-band cells [lo_j, hi_j], at most 2h/ng + 1 of them, and the interval only moves
+ * right: cell i lives in slot i mod cap of a shared-memory ring of `cap` doubles (cap >= the widest row, checked by the caller),
+ * updated IN PLACE.  Thread t owns the L consecutive cells lo_j + tL .. (L odd: the float64 accesses of a half-warp then fall
+ * into 16 different bank pairs), adds them up, the block scans the 1024 partial sums (two shuffle scans, fixed order), and a
+ * second pass writes the running sums.  The binomials a row needs -- its scale, its seed, and the cells the previous row had
+ * outside the band -- are products of up to j factors; they are computed by GROUPS of G lanes (G = 1, 8 or 32 by j), each lane
+ * a strided share of the factors, combined by a butterfly of multiplies on (mantissa, exponent) pairs: warp 0 the scale, warp 1
+ * the seed, warps 2.. the cells, all at the same time.  ~1-2 us per row instead of ~20. */
+template <int G>
+__device__ __forceinline__ BinomME binom_me_group(int64_t t, int k, int gl) {
+    double num = 1.0, den = 1.0;
+    int ex = 0;
+    for (int r = 1 + gl; r <= k; r += G) {
+        num *= (double)(t - k + r);
+        den *= (double)r;
+        if (num > 0x1p400) {
+            num *= 0x1p-400;
+            ex += 400;
+        }
+        if (den > 0x1p400) {
+            den *= 0x1p-400;
+            ex -= 400;
+        }
+    }
+    int fe;
+    double mant = frexp(num / den, &fe); /* in [0.5, 1) */
+    ex += fe;
+#pragma unroll
+    for (int o = G / 2; o >= 1; o >>= 1) { /* a * b == b * a bit for bit: every lane of the group ends with the same pair */
+        const double m2 = __shfl_xor_sync(0xffffffffu, mant, o);
+        const int e2 = __shfl_xor_sync(0xffffffffu, ex, o);
+        int f2;
+        mant = frexp(mant * m2, &f2);
+        ex += e2 + f2;
+    }
+    BinomME b;
+    b.mant = mant;
+    b.ex = ex;
+    return b;
+}
+
+/* cells hi_p + 1 .. hi of the previous row (outside its band): C(i + k, k) * 2^-e_p, by groups of G lanes of warps 2.. */
+template <int G>
+__device__ __forceinline__ void rows_extend(double *ring, int cap, int64_t first, int64_t cnt, int k, int e_p, int tid, int nt) {
+    const int groups = (nt - 64) / G;         /* warps 0 and 1 are busy with the scale and the seed */
+    const int gid = (tid - 64) / G, gl = (tid - 64) % G;
+    for (int64_t base = 0; base < cnt; base += groups) { /* trip count uniform over the block: the shuffles need whole warps */
+        const int64_t q = base + gid;
+        const bool live = q < cnt;
+        const int64_t i = first + (live ? q : 0);
+        const BinomME b = binom_me_group<G>(i + k, live ? k : 0, gl);
+        if (live && gl == 0) ring[(int)(i % cap)] = ldexp(b.mant, b.ex - e_p);
+    }
+}
+
+__device__ double rows_scan_smem(const SweepConst &c, double *ring, int cap, int tid, int nt) {
+    __shared__ double s_warp[32];
+    __shared__ double s_seed_m;
+    __shared__ int s_seed_e, s_e;
+    const int64_t m = c.m, mg = c.mg, ng = c.ng, h = c.h;
+    const int n = (int)c.n;
+    const int lane = tid & 31, warp = tid >> 5;
+
+    int64_t hi_p = min(-floor_div(-(h), ng) - 1, m); /* row 0: inside the band no path has left it */
+    for (int64_t i = tid; i <= hi_p; i += nt) ring[(int)(i % cap)] = 0.0;
+    int e_p = 1;
+    __syncthreads();
+    for (int j = 1; j <= n; ++j) {
+        const int64_t lo = max(floor_div(mg * j - h, ng) + 1, (int64_t)0);
+        const int64_t hi = min(-floor_div(-(mg * j + h), ng) - 1, m);
+        if (warp == 0) {
+            const BinomME b = binom_me_group<32>(hi + j, j, lane);
+            if (lane == 0) s_e = b.ex;
+        } else if (warp == 1) {
+            const BinomME b = binom_me_group<32>(lo - 1 + j, lo >= 1 ? j : 0, lane);
+            if (lane == 0) {
+                s_seed_m = lo >= 1 ? b.mant : 0.0;
+                s_seed_e = b.ex;
+            }
+        } else {
+            const int k = j - 1;
+            if (k <= 32) rows_extend<1>(ring, cap, hi_p + 1, hi - hi_p, k, e_p, tid, nt);
+            else if (k <= 256) rows_extend<8>(ring, cap, hi_p + 1, hi - hi_p, k, e_p, tid, nt);
+            else rows_extend<32>(ring, cap, hi_p + 1, hi - hi_p, k, e_p, tid, nt);
+        }
+        __syncthreads();
+        const int e = s_e;
+        const double seed = ldexp(s_seed_m, s_seed_e - e);
+        const double scale = ldexp(1.0, e_p - e);
+        const int64_t w = hi - lo + 1;
+        const int L = (int)((max(w, (int64_t)1) + nt - 1) / nt) | 1;
+        const int64_t a0 = lo + (int64_t)tid * L, a1 = min(a0 + L, hi + 1);
+        const int cnt = a1 > a0 ? (int)(a1 - a0) : 0;
+        const int s0 = cnt ? (int)(a0 % cap) : 0;
+        double local = 0.0;
+        for (int q = 0, sl = s0; q < cnt; ++q) {
+            local += ring[sl] * scale;
+            if (++sl == cap) sl = 0;
+        }
+        double incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            double wv = lane < (nt >> 5) ? s_warp[lane] : 0.0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double v = __shfl_up_sync(0xffffffffu, wv, o);
+                if (lane >= o) wv += v;
+            }
+            s_warp[lane] = wv;
+        }
+        __syncthreads();
+        double run = seed + (warp > 0 ? s_warp[warp - 1] : 0.0) + (incl - local);
+        for (int q = 0, sl = s0; q < cnt; ++q) {
+            run += ring[sl] * scale;
+            ring[sl] = run;
+            if (++sl == cap) sl = 0;
+        }
+        hi_p = hi;
+        e_p = e;
+        __syncthreads();
+    }
+    if (tid == 0) return ring[(int)(m % cap)] / binom_scaled(m + n, n, e_p);
+    return 0.0;
+}
+
 extern __shared__ unsigned char drift_smem[];
 
 __global__ void __launch_bounds__(B2F_DRIFT_THREADS) k_drift_finish(DriftParams p) {
@@ -572,6 +709,12 @@ __global__ void __launch_bounds__(B2F_DRIFT_THREADS) k_drift_finish(DriftParams 
     c.T = m + n;
     c.ring = ring;
     double res;
+    if (n >= 2 && n <= (int64_t)p.rowscan_smem_max_n && m == m0 && m >= 1024 && (2 * h) / ng + 2 <= (int64_t)p.rowscan_cap) {
+        /* request-sized batch, band narrow enough for the row to stay in shared memory: n in-place prefix sums */
+        res = rows_scan_smem(c, reinterpret_cast<double *>(drift_smem), p.rowscan_cap, tid, nt);
+        if (tid == 0) p.p_val[out] = fmin(fmax(res, 0.0), 1.0);
+        return;
+    }
     if (p.row_scratch && n >= 2 && n <= (int64_t)p.rowscan_max_n && m == m0 && m >= 1024) {
         /* request-sized batch against the big reference table: n prefix sums instead of m + n dependent steps */
         double *rows2 = p.row_scratch + (int64_t)f * 2 * B2F_DRIFT_ROW_STRIDE(m0);

@@ -304,6 +304,13 @@ class Scorer:
         scol, ptrs, strides, _keep = columns
         if fmt is None:
             fmt = self.fmt if n >= self.rank_min_rows else self.fmt_small
+        if fmt == ROWS_RANKED and not getattr(self.encoder, "_ranker_attached", False):
+            # an explicit request for ranked rows on a scorer that writes float32 rows by default: hand the encoder the tables now
+            # (no job is in flight: one job at a time)
+            if not (self.encoder.ranked_ok and self.engine.info()["rank_ok"]
+                    and self._lib.b2f_encoder_attach_ranker(self.encoder._native_handle(), self.encoder._ranker) == 0):
+                raise ValueError("ranked rows are not available for this model")
+            self.encoder._ranker_attached = True
         self.last_fmt = fmt
         rc = self._lib.b2f_scorer_start(self._h, n, scol, ptrs, ptr(strides), fmt, out_mode, chunk_rows)
         if rc == -7:

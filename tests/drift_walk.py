@@ -205,3 +205,45 @@ def exact_p_rows(m0: int, n0: int, num: int):
         prev, lo_p, hi_p, e_prev = cur, lo, hi, e
     total = _binom_scaled(m + n, n, e_prev)
     return float(min(max(prev[m] / total, 0.0), 1.0)), 0
+
+
+def exact_p_rows_ring(m0: int, n0: int, num: int, cap: int = 26624, nt: int = 1024):
+    """`rows_scan_smem` step by step: the row lives in a ring of `cap` slots (cell i at i mod cap) and is updated in place;
+    thread t owns L (odd) consecutive cells from lo_j + t*L; cells the previous row had outside the band are written into the ring
+    before the scan.  -> (p, flag), or None when the band is too wide for the ring (the kernel takes another form then)."""
+    g = math.gcd(m0, n0)
+    m, n = max(m0, n0), min(m0, n0)
+    mg, ng = m // g, n // g
+    h = num // g
+    if (m0 // g) >= 2147483647.0 / (n0 // g):
+        return -1.0, 1
+    if h == 0:
+        return 1.0, 0
+    if (2 * h) // ng + 2 > cap:
+        return None
+    ring = np.full(cap, np.nan)  # NaN: a slot read before it was written poisons the result
+    hi_p = min(-((-h) // ng) - 1, m)
+    for i in range(hi_p + 1):
+        ring[i % cap] = 0.0
+    e_p = 1
+    for j in range(1, n + 1):
+        lo = max((mg * j - h) // ng + 1, 0)
+        hi = min(-((-(mg * j + h)) // ng) - 1, m)
+        e = _binom_exponent(hi + j, j)
+        seed = _binom_scaled(lo - 1 + j, j, e) if lo >= 1 else 0.0
+        for i in range(hi_p + 1, hi + 1):
+            ring[i % cap] = _binom_scaled(i + j - 1, j - 1, e_p)
+        scale = math.ldexp(1.0, e_p - e)
+        w = hi - lo + 1
+        L = ((max(w, 1) + nt - 1) // nt) | 1
+        # pass A: per-thread sums in cell order, exclusive scan in thread order
+        run = seed
+        for t in range(nt):
+            a0 = lo + t * L
+            a1 = min(a0 + L, hi + 1)
+            for i in range(a0, a1):  # pass B of thread t (its offset is the running total so far)
+                run += ring[i % cap] * scale
+                ring[i % cap] = run
+        hi_p, e_p = hi, e
+    total = _binom_scaled(m + n, n, e_p)
+    return float(min(max(ring[m % cap] / total, 0.0), 1.0)), 0

@@ -197,6 +197,34 @@ def test_row_scan_form_matches_scipy():
         assert abs(a - b) <= 1e-12 * max(a, 1e-300)
 
 
+def test_row_scan_ring_schedule_matches_scipy():
+    """The shared-memory schedule of the row scan (rows_scan_smem: ring of `cap` slots updated in place, L-cell thread shares,
+    cells entering the band written into the ring first) emulated step by step: a slot read before it is written, or
+    overwritten while still needed, would poison the result.  Small rings force many wrap-arounds."""
+    import math
+
+    import drift_walk as dw
+    from scipy.stats import _stats_pythran as sp
+
+    worst, ran = 0.0, 0
+    for m, n, cap, nt in [(300, 16, 64, 8), (300, 16, 301, 32), (1000, 37, 128, 16), (500, 125, 40, 4), (2048, 3, 1500, 64), (997, 64, 97, 8)]:
+        g = math.gcd(m, n)
+        lcm = m // g * n
+        for h in sorted({1, 2, 3, lcm // 50 + 1, lcm // 20 + 1, lcm // 10 + 1, lcm // 5 + 1, lcm // 3 + 1}):
+            res = dw.exact_p_rows_ring(m, n, h * g, cap=cap, nt=nt)
+            if res is None:
+                continue  # band wider than the ring: the kernel takes the global-scratch form or the sweep
+            want = min(max(sp._compute_outer_prob_inside_method(max(m, n), min(m, n), g, h), 0.0), 1.0)
+            worst = max(worst, abs(res[0] - want) / max(want, 1e-300))
+            ran += 1
+    assert ran >= 20 and worst <= 1e-12, (ran, worst)
+    m, n = 30000, 100
+    h = int(0.12 * m * n / math.gcd(m, n))
+    want = min(max(sp._compute_outer_prob_inside_method(m, n, math.gcd(m, n), h), 0.0), 1.0)
+    got, _ = dw.exact_p_rows_ring(m, n, h * math.gcd(m, n))
+    assert abs(got - want) <= 1e-12 * max(want, 1e-300)
+
+
 def test_native_kstwo_sf_matches_scipy():
     """b2f_kstwo_sf (host, csrc/drift_api.cuh) restates the branch scipy's ks_2samp takes when the exact method is not
     applicable (lcm of the sample sizes >= 2^31): kstwo.sf(D, round(m n / (m + n))).  Checked against scipy over the

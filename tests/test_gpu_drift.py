@@ -202,8 +202,9 @@ def test_drift_against_frozen_library_outputs(curated, inference):
 
 
 def test_row_scan_and_sweep_agree(curated):
-    """Request-sized batches take the row-scan form of the exact p-value (B2F_DRIFT_ROWSCAN: batches of 2 .. 128 rows), larger
-    ones the anti-diagonal sweep; the same batches through both forms give the same p-values (and both equal scipy's, above)."""
+    """Request-sized batches take a row-scan form of the exact p-value -- the row resident in shared memory (2 .. 1024 rows, band
+    narrower than the ring), else through the global scratch (2 .. 48 rows) -- larger ones the anti-diagonal sweep; the same
+    batches through all three forms give the same p-values (and all equal scipy's, above)."""
     import os
 
     from oracle import reference_pipeline as rp
@@ -212,27 +213,33 @@ def test_row_scan_and_sweep_agree(curated):
 
     ref = curated[rp.FEATURES]
     rng = np.random.default_rng(11)
-    batches = [ref.iloc[rng.integers(0, len(ref), n)].reset_index(drop=True) for n in (2, 3, 16, 17, 64, 127, 128)]
+    batches = [ref.iloc[rng.integers(0, len(ref), n)].reset_index(drop=True) for n in (2, 3, 16, 17, 48, 64, 127, 128, 250, 600, 1000, 1024)]
     shifted = ref.iloc[:40].copy()
     for c in rp.NUMERIC_FEATURES:
-        shifted[c] = shifted[c] * 1.7 + 3.0
+        shifted[c] = shifted[c] * 1.7 + 3.0  # wide bands: some features leave the shared-memory ring
     batches.append(shifted)
+    slightly = ref.iloc[1000:1300].copy()
+    for c in rp.NUMERIC_FEATURES:
+        slightly[c] = slightly[c] * 1.02
+    batches.append(slightly)
     det = TabularDrift(ref, rp.CATEGORICAL_FEATURES, device=0)
     try:
         a = [det.statistics(b) for b in batches]
-        for b in batches:
+        for b in batches[:8] + batches[-2:]:
             _check(det, ref, b)
     finally:
         det.close()
-    os.environ["B2F_DRIFT_ROWSCAN"] = "0"
-    try:
-        det = TabularDrift(ref, rp.CATEGORICAL_FEATURES, device=0)
-    finally:
-        os.environ.pop("B2F_DRIFT_ROWSCAN")
-    try:
-        for b, (p, stat, flags) in zip(batches, a):
-            p2, stat2, flags2 = det.statistics(b)
-            assert (flags == flags2).all() and (stat == stat2).all()
-            assert np.abs(p - p2).max() <= 1e-11 * np.maximum(np.abs(p2), 1e-300).max()
-    finally:
-        det.close()
+    for env in ({"B2F_DRIFT_ROWSCAN": "0"}, {"B2F_DRIFT_ROWSCAN_SMEM": "0"}):
+        os.environ.update(env)
+        try:
+            det = TabularDrift(ref, rp.CATEGORICAL_FEATURES, device=0)
+        finally:
+            for k in env:
+                os.environ.pop(k)
+        try:
+            for b, (p, stat, flags) in zip(batches, a):
+                p2, stat2, flags2 = det.statistics(b)
+                assert (flags == flags2).all() and (stat == stat2).all()
+                assert np.abs(p - p2).max() <= 1e-11 * np.maximum(np.abs(p2), 1e-300).max(), (env, len(b))
+        finally:
+            det.close()

@@ -1,4 +1,5 @@
-"""gpurun helper: K3 device / call time by batch size (row-scan form vs anti-diagonal sweep), scipy beside it."""
+"""gpurun helper: K3 device / call time by batch size: row scan in shared memory, row scan through the global scratch (<= 48 rows),
+anti-diagonal sweep."""
 import json, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,12 +11,16 @@ base = training.load_base_frame()
 ref = base[ALL_FEATURES]
 rng = np.random.default_rng(7)
 out = {}
-for mode in ("rowscan", "sweep"):
+for mode in ("rowscan", "rowscan_global", "sweep"):
+    os.environ.pop("B2F_DRIFT_ROWSCAN", None)
+    os.environ.pop("B2F_DRIFT_ROWSCAN_SMEM", None)
     if mode == "sweep":
         os.environ["B2F_DRIFT_ROWSCAN"] = "0"
+    if mode == "rowscan_global":
+        os.environ["B2F_DRIFT_ROWSCAN_SMEM"] = "0"
     det = TabularDrift(ref, CATEGORICAL_FEATURES, device=0)
     rows = {}
-    for n in (1, 2, 16, 64, 128, 129, 1000):
+    for n in (1, 2, 16, 48, 64, 128, 250, 512, 1000, 1025):
         batch = ref.iloc[rng.integers(0, len(ref), n)].reset_index(drop=True)
         det.statistics(batch)
         dev, wall = [], []
