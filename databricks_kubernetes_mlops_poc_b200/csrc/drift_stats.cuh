@@ -470,12 +470,25 @@ __device__ double rows_scan(const SweepConst &c, double *buf0, double *buf1, int
  * outside the band -- are products of up to j factors; they are computed by GROUPS of G lanes (G = 1, 8 or 32 by j), each lane
  * a strided share of the factors, combined by a butterfly of multiplies on (mantissa, exponent) pairs: warp 0 the scale, warp 1
  * the seed, warps 2.. the cells, all at the same time.  ~1-2 us per row instead of ~20. */
+/* frexp / ldexp for the values that occur here (positive, normal): two integer operations instead of the library routines */
+__device__ __forceinline__ double frexp_pos(double x, int &e) {
+    int hi = __double2hiint(x);
+    e = ((hi >> 20) & 0x7ff) - 1022;
+    hi = (hi & 0x800fffff) | 0x3fe00000;
+    return __hiloint2double(hi, __double2loint(x)); /* in [0.5, 1) */
+}
+__device__ __forceinline__ double ldexp_fast(double x, int d) {
+    if (d > -1000 && d < 1000) return x * __hiloint2double((d + 1023) << 20, 0); /* exact: x is normal and stays normal */
+    return ldexp(x, d);
+}
+
 template <int G>
 __device__ __forceinline__ BinomME binom_me_group(int64_t t, int k, int gl) {
     double num = 1.0, den = 1.0;
     int ex = 0;
+    const double base = (double)(t - k);
     for (int r = 1 + gl; r <= k; r += G) {
-        num *= (double)(t - k + r);
+        num *= base + (double)r;
         den *= (double)r;
         if (num > 0x1p400) {
             num *= 0x1p-400;
@@ -487,14 +500,14 @@ __device__ __forceinline__ BinomME binom_me_group(int64_t t, int k, int gl) {
         }
     }
     int fe;
-    double mant = frexp(num / den, &fe); /* in [0.5, 1) */
+    double mant = frexp_pos(num / den, fe); /* in [0.5, 1) */
     ex += fe;
 #pragma unroll
     for (int o = G / 2; o >= 1; o >>= 1) { /* a * b == b * a bit for bit: every lane of the group ends with the same pair */
         const double m2 = __shfl_xor_sync(0xffffffffu, mant, o);
         const int e2 = __shfl_xor_sync(0xffffffffu, ex, o);
         int f2;
-        mant = frexp(mant * m2, &f2);
+        mant = frexp_pos(mant * m2, f2);
         ex += e2 + f2;
     }
     BinomME b;
@@ -503,9 +516,10 @@ __device__ __forceinline__ BinomME binom_me_group(int64_t t, int k, int gl) {
     return b;
 }
 
-/* cells hi_p + 1 .. hi of the previous row (outside its band): C(i + k, k) * 2^-e_p, by groups of G lanes of warps 2.. */
+/* cells first .. first + cnt - 1 of the previous row (outside its band): C(i + k, k) * 2^-e_p, by groups of G lanes of warps 2..;
+ * slot0 = ring slot of cell `first` */
 template <int G>
-__device__ __forceinline__ void rows_extend(double *ring, int cap, int64_t first, int64_t cnt, int k, int e_p, int tid, int nt) {
+__device__ __forceinline__ void rows_extend(double *ring, uint32_t cap, int64_t first, uint32_t slot0, int64_t cnt, int k, int e_p, int tid, int nt) {
     const int groups = (nt - 64) / G;         /* warps 0 and 1 are busy with the scale and the seed */
     const int gid = (tid - 64) / G, gl = (tid - 64) % G;
     for (int64_t base = 0; base < cnt; base += groups) { /* trip count uniform over the block: the shuffles need whole warps */
@@ -513,25 +527,37 @@ __device__ __forceinline__ void rows_extend(double *ring, int cap, int64_t first
         const bool live = q < cnt;
         const int64_t i = first + (live ? q : 0);
         const BinomME b = binom_me_group<G>(i + k, live ? k : 0, gl);
-        if (live && gl == 0) ring[(int)(i % cap)] = ldexp(b.mant, b.ex - e_p);
+        if (live && gl == 0) ring[(slot0 + (uint32_t)q) % cap] = ldexp_fast(b.mant, b.ex - e_p);
     }
 }
 
-__device__ double rows_scan_smem(const SweepConst &c, double *ring, int cap, int tid, int nt) {
+__device__ double rows_scan_smem(const SweepConst &c, double *ring, int cap_i, int tid, int nt) {
     __shared__ double s_warp[32];
     __shared__ double s_seed_m;
     __shared__ int s_seed_e, s_e;
     const int64_t m = c.m, mg = c.mg, ng = c.ng, h = c.h;
     const int n = (int)c.n;
+    const uint32_t cap = (uint32_t)cap_i;
     const int lane = tid & 31, warp = tid >> 5;
 
-    int64_t hi_p = min(-floor_div(-(h), ng) - 1, m); /* row 0: inside the band no path has left it */
-    for (int64_t i = tid; i <= hi_p; i += nt) ring[(int)(i % cap)] = 0.0;
+    /* band limits without a division per row: lo_j = floor((mg j - h) / ng) + 1, hi_j = floor((mg j + h - 1) / ng), kept as
+     * quotient + remainder and advanced by (mg div ng, mg mod ng) */
+    const int64_t dq = mg / ng, dr = mg % ng;
+    int64_t qa = floor_div(-h, ng), ra = -h - qa * ng;
+    int64_t qb = floor_div(h - 1, ng), rb = h - 1 - qb * ng;
+
+    int64_t lo_p = 0, hi_p = min(qb, m); /* row 0: cells 0 .. hi_0, inside the band no path has left it */
+    uint32_t lo_slot = 0;                /* ring slot of cell lo_p */
+    for (int64_t i = tid; i <= hi_p; i += nt) ring[(uint32_t)i % cap] = 0.0;
     int e_p = 1;
     __syncthreads();
     for (int j = 1; j <= n; ++j) {
-        const int64_t lo = max(floor_div(mg * j - h, ng) + 1, (int64_t)0);
-        const int64_t hi = min(-floor_div(-(mg * j + h), ng) - 1, m);
+        qa += dq, ra += dr;
+        if (ra >= ng) ra -= ng, ++qa;
+        qb += dq, rb += dr;
+        if (rb >= ng) rb -= ng, ++qb;
+        const int64_t lo = max(qa + 1, (int64_t)0), hi = min(qb, m);
+        const uint32_t hi_p_slot = (lo_slot + (uint32_t)(hi_p - lo_p)) % cap;
         if (warp == 0) {
             const BinomME b = binom_me_group<32>(hi + j, j, lane);
             if (lane == 0) s_e = b.ex;
@@ -543,23 +569,27 @@ __device__ double rows_scan_smem(const SweepConst &c, double *ring, int cap, int
             }
         } else {
             const int k = j - 1;
-            if (k <= 32) rows_extend<1>(ring, cap, hi_p + 1, hi - hi_p, k, e_p, tid, nt);
-            else if (k <= 256) rows_extend<8>(ring, cap, hi_p + 1, hi - hi_p, k, e_p, tid, nt);
-            else rows_extend<32>(ring, cap, hi_p + 1, hi - hi_p, k, e_p, tid, nt);
+            if (k <= 32) rows_extend<1>(ring, cap, hi_p + 1, hi_p_slot + 1u, hi - hi_p, k, e_p, tid, nt);
+            else if (k <= 256) rows_extend<8>(ring, cap, hi_p + 1, hi_p_slot + 1u, hi - hi_p, k, e_p, tid, nt);
+            else rows_extend<32>(ring, cap, hi_p + 1, hi_p_slot + 1u, hi - hi_p, k, e_p, tid, nt);
         }
+        lo_slot = (lo_slot + (uint32_t)(lo - lo_p)) % cap;
         __syncthreads();
         const int e = s_e;
-        const double seed = ldexp(s_seed_m, s_seed_e - e);
-        const double scale = ldexp(1.0, e_p - e);
+        const double seed = s_seed_m == 0.0 ? 0.0 : ldexp_fast(s_seed_m, s_seed_e - e);
+        const double scale = ldexp_fast(1.0, e_p - e);
         const int64_t w = hi - lo + 1;
-        const int L = (int)((max(w, (int64_t)1) + nt - 1) / nt) | 1;
-        const int64_t a0 = lo + (int64_t)tid * L, a1 = min(a0 + L, hi + 1);
+        const uint32_t L = (uint32_t)((max(w, (int64_t)1) + nt - 1) / nt) | 1u;
+        const int64_t a0 = lo + (int64_t)((uint32_t)tid * L), a1 = min(a0 + (int64_t)L, hi + 1);
         const int cnt = a1 > a0 ? (int)(a1 - a0) : 0;
-        const int s0 = cnt ? (int)(a0 % cap) : 0;
+        const uint32_t s0 = (lo_slot + (uint32_t)tid * L) % cap;
         double local = 0.0;
-        for (int q = 0, sl = s0; q < cnt; ++q) {
-            local += ring[sl] * scale;
-            if (++sl == cap) sl = 0;
+        {
+            uint32_t sl = s0;
+            for (int q = 0; q < cnt; ++q) {
+                local += ring[sl] * scale;
+                if (++sl == cap) sl = 0;
+            }
         }
         double incl = local;
 #pragma unroll
@@ -580,16 +610,20 @@ __device__ double rows_scan_smem(const SweepConst &c, double *ring, int cap, int
         }
         __syncthreads();
         double run = seed + (warp > 0 ? s_warp[warp - 1] : 0.0) + (incl - local);
-        for (int q = 0, sl = s0; q < cnt; ++q) {
-            run += ring[sl] * scale;
-            ring[sl] = run;
-            if (++sl == cap) sl = 0;
+        {
+            uint32_t sl = s0;
+            for (int q = 0; q < cnt; ++q) {
+                run += ring[sl] * scale;
+                ring[sl] = run;
+                if (++sl == cap) sl = 0;
+            }
         }
+        lo_p = lo;
         hi_p = hi;
         e_p = e;
         __syncthreads();
     }
-    if (tid == 0) return ring[(int)(m % cap)] / binom_scaled(m + n, n, e_p);
+    if (tid == 0) return ring[(lo_slot + (uint32_t)(m - lo_p)) % cap] / binom_scaled(m + n, n, e_p);
     return 0.0;
 }
 

@@ -20,7 +20,7 @@ for mode in ("rowscan", "rowscan_global", "sweep"):
         os.environ["B2F_DRIFT_ROWSCAN_SMEM"] = "0"
     det = TabularDrift(ref, CATEGORICAL_FEATURES, device=0)
     rows = {}
-    for n in (1, 2, 16, 48, 64, 128, 250, 512, 1000, 1025):
+    for n in (1, 2, 16, 48, 64, 128, 200, 250, 320, 512, 1000, 1025):
         batch = ref.iloc[rng.integers(0, len(ref), n)].reset_index(drop=True)
         det.statistics(batch)
         dev, wall = [], []
