@@ -296,7 +296,8 @@ extern "C" int b2f_drift_score(b2f_drift *d, int64_t n, const double *num_cols, 
     /* the big shared-memory ring only when this batch can take the shared-memory row scan: a launch that asks for 208 KB
      * re-partitions the SM's L1 / shared memory (measured: +0.1 ms on a single-row request) */
     const size_t ring_smem = 2 * B2F_DRIFT_RING_MAX * sizeof(double);
-    const size_t smem = (n >= 2 && n <= d->rowscan_smem_max_n) ? d->finish_smem : ring_smem;
+    static const bool force_big = getenv("B2F_DRIFT_FORCE_BIG_SMEM") != nullptr; /* experiment: the cost of the big launch alone */
+    const size_t smem = ((n >= 2 && n <= d->rowscan_smem_max_n) || force_big) ? std::max(d->finish_smem, (size_t)B2F_DRIFT_ROWSCAN_CAP * sizeof(double)) : ring_smem;
     k_drift_finish<<<(unsigned)F, B2F_DRIFT_THREADS, smem, d->stream>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_err(B2F_ECUDA, "drift kernel launch failed: %s", cudaGetErrorString(e));

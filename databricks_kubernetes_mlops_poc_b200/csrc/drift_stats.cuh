@@ -482,22 +482,16 @@ __device__ __forceinline__ double ldexp_fast(double x, int d) {
     return ldexp(x, d);
 }
 
+/* C(t, k) by a group of G lanes, lane gl multiplying the factors r = 1 + gl, 1 + gl + G, ...  Callers keep k <= 32 G, so a lane
+ * multiplies at most 32 factors below 2^31: no overflow check inside the loop. */
 template <int G>
 __device__ __forceinline__ BinomME binom_me_group(int64_t t, int k, int gl) {
     double num = 1.0, den = 1.0;
     int ex = 0;
-    const double base = (double)(t - k);
-    for (int r = 1 + gl; r <= k; r += G) {
-        num *= base + (double)r;
-        den *= (double)r;
-        if (num > 0x1p400) {
-            num *= 0x1p-400;
-            ex += 400;
-        }
-        if (den > 0x1p400) {
-            den *= 0x1p-400;
-            ex -= 400;
-        }
+    const double base = (double)(t - k), kd = (double)k;
+    for (double r = (double)(1 + gl); r <= kd; r += (double)G) {
+        num *= base + r;
+        den *= r;
     }
     int fe;
     double mant = frexp_pos(num / den, fe); /* in [0.5, 1) */
@@ -527,7 +521,11 @@ __device__ __forceinline__ void rows_extend(double *ring, uint32_t cap, int64_t 
         const bool live = q < cnt;
         const int64_t i = first + (live ? q : 0);
         const BinomME b = binom_me_group<G>(i + k, live ? k : 0, gl);
-        if (live && gl == 0) ring[(slot0 + (uint32_t)q) % cap] = ldexp_fast(b.mant, b.ex - e_p);
+        if (live && gl == 0) {
+            uint32_t sl = slot0 + (uint32_t)q; /* slot0 < cap, q < cap */
+            if (sl >= cap) sl -= cap;
+            ring[sl] = ldexp_fast(b.mant, b.ex - e_p);
+        }
     }
 }
 
@@ -557,7 +555,13 @@ __device__ double rows_scan_smem(const SweepConst &c, double *ring, int cap_i, i
         qb += dq, rb += dr;
         if (rb >= ng) rb -= ng, ++qb;
         const int64_t lo = max(qa + 1, (int64_t)0), hi = min(qb, m);
-        const uint32_t hi_p_slot = (lo_slot + (uint32_t)(hi_p - lo_p)) % cap;
+        /* the cells of the previous row this row reads and that row never computed (they were outside its band): from
+         * max(hi_p + 1, lo) -- when the band jumps past the previous one, the cells below lo are not needed, and writing them
+         * could wrap onto slots of cells that are */
+        lo_slot = (uint32_t)(((uint64_t)lo_slot + (uint64_t)(lo - lo_p)) % cap);
+        const int64_t first = max(hi_p + 1, lo);
+        uint32_t first_slot = lo_slot + (uint32_t)(first - lo); /* first - lo <= w <= cap */
+        if (first_slot >= cap) first_slot -= cap;
         if (warp == 0) {
             const BinomME b = binom_me_group<32>(hi + j, j, lane);
             if (lane == 0) s_e = b.ex;
@@ -569,20 +573,21 @@ __device__ double rows_scan_smem(const SweepConst &c, double *ring, int cap_i, i
             }
         } else {
             const int k = j - 1;
-            if (k <= 32) rows_extend<1>(ring, cap, hi_p + 1, hi_p_slot + 1u, hi - hi_p, k, e_p, tid, nt);
-            else if (k <= 256) rows_extend<8>(ring, cap, hi_p + 1, hi_p_slot + 1u, hi - hi_p, k, e_p, tid, nt);
-            else rows_extend<32>(ring, cap, hi_p + 1, hi_p_slot + 1u, hi - hi_p, k, e_p, tid, nt);
+            if (k <= 32) rows_extend<1>(ring, cap, first, first_slot, hi - first + 1, k, e_p, tid, nt);
+            else if (k <= 256) rows_extend<8>(ring, cap, first, first_slot, hi - first + 1, k, e_p, tid, nt);
+            else rows_extend<32>(ring, cap, first, first_slot, hi - first + 1, k, e_p, tid, nt);
         }
-        lo_slot = (lo_slot + (uint32_t)(lo - lo_p)) % cap;
         __syncthreads();
         const int e = s_e;
         const double seed = s_seed_m == 0.0 ? 0.0 : ldexp_fast(s_seed_m, s_seed_e - e);
         const double scale = ldexp_fast(1.0, e_p - e);
         const int64_t w = hi - lo + 1;
-        const uint32_t L = (uint32_t)((max(w, (int64_t)1) + nt - 1) / nt) | 1u;
+        const uint32_t L = (((uint32_t)max(w, (int64_t)1) + (uint32_t)nt - 1u) / (uint32_t)nt) | 1u; /* w <= cap */
         const int64_t a0 = lo + (int64_t)((uint32_t)tid * L), a1 = min(a0 + (int64_t)L, hi + 1);
         const int cnt = a1 > a0 ? (int)(a1 - a0) : 0;
-        const uint32_t s0 = (lo_slot + (uint32_t)tid * L) % cap;
+        uint32_t s0 = lo_slot + (uint32_t)tid * L; /* tid L < w + 2 nt <= 2 cap */
+        if (s0 >= cap) s0 -= cap;
+        if (s0 >= cap) s0 -= cap;
         double local = 0.0;
         {
             uint32_t sl = s0;

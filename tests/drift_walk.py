@@ -231,7 +231,11 @@ def exact_p_rows_ring(m0: int, n0: int, num: int, cap: int = 26624, nt: int = 10
         hi = min(-((-(mg * j + h)) // ng) - 1, m)
         e = _binom_exponent(hi + j, j)
         seed = _binom_scaled(lo - 1 + j, j, e) if lo >= 1 else 0.0
-        for i in range(hi_p + 1, hi + 1):
+        # cells below lo are not read by this row: writing them (in parallel, on the GPU) could wrap onto slots that are
+        written = {}
+        for i in range(max(hi_p + 1, lo), hi + 1):
+            assert i % cap not in written, "two cells of one extension share a slot"
+            written[i % cap] = i
             ring[i % cap] = _binom_scaled(i + j - 1, j - 1, e_p)
         scale = math.ldexp(1.0, e_p - e)
         w = hi - lo + 1
