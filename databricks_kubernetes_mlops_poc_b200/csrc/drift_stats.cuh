@@ -326,7 +326,8 @@ __device__ __forceinline__ double sweep_block(const SweepConst &c, int tid, int 
  * columns [t CH, (t+1) CH) and every load / store of a pass is coalesced; row j is scaled by 2^-E_j, E_j the exponent of
  * its largest binomial, so nothing overflows.  Sums run in a fixed order (deterministic).  p = W(m,n) / C(m+n, n). */
 #define B2F_DRIFT_ROWSCAN_MAX 48       /* global-scratch form: ~20 us per row, the sweep is faster beyond */
-#define B2F_DRIFT_ROWSCAN_SMEM_MAX 1024 /* shared-memory form: ~1-2 us per row */
+#define B2F_DRIFT_ROWSCAN_SMEM_MAX 448  /* shared-memory form: ~3.5 us per row; the sweep (2.0 ms at 30 000 reference rows) wins beyond ~480 */
+#define B2F_DRIFT_ROWSCAN_SMEM_LIMIT 1024 /* what B2F_DRIFT_ROWSCAN_SMEM may raise it to (32 factors per lane in the binomial products) */
 #define B2F_DRIFT_ROWSCAN_CAP 26624     /* doubles of the shared-memory row ring (208 KB; the kernel has 16 KB of static arrays) */
 /* doubles per scratch row: the transposed layout (i mod CH) * NT + i / CH spans CH * NT >= m + 1 slots */
 #define B2F_DRIFT_ROW_STRIDE(m) ((((int64_t)(m) + 1 + B2F_DRIFT_THREADS - 1) / B2F_DRIFT_THREADS) * B2F_DRIFT_THREADS)

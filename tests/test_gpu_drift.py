@@ -222,14 +222,14 @@ def test_row_scan_and_sweep_agree(curated):
     for c in rp.NUMERIC_FEATURES:
         slightly[c] = slightly[c] * 1.02
     batches.append(slightly)
-    det = TabularDrift(ref, rp.CATEGORICAL_FEATURES, device=0)
+    det = TabularDrift(ref, rp.CATEGORICAL_FEATURES, device=0)  # shared-memory row scan up to 448 rows, sweep beyond
     try:
         a = [det.statistics(b) for b in batches]
         for b in batches[:8] + batches[-2:]:
             _check(det, ref, b)
     finally:
         det.close()
-    for env in ({"B2F_DRIFT_ROWSCAN": "0"}, {"B2F_DRIFT_ROWSCAN_SMEM": "0"}):
+    for env in ({"B2F_DRIFT_ROWSCAN": "0"}, {"B2F_DRIFT_ROWSCAN_SMEM": "0"}, {"B2F_DRIFT_ROWSCAN_SMEM": "1024"}):
         os.environ.update(env)
         try:
             det = TabularDrift(ref, rp.CATEGORICAL_FEATURES, device=0)
