@@ -101,11 +101,6 @@ static int drift_init(b2f_drift *d, const double *ref_sorted, const int32_t *cat
     if (const char *rs = getenv("B2F_DRIFT_ROWSCAN_SMEM")) d->rowscan_smem_max_n = std::max(0, std::min(B2F_DRIFT_ROWSCAN_SMEM_LIMIT, atoi(rs)));
     d->finish_smem = 2 * B2F_DRIFT_RING_MAX * sizeof(double);
     if (d->rowscan_smem_max_n > 0) d->finish_smem = std::max(d->finish_smem, (size_t)B2F_DRIFT_ROWSCAN_CAP * sizeof(double));
-    /* both kernels ask for the same L1 / shared-memory split (all shared): a launch whose split differs from the previous
-     * kernel's waits for the SMs to drain and re-partition -- measured 0.11 ms per request when k_drift_count ran with the
-     * default split and k_drift_finish with 208 KB of shared memory */
-    CUDA_TRY(cudaFuncSetAttribute(k_drift_count, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CUDA_TRY(cudaFuncSetAttribute(k_drift_finish, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUDA_TRY(cudaFuncSetAttribute(k_drift_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(d->finish_smem, (size_t)B2F_DRIFT_ROWSCAN_CAP * sizeof(double))));
     return B2F_OK;
 }
@@ -298,8 +293,8 @@ extern "C" int b2f_drift_score(b2f_drift *d, int64_t n, const double *num_cols, 
     const int64_t total = n * F;
     const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)d->sm_count * 8));
     k_drift_count<<<blocks, 256, 0, d->stream>>>(p);
-    /* the big shared-memory ring only when this batch can take the shared-memory row scan: a launch that asks for 208 KB
-     * re-partitions the SM's L1 / shared memory (measured: +0.1 ms on a single-row request) */
+    /* the big shared-memory ring only when this batch can take the shared-memory row scan: with 208 KB of shared memory the SM
+     * keeps almost no L1, which the first part of the kernel (histogram scan) and k_drift_count's searches like to have */
     const size_t ring_smem = 2 * B2F_DRIFT_RING_MAX * sizeof(double);
     static const bool force_big = getenv("B2F_DRIFT_FORCE_BIG_SMEM") != nullptr; /* experiment: the cost of the big launch alone */
     const size_t smem = ((n >= 2 && n <= d->rowscan_smem_max_n) || force_big) ? std::max(d->finish_smem, (size_t)B2F_DRIFT_ROWSCAN_CAP * sizeof(double)) : ring_smem;

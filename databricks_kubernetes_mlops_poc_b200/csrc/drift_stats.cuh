@@ -328,7 +328,7 @@ __device__ __forceinline__ double sweep_block(const SweepConst &c, int tid, int 
 #define B2F_DRIFT_ROWSCAN_MAX 48       /* global-scratch form: ~20 us per row, the sweep is faster beyond */
 #define B2F_DRIFT_ROWSCAN_SMEM_MAX 448  /* shared-memory form: ~3.5 us per row; the sweep (2.0 ms at 30 000 reference rows) wins beyond ~480 */
 #define B2F_DRIFT_ROWSCAN_SMEM_LIMIT 1024 /* what B2F_DRIFT_ROWSCAN_SMEM may raise it to (32 factors per lane in the binomial products) */
-#define B2F_DRIFT_ROWSCAN_CAP 26624     /* doubles of the shared-memory row ring (208 KB; the kernel has 16 KB of static arrays) */
+#define B2F_DRIFT_ROWSCAN_CAP 28672     /* doubles of the shared-memory row ring (224 KB of the 227 KB a CTA may have) */
 /* doubles per scratch row: the transposed layout (i mod CH) * NT + i / CH spans CH * NT >= m + 1 slots */
 #define B2F_DRIFT_ROW_STRIDE(m) ((((int64_t)(m) + 1 + B2F_DRIFT_THREADS - 1) / B2F_DRIFT_THREADS) * B2F_DRIFT_THREADS)
 
@@ -650,57 +650,80 @@ __global__ void __launch_bounds__(B2F_DRIFT_THREADS) k_drift_finish(DriftParams 
         return;
     }
     const int out = p.n_cat + f;
-    __shared__ unsigned long long s_part_a[B2F_DRIFT_THREADS], s_part_b[B2F_DRIFT_THREADS];
+    __shared__ uint32_t s_wa[32], s_wb[32];
     __shared__ unsigned long long s_num;
 
-    /* ---- (1) K-S numerator: max over reference points of |n*(#ref <= r) - m0*(#batch <= r)| and the left limits */
+    /* ---- (1) K-S numerator: max over reference points of |n*(#ref <= r) - m0*(#batch <= r)| and the left limits.
+     *      Running counts over the m0 + 1 histogram bins: warp w owns a contiguous segment, lanes read consecutive bins
+     *      (coalesced), pass 1 adds the segment up, one barrier, pass 2 walks it again 32 bins at a time with shuffle scans.
+     *      (Round 1 gave each THREAD a contiguous run of 30 bins: every load of a warp touched 32 different lines, and the
+     *      1024 partial sums were scanned by one thread -- most of the 0.11 ms a single-row request took.) */
     const int64_t m0 = p.n_ref, n0 = p.n;
     const uint32_t *ha = p.hist_a + (int64_t)f * (m0 + 1);
     const uint32_t *hb = p.hist_b + (int64_t)f * (m0 + 1);
     const double *r = p.ref_sorted + (int64_t)f * m0;
-    const int64_t seg = (m0 + 1 + nt - 1) / nt;
-    const int64_t j0 = (int64_t)tid * seg, j1 = min(j0 + seg, m0 + 1);
-    unsigned long long sa = 0, sb = 0;
-    for (int64_t j = j0; j < j1; ++j) {
-        sa += ha[j];
-        sb += hb[j];
-    }
-    s_part_a[tid] = sa;
-    s_part_b[tid] = sb;
-    if (tid == 0) s_num = 0ull;
-    __syncthreads();
-    if (tid == 0) { /* exclusive scan of the per-thread partial sums */
-        unsigned long long ca = 0, cb = 0;
-        for (int k = 0; k < nt; ++k) {
-            const unsigned long long ta = s_part_a[k], tb = s_part_b[k];
-            s_part_a[k] = ca;
-            s_part_b[k] = cb;
-            ca += ta;
-            cb += tb;
-        }
-    }
-    __syncthreads();
     {
-        int64_t cle = (int64_t)s_part_a[tid], clt = (int64_t)s_part_b[tid]; /* running #batch <= r_j, #batch < r_j */
-        int64_t best = 0;
-        for (int64_t j = j0; j < j1 && j < m0; ++j) {
-            cle += ha[j]; /* x <= r_j  <=>  (#ref < x) <= j */
-            clt += hb[j]; /* x <  r_j  <=>  (#ref <= x) <= j */
-            const double rj = r[j];
-            const bool first = j == 0 || r[j - 1] != rj;     /* #ref <  r_j == j     */
-            const bool last = j == m0 - 1 || r[j + 1] != rj; /* #ref <= r_j == j + 1 */
-            if (last) {
-                int64_t v = (j + 1) * n0 - cle * m0;
-                if (v < 0) v = -v;
-                best = max(best, v);
-            }
-            if (first) {
-                int64_t v = j * n0 - clt * m0;
-                if (v < 0) v = -v;
-                best = max(best, v);
-            }
+        const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+        const int64_t total = m0 + 1;
+        const int64_t seg = ((total + nwarps - 1) / nwarps + 31) / 32 * 32;
+        const int64_t w0 = min((int64_t)warp * seg, total), w1 = min(w0 + seg, total);
+        uint32_t sa = 0, sb = 0; /* counts of batch elements: below 2^31 */
+        for (int64_t j = w0 + lane; j < w1; j += 32) {
+            sa += ha[j];
+            sb += hb[j];
         }
-        atomicMax(&s_num, (unsigned long long)best);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        }
+        if (lane == 0) {
+            s_wa[warp] = sa;
+            s_wb[warp] = sb;
+        }
+        if (tid == 0) s_num = 0ull;
+        __syncthreads();
+        uint32_t ca = 0, cb = 0; /* bins before this warp's segment */
+        for (int k = 0; k < warp; ++k) {
+            ca += s_wa[k];
+            cb += s_wb[k];
+        }
+        int64_t best = 0;
+        for (int64_t b = w0; b < w1; b += 32) {
+            const int64_t j = b + lane;
+            const bool in = j < w1;
+            uint32_t ia = in ? ha[j] : 0u, ib = in ? hb[j] : 0u;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t ua = __shfl_up_sync(0xffffffffu, ia, o), ub = __shfl_up_sync(0xffffffffu, ib, o);
+                if (lane >= o) {
+                    ia += ua;
+                    ib += ub;
+                }
+            }
+            if (in && j < m0) {
+                const int64_t cle = (int64_t)(ca + ia); /* #batch <= r_j:  x <= r_j  <=>  (#ref <  x) <= j */
+                const int64_t clt = (int64_t)(cb + ib); /* #batch <  r_j:  x <  r_j  <=>  (#ref <= x) <= j */
+                const double rj = r[j];
+                const bool first = j == 0 || r[j - 1] != rj;     /* #ref <  r_j == j     */
+                const bool last = j == m0 - 1 || r[j + 1] != rj; /* #ref <= r_j == j + 1 */
+                if (last) {
+                    int64_t v = (j + 1) * n0 - cle * m0;
+                    if (v < 0) v = -v;
+                    best = max(best, v);
+                }
+                if (first) {
+                    int64_t v = j * n0 - clt * m0;
+                    if (v < 0) v = -v;
+                    best = max(best, v);
+                }
+            }
+            ca += __shfl_sync(0xffffffffu, ia, 31);
+            cb += __shfl_sync(0xffffffffu, ib, 31);
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) best = max(best, (int64_t)__shfl_xor_sync(0xffffffffu, (long long)best, o));
+        if (lane == 0) atomicMax(&s_num, (unsigned long long)best);
     }
     __syncthreads();
     const int64_t num = (int64_t)s_num;
