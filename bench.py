@@ -362,7 +362,7 @@ def host_thread_share(dist: Dist) -> int:
 
     lib = _cabi.load_library()
     cores = os.cpu_count() or 2
-    per_node = max(1, cores // 2 // 2)  # two sockets, two hyper-threads per core on the B200 hosts
+    per_node = max(1, cores // 2)  # two sockets: the logical CPUs of one (8 ranks on 64 cores: every rank needs its hyper-threads too)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(dist.world)))
     ranks_per_node = max(1, (local_world + 1) // 2)
     share = per_node // ranks_per_node

@@ -57,6 +57,8 @@ struct b2f_ranktab {
 int b2f_simd_level(void);
 void b2f_simd_rank_column(const b2f_ranktab *t, const float *x, int64_t n, int64_t x_stride, uint16_t *out, int64_t out_stride, uint16_t nan_rank);
 int b2f_simd_cvt_column(const double *src, int64_t stride, int64_t n, float *dst); /* float64 -> float32; 1 = an inf / overflow was seen */
+int64_t b2f_simd_hash_codes(const void *offsets, int offsets_are_64, const uint8_t *data, int64_t data_bytes, int64_t nb, uint64_t m1, uint64_t m2,
+                            uint64_t m3, int shift, const void *slots, int32_t *codes); /* rows done from the start; -2 = hit that needs the full compare */
 void b2f_simd_pack_rows64(const int32_t *codes, const float *cols, int64_t ld, int n_cat, int n_num, int64_t nb, uint32_t *out);
 }
 

@@ -209,4 +209,69 @@ void b2f_simd_pack_rows64(const int32_t *codes, const float *cols, int64_t ld, i
         pack_rows64_scalar(codes, cols, ld, n_cat, n_num, 0, nb, out);
 }
 
+/* ---- vocabulary codes of a block of one string column, eight strings at a time (AVX-512F + DQ) ----------------------------
+ * The scalar lookup (row_encoder.h: enc_lookup) is ~30 instructions per string; here the same perfect hash runs on eight rows
+ * per step: two loads of the Arrow offsets (int32 or int64), a gather of the first 8 bytes and one of the last 8 bytes of each
+ * string, the length mask, three 64-bit multiplies, and three gathers of the 24-byte table entry {prefix, suffix, len | code}.
+ * Returns how many rows from the start were done (a multiple of 8; the caller finishes the rest with the scalar lookup).
+ * A hit on a string longer than 16 bytes still needs its middle compared: those rows get B2F_CODE_RECHECK. */
+#define B2F_CODE_RECHECK (-2)
+
+__attribute__((target("avx512f,avx512dq,avx512vl"))) static inline __m256i hash_codes_step(__m512i a, __m512i len64, const uint8_t *data, __m512i vm1,
+                                                                                            __m512i vm2, __m512i vm3, __m128i vshift, const void *slots) {
+    const __m512i one = _mm512_set1_epi64(1), three = _mm512_set1_epi64(3), lo32 = _mm512_set1_epi64(0xFFFFFFFFll);
+    const __m512i off2 = _mm512_max_epi64(_mm512_sub_epi64(len64, _mm512_set1_epi64(8)), _mm512_setzero_si512());
+    const __m512i p_raw = _mm512_i64gather_epi64(a, data, 1);
+    const __m512i q_raw = _mm512_i64gather_epi64(_mm512_add_epi64(a, off2), data, 1);
+    /* (1 << 8 len) - 1: a shift count >= 64 gives 0, minus one = all ones -- exactly the mask of a string of >= 8 bytes */
+    const __m512i mask = _mm512_sub_epi64(_mm512_sllv_epi64(one, _mm512_slli_epi64(len64, 3)), one);
+    const __m512i pp = _mm512_and_si512(p_raw, mask), qq = _mm512_and_si512(q_raw, mask);
+    const __m512i h = _mm512_xor_si512(_mm512_xor_si512(_mm512_mullo_epi64(pp, vm1), _mm512_mullo_epi64(qq, vm2)), _mm512_mullo_epi64(len64, vm3));
+    const __m512i idx = _mm512_mullo_epi64(_mm512_srl_epi64(h, vshift), three); /* entry = 3 x 8 bytes */
+    const __m512i ep = _mm512_i64gather_epi64(idx, slots, 8);
+    const __m512i es = _mm512_i64gather_epi64(_mm512_add_epi64(idx, one), slots, 8);
+    const __m512i el = _mm512_i64gather_epi64(_mm512_add_epi64(idx, _mm512_set1_epi64(2)), slots, 8);
+    const __mmask8 hit = _mm512_cmpeq_epi64_mask(ep, pp) & _mm512_cmpeq_epi64_mask(es, qq) & _mm512_cmpeq_epi64_mask(_mm512_and_si512(el, lo32), len64);
+    const __mmask8 longs = hit & _mm512_cmpgt_epi64_mask(len64, _mm512_set1_epi64(16));
+    __m256i code = _mm512_cvtepi64_epi32(_mm512_srli_epi64(el, 32));
+    code = _mm256_mask_blend_epi32(hit, _mm256_set1_epi32(-1), code);
+    return _mm256_mask_blend_epi32(longs, code, _mm256_set1_epi32(B2F_CODE_RECHECK));
+}
+
+__attribute__((target("avx512f,avx512dq,avx512vl"))) static int64_t hash_codes_avx512(const void *offsets, int offsets_are_64, const uint8_t *data,
+                                                                                      int64_t data_bytes, int64_t nb, uint64_t m1, uint64_t m2, uint64_t m3,
+                                                                                      int shift, const void *slots, int32_t *codes) {
+    const __m512i vm1 = _mm512_set1_epi64((long long)m1), vm2 = _mm512_set1_epi64((long long)m2), vm3 = _mm512_set1_epi64((long long)m3);
+    const __m128i vshift = _mm_cvtsi32_si128(shift);
+    int64_t i = 0;
+    if (offsets_are_64) {
+        const int64_t *o = static_cast<const int64_t *>(offsets);
+        for (; i + 8 <= nb; i += 8) {
+            if (o[i + 8] + 8 > data_bytes) break; /* the 8-byte loads of the last strings would leave the buffer */
+            const __m512i a = _mm512_loadu_si512(o + i), b = _mm512_loadu_si512(o + i + 1);
+            _mm256_storeu_si256(reinterpret_cast<__m256i *>(codes + i), hash_codes_step(a, _mm512_sub_epi64(b, a), data, vm1, vm2, vm3, vshift, slots));
+        }
+    } else {
+        const int32_t *o = static_cast<const int32_t *>(offsets);
+        for (; i + 8 <= nb; i += 8) {
+            if ((int64_t)o[i + 8] + 8 > data_bytes) break;
+            const __m512i a = _mm512_cvtepi32_epi64(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(o + i)));
+            const __m512i b = _mm512_cvtepi32_epi64(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(o + i + 1)));
+            _mm256_storeu_si256(reinterpret_cast<__m256i *>(codes + i), hash_codes_step(a, _mm512_sub_epi64(b, a), data, vm1, vm2, vm3, vshift, slots));
+        }
+    }
+    return i;
+}
+
+int64_t b2f_simd_hash_codes(const void *offsets, int offsets_are_64, const uint8_t *data, int64_t data_bytes, int64_t nb, uint64_t m1, uint64_t m2,
+                            uint64_t m3, int shift, const void *slots, int32_t *codes) {
+    static int ok = -1;
+    if (ok < 0) {
+        __builtin_cpu_init();
+        ok = (b2f_simd_level() == 2 && __builtin_cpu_supports("avx512dq") && __builtin_cpu_supports("avx512vl")) ? 1 : 0;
+    }
+    if (!ok || nb < 8) return 0;
+    return hash_codes_avx512(offsets, offsets_are_64, data, data_bytes, nb, m1, m2, m3, shift, slots, codes);
+}
+
 } /* extern "C" */

@@ -127,6 +127,23 @@ static inline int32_t enc_code(const b2f_encoder *e, int j, const b2f_str_column
     return enc_lookup(e, j, c.data + a, b - a, a + 8 <= c.data_bytes);
 }
 
+/* codes of rows [i0, i0 + nb) of categorical column j into out[0 .. nb): eight strings per step where the column allows it
+ * (no nulls -- host_simd.cpp), the scalar lookup for the rest and for hits that need their middle compared */
+static inline void enc_codes_block(const b2f_encoder *e, int j, const b2f_str_column &c, int64_t i0, int64_t nb, int32_t *out) {
+    int64_t done = 0;
+    if (!c.validity) {
+        static_assert(sizeof(EncEntry) == 24, "the vector lookup gathers 24-byte entries");
+        const EncHash &h = e->hash[j];
+        const int64_t k0 = i0 + c.offset;
+        const void *off = c.offsets_are_64 ? static_cast<const void *>(static_cast<const int64_t *>(c.offsets) + k0)
+                                           : static_cast<const void *>(static_cast<const int32_t *>(c.offsets) + k0);
+        done = b2f_simd_hash_codes(off, c.offsets_are_64, c.data, c.data_bytes, nb, h.m1, h.m2, h.m3, h.shift, h.slots.data(), out);
+        for (int64_t i = 0; i < done; ++i)
+            if (out[i] == -2) out[i] = enc_code(e, j, c, i0 + i);
+    }
+    for (int64_t i = done; i < nb; ++i) out[i] = enc_code(e, j, c, i0 + i);
+}
+
 /* ranked rows: blocks of B2F_RANK_BLOCK rows -- categorical block per row, float32 numerics transposed into a
  * column-major scratch, then one SIMD rank pass per feature over the block (forest_rank.h / host_simd.cpp) */
 static int enc_range_ranked(const b2f_encoder *e, int64_t lo, int64_t hi, const b2f_str_column *cats, const double *const *nums,
@@ -162,10 +179,7 @@ static int enc_range_packed(const b2f_encoder *e, int64_t lo, int64_t hi, const 
     int32_t codes[9 * B2F_RANK_BLOCK];
     for (int64_t b0 = lo; b0 < hi; b0 += B2F_RANK_BLOCK) {
         const int64_t nb = std::min<int64_t>(B2F_RANK_BLOCK, hi - b0);
-        for (int j = 0; j < nc; ++j) {
-            int32_t *cj = codes + (size_t)j * B2F_RANK_BLOCK;
-            for (int64_t i = 0; i < nb; ++i) cj[i] = enc_code(e, j, cats[j], b0 + i);
-        }
+        for (int j = 0; j < nc; ++j) enc_codes_block(e, j, cats[j], b0, nb, codes + (size_t)j * B2F_RANK_BLOCK);
         for (int k = 0; k < nn; ++k) bad |= b2f_simd_cvt_column(nums[k] + b0 * num_strides[k], num_strides[k], nb, cols + (size_t)k * B2F_RANK_BLOCK);
         b2f_simd_pack_rows64(codes, cols, B2F_RANK_BLOCK, nc, nn, nb, out + (size_t)b0 * 16);
     }
@@ -255,7 +269,7 @@ extern "C" int b2f_encoder_codes(const b2f_encoder *e, int64_t n, const b2f_str_
     auto work = [&](int64_t lo, int64_t hi) {
         for (int j = 0; j < e->n_cat; ++j) {
             int32_t *out = codes_out + (size_t)j * n;
-            for (int64_t i = lo; i < hi; ++i) out[i] = enc_code(e, j, cat_cols[j], i);
+            enc_codes_block(e, j, cat_cols[j], lo, hi - lo, out + lo);
         }
     };
     if (threads == 1) {

@@ -233,13 +233,22 @@ struct b2f_scorer {
     cudaEvent_t ev[B2F_SCORER_MAX_CHUNKS] = {};
     char err[256] = "";
     int64_t jobs = 0;
+    /* timeline of the current job (b2f_scorer_trace), microseconds since b2f_scorer_start: per chunk, when its last part was
+     * encoded (submission begins) and when its H2D / kernel / D2H had been enqueued */
+    std::chrono::steady_clock::time_point t_start;
+    double t_encoded[B2F_SCORER_MAX_CHUNKS] = {}, t_enqueued[B2F_SCORER_MAX_CHUNKS] = {};
 };
+
+static inline double scorer_us_since(const b2f_scorer *s) {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - s->t_start).count();
+}
 
 static void scorer_submit_chunk(b2f_scorer *s, int c) {
     /* H2D -> kernel(s) -> D2H for chunk c on the stream of slot (c mod streams); called by the worker that finished it */
     b2f_model *m = s->m;
     const int64_t lo = (int64_t)c * s->chunk_rows, cnt = std::min(s->chunk_rows, s->n - lo);
     int rc = B2F_OK;
+    s->t_encoded[c] = scorer_us_since(s);
     {
         std::lock_guard<std::mutex> lk(s->mu);
         Slot &sl = m->slots[c % B2F_STREAMS];
@@ -266,6 +275,7 @@ static void scorer_submit_chunk(b2f_scorer *s, int c) {
             snprintf(s->err, sizeof(s->err), "%s", b2f_last_error());
         }
     }
+    s->t_enqueued[c] = scorer_us_since(s);
     s->chunk_state[c].store(rc == B2F_OK ? 1 : rc, std::memory_order_release);
 }
 
@@ -370,6 +380,17 @@ extern "C" void b2f_scorer_destroy(b2f_scorer *s) {
  * Returns the number of chunks (>= 0) or a negative error.  Results appear in the scorer's pinned result buffer
  * (b2f_scorer_results) chunk by chunk; b2f_scorer_wait(chunk) blocks until that chunk is there.  The column buffers must stay
  * valid until the last chunk has been waited for.  One job at a time per scorer. */
+/* out[2 c] / out[2 c + 1]: microseconds from b2f_scorer_start to "chunk c encoded" / "chunk c's GPU work enqueued" (last job) */
+extern "C" int b2f_scorer_trace(const b2f_scorer *s, double *out, int max_chunks) {
+    if (!s || !out) return 0;
+    const int nc = std::min(s->n_chunks, max_chunks);
+    for (int c = 0; c < nc; ++c) {
+        out[2 * c] = s->t_encoded[c];
+        out[2 * c + 1] = s->t_enqueued[c];
+    }
+    return nc;
+}
+
 extern "C" int b2f_scorer_start(b2f_scorer *s, int64_t n, const b2f_str_column *cat_cols, const double *const *num_cols, const int64_t *num_strides,
                                 int row_format, int out_mode, int64_t chunk_rows) {
     if (!s || n < 0) return set_err(B2F_EINVAL, "bad argument");
@@ -423,6 +444,7 @@ extern "C" int b2f_scorer_start(b2f_scorer *s, int64_t n, const b2f_str_column *
     s->next_item.store(0);
     s->err[0] = 0;
     s->jobs++;
+    s->t_start = std::chrono::steady_clock::now();
     {
         std::lock_guard<std::mutex> lk(s->mu);
         s->generation.fetch_add(1, std::memory_order_release);

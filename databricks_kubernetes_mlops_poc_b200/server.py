@@ -38,7 +38,7 @@ from typing import AsyncGenerator
 
 import numpy as np
 import pandas as pd
-from fastapi import FastAPI, Request
+from fastapi import FastAPI, Request, Response
 
 from .ingest import NativeRequestParser, parse_rows, rows_to_frame  # noqa: F401  (rows_to_frame re-exported)
 from .schema import ALL_FEATURES, LoanApplicant, ModelOutput
@@ -259,7 +259,12 @@ def create_app(model=None, loader=None) -> FastAPI:
             "feature_drift_batch": dict(zip(ALL_FEATURES, drift_scores)),
         }
         log_pool.submit(_log_record, "ModelOutput", request_id, model_output)
-        return model_output
+        # Response side (reference app/main.py:42,86: `response_model=ModelOutput` makes FastAPI validate the dict field by
+        # field and run it through jsonable_encoder before rendering).  Every value here was produced by this handler with
+        # the declared types, so the body is rendered once, exactly as Starlette's JSONResponse would render the validated
+        # model (compact separators, allow_nan=False -> a NaN drift score is the same ValueError -> HTTP 500)
+        body = json.dumps(model_output, ensure_ascii=False, allow_nan=False, indent=None, separators=(",", ":")).encode("utf-8")
+        return Response(content=body, media_type="application/json")
 
     return app
 

@@ -248,6 +248,9 @@ b2f_scorer *b2f_scorer_create(b2f_model *m, const b2f_encoder *e, int threads /*
 /* the default size of a scorer's thread pool: three quarters of the CPUs of the GPU's NUMA node, at most 48, and at most the
  * cgroup's CPU bandwidth minus two (b2f_host_cpu_limit: cpu.max quota / period, 0.0 when unlimited) -- polling workers beyond
  * the quota get the whole container throttled */
+/* timeline of the last job, for tuning: out[2c], out[2c+1] = microseconds from b2f_scorer_start to "chunk c encoded" and to
+ * "chunk c's H2D / kernel / D2H enqueued"; returns the number of chunks written (<= max_chunks) */
+int b2f_scorer_trace(const b2f_scorer *s, double *out, int max_chunks);
 int b2f_host_threads_default(int device);
 double b2f_host_cpu_limit(void);
 void b2f_scorer_destroy(b2f_scorer *s);

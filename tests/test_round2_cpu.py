@@ -243,3 +243,63 @@ def test_packed_block_encoder_every_block_shape(curated, rf100d6):
     bad.loc[bad.index[1100], "payment_amount_3"] = -np.inf
     with pytest.raises(ValueError, match="infinity or a value too large"):
         enc._encode_native(bad, np.zeros((len(bad), 16), dtype=np.uint32), fmt=1)
+
+
+def test_vector_vocabulary_lookup_matches_a_dictionary():
+    """The eight-strings-per-step vocabulary lookup (host_simd.cpp: b2f_simd_hash_codes) against a Python dict: every
+    string length around the 8- and 16-byte boundaries, unknown strings that share prefix, suffix and length with a
+    vocabulary entry (only the middle differs), empty strings, the last strings of the buffer, int32 and int64 Arrow
+    offsets, sliced arrays, and a column with nulls (scalar path)."""
+    import ctypes as C
+
+    import pyarrow as pa
+
+    from databricks_kubernetes_mlops_poc_b200 import _cabi
+
+    lib = _cabi.load_library()
+    rng = np.random.default_rng(3)
+    alphabet = np.array(list("abcdefghijklmnopqrstuvwxyz_0123456789"))
+
+    def word(n):
+        return "".join(rng.choice(alphabet, n))
+
+    vocab = sorted({word(n) for n in (0, 1, 2, 5, 7, 8, 9, 12, 15, 16, 17, 18, 24, 33, 40) for _ in range(3)})
+    longs = [w for w in vocab if len(w) > 16]
+    twins = [w[:8] + word(len(w) - 16) + w[-8:] for w in longs]  # same (prefix, suffix, length), another middle
+    twins = [t for t in twins if t not in vocab]
+    unknown = [word(n) for n in (1, 3, 8, 9, 16, 17, 30)] + twins
+    pool = np.array(vocab + [u for u in unknown if u not in vocab], dtype=object)
+    want_of = {w: k for k, w in enumerate(vocab)}
+    blob = "".join(vocab).encode()
+    offs = np.cumsum([0] + [len(w.encode()) for w in vocab]).astype(np.int64)
+    counts = np.array([len(vocab)], dtype=np.int32)
+    null_codes = np.array([want_of[vocab[3]]], dtype=np.int32)
+    enc = lib.b2f_encoder_create(1, 0, _cabi.ptr(counts), blob, _cabi.ptr(offs), _cabi.ptr(null_codes))
+    assert enc
+    try:
+        for n in (1, 7, 8, 9, 64, 1000, 4099):
+            values = pool[rng.integers(0, len(pool), n)]
+            values[-1] = vocab[1] if len(vocab[1]) < 8 else values[-1]  # a short string at the very end of the buffer
+            for typ in (pa.string(), pa.large_string()):
+                for with_nulls in (False, True):
+                    vals = list(values)
+                    if with_nulls:
+                        for k in range(0, n, 5):
+                            vals[k] = None
+                    arr = pa.array(vals, type=typ)
+                    for sl in ((0, n), (min(3, n - 1), n)):
+                        a = arr.slice(sl[0], sl[1] - sl[0])
+                        validity, offsets, data = a.buffers()
+                        col = (_cabi.StrColumn * 1)()
+                        col[0].offsets = offsets.address
+                        col[0].data = data.address if data is not None else 0
+                        col[0].validity = validity.address if (validity is not None and a.null_count) else 0
+                        col[0].offset = a.offset
+                        col[0].data_bytes = data.size if data is not None else 0
+                        col[0].offsets_are_64 = 1 if typ == pa.large_string() else 0
+                        got = np.full(len(a), -99, dtype=np.int32)
+                        assert lib.b2f_encoder_codes(enc, len(a), col, _cabi.ptr(got), 1) == 0
+                        want = [int(null_codes[0]) if v is None else want_of.get(v, -1) for v in vals[sl[0]:sl[1]]]
+                        assert got.tolist() == want, (n, str(typ), with_nulls, sl)
+    finally:
+        lib.b2f_encoder_destroy(enc)
