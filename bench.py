@@ -743,7 +743,7 @@ def drift_section(base, flat, device):
     det = TabularDrift(ref, flat.cat_features, device=device)
     rng = np.random.default_rng(DATA_SEED + 7)
     rows = []
-    for n in (1, 1000, 65536):
+    for n in (1, 16, 128, 1000, 65536):  # closed form; row scan in shared memory (2..448 rows); sweep
         batch = ref.iloc[rng.integers(0, len(ref), n)].reset_index(drop=True)
         got = det.p_values(batch)  # warm-up + parity sample
         dev, wall = [], []
