@@ -10,7 +10,8 @@ from databricks_kubernetes_mlops_poc_b200.model import B200Model
 from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES
 
 dist = bench.Dist(1, False, solo=True)
-pipe, base = bench.get_pipeline("gbdt100d6", dist)
+MODEL = os.environ.get("TRACE_MODEL", "gbdt100d6")
+pipe, base = bench.get_pipeline(MODEL, dist)
 flat = flatten.flatten_pipeline(pipe)
 pv, pc, pn = training.synth_arrays(base, bench.BATCH, bench.DATA_SEED)
 df = training.arrays_to_frame(pv, pc, pn)[ALL_FEATURES]
@@ -42,8 +43,8 @@ for _ in range(K):
     rec.append({"columns": 1e6 * (t1 - t0), "start_call": 1e6 * (t2 - t1), "encoded": tr[0::2].tolist(), "enqueued": tr[1::2].tolist(),
                 "back": [1e6 * (b - t1) for b in back], "built": [1e6 * (b - t1) for b in built], "total": 1e6 * (built[-1] - t0)})
 med = lambda key: np.median(np.asarray([r[key] for r in rec]), axis=0)
-res = {"threads": sc.threads, "chunks": n_chunks, "chunk_rows": int(step), "us_since_start": {k: np.round(med(k), 1).tolist() for k in ("encoded", "enqueued", "back", "built")},
+res = {"model": MODEL, "row_format": sc.last_fmt, "threads": sc.threads, "chunks": n_chunks, "chunk_rows": int(step), "us_since_start": {k: np.round(med(k), 1).tolist() for k in ("encoded", "enqueued", "back", "built")},
        "columns_us": float(med("columns")), "start_call_us": float(med("start_call")), "total_us": float(med("total"))}
 print(json.dumps(res, indent=1))
-json.dump(res, open(f"gpurun_out/scorer_trace_c{chunk_rows}.json", "w"), indent=1)
+json.dump(res, open(f"gpurun_out/scorer_trace_{MODEL}_f{sc.last_fmt}_c{chunk_rows}.json", "w"), indent=1)
 model.close()
