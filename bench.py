@@ -351,21 +351,29 @@ def run_reference(args, dist: Dist):
 
 
 def host_thread_share(dist: Dist) -> int:
-    """Encoder threads for this rank: the library's default for one GPU (the GPU's NUMA node, capped by the container's CPU
-    bandwidth -- `b2f_host_threads_default`), and under torchrun this rank's share of the node's cores / of that bandwidth."""
+    """Encoder threads for this rank.  One rank: the library's default (the GPU's NUMA node, capped by the container's CPU
+    bandwidth -- `b2f_host_threads_default`).  Under torchrun the ranks share the host: a rank takes the physical cores of its
+    GPU's NUMA node divided by the ranks whose GPUs sit on that node, plus two, and never more than its share of the CPU
+    quota.  (Measured on the 8-GPU box, 2 x 32 cores, quota 96: 8 ranks x 10 threads 548 M rows/s, x 7: 489 M, x 13: 502 M;
+    4 ranks -- all four GPUs on node 0 -- x 10: 368 M, x 14: 306 M, x 22: 256 M.)"""
     env = os.environ.get("B200_HOST_THREADS")
     if env:
         return int(env)
     if dist.world == 1:
         return 0  # the library's default
+    import ctypes
+
     from databricks_kubernetes_mlops_poc_b200 import _cabi
 
     lib = _cabi.load_library()
-    cores = os.cpu_count() or 2
-    per_node = max(1, cores // 2)  # two sockets: the logical CPUs of one (8 ranks on 64 cores: every rank needs its hyper-threads too)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(dist.world)))
-    ranks_per_node = max(1, (local_world + 1) // 2)
-    share = per_node // ranks_per_node
+    ncpu = ctypes.c_int(0)
+    my_node = lib.b2f_device_numa_node(dist.local_rank, ctypes.byref(ncpu))
+    if my_node >= 0 and ncpu.value > 0:
+        on_my_node = sum(1 for r in range(local_world) if lib.b2f_device_numa_node(r, None) == my_node)
+        share = (ncpu.value // 2) // max(1, on_my_node) + 2  # two hyper-threads per core on the B200 hosts
+    else:
+        share = (os.cpu_count() or 2) // 2 // max(1, local_world) + 2
     limit = float(lib.b2f_host_cpu_limit())
     if limit > 0:
         share = min(share, (int(limit) - 2 * local_world) // local_world)

@@ -113,6 +113,25 @@ static int default_host_threads(int device) {
     return threads;
 }
 
+/* NUMA node of a GPU (sysfs numa_node of its PCI device), -1 when the topology is not exposed; *n_cpus = logical CPUs of that
+ * node this process may run on */
+extern "C" int b2f_device_numa_node(int device, int *n_cpus) {
+    if (n_cpus) *n_cpus = 0;
+    char bdf[32] = "";
+    if (cudaDeviceGetPCIBusId(bdf, sizeof(bdf), device) != cudaSuccess) return -1;
+    for (char *c = bdf; *c; ++c) *c = (char)tolower(*c);
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bdf);
+    int node = -1;
+    if (FILE *f = fopen(path, "r")) {
+        if (fscanf(f, "%d", &node) != 1) node = -1;
+        fclose(f);
+    }
+    cpu_set_t set;
+    if (node >= 0 && n_cpus && numa_cpus_of_device(device, &set)) *n_cpus = CPU_COUNT(&set);
+    return node;
+}
+
 extern "C" double b2f_host_cpu_limit(void) { return cgroup_cpu_limit(); }
 extern "C" int b2f_host_threads_default(int device) { return default_host_threads(device); }
 

@@ -253,6 +253,8 @@ b2f_scorer *b2f_scorer_create(b2f_model *m, const b2f_encoder *e, int threads /*
 int b2f_scorer_trace(const b2f_scorer *s, double *out, int max_chunks);
 int b2f_host_threads_default(int device);
 double b2f_host_cpu_limit(void);
+/* NUMA node of a GPU (-1: not exposed) and the number of logical CPUs of that node this process may use */
+int b2f_device_numa_node(int device, int *n_cpus);
 void b2f_scorer_destroy(b2f_scorer *s);
 /* out_mode: 0 = float proba1, 1 = double proba1, 3 = b2f_scored_full records (attached outlier forest; float32 row formats only).
  * chunk_rows 0 = choose.  Returns the number of chunks (>= 0) or a negative error; one job at a time per scorer; the column
