@@ -140,6 +140,7 @@ SIGNATURES = {
     "b2f_scorer_create": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int]),
     "b2f_scorer_destroy": (None, [C.c_void_p]),
     "b2f_scorer_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "b2f_scorer_chunk_range": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "b2f_host_threads_default": (C.c_int, [C.c_int]),
     "b2f_host_cpu_limit": (C.c_double, []),
     "b2f_device_numa_node": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),

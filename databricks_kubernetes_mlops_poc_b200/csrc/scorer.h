@@ -238,6 +238,7 @@ struct b2f_scorer {
     int64_t cap_rows = 0;
     /* current job */
     int64_t n = 0, chunk_rows = 0;
+    int64_t chunk_lo[B2F_SCORER_MAX_CHUNKS + 1] = {}; /* chunk c = rows [chunk_lo[c], chunk_lo[c + 1]) */
     int n_chunks = 0, parts_per_chunk = 1;
     int row_format = 0, out_mode = 1;
     size_t row_bytes = 0, out_bytes = 8;
@@ -265,9 +266,14 @@ static inline double scorer_us_since(const b2f_scorer *s) {
 static void scorer_submit_chunk(b2f_scorer *s, int c) {
     /* H2D -> kernel(s) -> D2H for chunk c on the stream of slot (c mod streams); called by the worker that finished it */
     b2f_model *m = s->m;
-    const int64_t lo = (int64_t)c * s->chunk_rows, cnt = std::min(s->chunk_rows, s->n - lo);
+    const int64_t lo = s->chunk_lo[c], cnt = s->chunk_lo[c + 1] - lo;
     int rc = B2F_OK;
     s->t_encoded[c] = scorer_us_since(s);
+    if (cnt <= 0) { /* cannot happen with the boundaries b2f_scorer_start computes; never hand CUDA an empty chunk */
+        s->t_enqueued[c] = s->t_encoded[c];
+        s->chunk_state[c].store(1, std::memory_order_release);
+        return;
+    }
     {
         std::lock_guard<std::mutex> lk(s->mu);
         Slot &sl = m->slots[c % B2F_STREAMS];
@@ -304,7 +310,7 @@ static bool scorer_work_one(b2f_scorer *s) {
     const int it = s->next_item.fetch_add(1, std::memory_order_relaxed);
     if (it >= n_items) return false;
     const int c = it / s->parts_per_chunk, part = it % s->parts_per_chunk; /* items go out in order: chunk 0 completes first */
-    const int64_t c_lo = (int64_t)c * s->chunk_rows, c_cnt = std::min(s->chunk_rows, s->n - c_lo);
+    const int64_t c_lo = s->chunk_lo[c], c_cnt = s->chunk_lo[c + 1] - c_lo;
     const int64_t lo = c_lo + c_cnt * part / s->parts_per_chunk, hi = c_lo + c_cnt * (part + 1) / s->parts_per_chunk;
     if (hi > lo && enc_range(s->e, lo, hi, s->cats, s->nums, s->strides, s->row_format, reinterpret_cast<uint32_t *>(s->h_rows))) s->bad_range.store(1);
     if (s->parts_left[c].fetch_sub(1, std::memory_order_acq_rel) == 1) scorer_submit_chunk(s, c);
@@ -425,6 +431,7 @@ extern "C" int b2f_scorer_start(b2f_scorer *s, int64_t n, const b2f_str_column *
         s->n_chunks = 0;
         return 0;
     }
+    const bool auto_chunks = chunk_rows <= 0;
     if (chunk_rows <= 0) {
         chunk_rows = n <= 8192 ? n : std::max<int64_t>(4096, ((n + 7) / 8 + 255) / 256 * 256);
         /* a forest that STREAMS through shared memory (500 trees x depth 8) makes the GPU the bound of a big request, and its
@@ -438,6 +445,18 @@ extern "C" int b2f_scorer_start(b2f_scorer *s, int64_t n, const b2f_str_column *
     if (n_chunks > B2F_SCORER_MAX_CHUNKS) {
         chunk_rows = ((n + B2F_SCORER_MAX_CHUNKS - 1) / B2F_SCORER_MAX_CHUNKS + 255) / 256 * 256;
         n_chunks = (int)((n + chunk_rows - 1) / chunk_rows);
+    }
+    /* chunk boundaries.  The caller turns results into Python objects more slowly than the pool encodes (23 us vs ~20 us per
+     * 8 192 rows), so the request ends one list-building time after the FIRST chunk is back: when the sizes are ours to choose,
+     * the first chunk is small (its encode + H2D + kernel + D2H round trip is ~50 us instead of ~95) and the others share the rest */
+    static const int64_t first_rows = getenv("B200_FIRST_CHUNK_ROWS") ? atoll(getenv("B200_FIRST_CHUNK_ROWS")) : 2048;
+    if (auto_chunks && n_chunks >= 4 && first_rows >= 256 && first_rows * 4 <= chunk_rows * 2) {
+        const int64_t rest = n - first_rows, each = ((rest + (n_chunks - 2)) / (n_chunks - 1) + 255) / 256 * 256;
+        s->chunk_lo[0] = 0;
+        for (int c = 1; c <= n_chunks; ++c) s->chunk_lo[c] = std::min(n, first_rows + (int64_t)(c - 1) * each);
+        s->chunk_lo[n_chunks] = n;
+    } else {
+        for (int c = 0; c <= n_chunks; ++c) s->chunk_lo[c] = std::min(n, (int64_t)c * chunk_rows);
     }
     CUDA_TRY(cudaSetDevice(s->m->device));
     if (n > s->cap_rows) {
@@ -503,4 +522,11 @@ extern "C" int b2f_scorer_wait(b2f_scorer *s, int chunk) {
 
 extern "C" const void *b2f_scorer_results(const b2f_scorer *s) { return s ? s->h_out : nullptr; }
 extern "C" int64_t b2f_scorer_chunk_rows(const b2f_scorer *s) { return s ? s->chunk_rows : 0; }
+/* rows [*lo, *lo + *cnt) of the request are chunk c of the current job (chunks need not be equal: see b2f_scorer_start) */
+extern "C" int b2f_scorer_chunk_range(const b2f_scorer *s, int c, int64_t *lo, int64_t *cnt) {
+    if (!s || c < 0 || c >= s->n_chunks || !lo || !cnt) return set_err(B2F_EINVAL, "bad chunk index");
+    *lo = s->chunk_lo[c];
+    *cnt = s->chunk_lo[c + 1] - s->chunk_lo[c];
+    return B2F_OK;
+}
 extern "C" int b2f_scorer_threads(const b2f_scorer *s) { return s ? s->n_threads : 0; }

@@ -172,22 +172,26 @@ class B200Model:
         # classifier only: ranked rows (half the PCIe bytes); with the outlier forest on the same rows: packed float32 rows
         n_chunks = sc.start(n, cols, out_mode=3 if full else 1, fmt=(1 if self.encoder.packed_ok else 0) if full else None)
         out = sc.results()
-        step = sc.chunk_rows
-        # Python lists are built chunk by chunk while later chunks are in flight (float objects recycled: _pylists.py)
+        bounds = sc.bounds
+        # Python lists are built chunk by chunk while later chunks are in flight (float objects recycled: _pylists.py); what does
+        # not depend on the results -- the empty lists, the all-zero outlier list of a classifier-only model -- is made while
+        # the first chunk is on its way
         preds = ListBuilder(n)
         flags = ListBuilder(n) if full else None
+        zeros = None if full else [0] * n
         t_first = None
         for c in range(n_chunks):
             sc.wait(c)
             if t_first is None:
                 t_first = time.perf_counter()
-            part = out[c * step:(c + 1) * step]
+            lo = bounds[c]
+            part = out[lo:bounds[c + 1]]
             if full:
-                preds.fill(c * step, part["proba1"])
-                flags.fill(c * step, part["is_outlier"])
+                preds.fill(lo, part["proba1"])
+                flags.fill(lo, part["is_outlier"])
             else:
-                preds.fill(c * step, part)
-        preds, flags = preds.items, (flags.items if full else None)
+                preds.fill(lo, part)
+        preds, flags = preds.items, (flags.items if full else zeros)
         t2 = time.perf_counter()
         self.last_timing = {"columns_s": t1 - t0, "first_chunk_s": (t_first or t2) - t1, "chunks_and_lists_s": t2 - t1, "chunks": n_chunks,
                             "threads": sc.threads, "row_format": sc.last_fmt}

@@ -31,19 +31,20 @@ for _ in range(K):
     t2 = time.perf_counter()
     out = sc.results()
     step = sc.chunk_rows
+    bounds = sc.bounds
     lb = ListBuilder(len(df))
     back, built = [], []
     for c in range(n_chunks):
         sc.wait(c)
         back.append(time.perf_counter())
-        lb.fill(c * step, out[c * step:(c + 1) * step])
+        lb.fill(bounds[c], out[bounds[c]:bounds[c + 1]])
         built.append(time.perf_counter())
     tr = np.zeros(2 * n_chunks)
     lib.b2f_scorer_trace(sc._h, _cabi.ptr(tr), n_chunks)
     rec.append({"columns": 1e6 * (t1 - t0), "start_call": 1e6 * (t2 - t1), "encoded": tr[0::2].tolist(), "enqueued": tr[1::2].tolist(),
                 "back": [1e6 * (b - t1) for b in back], "built": [1e6 * (b - t1) for b in built], "total": 1e6 * (built[-1] - t0)})
 med = lambda key: np.median(np.asarray([r[key] for r in rec]), axis=0)
-res = {"model": MODEL, "row_format": sc.last_fmt, "threads": sc.threads, "chunks": n_chunks, "chunk_rows": int(step), "us_since_start": {k: np.round(med(k), 1).tolist() for k in ("encoded", "enqueued", "back", "built")},
+res = {"model": MODEL, "row_format": sc.last_fmt, "threads": sc.threads, "chunks": n_chunks, "chunk_rows": int(step), "bounds": list(bounds), "us_since_start": {k: np.round(med(k), 1).tolist() for k in ("encoded", "enqueued", "back", "built")},
        "columns_us": float(med("columns")), "start_call_us": float(med("start_call")), "total_us": float(med("total"))}
 print(json.dumps(res, indent=1))
 json.dump(res, open(f"gpurun_out/scorer_trace_{MODEL}_f{sc.last_fmt}_c{chunk_rows}.json", "w"), indent=1)
