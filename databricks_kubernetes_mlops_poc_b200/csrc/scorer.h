@@ -446,10 +446,11 @@ extern "C" int b2f_scorer_start(b2f_scorer *s, int64_t n, const b2f_str_column *
         chunk_rows = ((n + B2F_SCORER_MAX_CHUNKS - 1) / B2F_SCORER_MAX_CHUNKS + 255) / 256 * 256;
         n_chunks = (int)((n + chunk_rows - 1) / chunk_rows);
     }
-    /* chunk boundaries.  The caller turns results into Python objects more slowly than the pool encodes (23 us vs ~20 us per
-     * 8 192 rows), so the request ends one list-building time after the FIRST chunk is back: when the sizes are ours to choose,
-     * the first chunk is small (its encode + H2D + kernel + D2H round trip is ~50 us instead of ~95) and the others share the rest */
-    static const int64_t first_rows = getenv("B200_FIRST_CHUNK_ROWS") ? atoll(getenv("B200_FIRST_CHUNK_ROWS")) : 2048;
+    /* chunk boundaries: equal chunks.  B200_FIRST_CHUNK_ROWS=<r> makes the first chunk of a library-chunked request r rows
+     * (the caller turns results into Python objects more slowly than the pool encodes, so the request ends one list-building
+     * time after the FIRST chunk is back); measured on B200 it does not pay -- a 1 024- or 2 048-row first chunk comes back
+     * no earlier than an 8 192-row one (157 / ~100 us vs 96 us after the start of the request) -- so it is off by default */
+    static const int64_t first_rows = getenv("B200_FIRST_CHUNK_ROWS") ? atoll(getenv("B200_FIRST_CHUNK_ROWS")) : 0;
     if (auto_chunks && n_chunks >= 4 && first_rows >= 256 && first_rows * 4 <= chunk_rows * 2) {
         const int64_t rest = n - first_rows, each = ((rest + (n_chunks - 2)) / (n_chunks - 1) + 255) / 256 * 256;
         s->chunk_lo[0] = 0;

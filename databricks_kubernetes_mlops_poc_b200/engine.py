@@ -320,7 +320,7 @@ class Scorer:
         self._n, self._mode = n, out_mode
         self._chunk = self._lib.b2f_scorer_chunk_rows(self._h)
         lo, cnt = C.c_int64(0), C.c_int64(0)
-        self.bounds = []  # chunk c = rows [bounds[c], bounds[c + 1]): the first chunk of a large request is small
+        self.bounds = []  # chunk c = rows [bounds[c], bounds[c + 1])
         for c in range(max(rc, 0)):
             check(self._lib.b2f_scorer_chunk_range(self._h, c, C.byref(lo), C.byref(cnt)), "b2f_scorer_chunk_range")
             self.bounds.append(lo.value)

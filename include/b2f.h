@@ -264,8 +264,8 @@ int b2f_scorer_start(b2f_scorer *s, int64_t n, const b2f_str_column *cat_cols, c
 int b2f_scorer_wait(b2f_scorer *s, int chunk);       /* chunk `chunk` (rows b2f_scorer_chunk_range) is in the result buffer */
 const void *b2f_scorer_results(const b2f_scorer *s); /* pinned result buffer of the current job: n x {float | double | b2f_scored_full} */
 int64_t b2f_scorer_chunk_rows(const b2f_scorer *s); /* nominal rows per chunk (every chunk, when chunk_rows was given to b2f_scorer_start) */
-/* the rows of chunk c.  With chunk_rows = 0 the first chunk of a large request is small (2 048 rows, B200_FIRST_CHUNK_ROWS) so
- * that the caller has results to work on early; the others share the rest */
+/* the rows of chunk c (chunks are equal except the last; B200_FIRST_CHUNK_ROWS=<r> gives a library-chunked request a first
+ * chunk of r rows) */
 int b2f_scorer_chunk_range(const b2f_scorer *s, int c, int64_t *lo, int64_t *cnt);
 int b2f_scorer_threads(const b2f_scorer *s);
 
