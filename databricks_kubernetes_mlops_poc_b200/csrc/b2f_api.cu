@@ -600,7 +600,11 @@ static int model_init_cuda(b2f_model *m, const uint8_t *blob, size_t nbytes) {
         }
     }
     /* latency kernel: while rows x groups warps still fit about two waves of the chip */
-    m->split_max_rows = std::max<int64_t>(2, (int64_t)m->sm_count * 64 / std::max(1, (int)m->hdr.n_groups));
+    /* the latency form (one CTA per 2 rows, warp = tree group) hands over to the warp-per-row kernel at 3 072 rows: measured on
+     * B200 (profiles/r02_split_threshold.json, synchronous 64-byte-row calls) it is never slower below that -- GBDT 500 x d8:
+     * 35 vs 60 us at 1 024 rows, 59 vs 71 at 3 072, equal at 4 096; GBDT 100 x d6: equal from 512 rows up.  (Round 1 scaled the
+     * threshold with the number of tree groups: 592 rows for 500 trees, which left 768..3 072-row requests on the slower kernel.) */
+    m->split_max_rows = 3072;
     if (const char *sp = getenv("B2F_SPLIT_MAX_ROWS")) m->split_max_rows = atoll(sp);
     if (kn_env_is("warp") || kn_env_is("tile")) m->split_max_rows = 0; /* tests pin one kernel */
     if (kn_env_is("split")) m->split_max_rows = INT64_MAX;
