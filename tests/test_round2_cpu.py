@@ -303,3 +303,24 @@ def test_vector_vocabulary_lookup_matches_a_dictionary():
                         assert got.tolist() == want, (n, str(typ), with_nulls, sl)
     finally:
         lib.b2f_encoder_destroy(enc)
+
+
+def test_host_cpu_limit_and_default_pool_size():
+    """The scorer's pool is sized from the container's CPU bandwidth (cgroup cpu.max): the C reading agrees with the bench's
+    Python reading, and the default never exceeds quota - 2 (nor 48)."""
+    import ctypes as C
+
+    import bench
+    from databricks_kubernetes_mlops_poc_b200 import _cabi
+
+    lib = _cabi.load_library()
+    limit = float(lib.b2f_host_cpu_limit())
+    assert limit >= 0.0 and abs(limit - bench.cpu_bandwidth()) < 1e-9
+    threads = lib.b2f_host_threads_default(0)  # without a GPU: the machine's CPUs instead of the GPU's NUMA node
+    assert 1 <= threads <= 48
+    if limit >= 3.0:
+        assert threads <= int(limit) - 2
+    ncpu = C.c_int(-1)
+    node = lib.b2f_device_numa_node(0, C.byref(ncpu))  # no GPU here: -1 and 0 CPUs; on a GPU box: the node and its CPUs
+    assert node >= -1 and ncpu.value >= 0
+    assert bench.reference_procs("rf") == 1 and 1 <= bench.reference_procs("gbdt") <= 64
