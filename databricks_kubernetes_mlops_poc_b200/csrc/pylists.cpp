@@ -50,7 +50,9 @@ inline PyObject *pooled_float(double v) {
     PyObject *o = slot;
     if (o && Py_REFCNT(o) == 1) {
         reinterpret_cast<PyFloatObject *>(o)->ob_fval = v; /* nobody else can see this object */
+        Py_SET_REFCNT(o, 2);                               /* the ring's reference + the list's */
         ++g_reused;
+        return o;
     } else {
         o = PyFloat_FromDouble(v);
         if (!o) return nullptr;
@@ -78,6 +80,11 @@ int b2f_py_list_fill_f64(PyObject *list, Py_ssize_t offset, const char *base, Py
     for (Py_ssize_t i = 0; i < n; ++i) {
         double v;
         memcpy(&v, base + i * stride, sizeof(v));
+        if (pooled) { /* the ring is read in order, the objects it points to are wherever pymalloc put them: fetch ahead */
+            Py_ssize_t ahead = g_cursor + 12;
+            if (ahead >= g_cap) ahead -= g_cap;
+            if (g_ring[ahead]) __builtin_prefetch(g_ring[ahead], 1, 3);
+        }
         PyObject *f = pooled ? pooled_float(v) : PyFloat_FromDouble(v);
         if (!f) return -1;
         PyObject *old = PyList_GET_ITEM(list, offset + i);
