@@ -41,12 +41,28 @@ def _torchrun(args, extra_env=None, timeout=600):
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
 
 
+def _json_objects(text: str) -> list:
+    """Every JSON object printed on a line of its own -- or glued to another rank's (two processes write to one pipe: a line
+    and its newline are not one atomic write)."""
+    dec, out = json.JSONDecoder(), []
+    for line in text.splitlines():
+        i = line.find("{")
+        while 0 <= i < len(line):
+            try:
+                obj, end = dec.raw_decode(line, i)
+            except json.JSONDecodeError:
+                break
+            out.append(obj)
+            i = line.find("{", end)
+    return out
+
+
 def test_two_rank_moments_merge(tmp_path):
     w = tmp_path / "worker.py"
     w.write_text(WORKER)
     r = _torchrun([str(w)])
     assert r.returncode == 0, r.stderr[-2000:]
-    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    lines = _json_objects(r.stdout)
     assert sorted(l["rank"] for l in lines) == [0, 1]
     assert all(l["ok"] and l["world"] == 2 for l in lines)
     assert sum(l["rows"] for l in lines) == 10007
@@ -74,7 +90,7 @@ def test_reference_arm_under_torchrun(tmp_path):
     r = _torchrun(["bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--model", "rf100d6"],
                   extra_env={"B2F_BENCH_CACHE": str(tmp_path)})
     assert r.returncode == 0, r.stderr[-2000:]
-    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    lines = _json_objects(r.stdout)
     assert len(lines) == 1
     d = lines[0]
     assert d["impl"] == "reference" and d["unit"] == "rows/s" and d["value"] > 0 and d["gpu_launches"] == 0
