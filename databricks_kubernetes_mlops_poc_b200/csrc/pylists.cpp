@@ -80,11 +80,6 @@ int b2f_py_list_fill_f64(PyObject *list, Py_ssize_t offset, const char *base, Py
     for (Py_ssize_t i = 0; i < n; ++i) {
         double v;
         memcpy(&v, base + i * stride, sizeof(v));
-        if (pooled) { /* the ring is read in order, the objects it points to are wherever pymalloc put them: fetch ahead */
-            Py_ssize_t ahead = g_cursor + 12;
-            if (ahead >= g_cap) ahead -= g_cap;
-            if (g_ring[ahead]) __builtin_prefetch(g_ring[ahead], 1, 3);
-        }
         PyObject *f = pooled ? pooled_float(v) : PyFloat_FromDouble(v);
         if (!f) return -1;
         PyObject *old = PyList_GET_ITEM(list, offset + i);
