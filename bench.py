@@ -388,6 +388,11 @@ def run_b200(args, dist: Dist):
     from databricks_kubernetes_mlops_poc_b200.schema import ALL_FEATURES
 
     K, W = args.steps, max(args.warmup, 3)
+    # one process per GPU: live on the GPU's socket (the DataFrame the encoder threads read, the Python heap the response lists
+    # are built in and the pinned staging then share a NUMA node; on the 8-GPU box ranks 4-7 serve GPUs of node 1)
+    bound_cpus = 0
+    if os.environ.get("B200_BIND_CALLER", "1") != "0":
+        bound_cpus = int(_cabi.load_library().b2f_bind_caller_near(dist.local_rank))
     pipe, base = get_pipeline(args.model, dist)
     flat = flatten.flatten_pipeline(pipe)
     model = B200Model(flat, devices=[dist.local_rank], host_threads=host_thread_share(dist))  # the plugin object (classifier only)
@@ -645,7 +650,7 @@ def run_b200(args, dist: Dist):
                 "api": "B200Model.predict(DataFrame of 9 string + 14 float64 columns) -> {'predictions': list[float], 'outliers': list, "
                        "'feature_drift_batch': dict}: the plugin call of reference app/main.py:72 (classifier only, like the reference arm)",
                 "breakdown": breakdown, "parity_max_abs_dp_vs_sklearn_2048rows": plugin_parity, "gpu_launches": int(launches_plugin),
-                "warmup_calls": plugin_warmup},
+                "warmup_calls": plugin_warmup, "process_bound_to_gpu_node_cpus": bound_cpus},
         "e2e_c_abi": {"value": cabi_value, "unit": "rows/s", "h2d_bytes_per_step": BATCH * row_bytes, "d2h_bytes_per_step": BATCH * 8,
                       "ms_per_step": 1e3 * dist.max(cabi_s) / K, "p50_ms": 1e3 * float(np.percentile(lat, 50)), "p99_ms": 1e3 * float(np.percentile(lat, 99)),
                       "api": f"b2f_predict_pairs(pre-encoded {row_bytes}-byte rows in pinned host memory) -> {{float32 proba, int32 label}} per row",

@@ -144,6 +144,7 @@ SIGNATURES = {
     "b2f_host_threads_default": (C.c_int, [C.c_int]),
     "b2f_host_cpu_limit": (C.c_double, []),
     "b2f_device_numa_node": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
+    "b2f_bind_caller_near": (C.c_int, [C.c_int]),
     "b2f_scorer_start": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(StrColumn), C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_int64]),
     "b2f_scorer_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "b2f_scorer_results": (C.c_void_p, [C.c_void_p]),

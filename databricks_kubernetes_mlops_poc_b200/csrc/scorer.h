@@ -113,6 +113,17 @@ static int default_host_threads(int device) {
     return threads;
 }
 
+/* bind the CALLING thread to the CPUs of a GPU's NUMA node (threads it creates afterwards inherit the mask; memory it touches
+ * first lands on that node).  For a process that serves one GPU: call it before building the request data, so that the
+ * DataFrame the encoder threads read, the Python heap the response is built in and the pinned staging all sit on the GPU's
+ * socket.  Returns the number of CPUs bound to, 0 when the topology is not exposed (nothing changed). */
+extern "C" int b2f_bind_caller_near(int device) {
+    cpu_set_t set;
+    if (!numa_cpus_of_device(device, &set)) return 0;
+    if (pthread_setaffinity_np(pthread_self(), sizeof(set), &set) != 0) return 0;
+    return CPU_COUNT(&set);
+}
+
 /* NUMA node of a GPU (sysfs numa_node of its PCI device), -1 when the topology is not exposed; *n_cpus = logical CPUs of that
  * node this process may run on */
 extern "C" int b2f_device_numa_node(int device, int *n_cpus) {

@@ -253,6 +253,9 @@ b2f_scorer *b2f_scorer_create(b2f_model *m, const b2f_encoder *e, int threads /*
 int b2f_scorer_trace(const b2f_scorer *s, double *out, int max_chunks);
 int b2f_host_threads_default(int device);
 double b2f_host_cpu_limit(void);
+/* bind the calling thread (and the threads it creates later) to the CPUs of the GPU's NUMA node; returns the CPU count, 0 = unchanged.
+ * A one-GPU serving process calls it before it builds request data: column buffers, response objects and staging then share a socket */
+int b2f_bind_caller_near(int device);
 /* NUMA node of a GPU (-1: not exposed) and the number of logical CPUs of that node this process may use */
 int b2f_device_numa_node(int device, int *n_cpus);
 void b2f_scorer_destroy(b2f_scorer *s);
