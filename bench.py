@@ -391,8 +391,10 @@ def run_b200(args, dist: Dist):
     # one process per GPU: live on the GPU's socket (the DataFrame the encoder threads read, the Python heap the response lists
     # are built in and the pinned staging then share a NUMA node; on the 8-GPU box ranks 4-7 serve GPUs of node 1)
     bound_cpus = 0
-    if os.environ.get("B200_BIND_CALLER", "1") != "0":
-        bound_cpus = int(_cabi.load_library().b2f_bind_caller_near(dist.local_rank))
+    lib0 = _cabi.load_library()
+    if os.environ.get("B200_BIND_CALLER", "1") != "0" and (dist.world > 1 or lib0.b2f_device_count() == 1):
+        # (not when ONE process drives several GPUs -- the config-4 stream leg binds a thread per GPU to that GPU's node itself)
+        bound_cpus = int(lib0.b2f_bind_caller_near(dist.local_rank))
     pipe, base = get_pipeline(args.model, dist)
     flat = flatten.flatten_pipeline(pipe)
     model = B200Model(flat, devices=[dist.local_rank], host_threads=host_thread_share(dist))  # the plugin object (classifier only)
