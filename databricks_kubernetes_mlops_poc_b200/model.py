@@ -169,7 +169,8 @@ class B200Model:
         if full:
             _reject_nan(df, self.numeric_features)
         t1 = time.perf_counter()
-        # classifier only: ranked rows (half the PCIe bytes); with the outlier forest on the same rows: packed float32 rows
+        # classifier only: the scorer's own choice (64-byte float32 rows: cheapest to encode; ranked rows with B200_SCORER_ROWS=ranked);
+        # with the outlier forest on the same rows: float32 rows (ranks are relative to ONE forest's split values)
         n_chunks = sc.start(n, cols, out_mode=3 if full else 1, fmt=(1 if self.encoder.packed_ok else 0) if full else None)
         out = sc.results()
         bounds = sc.bounds
